@@ -1,0 +1,90 @@
+"""Canonical file-level flow: header, one (Joint)WriteDataBlock per
+nMDCTLines-frame PCM block (the last one zero padded, pcmfile.py:79-82), Close() = one extra NON-joint block
+of zeros.  Decode: (Joint)ReadDataBlock for every block pair but the last, ReadDataBlock for the flush pair,
+first decoded block dropped (pacfileThem.py:1175-1177), saved overlap returned once at EOF (:178-185).
+This is the plain per-block loop of audiofile.py:24-38, not the reference __main__ with its look-ahead /
+block-switching driver (out of scope)."""
+from struct import unpack
+
+import numpy as np
+
+from .pacfile import CodingParams, PACWriter, PACReader
+from .pcm import pcm_to_fraction, fraction_to_pcm
+
+
+def make_params(sampleRate=48000, nChannels=2, numSamples=0, nMDCTLines=1024, nScaleBits=4, nMantSizeBits=4,
+                targetBitsPerSample=128000. / 48000.):
+    """pacfileThem.py:1105-1121 (the reference hard-codes 2.86 bits/sample; BASELINE uses 128 kb/s/ch)."""
+    cp = CodingParams()
+    cp.sampleRate = int(sampleRate)
+    cp.nChannels = nChannels
+    cp.numSamples = int(numSamples)
+    cp.bitsPerSample = 16
+    cp.nMDCTLines = cp.nSamplesPerBlock = nMDCTLines
+    cp.nScaleBits = nScaleBits
+    cp.nMantSizeBits = nMantSizeBits
+    cp.targetBitsPerSample = targetBitsPerSample
+    cp.bitReservoir = 0
+    cp.nSamplesShort = 128
+    cp.a = cp.b = nMDCTLines
+    cp.blkswBitA = cp.blkswBitB = 1
+    return cp
+
+
+def encode_pcm(pcm, joint=True, trace=False, **kw):
+    """pcm: int16 array [numSamples, nChannels] (interleaved frames).  Returns (pac bytes, per-block trace)."""
+    pcm = np.asarray(pcm, dtype=np.int16)
+    n, nCh = pcm.shape
+    cp = make_params(numSamples=n, nChannels=nCh, **kw)
+    w = PACWriter(cp)
+    L = cp.nMDCTLines
+    nBlocks = (n + L - 1) // L
+    blocks = []
+    for b in range(nBlocks):
+        seg = pcm[b * L:(b + 1) * L]
+        if seg.shape[0] < L:
+            seg = np.concatenate((seg, np.zeros((L - seg.shape[0], nCh), dtype=np.int16)))
+        data = [pcm_to_fraction(seg[:, c]) for c in range(nCh)]
+        r = w.JointWriteDataBlock(data, cp) if joint else w.WriteDataBlock(data, cp)
+        if trace:
+            blocks.append(r)
+    r = w.Close(cp)
+    if trace:
+        blocks.append(r)
+    return w.getvalue(), blocks
+
+
+def count_block_pairs(blob, nChannels):
+    """walk the <L nBytes> chain after the header."""
+    nBands = unpack('<L', blob[22:26])[0]
+    pos = 26 + 2 * nBands
+    n = 0
+    while pos < len(blob):
+        pos += 4 + unpack('<L', blob[pos:pos + 4])[0]
+        n += 1
+    return n // nChannels
+
+
+def decode_pac(blob, joint=True):
+    """Returns int16 PCM [nBlocks*nMDCTLines, nChannels]: pairs 1..B overlap-added with their predecessor plus
+    the final saved tail (B+1 pairs in the file -> B+1 PCM blocks; the last one is the flush tail)."""
+    r = PACReader(blob)
+    cp = r.params
+    cp.bitsPerSample = 16
+    nPairs = count_block_pairs(blob, cp.nChannels)
+    out = []
+    first = True
+    i = 0
+    while True:
+        if joint and i != nPairs - 1:
+            data = r.JointReadDataBlock(cp)
+        else:
+            data = r.ReadDataBlock(cp)
+        i += 1
+        if not data:
+            break
+        if first:
+            first = False
+            continue
+        out.append(np.stack([fraction_to_pcm(np.array(d)) for d in data], axis=1))
+    return np.concatenate(out, axis=0) if out else np.zeros((0, cp.nChannels), np.int16)
