@@ -1,0 +1,160 @@
+/*
+ * mrc.h -- C ABI of libmrc.so: the B200-native encode/decode hot path of the MRC ("Music 422 PAC")
+ * perceptual audio codec, a drop-in behind the reference's own seam.
+ *
+ * Reference interfaces replaced (file:line in laser55/mrcAudioCodec):
+ *   per-block seam     PACFile.Encode / JointEncode / Decode / JointDecode   pacfileThem.py:987-1019
+ *                      -> codecThem.Encode :205-231, JointEncode :262-278, Decode :30-63, JointDecode :65-134
+ *   whole-file loop    audiofile.py:24-38 driving PACFile.WriteFileHeader :586-619, WriteDataBlock :622-790,
+ *                      JointWriteDataBlock :793-972, Close :973-984, ReadFileHeader :130-158,
+ *                      ReadDataBlock :161-319, JointReadDataBlock :321-585 and the PCM sample conversion of
+ *                      PCMFile.ReadDataBlock pcmfile.py:68-102 / WriteDataBlock :156-185
+ *
+ * Conventions: every entry point returns 0 on success or a negative MRC_E_* code; mrc_last_error(ctx) gives a
+ * human-readable message.  No exceptions cross the boundary.  There is no CPU fallback: without a CUDA device
+ * mrc_create fails with MRC_E_CUDA.  A context is bound to one device and one CUDA stream; calls on one context
+ * must be serialised by the caller.  The library never keeps host pointers beyond the call that received them.
+ * All multi-byte values in .pac data are little-endian, bits are MSB-first (bitpack.py:36-101).
+ */
+#ifndef MRC_H_
+#define MRC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRC_VERSION 100
+
+#define MRC_OK 0
+#define MRC_E_INVALID (-1)   /* bad argument / unsupported configuration            */
+#define MRC_E_CUDA (-2)      /* CUDA error or no device                             */
+#define MRC_E_NOSPACE (-3)   /* output buffer too small (needed size is reported)   */
+#define MRC_E_FORMAT (-4)    /* malformed .pac input                                */
+#define MRC_E_STATE (-5)     /* tables not set, etc.                                */
+
+#define MRC_MAX_BANDS 32
+#define MRC_HUFF_LUT 65      /* mantissa values 0..64 can have a code; anything else is an escape (Appendix E) */
+#define MRC_N_HUFF_TABLES 4
+#define MRC_NO_TABLE 15
+
+#define MRC_PRECISION_FP64 0 /* code-exact mode                                      */
+#define MRC_PRECISION_FP32 1 /* fast mode (MDCT/SMR within 1e-5 relative)            */
+
+typedef struct mrc_ctx mrc_ctx;
+
+/* Mirrors the attribute bag the reference fills at pacfileThem.py:1105-1121. */
+typedef struct mrc_config {
+    int32_t device;                 /* CUDA device ordinal                                            */
+    int32_t sample_rate;            /* codingParams.sampleRate (int, pcmfile.py:46)                   */
+    int32_t n_mdct_lines;           /* codingParams.nMDCTLines: 256, 512, 1024 or 2048 (long blocks)  */
+    int32_t n_scale_bits;           /* codingParams.nScaleBits  (4)                                   */
+    int32_t n_mant_size_bits;       /* codingParams.nMantSizeBits (4)                                 */
+    int32_t joint;                  /* 1: JointWriteDataBlock flow (M/S), 0: WriteDataBlock flow      */
+    int32_t precision;              /* MRC_PRECISION_*                                                */
+    int32_t reserved0;
+    double target_bits_per_sample;  /* codingParams.targetBitsPerSample                               */
+    int64_t reserved1[4];
+} mrc_config;
+
+/* Data-independent tables, computed by the host exactly as the reference computes them (numpy), uploaded once.
+ * kbd_window = TransitionWindow(ones, L, L) window.py:104-121; hann_window window.py:36-42;
+ * bark = Bark(MDCTFreq) psychoac.py:29,143; quiet_intensity = Intensity(Thresh(MDCTFreq)) psychoac.py:155;
+ * band_nlines = AssignMDCTLinesFromFreqLimits psychoac.py:86-105; huff_* from training_data/*_table.pkl in
+ * alphabetical table order (percussive, silence, speech, tonal). */
+typedef struct mrc_tables {
+    int32_t n_bands;
+    int32_t n_huff_tables;                 /* must be MRC_N_HUFF_TABLES                                  */
+    const int32_t* band_nlines;            /* [n_bands]                                                  */
+    const double* kbd_window;              /* [2*n_mdct_lines]                                           */
+    const double* hann_window;             /* [2*n_mdct_lines]                                           */
+    const double* bark;                    /* [n_mdct_lines]                                             */
+    const double* quiet_intensity;         /* [n_mdct_lines]                                             */
+    const int32_t* huff_escape;            /* [n_huff_tables] escape value of each table                 */
+    const uint8_t* huff_len;               /* [n_huff_tables][MRC_HUFF_LUT] code length, 0 = not a key   */
+    const uint16_t* huff_code;             /* [n_huff_tables][MRC_HUFF_LUT] code bits (right aligned)    */
+} mrc_tables;
+
+int32_t mrc_version(void);
+const char* mrc_last_error(const mrc_ctx* ctx);   /* ctx may be NULL: message of the last failed mrc_create */
+
+int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out);
+int32_t mrc_destroy(mrc_ctx* ctx);
+int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t);
+
+/* Pinned host memory for PCM / bitstream buffers (optional; pageable memory works but copies slower). */
+int32_t mrc_host_alloc(void** p, int64_t bytes);
+int32_t mrc_host_free(void* p);
+
+/* ---- whole-file batch encode: replaces the audiofile.py:24-38 loop over PCMFile.ReadDataBlock +
+ * PACFile.(Joint)WriteDataBlock + Close for n_clips independent files ------------------------------------
+ * pcm                : interleaved 16-bit stereo frames of all clips back to back (host memory)
+ * clip_frame_offsets : [n_clips+1] frame offsets into pcm
+ * out / out_cap      : receives the n_clips .pac files back to back (header + block chunks + flush block)
+ * clip_byte_offsets  : [n_clips+1] byte offsets into out (written even on MRC_E_NOSPACE, so the caller can
+ *                      size the buffer: clip_byte_offsets[n_clips] is the total)                           */
+int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
+                         uint8_t* out, int64_t out_cap, int64_t* clip_byte_offsets);
+
+/* Same, with pcm and out in DEVICE memory of ctx's device (clip offset arrays stay on the host).  Used to time
+ * the kernels with inputs resident in HBM.  Runs on the context's stream and synchronises before returning. */
+int32_t mrc_encode_batch_device(mrc_ctx* ctx, const int16_t* d_pcm, const int64_t* clip_frame_offsets,
+                                int32_t n_clips, uint8_t* d_out, int64_t out_cap, int64_t* clip_byte_offsets);
+
+/* ---- whole-file batch decode: replaces the loop over PACFile.(Joint)ReadDataBlock + PCMFile.WriteDataBlock --
+ * pac / clip_byte_offsets : n_clips .pac files back to back (host memory)
+ * pcm_out / pcm_cap_frames: receives interleaved 16-bit frames; per clip (#block pairs) * n_mdct_lines frames
+ *                           (pairs 1..B overlap-added + the saved tail, first block dropped: pacfileThem.py
+ *                           :1175-1177, :178-185)
+ * clip_frame_offsets      : [n_clips+1] frame offsets into pcm_out (output)
+ * The last block pair of every file is read as a non-joint pair (Close() writes it so, Q10); the others follow
+ * ctx's `joint` flag.                                                                                       */
+int32_t mrc_decode_batch(mrc_ctx* ctx, const uint8_t* pac, const int64_t* clip_byte_offsets, int32_t n_clips,
+                         int16_t* pcm_out, int64_t pcm_cap_frames, int64_t* clip_frame_offsets);
+int32_t mrc_decode_batch_device(mrc_ctx* ctx, const uint8_t* d_pac, const uint8_t* h_pac,
+                                const int64_t* clip_byte_offsets, int32_t n_clips, int16_t* d_pcm_out,
+                                int64_t pcm_cap_frames, int64_t* clip_frame_offsets);
+
+/* ---- per-block seam (compat layer; explicit bit reservoir in/out) -----------------------------------------
+ * mrc_encode_block = codecThem.Encode (joint=0) / JointEncode (joint=1) on one block.
+ * data             : [2][2*n_mdct_lines] float64 signed fractions (prior block, current block) per channel
+ * reservoir        : in/out codingParams.bitReservoir
+ * scale_factor,bit_alloc : [2][n_bands]; mantissa: [2][n_mdct_lines] aligned to MDCT lines (0 where the band has
+ * no bits); overall_scale: [4] (joint: L,R,M,S; non-joint: ch0,ch1,-,-); ms_switch: [n_bands]; huff_table: [2];
+ * chunk_bytes: [2] size of each channel chunk as (Joint)WriteDataBlock would write it.                      */
+int32_t mrc_encode_block(mrc_ctx* ctx, const double* data, int32_t joint, int32_t* reservoir,
+                         int32_t* scale_factor, int32_t* bit_alloc, int32_t* mantissa, int32_t* overall_scale,
+                         int32_t* ms_switch, int32_t* huff_table, int32_t* chunk_bytes);
+/* mrc_decode_block = codecThem.Decode x2 (joint=0) / JointDecode (joint=1): returns the windowed IMDCT output
+ * [2][2*n_mdct_lines] (before overlap-add), like the reference functions. */
+int32_t mrc_decode_block(mrc_ctx* ctx, int32_t joint, const int32_t* scale_factor, const int32_t* bit_alloc,
+                         const int32_t* mantissa, const int32_t* overall_scale, const int32_t* ms_switch,
+                         double* data_out);
+
+/* ---- stage taps for parity tests (run the encode front end on whole clips and return intermediates) -------
+ * All output pointers may be NULL.  n_blocks_total = sum over clips of (ceil(frames/L) + 1).
+ * mdct_lines [n_blocks_total][4][L]  UNSCALED lines of L,R,M,S (M,S zero for non-joint blocks)
+ * overall_scale [n_blocks_total][4], ms_switch [n_blocks_total][n_bands], smr [n_blocks_total][4][n_bands],
+ * n_peaks [n_blocks_total][4] tonal maskers found per spectrum.                                              */
+int32_t mrc_stage_analysis(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
+                           double* mdct_lines, int32_t* overall_scale, int32_t* ms_switch, double* smr,
+                           int32_t* n_peaks);
+/* bit_alloc,scale_factor [n_blocks_total][2][n_bands]; mantissa [n_blocks_total][2][L]; huff_table
+ * [n_blocks_total][2]; reservoir [n_blocks_total] (codingParams.bitReservoir after the block);
+ * chunk_bytes [n_blocks_total][2].                                                                           */
+int32_t mrc_stage_alloc_quant(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets,
+                              int32_t n_clips, int32_t* bit_alloc, int32_t* scale_factor, int32_t* mantissa,
+                              int32_t* huff_table, int32_t* reservoir, int32_t* chunk_bytes);
+
+/* ---- instrumentation ------------------------------------------------------------------------------------- */
+/* Device time (ms, CUDA events on the context's stream) of the stages of the last encode/decode call:
+ * [0] analysis kernel, [1] alloc/quantise kernel, [2] pack kernels, [3] decode kernels, [4] H2D, [5] D2H,
+ * [6] total on stream; counters [0] kernel launches, [1] sum over spectra of tonal maskers, [2] blocks,
+ * [3] spectra analysed. */
+int32_t mrc_last_timing(const mrc_ctx* ctx, double* ms8, int64_t* counters8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRC_H_ */

@@ -1,0 +1,216 @@
+"""Python host side of the B200 codec: a thin object around one libmrc context (one GPU, one stream).
+
+Batch API (what is timed): encode_batch / decode_batch replace the reference's whole-file loops
+(audiofile.py:24-38 over pcmfile.py + pacfileThem.py).  The per-block seam with the reference's own function
+names lives in codec_gpu.py."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .tables import Tables
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Codec(object):
+    def __init__(self, sample_rate=48000, n_mdct_lines=1024, n_scale_bits=4, n_mant_size_bits=4,
+                 target_bits_per_sample=128000. / 48000., joint=True, precision="fp64", device=0,
+                 band_limits=None):
+        self.lib = _lib.load()
+        self.L = int(n_mdct_lines)
+        self.sample_rate = int(sample_rate)
+        self.joint = bool(joint)
+        self.precision = precision
+        cfg = _lib.MrcConfig()
+        cfg.device = int(device)
+        cfg.sample_rate = self.sample_rate
+        cfg.n_mdct_lines = self.L
+        cfg.n_scale_bits = int(n_scale_bits)
+        cfg.n_mant_size_bits = int(n_mant_size_bits)
+        cfg.joint = 1 if joint else 0
+        cfg.precision = {"fp64": _lib.PRECISION_FP64, "fp32": _lib.PRECISION_FP32}[precision]
+        cfg.target_bits_per_sample = float(target_bits_per_sample)
+        self._ctx = C.c_void_p()
+        rc = self.lib.mrc_create(C.byref(cfg), C.byref(self._ctx))
+        if rc != 0:
+            raise _lib.MrcError(rc, self.lib.mrc_last_error(None).decode())
+        self.tables = Tables(self.L, self.sample_rate, band_limits)
+        t = _lib.MrcTables()
+        T = self.tables
+        t.n_bands = T.n_bands
+        t.n_huff_tables = len(T.huff_escape)
+        t.band_nlines = T.band_nlines.ctypes.data_as(_lib.c_i32p)
+        t.kbd_window = T.kbd.ctypes.data_as(_lib.c_f64p)
+        t.hann_window = T.hann.ctypes.data_as(_lib.c_f64p)
+        t.bark = T.bark.ctypes.data_as(_lib.c_f64p)
+        t.quiet_intensity = T.quiet.ctypes.data_as(_lib.c_f64p)
+        t.huff_escape = T.huff_escape.ctypes.data_as(_lib.c_i32p)
+        t.huff_len = T.huff_len.ctypes.data_as(_lib.c_u8p)
+        t.huff_code = T.huff_code.ctypes.data_as(_lib.c_u16p)
+        self._check(self.lib.mrc_set_tables(self._ctx, C.byref(t)))
+        self.n_bands = T.n_bands
+
+    # ------------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.MrcError(rc, self.lib.mrc_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.lib.mrc_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def n_blocks(self, frames):
+        """block pairs per clip: ceil(frames/L) data blocks + the Close() flush block."""
+        return (int(frames) + self.L - 1) // self.L + 1
+
+    @staticmethod
+    def _concat(clips):
+        clips = [np.ascontiguousarray(c, dtype=np.int16).reshape(-1, 2) for c in clips]
+        off = np.zeros(len(clips) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([c.shape[0] for c in clips])
+        pcm = np.concatenate(clips, axis=0) if clips else np.zeros((0, 2), np.int16)
+        return np.ascontiguousarray(pcm), off
+
+    def nominal_capacity(self, frame_offsets):
+        fr = np.diff(frame_offsets)
+        nblk = (fr + self.L - 1) // self.L + 1
+        return int(np.sum(256 + nblk * (2 * 1.5 * self.L * 16 // 8 // 4 + 256)))
+
+    # ---- batch encode ----------------------------------------------------------------------------
+    def encode_batch(self, pcm, frame_offsets, out=None):
+        """pcm: int16 [frames,2] of all clips back to back (host), frame_offsets int64 [n+1].
+        Returns (out uint8 array, byte_offsets int64 [n+1])."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        frame_offsets = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+        n = len(frame_offsets) - 1
+        boff = np.zeros(n + 1, dtype=np.int64)
+        if out is None:
+            out = np.empty(self.nominal_capacity(frame_offsets), dtype=np.uint8)
+        rc = self.lib.mrc_encode_batch(self._ctx, _ptr(pcm), _ptr(frame_offsets), n, _ptr(out), out.size, _ptr(boff))
+        if rc == _lib.MRC_E_NOSPACE and boff[n] > out.size:
+            out = np.empty(int(boff[n]), dtype=np.uint8)
+            rc = self.lib.mrc_encode_batch(self._ctx, _ptr(pcm), _ptr(frame_offsets), n, _ptr(out), out.size,
+                                           _ptr(boff))
+        self._check(rc)
+        return out, boff
+
+    def encode_clips(self, clips):
+        """list of int16 [frames,2] arrays -> list of .pac byte strings."""
+        pcm, off = self._concat(clips)
+        out, boff = self.encode_batch(pcm, off)
+        return [out[boff[i]:boff[i + 1]].tobytes() for i in range(len(clips))]
+
+    def encode_batch_device(self, d_pcm_ptr, frame_offsets, d_out_ptr, out_cap):
+        """device-resident variant: raw device pointers (e.g. torch tensor .data_ptr())."""
+        frame_offsets = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+        n = len(frame_offsets) - 1
+        boff = np.zeros(n + 1, dtype=np.int64)
+        self._check(self.lib.mrc_encode_batch_device(self._ctx, C.c_void_p(d_pcm_ptr), _ptr(frame_offsets), n,
+                                                     C.c_void_p(d_out_ptr), int(out_cap), _ptr(boff)))
+        return boff
+
+    # ---- batch decode ----------------------------------------------------------------------------
+    def decode_batch(self, pac, byte_offsets, pcm_out=None):
+        pac = np.ascontiguousarray(pac, dtype=np.uint8)
+        byte_offsets = np.ascontiguousarray(byte_offsets, dtype=np.int64)
+        n = len(byte_offsets) - 1
+        foff = np.zeros(n + 1, dtype=np.int64)
+        if pcm_out is None:
+            # a chunk pair is at least ~2*(4+30) bytes, but size exactly: ask the library (NOSPACE reports sizes)
+            rc = self.lib.mrc_decode_batch(self._ctx, _ptr(pac), _ptr(byte_offsets), n, None, 0, _ptr(foff))
+            if rc not in (0, _lib.MRC_E_NOSPACE):
+                self._check(rc)
+            pcm_out = np.empty((int(foff[n]), 2), dtype=np.int16)
+        self._check(self.lib.mrc_decode_batch(self._ctx, _ptr(pac), _ptr(byte_offsets), n, _ptr(pcm_out),
+                                              pcm_out.shape[0], _ptr(foff)))
+        return pcm_out, foff
+
+    def decode_clips(self, blobs):
+        arrs = [np.frombuffer(b, dtype=np.uint8) for b in blobs]
+        off = np.zeros(len(arrs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([a.size for a in arrs])
+        pac = np.concatenate(arrs) if arrs else np.zeros(0, np.uint8)
+        pcm, foff = self.decode_batch(pac, off)
+        return [pcm[foff[i]:foff[i + 1]].copy() for i in range(len(blobs))]
+
+    def decode_batch_device(self, d_pac_ptr, h_pac, byte_offsets, d_pcm_ptr, pcm_cap_frames):
+        byte_offsets = np.ascontiguousarray(byte_offsets, dtype=np.int64)
+        n = len(byte_offsets) - 1
+        foff = np.zeros(n + 1, dtype=np.int64)
+        self._check(self.lib.mrc_decode_batch_device(self._ctx, C.c_void_p(d_pac_ptr), _ptr(h_pac), _ptr(byte_offsets),
+                                                     n, C.c_void_p(d_pcm_ptr), int(pcm_cap_frames), _ptr(foff)))
+        return foff
+
+    # ---- stage taps --------------------------------------------------------------------------------
+    def stage_analysis(self, clips):
+        pcm, off = self._concat(clips)
+        nb = sum(self.n_blocks(c) for c in np.diff(off))
+        lines = np.zeros((nb, 4, self.L), np.float64)
+        ovs = np.zeros((nb, 4), np.int32)
+        ms = np.zeros((nb, self.n_bands), np.int32)
+        smr = np.zeros((nb, 4, self.n_bands), np.float64)
+        npk = np.zeros((nb, 4), np.int32)
+        self._check(self.lib.mrc_stage_analysis(self._ctx, _ptr(pcm), _ptr(off), len(clips), _ptr(lines), _ptr(ovs),
+                                                _ptr(ms), _ptr(smr), _ptr(npk)))
+        return dict(mdct=lines, overallScale=ovs, ms_switch=ms, smr=smr, n_peaks=npk)
+
+    def stage_alloc_quant(self, clips):
+        pcm, off = self._concat(clips)
+        nb = sum(self.n_blocks(c) for c in np.diff(off))
+        ba = np.zeros((nb, 2, self.n_bands), np.int32)
+        sf = np.zeros((nb, 2, self.n_bands), np.int32)
+        mant = np.zeros((nb, 2, self.L), np.int32)
+        ht = np.zeros((nb, 2), np.int32)
+        res = np.zeros(nb, np.int32)
+        cb = np.zeros((nb, 2), np.int32)
+        self._check(self.lib.mrc_stage_alloc_quant(self._ctx, _ptr(pcm), _ptr(off), len(clips), _ptr(ba), _ptr(sf),
+                                                   _ptr(mant), _ptr(ht), _ptr(res), _ptr(cb)))
+        return dict(bitAlloc=ba, scaleFactor=sf, mantissa=mant, huffTable=ht, reservoir=res, chunkBytes=cb)
+
+    # ---- per-block seam ------------------------------------------------------------------------------
+    def encode_block(self, data, joint, reservoir):
+        """data: float64 [2, 2L].  Returns dict + new reservoir."""
+        data = np.ascontiguousarray(data, dtype=np.float64).reshape(2, 2 * self.L)
+        res = np.array([int(reservoir)], dtype=np.int32)
+        sf = np.zeros((2, self.n_bands), np.int32)
+        ba = np.zeros((2, self.n_bands), np.int32)
+        mant = np.zeros((2, self.L), np.int32)
+        ovs = np.zeros(4, np.int32)
+        ms = np.zeros(self.n_bands, np.int32)
+        ht = np.zeros(2, np.int32)
+        cb = np.zeros(2, np.int32)
+        self._check(self.lib.mrc_encode_block(self._ctx, _ptr(data), 1 if joint else 0, _ptr(res), _ptr(sf), _ptr(ba),
+                                              _ptr(mant), _ptr(ovs), _ptr(ms), _ptr(ht), _ptr(cb)))
+        return dict(scaleFactor=sf, bitAlloc=ba, mantissa=mant, overallScale=ovs, ms_switch=ms, huffTable=ht,
+                    chunkBytes=cb), int(res[0])
+
+    def decode_block(self, joint, scaleFactor, bitAlloc, mantissa, overallScale, ms_switch=None):
+        sf = np.ascontiguousarray(scaleFactor, dtype=np.int32).reshape(2, self.n_bands)
+        ba = np.ascontiguousarray(bitAlloc, dtype=np.int32).reshape(2, self.n_bands)
+        mant = np.ascontiguousarray(mantissa, dtype=np.int32).reshape(2, self.L)
+        ovs = np.zeros(4, np.int32)
+        o = np.asarray(overallScale, dtype=np.int32).ravel()
+        ovs[:o.size] = o
+        ms = np.zeros(self.n_bands, np.int32) if ms_switch is None else \
+            np.ascontiguousarray(ms_switch, dtype=np.int32)
+        out = np.zeros((2, 2 * self.L), np.float64)
+        self._check(self.lib.mrc_decode_block(self._ctx, 1 if joint else 0, _ptr(sf), _ptr(ba), _ptr(mant), _ptr(ovs),
+                                              _ptr(ms), _ptr(out)))
+        return out
+
+    def last_timing(self):
+        ms = np.zeros(8, np.float64)
+        cnt = np.zeros(8, np.int64)
+        self.lib.mrc_last_timing(self._ctx, _ptr(ms), _ptr(cnt))
+        return dict(analysis_ms=ms[0], quant_ms=ms[1], pack_ms=ms[2], decode_ms=ms[3], h2d_ms=ms[4], d2h_ms=ms[5],
+                    total_ms=ms[6], launches=int(cnt[0]), maskers=int(cnt[1]), blocks=int(cnt[2]))

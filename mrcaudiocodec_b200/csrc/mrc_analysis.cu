@@ -1,0 +1,455 @@
+// mrc_analysis.cu -- K1/K2: framing + PCM conversion + M/S + KBD window + MDCT (N/4-point complex FFT) +
+// Hann-windowed FFT + tonal masker detection + Bark-domain spreading + SMR + grant-order sort, fused in one CTA
+// per 2L-sample block, everything staged in shared memory.
+//
+// Reference path restated here (file:line in laser55/mrcAudioCodec):
+//   pcmfile.py:87-101 + quantize.py:90-111   int16 -> signed fraction (Q1: -32768 -> 0.0)
+//   pacfileThem.py:799-802                    block = concat(prior, current)
+//   codecThem.py:363-364                      Mid/Side in the time domain
+//   window.py:104-121, mdct.py:53-96          KBD window, MDCT with n0=(b+1)/2 and the 2/N factor
+//   ms_stereo.py:5-27                         ms_switch per band on the unscaled L/R lines
+//   quantize.py:114-146 (codecThem.py:440-454) overall scale factor, lines *= 2^scale
+//   psychoac.py:134-173, :31-78               masked threshold (tonal maskers only, Q2 integer frequency step)
+//   psychoac.py:176-219, ms_stereo.py:70-81   SMR per band and M/S vs L/R selection
+//   bitalloc.py:106-155                       (order of grants only: the allocation itself needs the reservoir)
+//
+// One CTA = one block, NT = L/2 threads; thread t owns MDCT lines t and t+L/2.
+#include "mrc_internal.cuh"
+#include "mrc_math.cuh"
+
+namespace {
+
+template <typename T>
+struct Smem {
+    T* sx;          // [2][2L]  time samples L, R
+    cpx<T>* buf;    // [L]      FFT work buffer
+    T* lines;       // [4][L]   MDCT lines L,R,M,S
+    T* xi;          // [L]      FFT intensity, later SMR-per-line scratch
+    T* pz;          // [L/2]    peak Bark position
+    T* ps15;        // [L/2]    peak SPL - 15
+    T* pg;          // [L/2]    0.37*max(SPL-40,0)
+    int* pbin;      // [L/2]
+    T* skey;        // [1024]   sort keys
+    uint16_t* sid;  // [1024]   sort ids
+};
+
+template <typename T>
+__device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
+    Smem<T> s;
+    T* p = reinterpret_cast<T*>(raw);
+    s.sx = p;            p += 4 * L;
+    s.buf = reinterpret_cast<cpx<T>*>(p); p += 2 * L;
+    s.lines = p;         p += 4 * L;
+    s.xi = p;            p += L;
+    s.pz = p;            p += L / 2;
+    s.ps15 = p;          p += L / 2;
+    s.pg = p;            p += L / 2;
+    s.pbin = reinterpret_cast<int*>(p); p += L / 2;   // int fits in a T slot (sizeof(T) >= 4)
+    s.skey = p;          p += 1024;
+    s.sid = reinterpret_cast<uint16_t*>(p);
+    return s;
+}
+
+// in-place radix-2 decimation-in-time FFT of size 2^logn on bit-reversed input; `nthr` threads of this group
+// (local id lt) each do n/(2*nthr) butterflies per stage.  tw[k] = exp(-2*pi*j*k/Ltab), Ltab = 2^logLtab.
+template <typename T>
+__device__ __forceinline__ void fft_dit(cpx<T>* a, int logn, int lt, int nthr, const cpx<T>* __restrict__ tw,
+                                        int logLtab) {
+    const int nb = 1 << (logn - 1);
+    for (int s = 1; s <= logn; ++s) {
+        const int half = 1 << (s - 1);
+        for (int i = lt; i < nb; i += nthr) {
+            const int j = i & (half - 1);
+            const int base = ((i >> (s - 1)) << s) + j;
+            const cpx<T> w = tw[j << (logLtab - s)];
+            const cpx<T> u = a[base];
+            const cpx<T> v = a[base + half];
+            const T vx = v.x * w.x - v.y * w.y;
+            const T vy = v.x * w.y + v.y * w.x;
+            a[base].x = u.x + vx;          a[base].y = u.y + vy;
+            a[base + half].x = u.x - vx;   a[base + half].y = u.y - vy;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// time sample of spectrum c (0 L, 1 R, 2 M, 3 S) -- codecThem.py:363-364
+template <typename T>
+__device__ __forceinline__ T tsample(const T* sx, int N, int c, int n) {
+    const T l = sx[n], r = sx[N + n];
+    if (c == 0) return l;
+    if (c == 1) return r;
+    if (c == 2) return (l + r) / T(2);
+    return (l - r) / T(2);
+}
+
+template <typename T, int LOGL>
+__global__ void __launch_bounds__(1 << (LOGL - 1))
+analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __restrict__ pcm,
+                const double* __restrict__ xin, int g0, Handoff<T> ho, AnalysisTaps<T> taps,
+                unsigned long long* peak_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int L = 1 << LOGL, N = 2 * L, Q = L / 2, logL = LOGL, NT = Q, nwarp = NT >> 5;
+    const int nb = tb.nb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Smem<T> sm = carve<T>(smem_raw, L);
+
+    __shared__ int s_clip, s_b, s_nblk_clip;
+    __shared__ T s_red[4][32];
+    __shared__ T s_smr[4][MRC_BSTRIDE];
+    __shared__ int s_scale[4];
+    __shared__ unsigned int s_ms;
+    __shared__ int s_wcnt[33];
+    __shared__ int s_npk;
+
+    const int g = g0 + blockIdx.x;            // global block index
+    const int lb = blockIdx.x;                // index inside this wave's hand-off buffers
+    if (tid == 0) {
+        int lo = 0, hi = cm.n_clips;          // last clip whose first block <= g
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cm.clip_blk0[mid] <= g) lo = mid; else hi = mid;
+        }
+        s_clip = lo;
+        s_b = g - cm.clip_blk0[lo];
+        s_nblk_clip = cm.clip_blk0[lo + 1] - cm.clip_blk0[lo];
+        s_ms = 0u;
+    }
+    __syncthreads();
+    const int b = s_b;
+    const bool is_flush = (b == s_nblk_clip - 1);
+    const bool joint = cp.joint && !(cp.flush_nonjoint && is_flush);
+    const int nspec = joint ? 4 : 2;
+
+    // ---- phase 0: frame [ (b-1)L, (b+1)L ) of the clip, zero outside ------------------------------------
+    if (xin != nullptr) {
+        for (int i = tid; i < 2 * N; i += NT) sm.sx[i] = T(xin[(size_t)g * 2 * N + i]);
+    } else {
+        const long long frames = cm.clip_off[s_clip + 1] - cm.clip_off[s_clip];
+        const uint32_t* __restrict__ p32 = reinterpret_cast<const uint32_t*>(pcm) + cm.clip_off[s_clip];
+        const long long s0 = (long long)(b - 1) * L;
+        for (int n = tid; n < N; n += NT) {
+            const long long s = s0 + n;
+            uint32_t w = 0;
+            if (s >= 0 && s < frames) w = __ldg(p32 + s);
+            const int cl = (int)(short)(w & 0xffffu), cr = (int)(short)(w >> 16);
+            sm.sx[n] = pcm_to_fraction<T>(cl);
+            sm.sx[N + n] = pcm_to_fraction<T>(cr);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1: KBD window + MDCT, two spectra at a time (each an L/2-point complex FFT) --------------
+    {
+        const int grp = tid / (NT / 2), lt = tid - grp * (NT / 2), gthr = NT / 2;
+        const T two_over_n = T(2) / T(N);
+        for (int pair = 0; pair < nspec / 2; ++pair) {
+            const int c = pair * 2 + grp;
+            cpx<T>* a = sm.buf + grp * Q;
+            for (int n = lt; n < Q; n += gthr) {
+                T re, im;
+                auto y = [&](int i) { return tb.kbd[i] * tsample(sm.sx, N, c, i); };
+                if (n < Q / 2) {
+                    re = -y(3 * Q - 1 - 2 * n) - y(3 * Q + 2 * n);
+                    im = y(Q - 1 - 2 * n) - y(Q + 2 * n);
+                } else {
+                    re = y(2 * n - Q) - y(3 * Q - 1 - 2 * n);
+                    im = -y(Q + 2 * n) - y(5 * Q - 1 - 2 * n);
+                }
+                const cpx<T> w = tb.tw_pre[n];
+                const int r = (int)(__brev((unsigned)n) >> (32 - (logL - 1)));
+                a[r].x = re * w.x - im * w.y;
+                a[r].y = re * w.y + im * w.x;
+            }
+            __syncthreads();
+            fft_dit<T>(a, logL - 1, lt, gthr, tb.tw_fft, logL);
+            T* X = sm.lines + c * L;
+            for (int k = lt; k < Q; k += gthr) {
+                const cpx<T> w = tb.tw_post[k];
+                const cpx<T> t = a[k];
+                X[2 * k] = two_over_n * (t.x * w.x - t.y * w.y);
+                X[L - 1 - 2 * k] = -two_over_n * (t.x * w.y + t.y * w.x);
+            }
+            __syncthreads();
+        }
+    }
+
+    if (taps.lines4 != nullptr) {
+        T* o = taps.lines4 + (size_t)lb * 4 * L;
+        for (int i = tid; i < 4 * L; i += NT) o[i] = (i < nspec * L) ? sm.lines[i] : T(0);
+    }
+
+    // ---- phase 2: ms_switch on the unscaled L/R lines (ms_stereo.py:5-27) -------------------------------
+    if (joint) {
+        for (int bd = warp; bd < nb; bd += nwarp) {
+            const int lo = tb.band_lo[bd], n = tb.band_n[bd];
+            T sd = 0, ss = 0;
+            for (int i = lane; i < n; i += 32) {
+                const T l = sm.lines[lo + i], r = sm.lines[L + lo + i];
+                const T l2 = l * l, r2 = r * r;
+                sd += fabs(l2 - r2);
+                ss += fabs(l2 + r2);
+            }
+            sd = warp_sum(sd);
+            ss = warp_sum(ss);
+            if (lane == 0 && sd < T(0.8) * ss) atomicOr(&s_ms, 1u << bd);
+        }
+    }
+
+    // ---- phase 3: overall scale factors (quantize.py:114-146 with nMantBits=5), lines *= 2^scale --------
+    {
+        T mx[4] = {0, 0, 0, 0};
+        for (int i = tid; i < L; i += NT)
+            for (int c = 0; c < nspec; ++c) mx[c] = fmax(mx[c], fabs(sm.lines[c * L + i]));
+        for (int c = 0; c < nspec; ++c) {
+            const T v = warp_max(mx[c]);
+            if (lane == 0) s_red[c][warp] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int c = 0; c < nspec; ++c) {
+                T v = (lane < nwarp) ? s_red[c][lane] : T(0);
+                v = warp_max(v);
+                if (lane == 0) s_scale[c] = scale_factor_of((double)v, cp.n_scale_bits, 5);
+            }
+            if (lane == 0 && nspec == 2) s_scale[2] = s_scale[3] = 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < L; i += NT)
+            for (int c = 0; c < nspec; ++c) sm.lines[c * L + i] *= T(1 << s_scale[c]);
+        // (no sync needed yet: the next reader of `lines` is after several barriers)
+    }
+
+    // ---- phase 4: psychoacoustic model per spectrum ------------------------------------------------------
+    const T xi_den = T(N) * T(N) * T(0.375);
+    int my_peaks = 0;
+    for (int c = 0; c < nspec; ++c) {
+        // a. Hann window, real 2L-point FFT through an L-point complex FFT
+        for (int n = tid; n < L; n += NT) {
+            const int r = (int)(__brev((unsigned)n) >> (32 - logL));
+            sm.buf[r].x = tb.hann[2 * n] * tsample(sm.sx, N, c, 2 * n);
+            sm.buf[r].y = tb.hann[2 * n + 1] * tsample(sm.sx, N, c, 2 * n + 1);
+        }
+        __syncthreads();
+        fft_dit<T>(sm.buf, logL, tid, NT, tb.tw_fft, logL);
+        // b. X[k] = E[k] + W^k O[k];  XI = 4|X|^2 / (N^2 * 3/8)   (psychoac.py:151)
+        for (int k = tid; k < L; k += NT) {
+            const cpx<T> zk = sm.buf[k], zc = sm.buf[(L - k) & (L - 1)];
+            const T ex = (zk.x + zc.x) * T(0.5), ey = (zk.y - zc.y) * T(0.5);
+            const T dx = zk.x - zc.x, dy = zk.y + zc.y;           // D = Zk - conj(Zc)
+            const T ox = dy * T(0.5), oy = -dx * T(0.5);          // O = D / (2j)
+            const cpx<T> w = tb.tw_rfft[k];
+            const T xr = ex + (ox * w.x - oy * w.y), xim = ey + (ox * w.y + oy * w.x);
+            sm.xi[k] = T(4) * (xr * xr + xim * xim) / xi_den;
+        }
+        __syncthreads();
+        // c. strict local maxima at bins 1 .. L-102, ascending order (psychoac.py:158-170)
+        {
+            int found = -1;
+            for (int t = tid; t < Q; t += NT) {       // NT == Q: one trip
+                const int p0 = 2 * t, p1 = p0 + 1;
+                if (p0 >= 1 && p0 <= L - 102 && sm.xi[p0] > sm.xi[p0 - 1] && sm.xi[p0] > sm.xi[p0 + 1]) found = p0;
+                if (p1 <= L - 102 && sm.xi[p1] > sm.xi[p1 - 1] && sm.xi[p1] > sm.xi[p1 + 1]) found = p1;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, found >= 0);
+            if (lane == 0) s_wcnt[warp] = __popc(bal);
+            __syncthreads();
+            if (warp == 0) {
+                int v = (lane < nwarp) ? s_wcnt[lane] : 0;
+                int incl = v;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                s_wcnt[lane] = incl - v;
+                if (lane == 31) s_npk = incl;
+            }
+            __syncthreads();
+            if (found >= 0) sm.pbin[s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u))] = found;
+            __syncthreads();
+        }
+        const int npk = s_npk;
+        // d. masker parameters (psychoac.py:163-165, :37-49)
+        for (int i = tid; i < npk; i += NT) {
+            const int p = sm.pbin[i];
+            const T x0 = sm.xi[p - 1], x1 = sm.xi[p], x2 = sm.xi[p + 1];
+            const T sum = (x0 + x1) + x2;
+            const T spl = fmax(T(96) + T(10) * m_log10(sum), T(-30));
+            const T num = (T(p - 1) * x0 + T(p) * x1) + T(p + 1) * x2;
+            const T f = (T(tb.fstep) * num) / sum;
+            const T fq = f / T(7500);
+            sm.pz[i] = T(13) * m_atan(T(0.76) * f / T(1000)) + T(3.5) * m_atan(fq * fq);
+            sm.ps15[i] = spl - T(15);
+            sm.pg[i] = T(0.37) * fmax(spl - T(40), T(0));
+        }
+        if (tid == 0) my_peaks += npk;
+        __syncthreads();
+        // e. spreading: thread owns lines tid and tid+Q, maskers summed in ascending order (psychoac.py:68-78,168)
+        {
+            const int k0 = tid, k1 = tid + Q;
+            const T z0 = tb.bark[k0], z1 = tb.bark[k1];
+            T a0 = tb.quiet[k0], a1 = tb.quiet[k1];
+            for (int m = 0; m < npk; ++m) {
+                const T zm = sm.pz[m], s15 = sm.ps15[m], gg = sm.pg[m];
+                a0 += masker_intensity(z0 - zm, s15, gg);
+                a1 += masker_intensity(z1 - zm, s15, gg);
+            }
+            // f. SMR per line (psychoac.py:212-214)
+            const T sc6 = T(6) * T(s_scale[c]);
+            const T X0 = sm.lines[c * L + k0], X1 = sm.lines[c * L + k1];
+            const T thr0 = fmax(T(96) + T(10) * m_log10(a0), T(-30));
+            const T thr1 = fmax(T(96) + T(10) * m_log10(a1), T(-30));
+            const T sp0 = fmax(T(96) + T(10) * m_log10((T(2) * (X0 * X0)) / T(0.5)), T(-30)) - sc6;
+            const T sp1 = fmax(T(96) + T(10) * m_log10((T(2) * (X1 * X1)) / T(0.5)), T(-30)) - sc6;
+            sm.xi[k0] = sp0 - thr0;
+            sm.xi[k1] = sp1 - thr1;
+        }
+        __syncthreads();
+        for (int bd = warp; bd < nb; bd += nwarp) {
+            const int lo = tb.band_lo[bd], n = tb.band_n[bd];
+            T v = -INFINITY;
+            for (int i = lane; i < n; i += 32) v = fmax(v, sm.xi[lo + i]);
+            v = warp_max(v);
+            if (lane == 0) s_smr[c][bd] = v;
+        }
+        __syncthreads();
+        if (taps.npeaks != nullptr && tid == 0) taps.npeaks[lb * 4 + c] = npk;
+    }
+    if (tid == 0) {
+        if (peak_counter) atomicAdd(peak_counter, (unsigned long long)my_peaks);
+        if (taps.npeaks != nullptr) for (int c = nspec; c < 4; ++c) taps.npeaks[lb * 4 + c] = 0;
+    }
+    if (taps.smr4 != nullptr) {
+        for (int i = tid; i < 4 * MRC_BSTRIDE; i += NT) {
+            const int c = i / MRC_BSTRIDE, bd = i % MRC_BSTRIDE;
+            taps.smr4[(size_t)lb * 4 * MRC_BSTRIDE + i] = (c < nspec && bd < nb) ? s_smr[c][bd] : T(0);
+        }
+    }
+
+    // ---- phase 5: per band pick (M,S) or (L,R) (ms_stereo.py:70-81; codecThem.py:509-559) ---------------
+    const unsigned ms = s_ms;
+    {
+        T* oA = ho.lines + (size_t)lb * 2 * L;
+        T* oB = oA + L;
+        for (int k = tid; k < L; k += NT) {
+            const bool m = (ms >> tb.line2band[k]) & 1u;
+            oA[k] = sm.lines[(m ? 2 : 0) * L + k];
+            oB[k] = sm.lines[(m ? 3 : 1) * L + k];
+        }
+        for (int w2 = warp; w2 < 2 * nb; w2 += nwarp) {
+            const int ch = w2 / nb, bd = w2 - ch * nb;
+            const bool m = (ms >> bd) & 1u;
+            const T* src = sm.lines + ((m ? 2 : 0) + ch) * L + tb.band_lo[bd];
+            const int n = tb.band_n[bd];
+            T v = 0;
+            for (int i = lane; i < n; i += 32) v = fmax(v, fabs(src[i]));
+            v = warp_max(v);
+            if (lane == 0) {
+                ho.bandmax[(size_t)lb * 2 * MRC_BSTRIDE + ch * MRC_BSTRIDE + bd] = v;
+                ho.smr[(size_t)lb * 2 * MRC_BSTRIDE + ch * MRC_BSTRIDE + bd] = s_smr[(m ? 2 : 0) + ch][bd];
+            }
+        }
+        if (tid < 4) ho.ovs[lb * 4 + tid] = (uint8_t)s_scale[tid];
+        if (tid == 0) ho.ms[lb] = ms;
+    }
+
+    // ---- phase 6: order of the water-filling grants (bitalloc.py:131-149) --------------------------------
+    // Each band's SMR trajectory (smr, -12, -6, -6, ...) is independent of the other bands, so the greedy
+    // arg-max visits the (band, level) tokens in globally sorted order: key descending, first (lowest) band on
+    // ties.  Joint blocks sort 2*nb bands together; non-joint blocks sort each channel on its own.
+    {
+        const int ntok = 2 * nb * MRC_MAX_LEVELS;
+        for (int i = tid; i < 1024; i += NT) {
+            T key = -INFINITY;
+            uint16_t id = 0xffffu;
+            if (i < ntok) {
+                const int bb = i / MRC_MAX_LEVELS, lvl = i - bb * MRC_MAX_LEVELS;     // bb in [0, 2nb)
+                const int ch = bb / nb, bd = bb - ch * nb;
+                const bool m = (ms >> bd) & 1u;
+                T v = s_smr[(m ? 2 : 0) + ch][bd];
+                if (lvl >= 1) v -= T(12);
+                for (int q = 1; q < lvl; ++q) v -= T(6);
+                key = v;
+                id = (uint16_t)(bb | (lvl << 8));
+            }
+            sm.skey[i] = key;
+            sm.sid[i] = id;
+        }
+        __syncthreads();
+        const int split = joint ? 0x7fffffff : nb;      // non-joint: channel 1 bands (>= nb) sort after channel 0
+        auto before = [&](T ka, uint16_t ia, T kb, uint16_t ib) -> bool {
+            const int ba = ia & 0xff, bbb = ib & 0xff;
+            if (ia == 0xffffu || ib == 0xffffu) return ib == 0xffffu && ia != 0xffffu;
+            const int ca = ba >= split, cb = bbb >= split;
+            if (ca != cb) return ca < cb;
+            if (ka != kb) return ka > kb;
+            if (ba != bbb) return ba < bbb;
+            return ia < ib;
+        };
+        for (int k = 2; k <= 1024; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < 512; t += NT) {
+                    const int i = ((t / j) * 2 * j) + (t % j);
+                    const int ixj = i + j;
+                    const bool up = ((i & k) == 0);
+                    const T ka = sm.skey[i], kb = sm.skey[ixj];
+                    const uint16_t ia = sm.sid[i], ib = sm.sid[ixj];
+                    const bool sw = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
+                    if (sw) {
+                        sm.skey[i] = kb; sm.skey[ixj] = ka;
+                        sm.sid[i] = ib;  sm.sid[ixj] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        uint16_t* ot = ho.tokens + (size_t)lb * MRC_TOK_STRIDE;
+        for (int i = tid; i < MRC_TOK_STRIDE; i += NT) ot[i] = sm.sid[i];
+    }
+}
+
+}  // namespace
+
+size_t analysis_smem_bytes(int L, int elem) {
+    return (size_t)(13 * L) * elem + 1024 * elem + 1024 * 2;
+}
+
+template <typename T>
+void launch_analysis(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const ClipMap& cm,
+                     const int16_t* pcm, const double* xin, int g0, int nblk, Handoff<T> ho, AnalysisTaps<T> taps,
+                     unsigned long long* peak_counter) {
+    if (nblk <= 0) return;
+    const size_t smem = analysis_smem_bytes(tb.L, sizeof(T));
+#define MRC_LAUNCH_ANALYSIS(LG)                                                                                  \
+    case LG:                                                                                                     \
+        cudaFuncSetAttribute(analysis_kernel<T, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        analysis_kernel<T, LG><<<nblk, 1 << (LG - 1), smem, st>>>(tb, cp, cm, pcm, xin, g0, ho, taps,            \
+                                                                  peak_counter);                                 \
+        break;
+    switch (tb.logL) {
+        MRC_LAUNCH_ANALYSIS(8)
+        MRC_LAUNCH_ANALYSIS(9)
+        MRC_LAUNCH_ANALYSIS(10)
+        MRC_LAUNCH_ANALYSIS(11)
+        default: break;
+    }
+#undef MRC_LAUNCH_ANALYSIS
+}
+
+template void launch_analysis<double>(cudaStream_t, const DevTables<double>&, const CodecParams&, const ClipMap&,
+                                      const int16_t*, const double*, int, int, Handoff<double>,
+                                      AnalysisTaps<double>, unsigned long long*);
+template void launch_analysis<float>(cudaStream_t, const DevTables<float>&, const CodecParams&, const ClipMap&,
+                                     const int16_t*, const double*, int, int, Handoff<float>, AnalysisTaps<float>,
+                                     unsigned long long*);

@@ -1,0 +1,674 @@
+// mrc_api.cu -- host side of libmrc.so: context, tables, wave scheduling and the extern "C" entry points
+// declared in include/mrc.h.  No CPU implementation of any codec stage lives here: every stage is a kernel.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "mrc_internal.cuh"
+#include "mrc_decode.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct TablesDev {
+    Buf kbd, hann, tw_pre, tw_post, tw_fft, tw_rfft, bark, quiet;
+};
+
+}  // namespace
+
+struct mrc_ctx {
+    mrc_config cfg;
+    int L = 0, logL = 0, nb = 0;
+    bool tables_set = false;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    TablesDev td, tf;                 // double and float copies
+    Buf band_lo, band_n, line2band, huff, header;
+    DevTables<double> tbd;
+    DevTables<float> tbf;
+    HuffDev h_huff;
+    CodecParams cp;
+    std::vector<int> h_band_lo, h_band_n;
+    uint8_t h_header[4 + 18 + 4 + 2 * MRC_MAX_BANDS];
+
+    // scratch (grow only)
+    Buf clip_off, clip_blk0, clip_bytes, clip_base, running, overflow, peakctr, res_in, res_out;
+    Buf ho_lines, ho_bandmax, ho_smr, ho_tokens, ho_ovs, ho_ms;
+    Buf q_alloc, q_sf, q_table, q_mant, q_cbytes, q_coff, q_res;
+    Buf tap_lines, tap_smr, tap_npk;
+    Buf pcm_dev, out_dev, xin_dev;
+    Buf dec[16];
+
+    double ms[8] = {0};
+    int64_t counters[8] = {0};
+    cudaEvent_t ev[8] = {nullptr};
+};
+
+namespace {
+
+int fail(mrc_ctx* c, int code, const char* fmt, const char* detail = "") {
+    char tmp[512];
+    snprintf(tmp, sizeof tmp, fmt, detail);
+    if (c) c->err = tmp; else g_create_error = tmp;
+    return code;
+}
+
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) return fail(ctx, MRC_E_CUDA, "CUDA error: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+cudaError_t ensure(Buf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e == cudaSuccess) b.cap = want;
+    return e;
+}
+
+void release(Buf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+template <typename T>
+cudaError_t upload(Buf& b, const std::vector<T>& v, cudaStream_t st) {
+    cudaError_t e = ensure(b, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+template <typename T>
+cudaError_t upload_tables(mrc_ctx* c, TablesDev& d, DevTables<T>& tb, const mrc_tables* t) {
+    const int L = c->L, N = 2 * L;
+    std::vector<T> kbd(N), hann(N), bark(L), quiet(L);
+    for (int i = 0; i < N; ++i) { kbd[i] = (T)t->kbd_window[i]; hann[i] = (T)t->hann_window[i]; }
+    for (int i = 0; i < L; ++i) { bark[i] = (T)t->bark[i]; quiet[i] = (T)t->quiet_intensity[i]; }
+    // twiddles: angles are exact dyadic fractions of pi, evaluated in double by the host libm
+    std::vector<cpx<T>> pre(L / 2), post(L / 2), fft(L / 2), rfft(L);
+    const double pi = 3.14159265358979323846;
+    for (int n = 0; n < L / 2; ++n) {
+        const double a = -pi * (4.0 * n + 1.0) / (4.0 * L);
+        pre[n].x = (T)cos(a); pre[n].y = (T)sin(a);
+        const double b = -pi * n / (double)L;
+        post[n].x = (T)cos(b); post[n].y = (T)sin(b);
+        const double f = -2.0 * pi * n / (double)L;
+        fft[n].x = (T)cos(f); fft[n].y = (T)sin(f);
+    }
+    for (int k = 0; k < L; ++k) {
+        const double a = -2.0 * pi * k / (double)N;
+        rfft[k].x = (T)cos(a); rfft[k].y = (T)sin(a);
+    }
+    cudaError_t e;
+    if ((e = upload(d.kbd, kbd, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.hann, hann, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.bark, bark, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.quiet, quiet, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.tw_pre, pre, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.tw_post, post, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.tw_fft, fft, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.tw_rfft, rfft, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;   // host vectors die at scope exit
+    tb.L = L; tb.logL = c->logL; tb.nb = c->nb; tb.sample_rate = c->cfg.sample_rate;
+    tb.fstep = c->cfg.sample_rate / N;
+    tb.kbd = (const T*)d.kbd.p; tb.hann = (const T*)d.hann.p;
+    tb.tw_pre = (const cpx<T>*)d.tw_pre.p; tb.tw_post = (const cpx<T>*)d.tw_post.p;
+    tb.tw_fft = (const cpx<T>*)d.tw_fft.p; tb.tw_rfft = (const cpx<T>*)d.tw_rfft.p;
+    tb.bark = (const T*)d.bark.p; tb.quiet = (const T*)d.quiet.p;
+    tb.band_lo = (const int*)c->band_lo.p; tb.band_n = (const int*)c->band_n.p;
+    tb.line2band = (const uint8_t*)c->line2band.p;
+    return cudaSuccess;
+}
+
+struct EncodeJob {
+    // inputs (exactly one of d_pcm / d_xin)
+    const int16_t* d_pcm = nullptr;
+    const double* d_xin = nullptr;
+    const int64_t* h_clip_off = nullptr;   // [n_clips+1]
+    int n_clips = 0;
+    bool flush_nonjoint = true;
+    int joint = 1;
+    const int32_t* h_res_in = nullptr;     // [n_clips] or null
+    int32_t* h_res_out = nullptr;
+    // packed output (device), optional
+    uint8_t* d_out = nullptr;
+    int64_t out_cap = 0;
+    int64_t* h_clip_byte_off = nullptr;    // [n_clips+1]
+    // taps to host, optional
+    double* t_lines = nullptr; int32_t* t_ovs = nullptr; int32_t* t_ms = nullptr; double* t_smr = nullptr;
+    int32_t* t_npk = nullptr;
+    int32_t* t_alloc = nullptr; int32_t* t_sf = nullptr; int32_t* t_mant = nullptr; int32_t* t_table = nullptr;
+    int32_t* t_res = nullptr; int32_t* t_cbytes = nullptr;
+    bool need_quant = true;
+};
+
+constexpr int WAVE_BLOCKS = 1 << 18;   // hand-off of one wave stays below ~5 GB in fp64
+
+template <typename T>
+int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
+    const int L = ctx->L, nb = ctx->nb, nc = job.n_clips;
+    cudaStream_t st = ctx->stream;
+    // ---- block map ----
+    std::vector<int32_t> blk0(nc + 1);
+    long long tot = 0;
+    for (int c = 0; c < nc; ++c) {
+        const long long fr = job.h_clip_off[c + 1] - job.h_clip_off[c];
+        if (fr < 0) return fail(ctx, MRC_E_INVALID, "clip_frame_offsets must be non-decreasing");
+        blk0[c] = (int32_t)tot;
+        tot += job.d_xin ? fr / (2 * L) : (fr + L - 1) / L + (job.flush_nonjoint ? 1 : 0);
+        if (tot > 0x7fff0000ll) return fail(ctx, MRC_E_INVALID, "too many blocks in one call");
+    }
+    blk0[nc] = (int32_t)tot;
+    const int nblk_total = (int)tot;
+    std::vector<int64_t> coff(job.h_clip_off, job.h_clip_off + nc + 1);
+    CK(upload(ctx->clip_off, coff, st));
+    CK(upload(ctx->clip_blk0, blk0, st));
+    CK(ensure(ctx->clip_bytes, (size_t)(nc + 1) * 8));
+    CK(ensure(ctx->clip_base, (size_t)(nc + 2) * 8));
+    CK(ensure(ctx->running, 8));
+    CK(ensure(ctx->overflow, 4));
+    CK(ensure(ctx->peakctr, 8));
+    CK(cudaMemsetAsync(ctx->running.p, 0, 8, st));
+    CK(cudaMemsetAsync(ctx->overflow.p, 0, 4, st));
+    CK(cudaMemsetAsync(ctx->peakctr.p, 0, 8, st));
+    const int32_t* d_res_in = nullptr;
+    int32_t* d_res_out = nullptr;
+    if (job.h_res_in) {
+        CK(ensure(ctx->res_in, (size_t)nc * 4));
+        CK(cudaMemcpyAsync(ctx->res_in.p, job.h_res_in, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+        d_res_in = (const int32_t*)ctx->res_in.p;
+    }
+    if (job.h_res_out) {
+        CK(ensure(ctx->res_out, (size_t)nc * 4));
+        d_res_out = (int32_t*)ctx->res_out.p;
+    }
+    ClipMap cm;
+    cm.clip_off = (const int64_t*)ctx->clip_off.p;
+    cm.clip_blk0 = (const int32_t*)ctx->clip_blk0.p;
+    cm.n_clips = nc;
+    CodecParams cp = ctx->cp;
+    cp.joint = job.joint;
+    cp.flush_nonjoint = job.flush_nonjoint ? 1 : 0;
+
+    // ---- waves of whole clips ----
+    std::vector<std::pair<int, int>> waves;     // [c0, c1)
+    int maxw = 0, maxc = 0;
+    for (int c = 0; c < nc;) {
+        int c1 = c + 1;
+        while (c1 < nc && blk0[c1 + 1] - blk0[c] <= WAVE_BLOCKS) ++c1;
+        waves.push_back({c, c1});
+        maxw = std::max(maxw, blk0[c1] - blk0[c]);
+        maxc = std::max(maxc, c1 - c);
+        c = c1;
+    }
+    const size_t W = (size_t)std::max(maxw, 1);
+    CK(ensure(ctx->ho_lines, W * 2 * L * sizeof(T)));
+    CK(ensure(ctx->ho_bandmax, W * 2 * MRC_BSTRIDE * sizeof(T)));
+    CK(ensure(ctx->ho_smr, W * 2 * MRC_BSTRIDE * sizeof(T)));
+    CK(ensure(ctx->ho_tokens, W * MRC_TOK_STRIDE * 2));
+    CK(ensure(ctx->ho_ovs, W * 4));
+    CK(ensure(ctx->ho_ms, W * 4));
+    CK(ensure(ctx->q_alloc, W * 2 * MRC_BSTRIDE));
+    CK(ensure(ctx->q_sf, W * 2 * MRC_BSTRIDE));
+    CK(ensure(ctx->q_table, W * 2));
+    CK(ensure(ctx->q_mant, W * 2 * L * 2));
+    CK(ensure(ctx->q_cbytes, W * 2 * 4));
+    CK(ensure(ctx->q_coff, W * 2 * 8));
+    CK(ensure(ctx->q_res, W * 4));
+    const bool want_atap = job.t_lines || job.t_smr || job.t_npk;
+    if (want_atap) {
+        CK(ensure(ctx->tap_lines, W * 4 * L * sizeof(T)));
+        CK(ensure(ctx->tap_smr, W * 4 * MRC_BSTRIDE * sizeof(T)));
+        CK(ensure(ctx->tap_npk, W * 4 * 4));
+    }
+    Handoff<T> ho;
+    ho.lines = (T*)ctx->ho_lines.p; ho.bandmax = (T*)ctx->ho_bandmax.p; ho.smr = (T*)ctx->ho_smr.p;
+    ho.tokens = (uint16_t*)ctx->ho_tokens.p; ho.ovs = (uint8_t*)ctx->ho_ovs.p; ho.ms = (uint32_t*)ctx->ho_ms.p;
+    QuantOut qo;
+    qo.alloc = (uint8_t*)ctx->q_alloc.p; qo.sf = (uint8_t*)ctx->q_sf.p; qo.table = (uint8_t*)ctx->q_table.p;
+    qo.mant = (uint16_t*)ctx->q_mant.p; qo.chunk_bytes = (uint32_t*)ctx->q_cbytes.p;
+    qo.chunk_off = (int64_t*)ctx->q_coff.p; qo.reservoir = (int32_t*)ctx->q_res.p;
+    qo.clip_bytes = (int64_t*)ctx->clip_bytes.p;
+    AnalysisTaps<T> taps;
+    taps.lines4 = want_atap ? (T*)ctx->tap_lines.p : nullptr;
+    taps.smr4 = want_atap ? (T*)ctx->tap_smr.p : nullptr;
+    taps.npeaks = want_atap ? (int32_t*)ctx->tap_npk.p : nullptr;
+
+    float t_an = 0, t_q = 0, t_pk = 0;
+    int launches = 0;
+    std::vector<unsigned char> hb;     // host bounce buffer for taps
+    for (auto& w : waves) {
+        const int c0 = w.first, c1 = w.second, g0 = blk0[c0], nblk = blk0[c1] - blk0[c0];
+        if (nblk == 0) {
+            // clips without blocks (xin mode only): nothing to do
+            continue;
+        }
+        CK(cudaEventRecord(ctx->ev[0], st));
+        launch_analysis<T>(st, tb, cp, cm, job.d_pcm, job.d_xin, g0, nblk, ho, taps,
+                           (unsigned long long*)ctx->peakctr.p);
+        CK(cudaEventRecord(ctx->ev[1], st));
+        ++launches;
+        if (job.need_quant) {
+            launch_quant<T>(st, tb, cp, (const HuffDev*)ctx->huff.p, cm, c0, c1 - c0, g0, ho, qo, d_res_in, d_res_out);
+            ++launches;
+        }
+        CK(cudaEventRecord(ctx->ev[2], st));
+        if (job.d_out) {
+            launch_clip_scan(st, qo.clip_bytes, (int64_t*)ctx->clip_base.p, c0, c1 - c0, (int64_t*)ctx->running.p);
+            launch_pack(st, cp, (const HuffDev*)ctx->huff.p, tb.band_lo, tb.band_n, tb.line2band, cm, g0, nblk, qo,
+                        ho.ovs, ho.ms, (const int64_t*)ctx->clip_base.p, job.d_out, job.out_cap,
+                        (const uint8_t*)ctx->header.p, (int*)ctx->overflow.p);
+            launches += 2;
+        }
+        CK(cudaEventRecord(ctx->ev[3], st));
+        CK(cudaGetLastError());
+        // ---- taps of this wave to the host ----
+        auto fetch = [&](const void* dsrc, size_t bytes) -> cudaError_t {
+            hb.resize(bytes);
+            cudaError_t e = cudaMemcpyAsync(hb.data(), dsrc, bytes, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            return cudaStreamSynchronize(st);
+        };
+        if (job.t_lines) {
+            CK(fetch(taps.lines4, (size_t)nblk * 4 * L * sizeof(T)));
+            const T* s = (const T*)hb.data();
+            double* d = job.t_lines + (size_t)g0 * 4 * L;
+            for (size_t i = 0; i < (size_t)nblk * 4 * L; ++i) d[i] = (double)s[i];
+        }
+        if (job.t_smr) {
+            CK(fetch(taps.smr4, (size_t)nblk * 4 * MRC_BSTRIDE * sizeof(T)));
+            const T* s = (const T*)hb.data();
+            for (int b = 0; b < nblk; ++b)
+                for (int c = 0; c < 4; ++c)
+                    for (int k = 0; k < nb; ++k)
+                        job.t_smr[((size_t)(g0 + b) * 4 + c) * nb + k] = (double)s[((size_t)b * 4 + c) * MRC_BSTRIDE + k];
+        }
+        if (job.t_npk) {
+            CK(fetch(taps.npeaks, (size_t)nblk * 16));
+            memcpy(job.t_npk + (size_t)g0 * 4, hb.data(), (size_t)nblk * 16);
+        }
+        if (job.t_ovs) {
+            CK(fetch(ho.ovs, (size_t)nblk * 4));
+            for (size_t i = 0; i < (size_t)nblk * 4; ++i) job.t_ovs[(size_t)g0 * 4 + i] = hb[i];
+        }
+        if (job.t_ms) {
+            CK(fetch(ho.ms, (size_t)nblk * 4));
+            const uint32_t* s = (const uint32_t*)hb.data();
+            for (int b = 0; b < nblk; ++b)
+                for (int k = 0; k < nb; ++k) job.t_ms[(size_t)(g0 + b) * nb + k] = (s[b] >> k) & 1u;
+        }
+        if (job.t_alloc || job.t_sf) {
+            for (int which = 0; which < 2; ++which) {
+                int32_t* dst = which ? job.t_sf : job.t_alloc;
+                if (!dst) continue;
+                CK(fetch(which ? qo.sf : qo.alloc, (size_t)nblk * 2 * MRC_BSTRIDE));
+                for (int b = 0; b < nblk; ++b)
+                    for (int c = 0; c < 2; ++c)
+                        for (int k = 0; k < nb; ++k)
+                            dst[((size_t)(g0 + b) * 2 + c) * nb + k] = hb[((size_t)b * 2 + c) * MRC_BSTRIDE + k];
+            }
+        }
+        if (job.t_mant) {
+            CK(fetch(qo.mant, (size_t)nblk * 2 * L * 2));
+            const uint16_t* s = (const uint16_t*)hb.data();
+            int32_t* d = job.t_mant + (size_t)g0 * 2 * L;
+            for (size_t i = 0; i < (size_t)nblk * 2 * L; ++i) d[i] = s[i];
+        }
+        if (job.t_table) {
+            CK(fetch(qo.table, (size_t)nblk * 2));
+            for (size_t i = 0; i < (size_t)nblk * 2; ++i) job.t_table[(size_t)g0 * 2 + i] = hb[i];
+        }
+        if (job.t_res) {
+            CK(fetch(qo.reservoir, (size_t)nblk * 4));
+            memcpy(job.t_res + g0, hb.data(), (size_t)nblk * 4);
+        }
+        if (job.t_cbytes) {
+            CK(fetch(qo.chunk_bytes, (size_t)nblk * 8));
+            memcpy(job.t_cbytes + (size_t)g0 * 2, hb.data(), (size_t)nblk * 8);
+        }
+        CK(cudaEventSynchronize(ctx->ev[3]));
+        float t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1])); t_an += t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); t_q += t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3])); t_pk += t;
+    }
+    ctx->ms[0] = t_an; ctx->ms[1] = t_q; ctx->ms[2] = t_pk;
+    ctx->counters[0] = launches;
+    ctx->counters[2] = nblk_total;
+    unsigned long long pk = 0;
+    CK(cudaMemcpyAsync(&pk, ctx->peakctr.p, 8, cudaMemcpyDeviceToHost, st));
+    if (job.h_res_out) CK(cudaMemcpyAsync(job.h_res_out, d_res_out, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+    int ovf = 0;
+    if (job.d_out) {
+        CK(cudaMemcpyAsync(job.h_clip_byte_off, ctx->clip_base.p, (size_t)(nc + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ovf, ctx->overflow.p, 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    ctx->counters[1] = (int64_t)pk;
+    if (job.d_out && nblk_total == 0) for (int c = 0; c <= nc; ++c) job.h_clip_byte_off[c] = 0;
+    if (ovf) return fail(ctx, MRC_E_NOSPACE, "output buffer too small for the encoded batch");
+    return MRC_OK;
+}
+
+int run_encode(mrc_ctx* ctx, const EncodeJob& job) {
+    if (!ctx->tables_set) return fail(ctx, MRC_E_STATE, "mrc_set_tables has not been called");
+    if (ctx->cfg.precision == MRC_PRECISION_FP32) return run_encode_t<float>(ctx, job, ctx->tbf);
+    return run_encode_t<double>(ctx, job, ctx->tbd);
+}
+
+int64_t worst_case_bytes(const mrc_ctx* ctx, const int64_t* off, int nc) {
+    const int L = ctx->L;
+    // every mantissa escaped at 16 bits: (9+16) bits per line plus chunk headers
+    const int64_t per_chunk = 4 + (6 + 4 * ctx->cfg.n_scale_bits + ctx->nb + ctx->nb * 8 + (int64_t)L * 25 + 7) / 8;
+    int64_t tot = 0;
+    for (int c = 0; c < nc; ++c) {
+        const int64_t fr = off[c + 1] - off[c];
+        tot += (int64_t)sizeof(ctx->h_header) + ((fr + L - 1) / L + 1) * 2 * per_chunk;
+    }
+    return tot;
+}
+
+int64_t nominal_bytes(const mrc_ctx* ctx, const int64_t* off, int nc) {
+    const int L = ctx->L;
+    int64_t tot = 0;
+    for (int c = 0; c < nc; ++c) {
+        const int64_t fr = off[c + 1] - off[c];
+        const int64_t nblk = (fr + L - 1) / L + 1;
+        tot += 128 + nblk * (int64_t)(2.0 * ctx->cfg.target_bits_per_sample * L / 8.0 + 64);
+    }
+    return tot;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int32_t mrc_version(void) { return MRC_VERSION; }
+
+const char* mrc_last_error(const mrc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out) {
+    mrc_ctx* ctx = nullptr;
+    if (!cfg || !out) return fail(nullptr, MRC_E_INVALID, "null argument");
+    *out = nullptr;
+    int logL = 0;
+    while ((1 << logL) < cfg->n_mdct_lines) ++logL;
+    if ((1 << logL) != cfg->n_mdct_lines || logL < 8 || logL > 11)
+        return fail(nullptr, MRC_E_INVALID, "n_mdct_lines must be 256, 512, 1024 or 2048");
+    if (cfg->n_scale_bits < 1 || cfg->n_scale_bits > 4 || cfg->n_mant_size_bits < 1 || cfg->n_mant_size_bits > 4)
+        return fail(nullptr, MRC_E_INVALID, "n_scale_bits and n_mant_size_bits must be in 1..4");
+    if (cfg->precision != MRC_PRECISION_FP64 && cfg->precision != MRC_PRECISION_FP32)
+        return fail(nullptr, MRC_E_INVALID, "unknown precision");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, MRC_E_CUDA, "no usable CUDA device (%s); libmrc has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "bad device ordinal");
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess)
+        return fail(nullptr, MRC_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ctx = new mrc_ctx();
+    ctx->cfg = *cfg;
+    ctx->L = cfg->n_mdct_lines;
+    ctx->logL = logL;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return MRC_OK;
+}
+
+int32_t mrc_destroy(mrc_ctx* ctx) {
+    if (!ctx) return MRC_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    Buf* all[] = {&ctx->td.kbd, &ctx->td.hann, &ctx->td.tw_pre, &ctx->td.tw_post, &ctx->td.tw_fft, &ctx->td.tw_rfft,
+                  &ctx->td.bark, &ctx->td.quiet, &ctx->tf.kbd, &ctx->tf.hann, &ctx->tf.tw_pre, &ctx->tf.tw_post,
+                  &ctx->tf.tw_fft, &ctx->tf.tw_rfft, &ctx->tf.bark, &ctx->tf.quiet, &ctx->band_lo, &ctx->band_n,
+                  &ctx->line2band, &ctx->huff, &ctx->header, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,
+                  &ctx->clip_base, &ctx->running, &ctx->overflow, &ctx->peakctr, &ctx->res_in, &ctx->res_out,
+                  &ctx->ho_lines, &ctx->ho_bandmax, &ctx->ho_smr, &ctx->ho_tokens, &ctx->ho_ovs, &ctx->ho_ms,
+                  &ctx->q_alloc, &ctx->q_sf, &ctx->q_table, &ctx->q_mant, &ctx->q_cbytes, &ctx->q_coff, &ctx->q_res,
+                  &ctx->tap_lines, &ctx->tap_smr, &ctx->tap_npk, &ctx->pcm_dev, &ctx->out_dev, &ctx->xin_dev};
+    for (Buf* b : all) release(*b);
+    for (auto& b : ctx->dec) release(b);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MRC_OK;
+}
+
+int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
+    if (!ctx || !t) return MRC_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    if (t->n_bands < 1 || t->n_bands > MRC_MAX_BANDS) return fail(ctx, MRC_E_INVALID, "n_bands out of range");
+    if (t->n_huff_tables != MRC_N_HUFF_TABLES) return fail(ctx, MRC_E_INVALID, "exactly four Huffman tables expected");
+    const int L = ctx->L;
+    ctx->nb = t->n_bands;
+    ctx->h_band_lo.assign(t->n_bands, 0);
+    ctx->h_band_n.assign(t->n_bands, 0);
+    int acc = 0;
+    for (int b = 0; b < t->n_bands; ++b) {
+        if (t->band_nlines[b] < 1)
+            return fail(ctx, MRC_E_INVALID, "empty scale factor band (the reference crashes on these too)");
+        ctx->h_band_lo[b] = acc;
+        ctx->h_band_n[b] = t->band_nlines[b];
+        acc += t->band_nlines[b];
+    }
+    if (acc != L) return fail(ctx, MRC_E_INVALID, "band_nlines must sum to n_mdct_lines");
+    std::vector<uint8_t> l2b(L);
+    for (int b = 0; b < t->n_bands; ++b)
+        for (int i = 0; i < ctx->h_band_n[b]; ++i) l2b[ctx->h_band_lo[b] + i] = (uint8_t)b;
+    CK(upload(ctx->band_lo, ctx->h_band_lo, ctx->stream));
+    CK(upload(ctx->band_n, ctx->h_band_n, ctx->stream));
+    CK(upload(ctx->line2band, l2b, ctx->stream));
+    // Huffman LUTs
+    HuffDev& h = ctx->h_huff;
+    memset(&h, 0, sizeof h);
+    for (int tb = 0; tb < MRC_N_HUFF_TABLES; ++tb) {
+        for (int v = 0; v < MRC_HUFF_LUT; ++v) {
+            h.len[tb][v] = t->huff_len[tb * MRC_HUFF_LUT + v];
+            h.code[tb][v] = t->huff_code[tb * MRC_HUFF_LUT + v];
+        }
+        const int esc = t->huff_escape[tb];
+        if (esc < 0 || esc >= MRC_HUFF_LUT || h.len[tb][esc] == 0)
+            return fail(ctx, MRC_E_INVALID, "escape value must be a key of its table");
+        h.esc[tb] = esc;
+        h.esc_len[tb] = h.len[tb][esc];
+        h.esc_code[tb] = h.code[tb][esc];
+    }
+    CK(ensure(ctx->huff, sizeof(HuffDev)));
+    CK(cudaMemcpyAsync(ctx->huff.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(upload_tables<double>(ctx, ctx->td, ctx->tbd, t));
+    CK(upload_tables<float>(ctx, ctx->tf, ctx->tbf, t));
+    // bit budgets up to the point where the reservoir is added, in the reference's order of operations
+    const mrc_config& c = ctx->cfg;
+    const int halfN = L;
+    {   // codecThem.py:381-391
+        double B = c.target_bits_per_sample * halfN;
+        B -= c.n_scale_bits * t->n_bands;
+        B -= c.n_mant_size_bits * t->n_bands;
+        B += B;
+        B -= t->n_bands;
+        B -= c.n_scale_bits * 4;
+        ctx->cp.budget_joint = B;
+    }
+    {   // codecThem.py:299-306
+        double B = c.target_bits_per_sample * halfN;
+        B -= c.n_scale_bits * (t->n_bands + 1);
+        B -= c.n_mant_size_bits * t->n_bands;
+        B -= 1;
+        B -= 1;
+        ctx->cp.budget_single = B;
+    }
+    ctx->cp.L = L; ctx->cp.nb = t->n_bands;
+    ctx->cp.n_scale_bits = c.n_scale_bits; ctx->cp.n_mant_size_bits = c.n_mant_size_bits;
+    ctx->cp.max_mant_bits = std::min(16, 1 << c.n_mant_size_bits);
+    ctx->cp.joint = c.joint; ctx->cp.flush_nonjoint = 1;
+    if (ctx->cp.max_mant_bits != 16) return fail(ctx, MRC_E_INVALID, "only n_mant_size_bits = 4 (16-bit cap) is supported");
+    // .pac header template (pacfileThem.py:592-613); numSamples is patched per clip by the pack kernel
+    uint8_t* hd = ctx->h_header;
+    memset(hd, 0, sizeof ctx->h_header);
+    memcpy(hd, "PAC ", 4);
+    auto put32 = [&](int o, uint32_t v) { for (int i = 0; i < 4; ++i) hd[o + i] = (uint8_t)(v >> (8 * i)); };
+    auto put16 = [&](int o, uint32_t v) { for (int i = 0; i < 2; ++i) hd[o + i] = (uint8_t)(v >> (8 * i)); };
+    put32(4, (uint32_t)c.sample_rate); put16(8, 2); put32(10, 0); put32(14, (uint32_t)L);
+    put16(18, (uint32_t)c.n_scale_bits); put16(20, (uint32_t)c.n_mant_size_bits); put32(22, (uint32_t)t->n_bands);
+    for (int b = 0; b < t->n_bands; ++b) put16(26 + 2 * b, (uint32_t)t->band_nlines[b]);
+    ctx->cp.header_bytes = 26 + 2 * t->n_bands;
+    CK(ensure(ctx->header, sizeof ctx->h_header));
+    CK(cudaMemcpyAsync(ctx->header.p, hd, sizeof ctx->h_header, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tables_set = true;
+    return MRC_OK;
+}
+
+int32_t mrc_host_alloc(void** p, int64_t bytes) {
+    if (!p || bytes < 0) return MRC_E_INVALID;
+    return cudaMallocHost(p, (size_t)std::max<int64_t>(bytes, 1)) == cudaSuccess ? MRC_OK : MRC_E_CUDA;
+}
+int32_t mrc_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MRC_OK : MRC_E_CUDA; }
+
+int32_t mrc_encode_batch_device(mrc_ctx* ctx, const int16_t* d_pcm, const int64_t* clip_frame_offsets,
+                                int32_t n_clips, uint8_t* d_out, int64_t out_cap, int64_t* clip_byte_offsets) {
+    if (!ctx) return MRC_E_INVALID;
+    if (!clip_frame_offsets || !clip_byte_offsets || n_clips < 0 || (!d_out && out_cap > 0))
+        return fail(ctx, MRC_E_INVALID, "bad argument");
+    cudaSetDevice(ctx->cfg.device);
+    EncodeJob job;
+    job.d_pcm = d_pcm; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
+    job.joint = ctx->cfg.joint; job.flush_nonjoint = true;
+    job.d_out = d_out; job.out_cap = out_cap; job.h_clip_byte_off = clip_byte_offsets;
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    const int rc = run_encode(ctx, job);
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    cudaEventSynchronize(ctx->ev[5]);
+    float t = 0;
+    cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]);
+    ctx->ms[6] = t; ctx->ms[4] = ctx->ms[5] = 0;
+    return rc;
+}
+
+int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
+                         uint8_t* out, int64_t out_cap, int64_t* clip_byte_offsets) {
+    if (!ctx) return MRC_E_INVALID;
+    if (!clip_frame_offsets || !clip_byte_offsets || n_clips < 0) return fail(ctx, MRC_E_INVALID, "bad argument");
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    const int64_t frames = clip_frame_offsets[n_clips] - clip_frame_offsets[0];
+    if (clip_frame_offsets[0] != 0) return fail(ctx, MRC_E_INVALID, "clip_frame_offsets[0] must be 0");
+    CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(frames, 1) * 4));
+    // device staging for the bitstream: nominal size with head-room, never more than the worst case
+    int64_t cap = std::min(worst_case_bytes(ctx, clip_frame_offsets, n_clips),
+                           std::max<int64_t>(2 * nominal_bytes(ctx, clip_frame_offsets, n_clips), out_cap));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(ensure(ctx->out_dev, (size_t)cap));
+        CK(cudaEventRecord(ctx->ev[4], st));
+        if (frames > 0) CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)frames * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->ev[6], st));
+        EncodeJob job;
+        job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
+        job.joint = ctx->cfg.joint; job.flush_nonjoint = true;
+        job.d_out = (uint8_t*)ctx->out_dev.p; job.out_cap = cap; job.h_clip_byte_off = clip_byte_offsets;
+        const int rc = run_encode(ctx, job);
+        if (rc == MRC_E_NOSPACE && attempt == 0) {          // staging too small: retry once at the worst case
+            cap = worst_case_bytes(ctx, clip_frame_offsets, n_clips);
+            continue;
+        }
+        if (rc != MRC_OK) return rc;
+        break;
+    }
+    const int64_t total = clip_byte_offsets[n_clips];
+    if (total > out_cap) return fail(ctx, MRC_E_NOSPACE, "output buffer too small (clip_byte_offsets holds the sizes)");
+    CK(cudaEventRecord(ctx->ev[7], st));
+    if (total > 0) CK(cudaMemcpyAsync(out, ctx->out_dev.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    float t = 0;
+    cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[6]); ctx->ms[4] = t;
+    cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[5]); ctx->ms[5] = t;
+    cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]); ctx->ms[6] = t;
+    return MRC_OK;
+}
+
+int32_t mrc_stage_analysis(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
+                           double* mdct_lines, int32_t* overall_scale, int32_t* ms_switch, double* smr,
+                           int32_t* n_peaks) {
+    if (!ctx || !clip_frame_offsets || n_clips < 0) return MRC_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    const int64_t frames = clip_frame_offsets[n_clips];
+    CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(frames, 1) * 4));
+    if (frames > 0) CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EncodeJob job;
+    job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
+    job.joint = ctx->cfg.joint; job.flush_nonjoint = true; job.need_quant = false;
+    job.t_lines = mdct_lines; job.t_ovs = overall_scale; job.t_ms = ms_switch; job.t_smr = smr; job.t_npk = n_peaks;
+    return run_encode(ctx, job);
+}
+
+int32_t mrc_stage_alloc_quant(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets,
+                              int32_t n_clips, int32_t* bit_alloc, int32_t* scale_factor, int32_t* mantissa,
+                              int32_t* huff_table, int32_t* reservoir, int32_t* chunk_bytes) {
+    if (!ctx || !clip_frame_offsets || n_clips < 0) return MRC_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    const int64_t frames = clip_frame_offsets[n_clips];
+    CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(frames, 1) * 4));
+    if (frames > 0) CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+    EncodeJob job;
+    job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
+    job.joint = ctx->cfg.joint; job.flush_nonjoint = true;
+    job.t_alloc = bit_alloc; job.t_sf = scale_factor; job.t_mant = mantissa; job.t_table = huff_table;
+    job.t_res = reservoir; job.t_cbytes = chunk_bytes;
+    return run_encode(ctx, job);
+}
+
+int32_t mrc_encode_block(mrc_ctx* ctx, const double* data, int32_t joint, int32_t* reservoir,
+                         int32_t* scale_factor, int32_t* bit_alloc, int32_t* mantissa, int32_t* overall_scale,
+                         int32_t* ms_switch, int32_t* huff_table, int32_t* chunk_bytes) {
+    if (!ctx || !data || !reservoir) return MRC_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    const int N = 2 * ctx->L;
+    CK(ensure(ctx->xin_dev, (size_t)2 * N * 8));
+    CK(cudaMemcpyAsync(ctx->xin_dev.p, data, (size_t)2 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t off[2] = {0, N};
+    int32_t res_in = *reservoir, res_out = 0;
+    EncodeJob job;
+    job.d_xin = (const double*)ctx->xin_dev.p; job.h_clip_off = off; job.n_clips = 1;
+    job.joint = joint ? 1 : 0; job.flush_nonjoint = false;
+    job.h_res_in = &res_in; job.h_res_out = &res_out;
+    job.t_alloc = bit_alloc; job.t_sf = scale_factor; job.t_mant = mantissa; job.t_table = huff_table;
+    job.t_cbytes = chunk_bytes; job.t_ovs = overall_scale; job.t_ms = ms_switch;
+    const int rc = run_encode(ctx, job);
+    if (rc == MRC_OK) *reservoir = res_out;
+    return rc;
+}
+
+int32_t mrc_last_timing(const mrc_ctx* ctx, double* ms8, int64_t* counters8) {
+    if (!ctx) return MRC_E_INVALID;
+    if (ms8) memcpy(ms8, ctx->ms, sizeof ctx->ms);
+    if (counters8) memcpy(counters8, ctx->counters, sizeof ctx->counters);
+    return MRC_OK;
+}
+
+}  // extern "C"
+
+#include "mrc_api_decode.inc"

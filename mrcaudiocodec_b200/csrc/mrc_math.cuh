@@ -1,0 +1,81 @@
+// mrc_math.cuh -- scalar device helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+__device__ __forceinline__ double m_log10(double x) { return log10(x); }
+__device__ __forceinline__ float m_log10(float x) { return __log2f(x) * 0.30102999566398120f; }
+__device__ __forceinline__ double m_exp10(double x) { return exp10(x); }
+__device__ __forceinline__ float m_exp10(float x) { return exp2f(x * 3.3219280948873623f); }
+__device__ __forceinline__ double m_atan(double x) { return atan(x); }
+__device__ __forceinline__ float m_atan(float x) { return atanf(x); }
+
+// pcmfile.py:87-101 with quantize.py:90-111 at 16 bits: x = sign * (2*|c|) / 65535 ; |c| = 32768 -> 0.0 (Q1)
+template <typename T>
+__device__ __forceinline__ T pcm_to_fraction(int c) {
+    if (c == -32768) return T(0);
+    const int mag = c < 0 ? -c : c;
+    const double v = __ddiv_rn(__dmul_rn((double)mag, 2.0), 65535.0);
+    return T(c < 0 ? -v : v);
+}
+
+// quantize.py:12-38 magnitude code of |x| with nBits (sign handled by the caller).
+// code = trunc(((2^nBits - 1)*|x| + 1) / 2): multiply, add, divide -- three roundings, no FMA (Appendix A).
+__device__ __forceinline__ long long quant_mag_code(double ax, int nBits) {
+    if (ax >= 1.0) return (1ll << (nBits - 1)) - 1;
+    const double full = (double)((1ll << nBits) - 1);
+    return (long long)__ddiv_rn(__dadd_rn(__dmul_rn(full, ax), 1.0), 2.0);
+}
+
+// quantize.py:114-146: leading zeros of the magnitude code, capped at 2^nScaleBits - 1.
+// int(math.log(code, 2)) == 63 - clz(code) for every reachable code (tests/test_oracle_kat.py).
+__device__ __forceinline__ int scale_factor_of(double ax, int nScaleBits, int nMantBits) {
+    const int cap = (1 << nScaleBits) - 1;
+    const int nBits = cap + nMantBits;
+    const long long code = quant_mag_code(ax, nBits);
+    const int top = code > 0 ? 63 - __clzll(code) : 0;
+    const int lz = (nBits - 2) - top;
+    return lz < cap ? lz : cap;
+}
+
+// quantize.py:294-322: block-floating-point mantissa of one line.
+__device__ __forceinline__ int mantissa_of(double x, int scale, int nScaleBits, int nMantBits) {
+    const int cap = (1 << nScaleBits) - 1;
+    const int nBits = cap + nMantBits;
+    long long code = quant_mag_code(fabs(x), nBits);
+    if (x == 0.0) code = 0;
+    if (scale != cap) code >>= (cap - scale);
+    return (int)code + ((x < 0.0) ? (1 << (nMantBits - 1)) : 0);
+}
+
+// quantize.py:325-357 + :90-111: inverse of mantissa_of.
+__device__ __forceinline__ double dequantize_of(int mant, int scale, int nScaleBits, int nMantBits) {
+    const int cap = (1 << nScaleBits) - 1;
+    const int nBits = cap + nMantBits;
+    const int signbit = 1 << (nMantBits - 1);
+    const bool neg = mant >= signbit;
+    long long mag = neg ? mant - signbit : mant;
+    if (scale != cap) {
+        const int sh = cap - scale;
+        const long long m0 = mag;
+        mag <<= sh;
+        if (sh > 0 && m0 > 0) mag += 1ll << (sh - 1);
+    }
+    const double s = neg ? -1.0 : 1.0;
+    return __ddiv_rn(__dmul_rn(__dmul_rn(s, (double)mag), 2.0), (double)((1ll << nBits) - 1));
+}
+
+// psychoac.py:68-78 for one (masker, line) pair: intensity of a tonal masker at Bark distance dz.
+//   s15 = SPL - 15, g = 0.37*max(SPL-40, 0)
+template <typename T>
+__device__ __forceinline__ T masker_intensity(T dz, T s15, T g) {
+    const T adz = fabs(dz);
+    const T t = adz - T(0.5);
+    T e = s15;
+    if (adz > T(0.5)) {
+        e = e + T(-27) * t;
+        if (dz > T(0.5)) e = e + g * t;
+    }
+    return m_exp10((e - T(96)) / T(10));
+}

@@ -1,0 +1,194 @@
+// mrc_pack.cu -- K4: bit-packing of the channel chunks, one CTA per (block, channel).
+//   chunk layout and size         pacfileThem.py:651-789 (non-joint) / :825-970 (joint); SURVEY.md Appendix B
+//   MSB-first bit writer          bitpack.py:36-101
+//   file header                   pacfileThem.py:586-613 (numSamples quirk Q9)
+// Code lengths of the 1024 mantissas go through a block-wide exclusive scan; every symbol is then OR-ed into a
+// zeroed shared-memory bit buffer at its own offset and the finished chunk is streamed out with its <L nBytes
+// prefix.
+#include "mrc_internal.cuh"
+
+namespace {
+
+constexpr int PT = 256;
+
+__global__ void __launch_bounds__(PT)
+pack_kernel(CodecParams cp, const HuffDev* __restrict__ huff, const int* __restrict__ band_lo,
+            const int* __restrict__ band_n, const uint8_t* __restrict__ line2band, ClipMap cm, int g0, QuantOut qo,
+            const uint8_t* __restrict__ ovs, const uint32_t* __restrict__ msv, const int64_t* __restrict__ clip_base,
+            uint8_t* __restrict__ out, long long out_cap, const uint8_t* __restrict__ header_template,
+            int* overflow_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* bitbuf = reinterpret_cast<uint32_t*>(smem_raw);
+    const int L = cp.L, nb = cp.nb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t lb = blockIdx.x >> 1;
+    const int ch = blockIdx.x & 1;
+    const int g = g0 + (int)lb;
+
+    __shared__ int s_clip, s_b, s_nblk;
+    __shared__ int s_alloc[MRC_BSTRIDE], s_sf[MRC_BSTRIDE];
+    __shared__ int s_wsum[PT / 32];
+    __shared__ HuffDev s_h;
+    if (tid == 0) {
+        int lo = 0, hi = cm.n_clips;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cm.clip_blk0[mid] <= g) lo = mid; else hi = mid;
+        }
+        s_clip = lo;
+        s_b = g - cm.clip_blk0[lo];
+        s_nblk = cm.clip_blk0[lo + 1] - cm.clip_blk0[lo];
+    }
+    if (tid < nb) {
+        s_alloc[tid] = qo.alloc[(lb * 2 + ch) * MRC_BSTRIDE + tid];
+        s_sf[tid] = qo.sf[(lb * 2 + ch) * MRC_BSTRIDE + tid];
+    }
+    for (int i = tid; i < (int)(sizeof(HuffDev) / 4); i += PT)
+        reinterpret_cast<uint32_t*>(&s_h)[i] = reinterpret_cast<const uint32_t*>(huff)[i];
+    const int nbytes = (int)qo.chunk_bytes[lb * 2 + ch];
+    const int nwords = (nbytes + 3) / 4 + 2;
+    for (int i = tid; i < nwords; i += PT) bitbuf[i] = 0u;
+    __syncthreads();
+
+    const bool joint = cp.joint && !(cp.flush_nonjoint && s_b == s_nblk - 1);
+    const int table = qo.table[lb * 2 + ch];
+    const int band_hdr = cp.n_mant_size_bits + cp.n_scale_bits;
+    int hdr_bits = 4 + 1 + 1;
+    if (joint) hdr_bits += (ch == 0) ? 4 * cp.n_scale_bits + nb : 0;
+    else hdr_bits += cp.n_scale_bits;
+
+    auto put = [&](int pos, uint32_t v, int n) {       // n <= 32 bits of v at bit position pos, MSB first
+        if (n <= 0) return;
+        const int w = pos >> 5, off = pos & 31;
+        const unsigned long long x = (unsigned long long)v << (64 - off - n);
+        const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+        if (hi) atomicOr(&bitbuf[w], hi);
+        if (lo) atomicOr(&bitbuf[w + 1], lo);
+    };
+
+    // per-line symbols: LPT consecutive lines per thread
+    const int LPT = L / PT;                      // 1, 2, 4 or 8
+    const uint16_t* mant = qo.mant + (lb * 2 + ch) * L;
+    uint32_t sym[8];
+    int slen[8];
+    int local = 0;
+    for (int i = 0; i < LPT; ++i) {
+        const int k = tid * LPT + i;
+        const int Rb = s_alloc[line2band[k]];
+        const int m = mant[k];
+        int n = 0;
+        uint32_t v = 0;
+        if (Rb) {
+            if (table == MRC_NO_TABLE) { n = Rb; v = (uint32_t)m; }
+            else {
+                const int len = (m < MRC_HUFF_LUT) ? s_h.len[table][m] : 0;
+                if (len && m != s_h.esc[table]) { n = len; v = s_h.code[table][m]; }
+                else { n = s_h.esc_len[table] + Rb; v = ((uint32_t)s_h.esc_code[table] << Rb) | (uint32_t)m; }
+            }
+        }
+        sym[i] = v;
+        slen[i] = n;
+        local += n;
+    }
+    // block-wide exclusive scan of `local`
+    int incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+    int pos = woff + incl - local;               // mantissa bits before this thread's first line
+    for (int i = 0; i < LPT; ++i) {
+        const int k = tid * LPT + i;
+        const int bd = line2band[k];
+        const int p = hdr_bits + band_hdr * (bd + 1) + pos;
+        if (k == band_lo[bd]) {                   // first line of a band also writes the band header
+            const int a = s_alloc[bd];
+            put(p - band_hdr, (uint32_t)(((a ? a - 1 : 0) << cp.n_scale_bits) | s_sf[bd]), band_hdr);
+        }
+        put(p, sym[i], slen[i]);
+        pos += slen[i];
+    }
+    if (tid == 0) {
+        put(0, (uint32_t)table, 4);               // huffTable(4); blkswA, blkswB = 0 for long blocks
+        int p = 6;
+        if (joint) {
+            if (ch == 0) {
+                for (int i = 0; i < 4; ++i) { put(p, ovs[lb * 4 + i], cp.n_scale_bits); p += cp.n_scale_bits; }
+                const uint32_t ms = msv[lb];
+                for (int bd = 0; bd < nb; ++bd) put(p + bd, (ms >> bd) & 1u, 1);
+            }
+        } else {
+            put(p, ovs[lb * 4 + ch], cp.n_scale_bits);
+        }
+    }
+    __syncthreads();
+
+    const long long dst_off = clip_base[s_clip] + qo.chunk_off[lb * 2 + ch];
+    if (dst_off + 4 + nbytes > out_cap) {         // never write past the caller's buffer; the host reports NOSPACE
+        if (tid == 0) *overflow_flag = 1;
+        return;
+    }
+    uint8_t* dst = out + dst_off;
+    if (tid < 4) dst[tid] = (uint8_t)((uint32_t)nbytes >> (8 * tid));       // <L nBytes
+    for (int i = tid; i < nbytes; i += PT) dst[4 + i] = (uint8_t)(bitbuf[i >> 2] >> (24 - 8 * (i & 3)));
+
+    if (s_b == 0 && ch == 0) {                    // first chunk of a clip also writes the file header
+        uint8_t* h = out + clip_base[s_clip];
+        for (int i = tid; i < cp.header_bytes; i += PT) h[i] = header_template[i];
+        __syncthreads();
+        if (tid == 0) {
+            long long ns = cm.clip_off[s_clip + 1] - cm.clip_off[s_clip];
+            if (ns % L == 0) ns += L;             // Q9: bumped only when already a multiple
+            for (int i = 0; i < 4; ++i) h[10 + i] = (uint8_t)((unsigned long long)ns >> (8 * i));
+        }
+    }
+}
+
+__global__ void clip_scan_kernel(const int64_t* __restrict__ clip_bytes, int64_t* __restrict__ clip_base, int c0,
+                                 int n, int64_t* running) {
+    __shared__ long long s_w[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = *running;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        const long long v = (i < n) ? clip_bytes[c0 + i] : 0;
+        long long incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        long long woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_w[w];
+        const long long carry = s_carry;
+        if (i < n) clip_base[c0 + i] = carry + woff + incl - v;
+        __syncthreads();
+        if (tid == blockDim.x - 1) s_carry = carry + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) { *running = s_carry; clip_base[c0 + n] = s_carry; }
+}
+
+}  // namespace
+
+void launch_clip_scan(cudaStream_t st, const int64_t* clip_bytes, int64_t* clip_base, int c0, int n,
+                      int64_t* running) {
+    clip_scan_kernel<<<1, 256, 0, st>>>(clip_bytes, clip_base, c0, n, running);
+}
+
+void launch_pack(cudaStream_t st, const CodecParams& cp, const HuffDev* huff, const int* band_lo, const int* band_n,
+                 const uint8_t* line2band, const ClipMap& cm, int g0, int nblk, QuantOut qo, const uint8_t* ovs,
+                 const uint32_t* ms, const int64_t* clip_base, uint8_t* out, long long out_cap,
+                 const uint8_t* header_template, int* overflow_flag) {
+    if (nblk <= 0) return;
+    const size_t smem = (size_t)cp.L * 25 / 8 + 512;
+    pack_kernel<<<2 * nblk, PT, smem, st>>>(cp, huff, band_lo, band_n, line2band, cm, g0, qo, ovs, ms, clip_base,
+                                            out, out_cap, header_template, overflow_flag);
+}
