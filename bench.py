@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- encoded audio-seconds per second on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (libmrc.so on the GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+A step = one pass of the encode hot path (PCM frames -> .pac bytes) over one synthetic stream per GPU.
+Workload at N=1: BASELINE.json configs[1], a 1 h 48 kHz stereo 16-bit stream (tones + noise + transients + silent
+and -70 dBFS seconds), joint M/S, 128 kb/s/ch, fp64 code-exact mode.  N>1: every rank encodes its own 1 h stream
+(weak scaling, no data-path collective), then one NCCL all-gather of the per-rank bitstream lengths.
+`value` is measured with the PCM already in HBM and the bitstream left in HBM; `e2e` goes through the public host
+API (mrc_encode_batch via mrcaudiocodec_b200.Codec.encode_batch) with pinned host buffers, H2D and D2H inside the
+timed region.  The input (691 MB) is larger than L2 (126 MB), so nothing is cache-resident between steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 48000
+TBPS = 128000.0 / 48000.0
+METRIC = "encoded audio-seconds/sec, 48 kHz stereo 128 kb/s/ch"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seconds", type=float, default=3600.0, help="stream length per GPU")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-seconds", type=float, default=1.5)
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops(n_blocks_joint, n_blocks_flush, maskers, L=1024):
+    """SURVEY.md §8d, reference formulation: per spectrum MDCT (N + 2N + 5N log2 N + 2N) + Hann FFT
+    (N + 2.5 N log2 N + 1.5 N) + ~75 kFLOP for log10/quantise/MS, plus 40 FLOP per (masker, line) pair."""
+    N = 2 * L
+    lg = np.log2(N)
+    per_spec = (N + 2 * N + 5 * N * lg + 2 * N) + (N + 2.5 * N * lg + 1.5 * N) + 75000.0
+    spectra = 4 * n_blocks_joint + 2 * n_blocks_flush
+    return spectra * per_spec + 40.0 * L * maskers
+
+
+def run_reference(args, rank, world):
+    """The reference algorithm (oracle port -- the Python-2 reference itself cannot run here) on the host
+    cores: every worker process encodes its own bounded sample of the 1 h workload."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import multiprocessing as mp
+    from mrcaudiocodec_b200 import synth
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = max(1, min(cores, 64))
+    sample_s = args.cpu_sample_seconds
+    pcm = synth.synth_clip(0, max(sample_s * cores, 10.0), fast=True)
+    n = int(sample_s * SR)
+    segs = [pcm[i * n:(i + 1) * n] for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(args.warmup, 0) and 1):
+            pool.map(_oracle_encode, [s[:SR // 4] for s in segs])
+        t0 = time.time()
+        for _ in range(args.steps):
+            pool.map(_oracle_encode, segs)
+        dt = time.time() - t0
+    audio = args.steps * cores * sample_s
+    v = audio / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "1 h synthetic 48 kHz stereo stream, joint M/S, 128 kb/s/ch, fp64 (configs[1]); "
+                                   "each step = %d independent %.1f s samples of it, one per host core" % (cores, sample_s)},
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": "%d x %.1f s segments per step, %d steps (oracle/mrc_oracle, numpy)" %
+                                       (cores, sample_s, args.steps)},
+            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def _oracle_encode(pcm):
+    import mrc_oracle as o
+    blob, _ = o.driver.encode_pcm(pcm, joint=True)
+    return len(blob)
+
+
+def cpu_baseline(pcm, seconds):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mrc_oracle as o
+    n = int(seconds * SR)
+    o.driver.encode_pcm(pcm[:2048], joint=True)          # warm the table caches
+    t0 = time.time()
+    o.driver.encode_pcm(pcm[:n], joint=True)
+    dt = time.time() - t0
+    return {"value": seconds / dt, "unit": "audio-s/s", "cores": 1, "kind": "port",
+            "sample": "first %.1f s of the same stream, oracle/mrc_oracle (numpy restatement of the reference), "
+                      "1 thread, %.1f s of CPU time" % (seconds, dt)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mrcaudiocodec_b200 import Codec, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    seconds = args.seconds
+    threads = max(1, min(16, (os.cpu_count() or 8) // max(world, 1)))
+    pcm = synth.synth_clip(rank, seconds, threads=threads, fast=True)            # [frames, 2] int16
+    frames = pcm.shape[0]
+    off = np.array([0, frames], dtype=np.int64)
+    codec = Codec(device=local, precision=args.precision)
+    L = codec.L
+    nblk = codec.n_blocks(frames)
+
+    # device-resident buffers (torch is plumbing: device memory + NCCL)
+    d_pcm = torch.from_numpy(pcm).to(dev)
+    cap = int(2.0 * TBPS * 2 * frames / 8) + (1 << 20)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    h_pcm = torch.from_numpy(pcm).pin_memory()
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    h_pcm_np, h_out_np = h_pcm.numpy(), h_out.numpy()
+    lens = torch.zeros(1, dtype=torch.int64, device=dev)
+    gathered = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_device():
+        boff = codec.encode_batch_device(d_pcm.data_ptr(), off, d_out.data_ptr(), cap)
+        if world > 1:                    # the path's only collective: per-shard bitstream lengths -> offsets
+            lens[0] = int(boff[1])
+            dist.all_gather(gathered, lens)
+        return int(boff[1])
+
+    def step_e2e():
+        out, boff = codec.encode_batch(h_pcm_np, off, out=h_out_np)
+        if world > 1:
+            lens[0] = int(boff[1])
+            dist.all_gather(gathered, lens)
+        return int(boff[1])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        dev_ms, launches, maskers, stage = 0.0, 0, 0, np.zeros(3)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            nbytes = fn()
+            t = codec.last_timing()
+            dev_ms += t["total_ms"]
+            launches += t["launches"]
+            maskers = t["maskers"]
+            stage += np.array([t["analysis_ms"], t["quant_ms"], t["pack_ms"]])
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        tt = torch.tensor([wall, dev_ms / 1000.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return dict(wall=float(tt[0]), dev=float(tt[1]), launches=launches, maskers=maskers, nbytes=nbytes,
+                    stage_ms=(stage / args.steps).tolist(), clocks=clocks)
+
+    peaks = codec.measure_peaks()
+    r_dev = timed(step_device)
+    r_e2e = timed(step_e2e)
+
+    audio_total = world * seconds * args.steps
+    value = audio_total / r_dev["wall"]
+    e2e_value = audio_total / r_e2e["wall"]
+
+    if rank == 0:
+        mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if os.path.exists(mp_path):
+            try:
+                hbm_peak = float(json.load(open(mp_path))["hbm_gbs"])
+                hbm_src = "MEASURED_PEAKS.json"
+            except Exception:
+                pass
+        an_ms = r_dev["stage_ms"][0]
+        flops = algorithmic_flops(nblk - 1, 1, r_dev["maskers"], L)
+        is64 = args.precision == "fp64"
+        peak_tf = peaks["fp64_tflops"] if is64 else peaks["fp32_tflops"]
+        ach_tf = flops / (an_ms * 1e-3) / 1e12
+        alg_bytes = nblk * (4096 + 2 * L * (8 if is64 else 4) * 1 + 64 * 2 * (8 if is64 else 4) + 1536 + 8)
+        line = {
+            "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * r_dev["wall"] / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is64 else "f32", "data": "synthetic",
+            "config": {"workload": "%.0f s synthetic 48 kHz stereo 16-bit stream per GPU (BASELINE configs[1] = 1 h), "
+                                   "joint M/S, 128 kb/s/ch, %s mode, long blocks N=2048" % (seconds, args.precision),
+                       "l2": "input %.0f MB per step > 126 MB L2, no flush needed" % (frames * 4 / 1e6),
+                       "blocks_per_step": nblk, "bitstream_bytes": r_dev["nbytes"]},
+            "device_ms_per_step": 1000.0 * r_dev["dev"] / args.steps,
+            "stage_ms_per_step": {"analysis": r_dev["stage_ms"][0], "alloc_quant": r_dev["stage_ms"][1],
+                                  "pack": r_dev["stage_ms"][2]},
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(frames * 4),
+                    "d2h_bytes_per_step": int(r_e2e["nbytes"]), "ms_per_step": 1000.0 * r_e2e["wall"] / args.steps},
+            "gpu_launches": int(r_dev["launches"]),
+            "clocks": r_dev["clocks"],
+            "roofline": {"kernel": "analysis_kernel (MDCT + psychoacoustics, fused)",
+                         "bound": "fp64" if is64 else "fp32", "achieved": ach_tf, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "peak_source": "mrc_measure_peaks (FMA chain on this GPU, this run)",
+                         "work": "SURVEY 8d reference formulation, %d maskers measured" % r_dev["maskers"],
+                         "avg_launch_ms": an_ms},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (an_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": alg_bytes / (an_ms * 1e-3) / 1e9 / hbm_peak,
+                             "peak_source": hbm_src, "traffic": None},
+            "pipe_peaks": peaks,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(pcm, args.cpu_sample_seconds)
+        print(json.dumps(line))
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

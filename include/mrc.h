@@ -117,7 +117,8 @@ int32_t mrc_decode_batch_device(mrc_ctx* ctx, const uint8_t* d_pac, const uint8_
                                 int64_t pcm_cap_frames, int64_t* clip_frame_offsets);
 
 /* ---- per-block seam (compat layer; explicit bit reservoir in/out) -----------------------------------------
- * mrc_encode_block = codecThem.Encode (joint=0) / JointEncode (joint=1) on one block.
+ * mrc_encode_block = codecThem.Encode (joint=0) / JointEncode (joint=1) on one block; joint|2 skips the Huffman
+ * stage (EncodeNoHuff, codecThem.py:234-260: table 15, no reservoir credit).
  * data             : [2][2*n_mdct_lines] float64 signed fractions (prior block, current block) per channel
  * reservoir        : in/out codingParams.bitReservoir
  * scale_factor,bit_alloc : [2][n_bands]; mantissa: [2][n_mdct_lines] aligned to MDCT lines (0 where the band has
@@ -153,6 +154,9 @@ int32_t mrc_stage_alloc_quant(mrc_ctx* ctx, const int16_t* pcm, const int64_t* c
  * [6] total on stream; counters [0] kernel launches, [1] sum over spectra of tonal maskers, [2] blocks,
  * [3] spectra analysed. */
 int32_t mrc_last_timing(const mrc_ctx* ctx, double* ms8, int64_t* counters8);
+/* Micro-benchmarks of this GPU's pipes, for the roofline denominators MEASURED_PEAKS.json does not carry:
+ * out4[0] FP64 FMA TFLOP/s, [1] FP32 FMA TFLOP/s, [2] MUFU.EX2 Gop/s, [3] device copy GB/s (read+write). */
+int32_t mrc_measure_peaks(mrc_ctx* ctx, double* out4);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,7 @@ class MrcError(RuntimeError):
 EXPORTS = ["mrc_version", "mrc_last_error", "mrc_create", "mrc_destroy", "mrc_set_tables", "mrc_host_alloc",
            "mrc_host_free", "mrc_encode_batch", "mrc_encode_batch_device", "mrc_decode_batch",
            "mrc_decode_batch_device", "mrc_encode_block", "mrc_decode_block", "mrc_stage_analysis",
-           "mrc_stage_alloc_quant", "mrc_last_timing"]
+           "mrc_stage_alloc_quant", "mrc_last_timing", "mrc_measure_peaks"]
 
 _lib = None
 
@@ -72,6 +72,7 @@ def load():
     lib.mrc_stage_analysis.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.mrc_stage_alloc_quant.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
     lib.mrc_last_timing.argtypes = [vp, vp, vp]
+    lib.mrc_measure_peaks.argtypes = [vp, vp]
     for name in EXPORTS:
         f = getattr(lib, name)
         if name not in ("mrc_last_error",):

@@ -208,6 +208,12 @@ class Codec(object):
                                               _ptr(ms), _ptr(out)))
         return out
 
+    def measure_peaks(self):
+        out = np.zeros(4, np.float64)
+        self._check(self.lib.mrc_measure_peaks(self._ctx, _ptr(out)))
+        return dict(fp64_tflops=float(out[0]), fp32_tflops=float(out[1]), mufu_gops=float(out[2]),
+                    copy_gbs=float(out[3]))
+
     def last_timing(self):
         ms = np.zeros(8, np.float64)
         cnt = np.zeros(8, np.int64)

@@ -144,6 +144,7 @@ struct EncodeJob {
     int n_clips = 0;
     bool flush_nonjoint = true;
     int joint = 1;
+    int no_huff = 0;
     const int32_t* h_res_in = nullptr;     // [n_clips] or null
     int32_t* h_res_out = nullptr;
     // packed output (device), optional
@@ -205,6 +206,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     CodecParams cp = ctx->cp;
     cp.joint = job.joint;
     cp.flush_nonjoint = job.flush_nonjoint ? 1 : 0;
+    cp.no_huff = job.no_huff;
 
     // ---- waves of whole clips ----
     std::vector<std::pair<int, int>> waves;     // [c0, c1)
@@ -523,7 +525,7 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     ctx->cp.L = L; ctx->cp.nb = t->n_bands;
     ctx->cp.n_scale_bits = c.n_scale_bits; ctx->cp.n_mant_size_bits = c.n_mant_size_bits;
     ctx->cp.max_mant_bits = std::min(16, 1 << c.n_mant_size_bits);
-    ctx->cp.joint = c.joint; ctx->cp.flush_nonjoint = 1;
+    ctx->cp.joint = c.joint; ctx->cp.flush_nonjoint = 1; ctx->cp.no_huff = 0;
     if (ctx->cp.max_mant_bits != 16) return fail(ctx, MRC_E_INVALID, "only n_mant_size_bits = 4 (16-bit cap) is supported");
     // .pac header template (pacfileThem.py:592-613); numSamples is patched per clip by the pack kernel
     uint8_t* hd = ctx->h_header;
@@ -653,13 +655,19 @@ int32_t mrc_encode_block(mrc_ctx* ctx, const double* data, int32_t joint, int32_
     int32_t res_in = *reservoir, res_out = 0;
     EncodeJob job;
     job.d_xin = (const double*)ctx->xin_dev.p; job.h_clip_off = off; job.n_clips = 1;
-    job.joint = joint ? 1 : 0; job.flush_nonjoint = false;
+    job.joint = (joint & 1) ? 1 : 0; job.no_huff = (joint & 2) ? 1 : 0; job.flush_nonjoint = false;
     job.h_res_in = &res_in; job.h_res_out = &res_out;
     job.t_alloc = bit_alloc; job.t_sf = scale_factor; job.t_mant = mantissa; job.t_table = huff_table;
     job.t_cbytes = chunk_bytes; job.t_ovs = overall_scale; job.t_ms = ms_switch;
     const int rc = run_encode(ctx, job);
     if (rc == MRC_OK) *reservoir = res_out;
     return rc;
+}
+
+int32_t mrc_measure_peaks(mrc_ctx* ctx, double* out4) {
+    if (!ctx || !out4) return MRC_E_INVALID;
+    cudaSetDevice(ctx->cfg.device);
+    return measure_peaks(ctx->stream, out4) == 0 ? MRC_OK : fail(ctx, MRC_E_CUDA, "peak micro-benchmark failed");
 }
 
 int32_t mrc_last_timing(const mrc_ctx* ctx, double* ms8, int64_t* counters8) {

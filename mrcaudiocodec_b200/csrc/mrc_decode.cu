@@ -1,2 +1,384 @@
-// mrc_decode.cu -- decode kernels (K5).  Filled in below.
+// mrc_decode.cu -- K5: the decode mirror path.
+//   chunk parse                     pacfileThem.py:161-319 (ReadDataBlock) / :321-585 (JointReadDataBlock);
+//                                   bit reader bitpack.py:104-170; prefix-code walk :445-480 (here a 9-bit LUT)
+//   dequantise                      codecThem.py:30-63 / :65-134 with quantize.py:325-357, :90-111
+//   M/S reconstruct                 ms_stereo.py:33-49
+//   IMDCT + window                  mdct.py:98-122 (here an L/2-point complex FFT DCT-IV), window.py:104-121
+//   overlap-add, first block drop   pacfileThem.py:312-314, :575-580, :1175-1177, :178-185
+//   PCM conversion                  pcmfile.py:164-174 with quantize.py:61-87 at 16 bits
+// One CTA per block pair (both channels), NT = L/2 threads.  A malformed chunk (reads past its nBytes, block
+// switching bits set, unknown table id) raises the error flag and decodes as silence instead of reading on.
 #include "mrc_decode.cuh"
+#include "mrc_math.cuh"
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ void fft_dit_d(cpx<T>* a, int logn, int lt, int nthr, const cpx<T>* __restrict__ tw,
+                                          int logLtab) {
+    const int nb = 1 << (logn - 1);
+    for (int s = 1; s <= logn; ++s) {
+        const int half = 1 << (s - 1);
+        for (int i = lt; i < nb; i += nthr) {
+            const int j = i & (half - 1);
+            const int base = ((i >> (s - 1)) << s) + j;
+            const cpx<T> w = tw[j << (logLtab - s)];
+            const cpx<T> u = a[base];
+            const cpx<T> v = a[base + half];
+            const T vx = v.x * w.x - v.y * w.y;
+            const T vy = v.x * w.y + v.y * w.x;
+            a[base].x = u.x + vx;          a[base].y = u.y + vy;
+            a[base + half].x = u.x - vx;   a[base + half].y = u.y - vy;
+        }
+        __syncthreads();
+    }
+}
+
+struct BitReader {
+    const uint32_t* w;       // big-endian words in shared memory
+    int pos, nbits;
+    bool bad;
+    __device__ __forceinline__ uint32_t peek(int n) const {     // n in 1..32
+        const int i = pos >> 5, off = pos & 31;
+        const unsigned long long x = ((unsigned long long)w[i] << 32) | w[i + 1];
+        return (uint32_t)((x << off) >> (64 - n));
+    }
+    __device__ __forceinline__ uint32_t read(int n) {
+        if (n <= 0) return 0;
+        if (pos + n > nbits) { bad = true; pos = nbits; return 0; }
+        const uint32_t v = peek(n);
+        pos += n;
+        return v;
+    }
+};
+
+// shared-memory working set of one pair
+template <typename T>
+struct DSmem {
+    uint32_t* cw;        // [2][cwords]  chunk payloads as big-endian words
+    int* mant;           // [2][L]
+    T* lines;            // [2][L]       dequantised MDCT lines (after M/S reconstruct: L, R)
+    cpx<T>* buf;         // [L]          two L/2-point FFTs
+    T* v;                // [2][L]       DCT-IV outputs
+};
+
+template <typename T>
+__device__ __forceinline__ DSmem<T> dcarve(unsigned char* raw, int L, int cwords) {
+    DSmem<T> s;
+    T* p = reinterpret_cast<T*>(raw);
+    s.lines = p;  p += 2 * L;
+    s.buf = reinterpret_cast<cpx<T>*>(p);  p += 2 * L;
+    s.v = p;      p += 2 * L;
+    s.mant = reinterpret_cast<int*>(p);
+    s.cw = reinterpret_cast<uint32_t*>(s.mant + 2 * L);
+    (void)cwords;
+    return s;
+}
+
+// dequantise + rescale + M/S + IMDCT + window; ints in shared memory.  Writes y[2][2L] to global.
+template <typename T, int LOGL>
+__device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecParams& cp, DSmem<T>& sm, bool joint,
+                                           const int* s_alloc, const int* s_sf, const int* s_ovs, unsigned ms,
+                                           T* __restrict__ yout) {
+    constexpr int L = 1 << LOGL, Q = L / 2, NT = Q;
+    const int tid = threadIdx.x, nb = tb.nb;
+    // dequantise (codecThem.py:44-52 / :96-115) -- arithmetic in double in both precisions (a handful of ops)
+    for (int i = tid; i < 2 * L; i += NT) {
+        const int ch = i / L, k = i - ch * L;
+        const int bd = tb.line2band[k];
+        const int Rb = s_alloc[ch * MRC_BSTRIDE + bd];
+        double x = 0.0;
+        if (Rb) {
+            x = dequantize_of(sm.mant[i], s_sf[ch * MRC_BSTRIDE + bd], cp.n_scale_bits, Rb);
+            const int sc = joint ? s_ovs[((ms >> bd) & 1u) ? 2 + ch : ch] : s_ovs[ch];
+            x = x / (double)(1 << sc);
+        }
+        sm.lines[i] = T(x);
+    }
+    __syncthreads();
+    if (joint) {      // ms_stereo.py:33-49
+        for (int k = tid; k < L; k += NT) {
+            if ((ms >> tb.line2band[k]) & 1u) {
+                const T m = sm.lines[k], s = sm.lines[L + k];
+                sm.lines[k] = m + s;
+                sm.lines[L + k] = m - s;
+            }
+        }
+        __syncthreads();
+    }
+    // DCT-IV of both channels: t[n] = (X[2n] + j X[L-1-2n]) * pre[n]; FFT; c = T*post; v[2k]=Re, v[L-1-2k]=-Im
+    {
+        const int grp = tid / (NT / 2), lt = tid - grp * (NT / 2), gthr = NT / 2;
+        const T* X = sm.lines + grp * L;
+        cpx<T>* a = sm.buf + grp * Q;
+        for (int n = lt; n < Q; n += gthr) {
+            const T re = X[2 * n], im = X[L - 1 - 2 * n];
+            const cpx<T> w = tb.tw_pre[n];
+            const int r = (int)(__brev((unsigned)n) >> (32 - (LOGL - 1)));
+            a[r].x = re * w.x - im * w.y;
+            a[r].y = re * w.y + im * w.x;
+        }
+        __syncthreads();
+        fft_dit_d<T>(a, LOGL - 1, lt, gthr, tb.tw_fft, LOGL);
+        T* v = sm.v + grp * L;
+        for (int k = lt; k < Q; k += gthr) {
+            const cpx<T> w = tb.tw_post[k];
+            const cpx<T> t = a[k];
+            v[2 * k] = t.x * w.x - t.y * w.y;
+            v[L - 1 - 2 * k] = -(t.x * w.y + t.y * w.x);
+        }
+        __syncthreads();
+    }
+    // unfold (x[n] = 2 v_ext[n + L/2]) and window
+    for (int i = tid; i < 4 * L; i += NT) {
+        const int ch = i / (2 * L), n = i - ch * 2 * L;
+        const T* v = sm.v + ch * L;
+        T x;
+        if (n < Q) x = v[n + Q];
+        else if (n < 3 * Q) x = -v[3 * Q - 1 - n];
+        else x = -v[n - 3 * Q];
+        yout[i] = (T(2) * x) * tb.kbd[n];
+    }
+}
+
+template <typename T, int LOGL>
+__global__ void __launch_bounds__(1 << (LOGL - 1))
+decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, const HuffDecDev* __restrict__ hdec,
+              DecodeMap dm, const uint8_t* __restrict__ pac, int p0, T* __restrict__ y, int* error_flag, int cwords) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int L = 1 << LOGL, NT = L / 2;
+    const int tid = threadIdx.x, nb = tb.nb;
+    DSmem<T> sm = dcarve<T>(smem_raw, L, cwords);
+    __shared__ int s_alloc[2 * MRC_BSTRIDE], s_sf[2 * MRC_BSTRIDE], s_ovs[4];
+    __shared__ unsigned s_ms;
+    __shared__ int s_bad, s_joint;
+    __shared__ int s_esc[MRC_N_HUFF_TABLES];
+
+    const int lp = blockIdx.x, p = p0 + lp;
+    if (tid == 0) {
+        int lo = 0, hi = dm.n_clips;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (dm.clip_pair0[mid] <= p) lo = mid; else hi = mid;
+        }
+        const int last = dm.clip_pair0[lo + 1] - 1;
+        s_joint = cp.joint && !(cp.flush_nonjoint && p == last);
+        s_ms = 0u;
+        s_bad = 0;
+    }
+    if (tid < MRC_N_HUFF_TABLES) s_esc[tid] = huff->esc[tid];
+    // stage both chunk payloads as big-endian words
+    for (int ch = 0; ch < 2; ++ch) {
+        const uint8_t* src = pac + dm.chunk_pos[2 * p + ch];
+        const int nbytes = min((int)dm.chunk_len[2 * p + ch], (cwords - 2) * 4);
+        uint32_t* dst = sm.cw + ch * cwords;
+        for (int wi = tid; wi < cwords; wi += NT) {
+            uint32_t w = 0;
+            const int b0 = wi * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (b0 + j < nbytes) w |= (uint32_t)__ldg(src + b0 + j) << (24 - 8 * j);
+            dst[wi] = w;
+        }
+    }
+    for (int i = tid; i < 2 * L; i += NT) sm.mant[i] = 0;
+    __syncthreads();
+    const bool joint = s_joint != 0;
+
+    // ---- bit-serial parse, one thread per channel chunk (threads 0 and 32) ------------------------------
+    if ((tid == 0 || tid == 32)) {
+        const int ch = tid >> 5;
+        BitReader br;
+        br.w = sm.cw + ch * cwords;
+        br.pos = 0;
+        br.nbits = 8 * min((int)dm.chunk_len[2 * p + ch], (cwords - 2) * 4);
+        br.bad = false;
+        const int table = (int)br.read(4);
+        const int swA = (int)br.read(1), swB = (int)br.read(1);
+        if (swA | swB) br.bad = true;                              // block switching is out of scope (§8 f1)
+        if (table != MRC_NO_TABLE && table >= MRC_N_HUFF_TABLES) br.bad = true;
+        if (joint) {
+            if (ch == 0) {
+                for (int i = 0; i < 4; ++i) s_ovs[i] = (int)br.read(cp.n_scale_bits);
+                unsigned ms = 0;
+                for (int bd = 0; bd < nb; ++bd) ms |= br.read(1) << bd;
+                s_ms = ms;
+            }
+        } else {
+            s_ovs[ch] = (int)br.read(cp.n_scale_bits);
+        }
+        int* mant = sm.mant + ch * L;
+        for (int bd = 0; bd < nb && !br.bad; ++bd) {
+            int ba = (int)br.read(cp.n_mant_size_bits);
+            if (ba) ba += 1;
+            s_alloc[ch * MRC_BSTRIDE + bd] = ba;
+            s_sf[ch * MRC_BSTRIDE + bd] = (int)br.read(cp.n_scale_bits);
+            if (!ba) continue;
+            const int lo = tb.band_lo[bd], n = tb.band_n[bd];
+            if (table == MRC_NO_TABLE) {
+                for (int j = 0; j < n; ++j) mant[lo + j] = (int)br.read(ba);
+            } else {
+                const uint16_t* lut = hdec->lut[table];
+                const int esc = s_esc[table];
+                for (int j = 0; j < n && !br.bad; ++j) {
+                    const int rem = br.nbits - br.pos;
+                    if (rem <= 0) { br.bad = true; break; }
+                    const uint32_t e = lut[br.peek(MRC_HUFF_PEEK)];
+                    const int len = e >> 8, val = e & 0xff;
+                    if (len == 0 || len > rem) { br.bad = true; break; }
+                    br.pos += len;
+                    mant[lo + j] = (val == esc) ? (int)br.read(ba) : val;
+                }
+            }
+        }
+        if (br.bad) {
+            s_bad = 1;
+            for (int bd = 0; bd < nb; ++bd) s_alloc[ch * MRC_BSTRIDE + bd] = 0;
+        }
+    }
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) atomicExch(error_flag, 1);
+        if (tid < 2 * nb) s_alloc[(tid / nb) * MRC_BSTRIDE + tid % nb] = 0;
+        if (tid < 4) s_ovs[tid] = 0;
+        __syncthreads();
+    }
+    synthesize<T, LOGL>(tb, cp, sm, joint, s_alloc, s_sf, s_ovs, s_ms, y + (size_t)lp * 4 * L);
+}
+
+template <typename T, int LOGL>
+__global__ void __launch_bounds__(1 << (LOGL - 1))
+decode_ints_kernel(DevTables<T> tb, CodecParams cp, int joint, const int32_t* __restrict__ sf,
+                   const int32_t* __restrict__ alloc, const int32_t* __restrict__ mant,
+                   const int32_t* __restrict__ ovs, const int32_t* __restrict__ ms, T* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int L = 1 << LOGL, NT = L / 2;
+    const int tid = threadIdx.x, nb = tb.nb, lp = blockIdx.x;
+    DSmem<T> sm = dcarve<T>(smem_raw, L, 0);
+    __shared__ int s_alloc[2 * MRC_BSTRIDE], s_sf[2 * MRC_BSTRIDE], s_ovs[4];
+    __shared__ unsigned s_ms;
+    if (tid == 0) s_ms = 0u;
+    __syncthreads();
+    if (tid < 2 * nb) {
+        const int ch = tid / nb, bd = tid - ch * nb;
+        s_alloc[ch * MRC_BSTRIDE + bd] = alloc[(size_t)lp * 2 * nb + tid];
+        s_sf[ch * MRC_BSTRIDE + bd] = sf[(size_t)lp * 2 * nb + tid];
+    }
+    if (tid < 4) s_ovs[tid] = ovs[(size_t)lp * 4 + tid];
+    if (tid < nb && ms[(size_t)lp * nb + tid]) atomicOr(&s_ms, 1u << tid);
+    for (int i = tid; i < 2 * L; i += NT) sm.mant[i] = mant[(size_t)lp * 2 * L + i];
+    __syncthreads();
+    synthesize<T, LOGL>(tb, cp, sm, joint != 0, s_alloc, s_sf, s_ovs, joint ? s_ms : 0u, y + (size_t)lp * 4 * L);
+}
+
+// pcmfile.py:164-174: sign/magnitude, |x|>=1 -> 32767 else trunc((65535|x|+1)/2)
+__device__ __forceinline__ int fraction_to_pcm(double x) {
+    const double ax = fabs(x);
+    const int q = (int)quant_mag_code(ax, 16);
+    return (x < 0.0) ? -q : q;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ola_kernel(CodecParams cp, DecodeMap dm, int p0, const T* __restrict__ y, const int64_t* __restrict__ clip_frame_off,
+           int16_t* __restrict__ pcm) {
+    const int L = cp.L, lp = blockIdx.x, p = p0 + lp, tid = threadIdx.x;
+    __shared__ int s_clip, s_last;
+    if (tid == 0) {
+        int lo = 0, hi = dm.n_clips;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (dm.clip_pair0[mid] <= p) lo = mid; else hi = mid;
+        }
+        s_clip = lo;
+        s_last = dm.clip_pair0[lo + 1] - 1;
+    }
+    __syncthreads();
+    const int j = p - dm.clip_pair0[s_clip];
+    const bool has_next = p < s_last;
+    const T* cur = y + (size_t)lp * 4 * L;           // [2][2L] of pair p
+    const T* nxt = cur + 4 * L;                       // pair p+1 (same wave: waves hold whole clips)
+    uint32_t* out = reinterpret_cast<uint32_t*>(pcm) + clip_frame_off[s_clip] + (long long)j * L;
+    for (int n = tid; n < L; n += blockDim.x) {
+        double l = (double)cur[L + n], r = (double)cur[2 * L + L + n];
+        if (has_next) {       // np.add(overlapAndAdd, decoded[:a]): saved tail first, then the new head
+            l = l + (double)nxt[n];
+            r = r + (double)nxt[2 * L + n];
+        }
+        const int cl = fraction_to_pcm(l), cr = fraction_to_pcm(r);
+        out[n] = ((uint32_t)(uint16_t)(int16_t)cl) | ((uint32_t)(uint16_t)(int16_t)cr << 16);
+    }
+}
+
+size_t decode_smem_bytes(int L, int elem, int cwords) {
+    return (size_t)6 * L * elem + (size_t)2 * L * 4 + (size_t)2 * cwords * 4;
+}
+
+int chunk_words(const CodecParams& cp) {
+    const int bits = 6 + 4 * cp.n_scale_bits + cp.nb + cp.nb * (cp.n_mant_size_bits + cp.n_scale_bits) + cp.L * 25;
+    return (bits + 31) / 32 + 2;
+}
+
+}  // namespace
+
+template <typename T>
+void launch_decode(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
+                   const HuffDecDev* hdec, const DecodeMap& dm, const uint8_t* pac, int p0, int npairs, T* y,
+                   int* error_flag) {
+    if (npairs <= 0) return;
+    const int cw = chunk_words(cp);
+    const size_t smem = decode_smem_bytes(tb.L, sizeof(T), cw);
+#define MRC_LAUNCH_DEC(LG)                                                                                     \
+    case LG:                                                                                                   \
+        cudaFuncSetAttribute(decode_kernel<T, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        decode_kernel<T, LG><<<npairs, 1 << (LG - 1), smem, st>>>(tb, cp, huff, hdec, dm, pac, p0, y,          \
+                                                                  error_flag, cw);                             \
+        break;
+    switch (tb.logL) {
+        MRC_LAUNCH_DEC(8)
+        MRC_LAUNCH_DEC(9)
+        MRC_LAUNCH_DEC(10)
+        MRC_LAUNCH_DEC(11)
+        default: break;
+    }
+#undef MRC_LAUNCH_DEC
+}
+
+template <typename T>
+void launch_decode_ints(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, int joint,
+                        const int32_t* sf, const int32_t* alloc, const int32_t* mant, const int32_t* ovs,
+                        const int32_t* ms, int npairs, T* y) {
+    if (npairs <= 0) return;
+    const size_t smem = decode_smem_bytes(tb.L, sizeof(T), 0);
+#define MRC_LAUNCH_DECI(LG)                                                                                    \
+    case LG:                                                                                                   \
+        cudaFuncSetAttribute(decode_ints_kernel<T, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        decode_ints_kernel<T, LG><<<npairs, 1 << (LG - 1), smem, st>>>(tb, cp, joint, sf, alloc, mant, ovs, ms, y); \
+        break;
+    switch (tb.logL) {
+        MRC_LAUNCH_DECI(8)
+        MRC_LAUNCH_DECI(9)
+        MRC_LAUNCH_DECI(10)
+        MRC_LAUNCH_DECI(11)
+        default: break;
+    }
+#undef MRC_LAUNCH_DECI
+}
+
+template <typename T>
+void launch_ola(cudaStream_t st, const CodecParams& cp, const DecodeMap& dm, int p0, int npairs, const T* y,
+                const int64_t* clip_frame_off, int16_t* pcm) {
+    if (npairs <= 0) return;
+    ola_kernel<T><<<npairs, 256, 0, st>>>(cp, dm, p0, y, clip_frame_off, pcm);
+}
+
+#define MRC_INST(T)                                                                                            \
+    template void launch_decode<T>(cudaStream_t, const DevTables<T>&, const CodecParams&, const HuffDev*,       \
+                                   const HuffDecDev*, const DecodeMap&, const uint8_t*, int, int, T*, int*);    \
+    template void launch_decode_ints<T>(cudaStream_t, const DevTables<T>&, const CodecParams&, int,             \
+                                        const int32_t*, const int32_t*, const int32_t*, const int32_t*,         \
+                                        const int32_t*, int, T*);                                               \
+    template void launch_ola<T>(cudaStream_t, const CodecParams&, const DecodeMap&, int, int, const T*,         \
+                                const int64_t*, int16_t*);
+MRC_INST(double)
+MRC_INST(float)

@@ -80,6 +80,7 @@ struct QuantOut {
 
 struct CodecParams {
     int L, nb, n_scale_bits, n_mant_size_bits, max_mant_bits, joint;
+    int no_huff;                 // 1: EncodeNoHuff (codecThem.py:234-260): table 15, no reservoir credit
     int flush_nonjoint;          // 1: the last block of every clip is the non-joint Close() flush block (Q10)
     double budget_joint;         // value of bitBudget just before `+= bitReservoir` (codecThem.py:381-391)
     double budget_single;        // value of bitBudget just before `+= bitReservoir` (codecThem.py:299-306)
@@ -107,3 +108,6 @@ void launch_clip_scan(cudaStream_t st, const int64_t* clip_bytes, int64_t* clip_
                       int64_t* running);
 
 size_t analysis_smem_bytes(int L, int elem);
+
+// mrc_peaks.cu
+int measure_peaks(cudaStream_t st, double* out);

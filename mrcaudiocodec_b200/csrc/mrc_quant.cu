@@ -214,7 +214,7 @@ quant_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, 
                     const int ch = ch0 + ci;
                     const int raw = s_raw[ch];
                     int best = raw, table = MRC_NO_TABLE, bits = raw;
-                    for (int t = 0; t < MRC_N_HUFF_TABLES; ++t) {
+                    for (int t = 0; t < MRC_N_HUFF_TABLES && !cp.no_huff; ++t) {
                         const int cost = (int)(s_acc[ch][t] & 0xffffu), extra = (int)(s_acc[ch][t] >> 16);
                         if (cost < best) { best = cost; table = t; bits = cost + extra; }
                     }

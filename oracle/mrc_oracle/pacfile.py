@@ -111,7 +111,7 @@ class PACWriter(object):
         for c in range(cp.nChannels):
             self._chunk(cp, [(O[c], cp.nScaleBits)], A[c], S[c], M[c], H[c])
         return dict(joint=False, scaleFactor=S, bitAlloc=A, mantissa=M, overallScale=O, huffTable=H,
-                    ms_switch=None, reservoir=cp.bitReservoir, tap=cp._tap)
+                    ms_switch=None, reservoir=cp.bitReservoir, tap=getattr(cp, "_tap", None))
 
     def JointWriteDataBlock(self, data, cp):
         """:793-972  channel 0 = M|L with the 4 overall scales and the ms bits, channel 1 = S|R."""
@@ -123,7 +123,7 @@ class PACWriter(object):
         self._chunk(cp, head0, A[0], S[0], M[0], H[0])
         self._chunk(cp, [], A[1], S[1], M[1], H[1])
         return dict(joint=True, scaleFactor=S, bitAlloc=A, mantissa=M, overallScale=O, huffTable=H,
-                    ms_switch=ms, reservoir=cp.bitReservoir, tap=cp._tap)
+                    ms_switch=ms, reservoir=cp.bitReservoir, tap=getattr(cp, "_tap", None))
 
     def Close(self, cp):
         """:973-984  flush: one extra NON-joint block of zeros (Q10)."""

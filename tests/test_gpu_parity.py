@@ -1,0 +1,218 @@
+"""GPU parity tests (run on the B200 box): libmrc.so through the C ABI vs (a) the golden vectors produced by the
+unmodified reference and (b) the oracle restatement on fresh seeds.  Integer outputs and bytes must be identical in
+fp64 mode; float taps are compared with the tolerance written next to each assert."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codecs():
+    from mrcaudiocodec_b200 import Codec
+    cache = {}
+
+    def get(sr=48000, joint=True, tbps=128000. / 48000., precision="fp64", L=1024):
+        key = (sr, joint, tbps, precision, L)
+        if key not in cache:
+            cache[key] = Codec(sample_rate=sr, joint=joint, target_bits_per_sample=tbps, precision=precision,
+                               n_mdct_lines=L)
+        return cache[key]
+    yield get
+    for c in cache.values():
+        c.close()
+
+
+def _cfg(g):
+    return int(g["sampleRate"]), bool(g["joint"]), float(g["tbps"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_bytes_identical(golden, codecs, name):
+    g = golden(name)
+    sr, joint, tbps = _cfg(g)
+    blob = codecs(sr, joint, tbps).encode_clips([g["pcm"]])[0]
+    assert blob == g["pac"].tobytes()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_stage_taps(golden, codecs, name):
+    g = golden(name)
+    sr, joint, tbps = _cfg(g)
+    c = codecs(sr, joint, tbps)
+    a = c.stage_analysis([g["pcm"]])
+    q = c.stage_alloc_quant([g["pcm"]])
+    isj = g["isJoint"]
+    nB = isj.shape[0]
+    for i in range(nB):
+        ns = 4 if isj[i] else 2
+        assert np.array_equal(a["overallScale"][i, :ns], g["overallScale"][i, :ns])
+        if isj[i]:
+            assert np.array_equal(a["ms_switch"][i], g["ms_switch"][i])
+    for k in ("bitAlloc", "scaleFactor", "mantissa", "huffTable", "reservoir"):
+        assert np.array_equal(q[k], g[k]), k
+    for i in range(g["mdct"].shape[0]):
+        ns = 4 if isj[i] else 2
+        ref = g["mdct"][i, :ns]
+        # MDCT lines: <= 1e-12 of the block maximum (the reference's own twiddle phases carry ~1e-13)
+        assert np.abs(a["mdct"][i, :ns] - ref).max() <= 1e-12 * np.abs(ref).max() + 1e-300
+        # SMR: <= 1e-9 dB
+        assert np.abs(a["smr"][i, :ns] - g["smr"][i, :ns]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_decode_matches_reference_decoder(golden, codecs, name):
+    g = golden(name)
+    sr, joint, tbps = _cfg(g)
+    pcm = codecs(sr, joint, tbps).decode_clips([g["pac"].tobytes()])[0]
+    assert pcm.shape == g["decoded"].shape
+    d = np.abs(pcm.astype(np.int64) - g["decoded"].astype(np.int64))
+    assert d.max() <= 1                                   # north_star: decoded PCM within 1 LSB
+    assert np.count_nonzero(d) <= 2, "fp64 decode should reproduce the reference decoder almost everywhere"
+
+
+@pytest.mark.parametrize("joint", [True, False])
+def test_fresh_seed_vs_oracle(codecs, joint):
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import synth
+    pcm = synth.synth_short(21, 0.6)
+    ob, _ = o.driver.encode_pcm(pcm, joint=joint)
+    c = codecs(48000, joint)
+    gb = c.encode_clips([pcm])[0]
+    assert gb == ob
+    od = o.driver.decode_pac(ob, joint=joint)
+    gd = c.decode_clips([gb])[0]
+    assert gd.shape == od.shape
+    assert np.abs(gd.astype(np.int64) - od.astype(np.int64)).max() <= 1
+
+
+def test_ragged_batch_and_edge_clips(codecs):
+    """empty clip, 1 frame, exactly L, L+1, silence, full scale incl. -32768 (Q1), identical L/R, hard-panned."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import synth
+    rng = np.random.default_rng(5)
+    base = synth.synth_short(31, 0.25)
+    full = rng.integers(-32768, 32768, size=(3000, 2)).astype(np.int16)
+    full[10, 0] = -32768
+    full[11, 1] = -32768
+    mono = base[:4000].copy()
+    mono[:, 1] = mono[:, 0]
+    pan = base[:4000].copy()
+    pan[:, 1] = 0
+    clips = [np.zeros((0, 2), np.int16), base[:1], base[:1024], base[:1025], np.zeros((2500, 2), np.int16),
+             full, mono, pan, base]
+    c = codecs(48000, True)
+    blobs = c.encode_clips(clips)
+    for i, (clip, blob) in enumerate(zip(clips, blobs)):
+        ob, _ = o.driver.encode_pcm(clip, joint=True)
+        assert blob == ob, "clip %d" % i
+        assert c.encode_clips([clip])[0] == blob, "batch vs single, clip %d" % i
+    dec = c.decode_clips(blobs)
+    for i, (clip, blob, d) in enumerate(zip(clips, blobs, dec)):
+        od = o.driver.decode_pac(blob, joint=True)
+        assert d.shape == od.shape, "clip %d" % i
+        assert d.shape[0] == c.n_blocks(clip.shape[0]) * 1024
+        if d.size:
+            assert np.abs(d.astype(np.int64) - od.astype(np.int64)).max() <= 1, "clip %d" % i
+
+
+def test_reference_seam_drop_in(golden):
+    """The reference-style PACFile loop of the oracle, with its `codec` module swapped for codec_gpu
+    (the monkey-patch INTEGRATION.md describes), writes the reference's bytes."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import codec_gpu
+    for name in ("joint48k_64", "indep48k_128"):
+        g = golden(name)
+        saved = o.pacfile.codec
+        o.pacfile.codec = codec_gpu
+        try:
+            blob, _ = o.driver.encode_pcm(g["pcm"][:12 * 1024], joint=bool(g["joint"]), sampleRate=int(g["sampleRate"]),
+                                          targetBitsPerSample=float(g["tbps"]))
+        finally:
+            o.pacfile.codec = saved
+        ref, _ = o.driver.encode_pcm(g["pcm"][:12 * 1024], joint=bool(g["joint"]), sampleRate=int(g["sampleRate"]),
+                                     targetBitsPerSample=float(g["tbps"]))
+        assert blob == ref
+
+
+def test_reference_seam_decode(golden):
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import codec_gpu
+    g = golden("joint48k_64")
+    blob = g["pac"].tobytes()
+    saved = o.pacfile.codec
+    o.pacfile.codec = codec_gpu
+    try:
+        dec = o.driver.decode_pac(blob, joint=True)
+    finally:
+        o.pacfile.codec = saved
+    d = np.abs(dec.astype(np.int64) - g["decoded"].astype(np.int64))
+    assert d.max() <= 1
+
+
+def test_malformed_stream_is_rejected(golden, codecs):
+    from mrcaudiocodec_b200 import _lib
+    g = golden("joint48k_128")
+    c = codecs(48000, True)
+    blob = bytearray(g["pac"].tobytes())
+    with pytest.raises(_lib.MrcError) as e:
+        c.decode_clips([bytes(blob[:len(blob) - 7])])         # truncated last chunk
+    assert e.value.code == _lib.MRC_E_FORMAT
+    bad = bytearray(blob)
+    bad[0:4] = b'RIFF'
+    with pytest.raises(_lib.MrcError) as e:
+        c.decode_clips([bytes(bad)])
+    assert e.value.code == _lib.MRC_E_FORMAT
+    # a chunk whose bits run out: shrink the first chunk's payload but keep the chain consistent
+    from mrcaudiocodec_b200 import pacfile
+    off, n = pacfile.chunk_index(bytes(blob))[2]
+    cut = bytes(blob[:off - 4]) + (8).to_bytes(4, "little") + bytes(blob[off:off + 8]) + bytes(blob[off + n:])
+    with pytest.raises(_lib.MrcError) as e:
+        c.decode_clips([cut])
+    assert e.value.code == _lib.MRC_E_FORMAT
+
+
+def test_fp32_fast_mode_tolerances(golden, codecs):
+    """fp32 fast mode: MDCT lines within 1e-5 of the block maximum, SMRs within 1e-5 relative (of the 96 dB
+    reference level), decoded PCM within 1 LSB of the fp64 decode, and the stream decodes with the oracle decoder."""
+    import mrc_oracle as o
+    g = golden("joint48k_128")
+    c32 = codecs(48000, True, precision="fp32")
+    c64 = codecs(48000, True)
+    a = c32.stage_analysis([g["pcm"]])
+    for i in range(g["mdct"].shape[0]):
+        ref = g["mdct"][i]
+        assert np.abs(a["mdct"][i] - ref).max() <= 1e-5 * np.abs(ref).max() + 1e-30
+        assert np.abs(a["smr"][i] - g["smr"][i]).max() <= 1e-5 * 96 * 10
+    blob = c32.encode_clips([g["pcm"]])[0]
+    od = o.driver.decode_pac(blob, joint=True)              # reference-algorithm decoder accepts the fp32 stream
+    assert od.shape == g["decoded"].shape
+    d32 = c32.decode_clips([g["pac"].tobytes()])[0]
+    d64 = c64.decode_clips([g["pac"].tobytes()])[0]
+    assert np.abs(d32.astype(np.int64) - d64.astype(np.int64)).max() <= 1
+
+
+def test_block_size_sweep_vs_oracle(codecs):
+    """config 5: N = 512, 1024, 4096 (nMDCTLines 256, 512, 2048) stay byte-exact against the oracle."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import synth
+    pcm = synth.synth_short(41, 0.3)
+    for L in (256, 512, 2048):
+        ob, _ = o.driver.encode_pcm(pcm, joint=True, nMDCTLines=L)
+        c = codecs(48000, True, L=L)
+        assert c.encode_clips([pcm])[0] == ob, L
+        od = o.driver.decode_pac(ob, joint=True)
+        gd = c.decode_clips([ob])[0]
+        assert np.abs(gd.astype(np.int64) - od.astype(np.int64)).max() <= 1, L
+
+
+def test_bitrate_sweep_vs_oracle(codecs):
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import synth
+    pcm = synth.synth_short(43, 0.25)
+    for kbps in (64, 96, 192, 256):
+        tbps = kbps * 1000. / 48000.
+        ob, _ = o.driver.encode_pcm(pcm, joint=True, targetBitsPerSample=tbps)
+        assert codecs(48000, True, tbps).encode_clips([pcm])[0] == ob, kbps
