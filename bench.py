@@ -217,7 +217,7 @@ def main():
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
-        dev_ms, launches, maskers, stage = 0.0, 0, 0, np.zeros(3)
+        dev_ms, launches, maskers, stage = 0.0, 0, 0, np.zeros(4)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             nbytes = fn()
@@ -225,7 +225,7 @@ def main():
             dev_ms += t["total_ms"]
             launches += t["launches"]
             maskers = t["maskers"]
-            stage += np.array([t["analysis_ms"], t["quant_ms"], t["pack_ms"]])
+            stage += np.array([t["analysis_ms"], t["cost_ms"], t["chain_ms"], t["pack_ms"]])
         barrier()
         wall = time.perf_counter() - t0
         clocks = sampler.stop()
@@ -267,8 +267,9 @@ def main():
                        "l2": "input %.0f MB per step > 126 MB L2, no flush needed" % (frames * 4 / 1e6),
                        "blocks_per_step": nblk, "bitstream_bytes": r_dev["nbytes"]},
             "device_ms_per_step": 1000.0 * r_dev["dev"] / args.steps,
-            "stage_ms_per_step": {"analysis": r_dev["stage_ms"][0], "alloc_quant": r_dev["stage_ms"][1],
-                                  "pack": r_dev["stage_ms"][2]},
+            "stage_ms_per_step": {"analysis": r_dev["stage_ms"][0], "cost": r_dev["stage_ms"][1],
+                                  "chain": r_dev["stage_ms"][2], "pack": r_dev["stage_ms"][3],
+                                  "note": "per-kernel sums; analysis+cost of wave w+1 overlap chain+pack of wave w"},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(frames * 4),
                     "d2h_bytes_per_step": int(r_e2e["nbytes"]), "ms_per_step": 1000.0 * r_e2e["wall"] / args.steps},
             "gpu_launches": int(r_dev["launches"]),

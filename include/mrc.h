@@ -149,10 +149,11 @@ int32_t mrc_stage_alloc_quant(mrc_ctx* ctx, const int16_t* pcm, const int64_t* c
                               int32_t* huff_table, int32_t* reservoir, int32_t* chunk_bytes);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------- */
-/* Device time (ms, CUDA events on the context's stream) of the stages of the last encode/decode call:
- * [0] analysis kernel, [1] alloc/quantise kernel, [2] pack kernels, [3] decode kernels, [4] H2D, [5] D2H,
- * [6] total on stream; counters [0] kernel launches, [1] sum over spectra of tonal maskers, [2] blocks,
- * [3] spectra analysed. */
+/* Device time (ms, CUDA events on the stream each kernel is launched on, summed over waves) of the stages of the
+ * last encode/decode call: [0] analysis kernels, [1] chain (serial reservoir walk) kernels, [2] clip-offset scan +
+ * quantise/pack kernels, [3] decode kernels, [4] H2D, [5] D2H, [6] whole call on the main stream, [7] cost kernels.
+ * Analysis+cost of wave w+1 overlap chain+pack of wave w, so [0]+[7]+[1]+[2] can exceed [6].
+ * counters [0] kernel launches, [1] sum over spectra of tonal maskers, [2] blocks, [4] waves. */
 int32_t mrc_last_timing(const mrc_ctx* ctx, double* ms8, int64_t* counters8);
 /* Micro-benchmarks of this GPU's pipes, for the roofline denominators MEASURED_PEAKS.json does not carry:
  * out4[0] FP64 FMA TFLOP/s, [1] FP32 FMA TFLOP/s, [2] MUFU.EX2 Gop/s, [3] device copy GB/s (read+write). */

@@ -218,5 +218,6 @@ class Codec(object):
         ms = np.zeros(8, np.float64)
         cnt = np.zeros(8, np.int64)
         self.lib.mrc_last_timing(self._ctx, _ptr(ms), _ptr(cnt))
-        return dict(analysis_ms=ms[0], quant_ms=ms[1], pack_ms=ms[2], decode_ms=ms[3], h2d_ms=ms[4], d2h_ms=ms[5],
-                    total_ms=ms[6], launches=int(cnt[0]), maskers=int(cnt[1]), blocks=int(cnt[2]))
+        return dict(analysis_ms=ms[0], chain_ms=ms[1], pack_ms=ms[2], decode_ms=ms[3], h2d_ms=ms[4], d2h_ms=ms[5],
+                    total_ms=ms[6], cost_ms=ms[7], launches=int(cnt[0]), maskers=int(cnt[1]), blocks=int(cnt[2]),
+                    waves=int(cnt[4]))

@@ -357,7 +357,8 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             v = warp_max(v);
             if (lane == 0) {
                 ho.bandmax[(size_t)lb * 2 * MRC_BSTRIDE + ch * MRC_BSTRIDE + bd] = v;
-                ho.smr[(size_t)lb * 2 * MRC_BSTRIDE + ch * MRC_BSTRIDE + bd] = s_smr[(m ? 2 : 0) + ch][bd];
+                if (ho.smr != nullptr)
+                    ho.smr[(size_t)lb * 2 * MRC_BSTRIDE + ch * MRC_BSTRIDE + bd] = s_smr[(m ? 2 : 0) + ch][bd];
             }
         }
         if (tid < 4) ho.ovs[lb * 4 + tid] = (uint8_t)s_scale[tid];

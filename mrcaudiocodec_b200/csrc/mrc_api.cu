@@ -43,9 +43,11 @@ struct mrc_ctx {
     uint8_t h_header[4 + 18 + 4 + 2 * MRC_MAX_BANDS];
 
     // scratch (grow only)
-    Buf clip_off, clip_blk0, clip_bytes, clip_base, running, overflow, peakctr, res_in, res_out;
-    Buf ho_lines, ho_bandmax, ho_smr, ho_tokens, ho_ovs, ho_ms;
-    Buf q_alloc, q_sf, q_table, q_mant, q_cbytes, q_coff, q_res;
+    Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out;
+    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, gmask, cblk; } sets[2];
+    Buf q_alloc, q_sf, q_mant;
+    cudaStream_t stream2 = nullptr;
+    std::vector<cudaEvent_t> evpool;
     Buf tap_lines, tap_smr, tap_npk;
     Buf pcm_dev, out_dev, xin_dev;
     Buf dec[16];
@@ -159,12 +161,25 @@ struct EncodeJob {
     bool need_quant = true;
 };
 
-constexpr int WAVE_BLOCKS = 1 << 18;   // hand-off of one wave stays below ~5 GB in fp64
+constexpr int WAVE_BLOCKS = 1 << 15;   // blocks per wave: ~1.8 GB of hand-off per buffer set in fp64
+constexpr int NSETS = 2;               // buffer sets: wave w+1 is analysed while wave w is chained and packed
 
+cudaEvent_t pool_event(mrc_ctx* ctx, size_t i) {
+    while (ctx->evpool.size() <= i) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        ctx->evpool.push_back(e);
+    }
+    return ctx->evpool[i];
+}
+
+// Waves are ranges of consecutive blocks (clips may straddle them: the chain kernel carries reservoir and byte
+// offset per clip from wave to wave).  Stream `stream2` runs analysis + cost of wave w+1 while `stream` runs the
+// chain walk, the clip-offset scan and quantise+pack of wave w.
 template <typename T>
 int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     const int L = ctx->L, nb = ctx->nb, nc = job.n_clips;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->stream, st2 = ctx->stream2;
     // ---- block map ----
     std::vector<int32_t> blk0(nc + 1);
     long long tot = 0;
@@ -182,9 +197,13 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     CK(upload(ctx->clip_blk0, blk0, st));
     CK(ensure(ctx->clip_bytes, (size_t)(nc + 1) * 8));
     CK(ensure(ctx->clip_base, (size_t)(nc + 2) * 8));
+    CK(ensure(ctx->clip_res, (size_t)(nc + 1) * 4));
+    CK(ensure(ctx->clip_run, (size_t)(nc + 1) * 8));
     CK(ensure(ctx->running, 8));
     CK(ensure(ctx->overflow, 4));
     CK(ensure(ctx->peakctr, 8));
+    CK(cudaMemsetAsync(ctx->clip_bytes.p, 0, (size_t)(nc + 1) * 8, st));
+    CK(cudaMemsetAsync(ctx->clip_base.p, 0, (size_t)(nc + 2) * 8, st));
     CK(cudaMemsetAsync(ctx->running.p, 0, 8, st));
     CK(cudaMemsetAsync(ctx->overflow.p, 0, 4, st));
     CK(cudaMemsetAsync(ctx->peakctr.p, 0, 8, st));
@@ -207,80 +226,104 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     cp.joint = job.joint;
     cp.flush_nonjoint = job.flush_nonjoint ? 1 : 0;
     cp.no_huff = job.no_huff;
+    int min_nl = 0x7fffffff;
+    for (int b = 0; b < nb; ++b) min_nl = std::min(min_nl, ctx->h_band_n[b]);
 
-    // ---- waves of whole clips ----
-    std::vector<std::pair<int, int>> waves;     // [c0, c1)
-    int maxw = 0, maxc = 0;
-    for (int c = 0; c < nc;) {
-        int c1 = c + 1;
-        while (c1 < nc && blk0[c1 + 1] - blk0[c] <= WAVE_BLOCKS) ++c1;
-        waves.push_back({c, c1});
-        maxw = std::max(maxw, blk0[c1] - blk0[c]);
-        maxc = std::max(maxc, c1 - c);
-        c = c1;
-    }
-    const size_t W = (size_t)std::max(maxw, 1);
-    CK(ensure(ctx->ho_lines, W * 2 * L * sizeof(T)));
-    CK(ensure(ctx->ho_bandmax, W * 2 * MRC_BSTRIDE * sizeof(T)));
-    CK(ensure(ctx->ho_smr, W * 2 * MRC_BSTRIDE * sizeof(T)));
-    CK(ensure(ctx->ho_tokens, W * MRC_TOK_STRIDE * 2));
-    CK(ensure(ctx->ho_ovs, W * 4));
-    CK(ensure(ctx->ho_ms, W * 4));
-    CK(ensure(ctx->q_alloc, W * 2 * MRC_BSTRIDE));
-    CK(ensure(ctx->q_sf, W * 2 * MRC_BSTRIDE));
-    CK(ensure(ctx->q_table, W * 2));
-    CK(ensure(ctx->q_mant, W * 2 * L * 2));
-    CK(ensure(ctx->q_cbytes, W * 2 * 4));
-    CK(ensure(ctx->q_coff, W * 2 * 8));
-    CK(ensure(ctx->q_res, W * 4));
+    // ---- buffer sets ----
     const bool want_atap = job.t_lines || job.t_smr || job.t_npk;
+    const bool want_qtap = job.t_alloc || job.t_sf || job.t_mant;
+    const bool any_tap = want_atap || want_qtap || job.t_ovs || job.t_ms || job.t_table || job.t_res || job.t_cbytes;
+    const size_t W = (size_t)std::max(std::min(nblk_total, WAVE_BLOCKS), 1);
+    const int nsets = (nblk_total > WAVE_BLOCKS) ? NSETS : 1;
+    Handoff<T> ho[NSETS];
+    ChainIO io[NSETS];
+    for (int s = 0; s < nsets; ++s) {
+        mrc_ctx::WaveSet& ws = ctx->sets[s];
+        CK(ensure(ws.lines, W * 2 * L * sizeof(T)));
+        CK(ensure(ws.bandmax, W * 2 * MRC_BSTRIDE * sizeof(T)));
+        CK(ensure(ws.tokens, W * MRC_TOK_STRIDE * 2));
+        CK(ensure(ws.ovs, W * 4));
+        CK(ensure(ws.ms, W * 4));
+        CK(ensure(ws.rec, W * MRC_REC_BYTES));
+        CK(ensure(ws.gmask, W * 32 * 4));
+        CK(ensure(ws.cblk, W * sizeof(ChainBlk)));
+        ho[s].lines = (T*)ws.lines.p; ho[s].bandmax = (T*)ws.bandmax.p; ho[s].smr = nullptr;
+        ho[s].tokens = (uint16_t*)ws.tokens.p; ho[s].ovs = (uint8_t*)ws.ovs.p; ho[s].ms = (uint32_t*)ws.ms.p;
+        io[s].rec = (const unsigned char*)ws.rec.p; io[s].gmask = (uint32_t*)ws.gmask.p;
+        io[s].cblk = (ChainBlk*)ws.cblk.p;
+        io[s].clip_res = (int32_t*)ctx->clip_res.p; io[s].clip_run = (int64_t*)ctx->clip_run.p;
+        io[s].clip_bytes = (int64_t*)ctx->clip_bytes.p;
+    }
+    PackTaps ptaps;
+    ptaps.alloc = ptaps.sf = nullptr; ptaps.mant = nullptr;
+    if (want_qtap) {
+        CK(ensure(ctx->q_alloc, W * 2 * MRC_BSTRIDE));
+        CK(ensure(ctx->q_sf, W * 2 * MRC_BSTRIDE));
+        CK(ensure(ctx->q_mant, W * 2 * L * 2));
+        ptaps.alloc = (uint8_t*)ctx->q_alloc.p; ptaps.sf = (uint8_t*)ctx->q_sf.p; ptaps.mant = (uint16_t*)ctx->q_mant.p;
+    }
+    AnalysisTaps<T> taps;
+    taps.lines4 = nullptr; taps.smr4 = nullptr; taps.npeaks = nullptr;
     if (want_atap) {
         CK(ensure(ctx->tap_lines, W * 4 * L * sizeof(T)));
         CK(ensure(ctx->tap_smr, W * 4 * MRC_BSTRIDE * sizeof(T)));
         CK(ensure(ctx->tap_npk, W * 4 * 4));
+        taps.lines4 = (T*)ctx->tap_lines.p; taps.smr4 = (T*)ctx->tap_smr.p; taps.npeaks = (int32_t*)ctx->tap_npk.p;
     }
-    Handoff<T> ho;
-    ho.lines = (T*)ctx->ho_lines.p; ho.bandmax = (T*)ctx->ho_bandmax.p; ho.smr = (T*)ctx->ho_smr.p;
-    ho.tokens = (uint16_t*)ctx->ho_tokens.p; ho.ovs = (uint8_t*)ctx->ho_ovs.p; ho.ms = (uint32_t*)ctx->ho_ms.p;
-    QuantOut qo;
-    qo.alloc = (uint8_t*)ctx->q_alloc.p; qo.sf = (uint8_t*)ctx->q_sf.p; qo.table = (uint8_t*)ctx->q_table.p;
-    qo.mant = (uint16_t*)ctx->q_mant.p; qo.chunk_bytes = (uint32_t*)ctx->q_cbytes.p;
-    qo.chunk_off = (int64_t*)ctx->q_coff.p; qo.reservoir = (int32_t*)ctx->q_res.p;
-    qo.clip_bytes = (int64_t*)ctx->clip_bytes.p;
-    AnalysisTaps<T> taps;
-    taps.lines4 = want_atap ? (T*)ctx->tap_lines.p : nullptr;
-    taps.smr4 = want_atap ? (T*)ctx->tap_smr.p : nullptr;
-    taps.npeaks = want_atap ? (int32_t*)ctx->tap_npk.p : nullptr;
 
-    float t_an = 0, t_q = 0, t_pk = 0;
+    const int nwaves = (nblk_total + WAVE_BLOCKS - 1) / WAVE_BLOCKS;
+    // events per wave: 0 analysis start, 1 analysis end, 2 cost end, 3 chain start, 4 chain end, 5 pack end
+    constexpr int EPW = 6;
+    for (int i = 0; i < nwaves * EPW; ++i) pool_event(ctx, (size_t)i);
+    auto ev = [&](int w, int k) { return ctx->evpool[(size_t)w * EPW + k]; };
+    // everything queued on `st` so far (tables of this call, PCM upload) must precede the first analysis
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaStreamWaitEvent(st2, ctx->ev[0], 0));
+
     int launches = 0;
     std::vector<unsigned char> hb;     // host bounce buffer for taps
-    for (auto& w : waves) {
-        const int c0 = w.first, c1 = w.second, g0 = blk0[c0], nblk = blk0[c1] - blk0[c0];
-        if (nblk == 0) {
-            // clips without blocks (xin mode only): nothing to do
-            continue;
-        }
-        CK(cudaEventRecord(ctx->ev[0], st));
-        launch_analysis<T>(st, tb, cp, cm, job.d_pcm, job.d_xin, g0, nblk, ho, taps,
+    int c_lo = 0;
+    for (int w = 0; w < nwaves; ++w) {
+        const int s = w % nsets;
+        const int g0 = w * WAVE_BLOCKS, nblk = std::min(WAVE_BLOCKS, nblk_total - g0);
+        while (blk0[c_lo + 1] <= g0) ++c_lo;                       // clip holding block g0
+        int c_hi = c_lo;
+        while (blk0[c_hi + 1] < g0 + nblk) ++c_hi;                 // clip holding block g0+nblk-1
+        const int nfin = (blk0[c_hi + 1] <= g0 + nblk) ? c_hi - c_lo + 1 : c_hi - c_lo;   // clips ending in this wave
+        // ---- stream 2: analysis + cost (needs buffer set s free: pack of wave w-nsets done) ----
+        if (w >= nsets) CK(cudaStreamWaitEvent(st2, ev(w - nsets, 5), 0));
+        CK(cudaEventRecord(ev(w, 0), st2));
+        launch_analysis<T>(st2, tb, cp, cm, job.d_pcm, job.d_xin, g0, nblk, ho[s], taps,
                            (unsigned long long*)ctx->peakctr.p);
-        CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaEventRecord(ev(w, 1), st2));
         ++launches;
         if (job.need_quant) {
-            launch_quant<T>(st, tb, cp, (const HuffDev*)ctx->huff.p, cm, c0, c1 - c0, g0, ho, qo, d_res_in, d_res_out);
+            launch_cost<T>(st2, tb, cp, (const HuffDev*)ctx->huff.p, cm, g0, nblk, ho[s], (unsigned char*)ctx->sets[s].rec.p);
             ++launches;
         }
-        CK(cudaEventRecord(ctx->ev[2], st));
-        if (job.d_out) {
-            launch_clip_scan(st, qo.clip_bytes, (int64_t*)ctx->clip_base.p, c0, c1 - c0, (int64_t*)ctx->running.p);
-            launch_pack(st, cp, (const HuffDev*)ctx->huff.p, tb.band_lo, tb.band_n, tb.line2band, cm, g0, nblk, qo,
-                        ho.ovs, ho.ms, (const int64_t*)ctx->clip_base.p, job.d_out, job.out_cap,
-                        (const uint8_t*)ctx->header.p, (int*)ctx->overflow.p);
-            launches += 2;
+        CK(cudaEventRecord(ev(w, 2), st2));
+        // ---- main stream: chain -> clip offsets -> quantise + pack ----
+        CK(cudaStreamWaitEvent(st, ev(w, 2), 0));
+        CK(cudaEventRecord(ev(w, 3), st));
+        if (job.need_quant) {
+            launch_chain(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, min_nl, io[s], d_res_in, d_res_out);
+            ++launches;
         }
-        CK(cudaEventRecord(ctx->ev[3], st));
+        CK(cudaEventRecord(ev(w, 4), st));
+        if (job.need_quant && (job.d_out || want_qtap)) {
+            if (nfin > 0) {
+                launch_clip_scan(st, io[s].clip_bytes, (int64_t*)ctx->clip_base.p, c_lo, nfin, (int64_t*)ctx->running.p);
+                ++launches;
+            }
+            launch_pack<T>(st, tb, cp, (const HuffDev*)ctx->huff.p, cm, g0, nblk, ho[s], io[s], ptaps,
+                           (const int64_t*)ctx->clip_base.p, job.d_out, job.out_cap, (const uint8_t*)ctx->header.p,
+                           (int*)ctx->overflow.p);
+            ++launches;
+        }
+        CK(cudaEventRecord(ev(w, 5), st));
         CK(cudaGetLastError());
-        // ---- taps of this wave to the host ----
+        if (!any_tap) continue;
+        // ---- taps of this wave to the host (parity runs only; synchronous) ----
         auto fetch = [&](const void* dsrc, size_t bytes) -> cudaError_t {
             hb.resize(bytes);
             cudaError_t e = cudaMemcpyAsync(hb.data(), dsrc, bytes, cudaMemcpyDeviceToHost, st);
@@ -289,37 +332,37 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         };
         if (job.t_lines) {
             CK(fetch(taps.lines4, (size_t)nblk * 4 * L * sizeof(T)));
-            const T* s = (const T*)hb.data();
+            const T* src = (const T*)hb.data();
             double* d = job.t_lines + (size_t)g0 * 4 * L;
-            for (size_t i = 0; i < (size_t)nblk * 4 * L; ++i) d[i] = (double)s[i];
+            for (size_t i = 0; i < (size_t)nblk * 4 * L; ++i) d[i] = (double)src[i];
         }
         if (job.t_smr) {
             CK(fetch(taps.smr4, (size_t)nblk * 4 * MRC_BSTRIDE * sizeof(T)));
-            const T* s = (const T*)hb.data();
+            const T* src = (const T*)hb.data();
             for (int b = 0; b < nblk; ++b)
                 for (int c = 0; c < 4; ++c)
                     for (int k = 0; k < nb; ++k)
-                        job.t_smr[((size_t)(g0 + b) * 4 + c) * nb + k] = (double)s[((size_t)b * 4 + c) * MRC_BSTRIDE + k];
+                        job.t_smr[((size_t)(g0 + b) * 4 + c) * nb + k] = (double)src[((size_t)b * 4 + c) * MRC_BSTRIDE + k];
         }
         if (job.t_npk) {
             CK(fetch(taps.npeaks, (size_t)nblk * 16));
             memcpy(job.t_npk + (size_t)g0 * 4, hb.data(), (size_t)nblk * 16);
         }
         if (job.t_ovs) {
-            CK(fetch(ho.ovs, (size_t)nblk * 4));
+            CK(fetch(ho[s].ovs, (size_t)nblk * 4));
             for (size_t i = 0; i < (size_t)nblk * 4; ++i) job.t_ovs[(size_t)g0 * 4 + i] = hb[i];
         }
         if (job.t_ms) {
-            CK(fetch(ho.ms, (size_t)nblk * 4));
-            const uint32_t* s = (const uint32_t*)hb.data();
+            CK(fetch(ho[s].ms, (size_t)nblk * 4));
+            const uint32_t* src = (const uint32_t*)hb.data();
             for (int b = 0; b < nblk; ++b)
-                for (int k = 0; k < nb; ++k) job.t_ms[(size_t)(g0 + b) * nb + k] = (s[b] >> k) & 1u;
+                for (int k = 0; k < nb; ++k) job.t_ms[(size_t)(g0 + b) * nb + k] = (src[b] >> k) & 1u;
         }
         if (job.t_alloc || job.t_sf) {
             for (int which = 0; which < 2; ++which) {
                 int32_t* dst = which ? job.t_sf : job.t_alloc;
                 if (!dst) continue;
-                CK(fetch(which ? qo.sf : qo.alloc, (size_t)nblk * 2 * MRC_BSTRIDE));
+                CK(fetch(which ? ptaps.sf : ptaps.alloc, (size_t)nblk * 2 * MRC_BSTRIDE));
                 for (int b = 0; b < nblk; ++b)
                     for (int c = 0; c < 2; ++c)
                         for (int k = 0; k < nb; ++k)
@@ -327,32 +370,23 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
             }
         }
         if (job.t_mant) {
-            CK(fetch(qo.mant, (size_t)nblk * 2 * L * 2));
-            const uint16_t* s = (const uint16_t*)hb.data();
+            CK(fetch(ptaps.mant, (size_t)nblk * 2 * L * 2));
+            const uint16_t* src = (const uint16_t*)hb.data();
             int32_t* d = job.t_mant + (size_t)g0 * 2 * L;
-            for (size_t i = 0; i < (size_t)nblk * 2 * L; ++i) d[i] = s[i];
+            for (size_t i = 0; i < (size_t)nblk * 2 * L; ++i) d[i] = src[i];
         }
-        if (job.t_table) {
-            CK(fetch(qo.table, (size_t)nblk * 2));
-            for (size_t i = 0; i < (size_t)nblk * 2; ++i) job.t_table[(size_t)g0 * 2 + i] = hb[i];
+        if (job.t_table || job.t_res || job.t_cbytes) {
+            CK(fetch(io[s].cblk, (size_t)nblk * sizeof(ChainBlk)));
+            const ChainBlk* src = (const ChainBlk*)hb.data();
+            for (int b = 0; b < nblk; ++b) {
+                if (job.t_table) { job.t_table[(size_t)(g0 + b) * 2] = src[b].table[0]; job.t_table[(size_t)(g0 + b) * 2 + 1] = src[b].table[1]; }
+                if (job.t_res) job.t_res[g0 + b] = src[b].reservoir;
+                if (job.t_cbytes) { job.t_cbytes[(size_t)(g0 + b) * 2] = (int32_t)src[b].chunk_bytes[0]; job.t_cbytes[(size_t)(g0 + b) * 2 + 1] = (int32_t)src[b].chunk_bytes[1]; }
+            }
         }
-        if (job.t_res) {
-            CK(fetch(qo.reservoir, (size_t)nblk * 4));
-            memcpy(job.t_res + g0, hb.data(), (size_t)nblk * 4);
-        }
-        if (job.t_cbytes) {
-            CK(fetch(qo.chunk_bytes, (size_t)nblk * 8));
-            memcpy(job.t_cbytes + (size_t)g0 * 2, hb.data(), (size_t)nblk * 8);
-        }
-        CK(cudaEventSynchronize(ctx->ev[3]));
-        float t;
-        CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1])); t_an += t;
-        CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); t_q += t;
-        CK(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3])); t_pk += t;
     }
-    ctx->ms[0] = t_an; ctx->ms[1] = t_q; ctx->ms[2] = t_pk;
-    ctx->counters[0] = launches;
-    ctx->counters[2] = nblk_total;
+    // the analysis stream has nothing outstanding that the main stream does not already wait for (event 2 of the
+    // last wave), so synchronising the main stream ends the call.
     unsigned long long pk = 0;
     CK(cudaMemcpyAsync(&pk, ctx->peakctr.p, 8, cudaMemcpyDeviceToHost, st));
     if (job.h_res_out) CK(cudaMemcpyAsync(job.h_res_out, d_res_out, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
@@ -362,6 +396,19 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         CK(cudaMemcpyAsync(&ovf, ctx->overflow.p, 4, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(st2));
+    float t_an = 0, t_cost = 0, t_chain = 0, t_pk = 0;
+    for (int w = 0; w < nwaves; ++w) {
+        float t;
+        CK(cudaEventElapsedTime(&t, ev(w, 0), ev(w, 1))); t_an += t;
+        CK(cudaEventElapsedTime(&t, ev(w, 1), ev(w, 2))); t_cost += t;
+        CK(cudaEventElapsedTime(&t, ev(w, 3), ev(w, 4))); t_chain += t;
+        CK(cudaEventElapsedTime(&t, ev(w, 4), ev(w, 5))); t_pk += t;
+    }
+    ctx->ms[0] = t_an; ctx->ms[1] = t_chain; ctx->ms[2] = t_pk; ctx->ms[7] = t_cost;
+    ctx->counters[0] = launches;
+    ctx->counters[2] = nblk_total;
+    ctx->counters[4] = nwaves;
     ctx->counters[1] = (int64_t)pk;
     if (job.d_out && nblk_total == 0) for (int c = 0; c <= nc; ++c) job.h_clip_byte_off[c] = 0;
     if (ovf) return fail(ctx, MRC_E_NOSPACE, "output buffer too small for the encoded batch");
@@ -433,6 +480,11 @@ int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out) {
         delete ctx;
         return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     *out = ctx;
     return MRC_OK;
@@ -447,12 +499,18 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
                   &ctx->tf.tw_fft, &ctx->tf.tw_rfft, &ctx->tf.bark, &ctx->tf.quiet, &ctx->band_lo, &ctx->band_n,
                   &ctx->line2band, &ctx->huff, &ctx->header, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,
                   &ctx->clip_base, &ctx->running, &ctx->overflow, &ctx->peakctr, &ctx->res_in, &ctx->res_out,
-                  &ctx->ho_lines, &ctx->ho_bandmax, &ctx->ho_smr, &ctx->ho_tokens, &ctx->ho_ovs, &ctx->ho_ms,
-                  &ctx->q_alloc, &ctx->q_sf, &ctx->q_table, &ctx->q_mant, &ctx->q_cbytes, &ctx->q_coff, &ctx->q_res,
+                  &ctx->clip_res, &ctx->clip_run, &ctx->q_alloc, &ctx->q_sf, &ctx->q_mant,
                   &ctx->tap_lines, &ctx->tap_smr, &ctx->tap_npk, &ctx->pcm_dev, &ctx->out_dev, &ctx->xin_dev};
     for (Buf* b : all) release(*b);
     for (auto& b : ctx->dec) release(b);
+    for (auto& ws : ctx->sets) {
+        Buf* wb[] = {&ws.lines, &ws.bandmax, &ws.tokens, &ws.ovs, &ws.ms, &ws.rec, &ws.gmask, &ws.cblk};
+        for (Buf* b : wb) release(*b);
+    }
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->evpool) if (ev) cudaEventDestroy(ev);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamDestroy(ctx->stream2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MRC_OK;
@@ -461,7 +519,8 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
 int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     if (!ctx || !t) return MRC_E_INVALID;
     cudaSetDevice(ctx->cfg.device);
-    if (t->n_bands < 1 || t->n_bands > MRC_MAX_BANDS) return fail(ctx, MRC_E_INVALID, "n_bands out of range");
+    if (t->n_bands < 1 || t->n_bands > MRC_CODED_BANDS)
+        return fail(ctx, MRC_E_INVALID, "n_bands out of range (1..25: the reference's tables have 25 or 9 bands)");
     if (t->n_huff_tables != MRC_N_HUFF_TABLES) return fail(ctx, MRC_E_INVALID, "exactly four Huffman tables expected");
     const int L = ctx->L;
     ctx->nb = t->n_bands;

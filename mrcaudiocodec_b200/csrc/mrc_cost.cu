@@ -1,0 +1,215 @@
+// mrc_cost.cu -- K3a: everything about the serial stage that does NOT depend on the bit reservoir, done in
+// parallel over blocks so that the serial walk (mrc_chain.cu) is left with a few hundred cycles per block.
+//
+// The reference allocates bits greedily (bitalloc.py:106-155), then quantises every band at its allocation
+// (codecThem.py:336-350 / :509-559, quantize.py:114-146, :294-322), then prices the mantissas under the four
+// trained Huffman books (codecThem.py:136-203) and credits the saving to the reservoir (:224 / :274).  Only the
+// *stopping point* of the greedy loop depends on the reservoir: the order of the grants was fixed by the analysis
+// kernel (tokens).  So for every band and every possible allocation 2..16 this kernel quantises the band and
+// prices it under the four books (15 * 2L quantisations per block, integer-exact), and re-orders the result into
+// grant order as *deltas*: granting token j changes book t's cost of that channel by d_cost[j][t] and the bits
+// actually written by d_wbits[j][t] (they differ by quirk Q4: a mantissa equal to the escape value is priced at
+// the escape code's length but written as escape code + raw bits).  With exclusive prefix sums every 32 tokens
+// ("checkpoints") the chain kernel gets the totals for "all tokens before chunk k granted" in one load.
+//
+// One CTA per block, 256 threads; thread <-> (band, level) pair, adjacent threads share a band (broadcast reads).
+#include "mrc_internal.cuh"
+#include "mrc_math.cuh"
+
+namespace {
+
+constexpr int CT = 256;
+
+struct LutEntry {            // per mantissa value 0..64 (65 = "not a key of any book"), 4 x 16-bit fields (book 0 low)
+    unsigned long long key;  // code length where the value is a key of the book, else 0
+    unsigned long long nk;   // 0xffff where it is not a key
+    unsigned long long esc;  // 0xffff where it is the book's escape value
+};
+
+__device__ __forceinline__ unsigned long long splat16(unsigned v) {
+    const unsigned long long x = v & 0xffffu;
+    return x | (x << 16) | (x << 32) | (x << 48);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT)
+cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, ClipMap cm, int g0, Handoff<T> ho,
+            unsigned char* __restrict__ rec) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = tb.L, nb = tb.nb, nb2 = 2 * nb, npair = nb2 * MRC_MAX_LEVELS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* s_lines = reinterpret_cast<double*>(smem_raw);                                   // [2][L]
+    unsigned long long* s_c4 = reinterpret_cast<unsigned long long*>(s_lines + 2 * L);       // [npair] cost
+    unsigned long long* s_w4 = s_c4 + MRC_NSLOT;                                             // [npair] bits written
+    __shared__ double s_bmax[2 * MRC_BSTRIDE];
+    __shared__ uint16_t s_tok[MRC_TOK_STRIDE];
+    __shared__ LutEntry s_lut[MRC_HUFF_LUT + 1];
+    __shared__ unsigned s_tot[MRC_NCHUNK][MRC_CK_WORDS];     // per chunk: acc[8], raw[2], bits total, local max
+    __shared__ int s_joint;
+    __shared__ int s_blo[MRC_BSTRIDE], s_bn[MRC_BSTRIDE];
+    __shared__ unsigned long long s_esclen4;
+
+    const size_t lb = blockIdx.x;
+    const int g = g0 + (int)lb;
+    if (tid == 0) {
+        int lo = 0, hi = cm.n_clips;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cm.clip_blk0[mid] <= g) lo = mid; else hi = mid;
+        }
+        const int last = cm.clip_blk0[lo + 1] - 1;
+        s_joint = cp.joint && !(cp.flush_nonjoint && g == last);
+        unsigned long long e4 = 0;
+        for (int t = 0; t < MRC_N_HUFF_TABLES; ++t) e4 |= (unsigned long long)(huff->esc_len[t] & 0xffff) << (16 * t);
+        s_esclen4 = e4;
+    }
+    if (tid <= MRC_HUFF_LUT) {
+        LutEntry e;
+        e.key = 0; e.nk = 0; e.esc = 0;
+        for (int t = 0; t < MRC_N_HUFF_TABLES; ++t) {
+            const unsigned len = (tid < MRC_HUFF_LUT) ? huff->len[t][tid] : 0u;
+            if (len) e.key |= (unsigned long long)len << (16 * t);
+            else e.nk |= 0xffffull << (16 * t);
+            if (tid < MRC_HUFF_LUT && tid == huff->esc[t]) e.esc |= 0xffffull << (16 * t);
+        }
+        s_lut[tid] = e;
+    }
+    if (tid < nb) { s_blo[tid] = tb.band_lo[tid]; s_bn[tid] = tb.band_n[tid]; }
+    {
+        const T* gl = ho.lines + lb * 2 * L;
+        for (int i = tid; i < 2 * L; i += CT) s_lines[i] = (double)gl[i];
+        const T* gm = ho.bandmax + lb * 2 * MRC_BSTRIDE;
+        if (tid < 2 * MRC_BSTRIDE) s_bmax[tid] = (double)gm[tid];
+        const uint16_t* gt = ho.tokens + lb * MRC_TOK_STRIDE;
+        for (int i = tid; i < MRC_TOK_STRIDE; i += CT) s_tok[i] = gt[i];
+    }
+    __syncthreads();
+    const bool joint = s_joint != 0;
+
+    // ---- phase 1: price every (band, level) ---------------------------------------------------------------
+    for (int p = tid; p < npair; p += CT) {
+        const int bb = p / MRC_MAX_LEVELS, lvl = p - bb * MRC_MAX_LEVELS;
+        const int ch = bb >= nb, bd = bb - ch * nb;
+        const int Rb = lvl + 2;
+        const int sf = scale_factor_of(s_bmax[ch * MRC_BSTRIDE + bd], cp.n_scale_bits, Rb);
+        const unsigned long long rb4 = splat16((unsigned)Rb);
+        const unsigned long long rbesc4 = rb4 + s_esclen4;                 // Rb + len(escape code), per book
+        const double* x = s_lines + ch * L + s_blo[bd];
+        const int n = s_bn[bd];
+        unsigned long long c4 = 0, w4 = 0;
+        for (int i = 0; i < n; ++i) {
+            const int m = mantissa_of(x[i], sf, cp.n_scale_bits, Rb);
+            const LutEntry e = s_lut[m < MRC_HUFF_LUT ? m : MRC_HUFF_LUT];
+            const unsigned long long c = e.key + (e.nk & rbesc4);
+            c4 += c;
+            w4 += c + (e.esc & rb4);
+        }
+        s_c4[p] = c4;
+        s_w4[p] = w4;
+    }
+    __syncthreads();
+
+    // ---- phase 2: grant order, deltas, chunk totals -------------------------------------------------------
+    unsigned char* out = rec + lb * (size_t)MRC_REC_BYTES;
+    uint32_t* o_tn = reinterpret_cast<uint32_t*>(out + MRC_REC_TN);
+    uint4* o_d = reinterpret_cast<uint4*>(out + MRC_REC_D);
+    uint32_t* o_ck = reinterpret_cast<uint32_t*>(out + MRC_REC_CK);
+    int32_t* o_mx = reinterpret_cast<int32_t*>(out + MRC_REC_MX);
+    const int per_group = nb * MRC_MAX_LEVELS;
+    for (int k = warp; k < MRC_NCHUNK; k += CT / 32) {
+        const int slot = k * 32 + lane;
+        int src = -1;                                   // index into the analysis kernel's sorted token list
+        if (joint) { if (slot < 2 * per_group) src = slot; }
+        else {
+            const int grp = slot >= MRC_GROUP_SLOTS, i = slot - grp * MRC_GROUP_SLOTS;
+            if (i < per_group) src = grp * per_group + i;
+        }
+        uint32_t tn = 0xffffffffu;
+        uint4 d = make_uint4(0u, 0u, 0u, 0u);
+        unsigned acc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        int cost = 0, n = 0, raw0 = 0, raw1 = 0;
+        const bool valid = src >= 0;
+        if (valid) {
+            const unsigned tok = s_tok[src];
+            const int bb = tok & 0xff, lvl = tok >> 8;
+            const int ch = bb >= nb, bd = bb - ch * nb;
+            n = s_bn[bd];
+            cost = lvl == 0 ? 2 * n : n;
+            tn = tok | ((uint32_t)n << 16);
+            const int p = bb * MRC_MAX_LEVELS + lvl;
+            const unsigned long long c1 = s_c4[p], w1 = s_w4[p];
+            const unsigned long long c0 = lvl ? s_c4[p - 1] : 0ull, w0 = lvl ? s_w4[p - 1] : 0ull;
+            unsigned dv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const unsigned dc = (unsigned)((c1 >> (16 * t)) & 0xffff) - (unsigned)((c0 >> (16 * t)) & 0xffff);
+                const unsigned dw = (unsigned)((w1 >> (16 * t)) & 0xffff) - (unsigned)((w0 >> (16 * t)) & 0xffff);
+                dv[t] = dc + (dw << 16);                // = dc + 65536*dw (mod 2^32): sums decode while totals < 65536
+                acc[ch * 4 + t] = dv[t];
+            }
+            d = make_uint4(dv[0], dv[1], dv[2], dv[3]);
+            if (ch) raw1 = cost; else raw0 = cost;
+        }
+        o_tn[slot] = tn;
+        o_d[slot] = d;
+        int incl = cost;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int need = valid ? (incl - cost) + n : (int)0x80000000;     // bits spent before this token + nLines
+        const int mxl = __reduce_max_sync(0xffffffffu, need);
+        unsigned tot[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot[i] = __reduce_add_sync(0xffffffffu, acc[i]);
+        const unsigned r0 = __reduce_add_sync(0xffffffffu, (unsigned)raw0);
+        const unsigned r1 = __reduce_add_sync(0xffffffffu, (unsigned)raw1);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_tot[k][i] = tot[i];
+            s_tot[k][8] = r0;
+            s_tot[k][9] = r1;
+            s_tot[k][10] = r0 + r1;
+            s_tot[k][11] = (unsigned)mxl;
+        }
+    }
+    __syncthreads();
+    // ---- phase 3: exclusive prefix over the chunks (restarting at the second group of a non-joint block) ---
+    if (tid < 10) {
+        unsigned run = 0;
+        for (int k = 0; k < MRC_NCHUNK; ++k) {
+            if (k == MRC_GROUP_CHUNKS && !joint) run = 0;
+            o_ck[k * MRC_CK_WORDS + tid] = run;
+            run += s_tot[k][tid];
+        }
+    } else if (tid < 12) {
+        for (int k = 0; k < MRC_NCHUNK; ++k) o_ck[k * MRC_CK_WORDS + tid] = 0u;
+    } else if (tid == 32) {
+        int spent = 0, mx = (int)0x80000000;
+        for (int k = 0; k < MRC_NCHUNK; ++k) {
+            if (k == MRC_GROUP_CHUNKS && !joint) { spent = 0; mx = (int)0x80000000; }
+            const int mxl = (int)s_tot[k][11];
+            if (mxl != (int)0x80000000) mx = max(mx, spent + mxl);
+            o_mx[k] = mx;
+            spent += (int)s_tot[k][10];
+        }
+        for (int k = MRC_NCHUNK; k < 32; ++k) o_mx[k] = 0x7fffffff;
+    }
+}
+
+}  // namespace
+
+template <typename T>
+void launch_cost(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
+                 const ClipMap& cm, int g0, int nblk, Handoff<T> ho, unsigned char* rec) {
+    if (nblk <= 0) return;
+    const size_t smem = (size_t)2 * tb.L * sizeof(double) + 2 * MRC_NSLOT * sizeof(unsigned long long);
+    cudaFuncSetAttribute(cost_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cost_kernel<T><<<nblk, CT, smem, st>>>(tb, cp, huff, cm, g0, ho, rec);
+}
+
+template void launch_cost<double>(cudaStream_t, const DevTables<double>&, const CodecParams&, const HuffDev*,
+                                  const ClipMap&, int, int, Handoff<double>, unsigned char*);
+template void launch_cost<float>(cudaStream_t, const DevTables<float>&, const CodecParams&, const HuffDev*,
+                                 const ClipMap&, int, int, Handoff<float>, unsigned char*);

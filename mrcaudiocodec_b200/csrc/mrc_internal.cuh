@@ -7,8 +7,12 @@
 //                                    tokens  [nblk][768]    u16   water-filling grant order (band | level<<8)
 //                                    ovs     [nblk][4]      u8    overall scale factors L,R,M,S
 //                                    ms      [nblk]         u32   ms_switch bit mask
-//   alloc/quantise kernel -> pack    alloc,sf [nblk][2][32] u8 ; table [nblk][2] u8 ; mant [nblk][2][L] u16 ;
-//                                    chunk_bytes [nblk][2] u32 ; chunk_off [nblk][2] i64 ; reservoir [nblk] i32
+//   cost kernel -> chain kernel      rec     [nblk][MRC_REC_BYTES]  per grant token (in grant order): band/level/
+//                                    nLines, Huffman cost deltas of the four books; per 32-token chunk: exclusive
+//                                    prefix sums ("checkpoints") and the running maximum of (bits spent + nLines)
+//   chain kernel -> pack             gmask   [nblk][32] u32  granted tokens per 32-token chunk
+//                                    cblk    [nblk] ChainBlk  table ids, chunk sizes and offsets, reservoir
+//   pack kernel (taps only)          alloc,sf [nblk][2][32] u8 ; mant [nblk][2][L] u16
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,6 +21,30 @@
 #define MRC_TOK_STRIDE 768      // >= 2*25*15 grant tokens per block
 #define MRC_MAX_LEVELS 15       // grants per band: 0->2, then +1 up to 16 bits
 #define MRC_BSTRIDE 32          // band stride in per-band arrays
+#define MRC_CODED_BANDS 25      // most bands per channel the grant-token machinery holds (25 * 15 <= MRC_GROUP_SLOTS)
+
+// ---- per-block record the cost kernel hands to the chain kernel (one TMA bulk copy per block) ---------------
+// Token slots: a joint block sorts the 2*nb bands of both channels into one grant order (slots 0 .. 2*nb*15-1);
+// a non-joint block has one order per channel: channel 0 in slots 0.., channel 1 in slots MRC_GROUP_SLOTS...
+// Unused slots hold 0xffffffff.
+#define MRC_NSLOT 768
+#define MRC_GROUP_SLOTS 384
+#define MRC_NCHUNK (MRC_NSLOT / 32)
+#define MRC_GROUP_CHUNKS (MRC_GROUP_SLOTS / 32)
+#define MRC_CK_WORDS 12         // per chunk: acc[2 channels][4 books] (cost | wbits<<16, mod 2^32), raw bits[2], pad[2]
+#define MRC_REC_TN 0                                   // u32 [768]   token (band | level<<8) | nLines<<16
+#define MRC_REC_D (MRC_NSLOT * 4)                      // uint4 [768] per book: d(cost) + 65536*d(bits written)
+#define MRC_REC_CK (MRC_REC_D + MRC_NSLOT * 16)        // u32 [24][12] exclusive prefix at the start of each chunk
+#define MRC_REC_MX (MRC_REC_CK + MRC_NCHUNK * MRC_CK_WORDS * 4)   // i32 [32] running max of (prefix bits + nLines)
+#define MRC_REC_BYTES (MRC_REC_MX + 32 * 4)            // 16640, a multiple of 16
+
+struct ChainBlk {                // what the chain kernel decides per block (32 bytes)
+    long long chunk_off[2];      // byte offset of each channel chunk (its <L prefix) inside the clip's .pac
+    unsigned int chunk_bytes[2]; // payload bytes of each channel chunk
+    int reservoir;               // codingParams.bitReservoir after the block
+    unsigned char table[2];      // Huffman table id per channel (15 = none)
+    unsigned char pad[2];
+};
 
 template <typename T> struct cpx { T x, y; };
 
@@ -67,15 +95,19 @@ struct AnalysisTaps {            // all nullable
     int32_t* npeaks;             // [nblk][4]
 };
 
-struct QuantOut {
-    uint8_t* alloc;
-    uint8_t* sf;
-    uint8_t* table;
-    uint16_t* mant;
-    uint32_t* chunk_bytes;
-    int64_t* chunk_off;
-    int32_t* reservoir;
-    int64_t* clip_bytes;         // [n_clips]
+struct ChainIO {
+    const unsigned char* rec;    // [nblk][MRC_REC_BYTES]   (wave-local)
+    uint32_t* gmask;             // [nblk][32]              (wave-local)
+    ChainBlk* cblk;              // [nblk]                  (wave-local)
+    int32_t* clip_res;           // [n_clips] reservoir carried from wave to wave
+    int64_t* clip_run;           // [n_clips] running byte offset inside the clip's .pac, carried likewise
+    int64_t* clip_bytes;         // [n_clips] final .pac size, written when the clip's last block is done
+};
+
+struct PackTaps {                // all nullable (parity taps)
+    uint8_t* alloc;              // [nblk][2][32]
+    uint8_t* sf;                 // [nblk][2][32]
+    uint16_t* mant;              // [nblk][2][L]
 };
 
 struct CodecParams {
@@ -93,15 +125,20 @@ void launch_analysis(cudaStream_t st, const DevTables<T>& tb, const CodecParams&
                      const int16_t* pcm, const double* xin, int g0, int nblk, Handoff<T> ho, AnalysisTaps<T> taps,
                      unsigned long long* peak_counter);
 
+// cost of every (band, level) under the four books, re-ordered into grant order with chunk checkpoints
 template <typename T>
-void launch_quant(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
-                  const ClipMap& cm, int c0, int nclips_wave, int g0, Handoff<T> ho, QuantOut qo,
-                  const int32_t* reservoir_in, int32_t* reservoir_out);
+void launch_cost(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
+                 const ClipMap& cm, int g0, int nblk, Handoff<T> ho, unsigned char* rec);
 
-void launch_pack(cudaStream_t st, const CodecParams& cp, const HuffDev* huff, const int* band_lo, const int* band_n,
-                 const uint8_t* line2band, const ClipMap& cm, int g0, int nblk, QuantOut qo, const uint8_t* ovs,
-                 const uint32_t* ms, const int64_t* clip_base, uint8_t* out, long long out_cap,
-                 const uint8_t* header_template, int* overflow_flag);
+// one warp per clip c0 .. c0+nclips-1 walks the clip's blocks that lie in [g0, g0+nblk)
+void launch_chain(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
+                  int min_nlines, ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out);
+
+template <typename T>
+void launch_pack(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
+                 const ClipMap& cm, int g0, int nblk, Handoff<T> ho, ChainIO io, PackTaps taps,
+                 const int64_t* clip_base, uint8_t* out, long long out_cap, const uint8_t* header_template,
+                 int* overflow_flag);
 
 // clip_base[c0+i] = *running + sum_{j<i} clip_bytes[c0+j]; *running += sum  (one CTA)
 void launch_clip_scan(cudaStream_t st, const int64_t* clip_bytes, int64_t* clip_base, int c0, int n,

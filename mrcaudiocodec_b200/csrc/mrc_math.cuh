@@ -22,10 +22,12 @@ __device__ __forceinline__ T pcm_to_fraction(int c) {
 
 // quantize.py:12-38 magnitude code of |x| with nBits (sign handled by the caller).
 // code = trunc(((2^nBits - 1)*|x| + 1) / 2): multiply, add, divide -- three roundings, no FMA (Appendix A).
-__device__ __forceinline__ long long quant_mag_code(double ax, int nBits) {
-    if (ax >= 1.0) return (1ll << (nBits - 1)) - 1;
+// The division by 2.0 is a multiplication by 0.5 here: exact in binary floating point (the operand is >= 1, so
+// no underflow), hence the same three roundings.  nBits <= 31, so the code fits an int.
+__device__ __forceinline__ int quant_mag_code(double ax, int nBits) {
+    if (ax >= 1.0) return (int)((1ll << (nBits - 1)) - 1);
     const double full = (double)((1ll << nBits) - 1);
-    return (long long)__ddiv_rn(__dadd_rn(__dmul_rn(full, ax), 1.0), 2.0);
+    return __double2int_rz(__dmul_rn(__dadd_rn(__dmul_rn(full, ax), 1.0), 0.5));
 }
 
 // quantize.py:114-146: leading zeros of the magnitude code, capped at 2^nScaleBits - 1.
@@ -33,8 +35,8 @@ __device__ __forceinline__ long long quant_mag_code(double ax, int nBits) {
 __device__ __forceinline__ int scale_factor_of(double ax, int nScaleBits, int nMantBits) {
     const int cap = (1 << nScaleBits) - 1;
     const int nBits = cap + nMantBits;
-    const long long code = quant_mag_code(ax, nBits);
-    const int top = code > 0 ? 63 - __clzll(code) : 0;
+    const int code = quant_mag_code(ax, nBits);
+    const int top = code > 0 ? 31 - __clz(code) : 0;
     const int lz = (nBits - 2) - top;
     return lz < cap ? lz : cap;
 }
@@ -43,10 +45,10 @@ __device__ __forceinline__ int scale_factor_of(double ax, int nScaleBits, int nM
 __device__ __forceinline__ int mantissa_of(double x, int scale, int nScaleBits, int nMantBits) {
     const int cap = (1 << nScaleBits) - 1;
     const int nBits = cap + nMantBits;
-    long long code = quant_mag_code(fabs(x), nBits);
+    int code = quant_mag_code(fabs(x), nBits);
     if (x == 0.0) code = 0;
     if (scale != cap) code >>= (cap - scale);
-    return (int)code + ((x < 0.0) ? (1 << (nMantBits - 1)) : 0);
+    return code + ((x < 0.0) ? (1 << (nMantBits - 1)) : 0);
 }
 
 // quantize.py:325-357 + :90-111: inverse of mantissa_of.

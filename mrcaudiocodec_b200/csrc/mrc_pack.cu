@@ -1,22 +1,25 @@
-// mrc_pack.cu -- K4: bit-packing of the channel chunks, one CTA per (block, channel).
+// mrc_pack.cu -- K4: quantisation at the chosen allocation + bit-packing of the channel chunks, one CTA per
+// (block, channel).
+//   allocation                    the chain kernel's grant masks over the presorted tokens (bitalloc.py:106-155)
+//   scale factors + mantissas     codecThem.py:336-350 / :509-559, quantize.py:114-146, :294-322
 //   chunk layout and size         pacfileThem.py:651-789 (non-joint) / :825-970 (joint); SURVEY.md Appendix B
 //   MSB-first bit writer          bitpack.py:36-101
 //   file header                   pacfileThem.py:586-613 (numSamples quirk Q9)
-// Code lengths of the 1024 mantissas go through a block-wide exclusive scan; every symbol is then OR-ed into a
+// Code lengths of the L mantissas go through a block-wide exclusive scan; every symbol is then OR-ed into a
 // zeroed shared-memory bit buffer at its own offset and the finished chunk is streamed out with its <L nBytes
 // prefix.
 #include "mrc_internal.cuh"
+#include "mrc_math.cuh"
 
 namespace {
 
 constexpr int PT = 256;
 
+template <typename T>
 __global__ void __launch_bounds__(PT)
-pack_kernel(CodecParams cp, const HuffDev* __restrict__ huff, const int* __restrict__ band_lo,
-            const int* __restrict__ band_n, const uint8_t* __restrict__ line2band, ClipMap cm, int g0, QuantOut qo,
-            const uint8_t* __restrict__ ovs, const uint32_t* __restrict__ msv, const int64_t* __restrict__ clip_base,
-            uint8_t* __restrict__ out, long long out_cap, const uint8_t* __restrict__ header_template,
-            int* overflow_flag) {
+pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, ClipMap cm, int g0, Handoff<T> ho,
+            ChainIO io, PackTaps taps, const int64_t* __restrict__ clip_base, uint8_t* __restrict__ out,
+            long long out_cap, const uint8_t* __restrict__ header_template, int* overflow_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* bitbuf = reinterpret_cast<uint32_t*>(smem_raw);
     const int L = cp.L, nb = cp.nb;
@@ -24,6 +27,8 @@ pack_kernel(CodecParams cp, const HuffDev* __restrict__ huff, const int* __restr
     const size_t lb = blockIdx.x >> 1;
     const int ch = blockIdx.x & 1;
     const int g = g0 + (int)lb;
+    const uint8_t* __restrict__ line2band = tb.line2band;
+    const int* __restrict__ band_lo = tb.band_lo;
 
     __shared__ int s_clip, s_b, s_nblk;
     __shared__ int s_alloc[MRC_BSTRIDE], s_sf[MRC_BSTRIDE];
@@ -39,19 +44,37 @@ pack_kernel(CodecParams cp, const HuffDev* __restrict__ huff, const int* __restr
         s_b = g - cm.clip_blk0[lo];
         s_nblk = cm.clip_blk0[lo + 1] - cm.clip_blk0[lo];
     }
-    if (tid < nb) {
-        s_alloc[tid] = qo.alloc[(lb * 2 + ch) * MRC_BSTRIDE + tid];
-        s_sf[tid] = qo.sf[(lb * 2 + ch) * MRC_BSTRIDE + tid];
-    }
+    if (tid < MRC_BSTRIDE) s_alloc[tid] = 0;
     for (int i = tid; i < (int)(sizeof(HuffDev) / 4); i += PT)
         reinterpret_cast<uint32_t*>(&s_h)[i] = reinterpret_cast<const uint32_t*>(huff)[i];
-    const int nbytes = (int)qo.chunk_bytes[lb * 2 + ch];
+    const ChainBlk cb = io.cblk[lb];
+    const int nbytes = (int)cb.chunk_bytes[ch];
     const int nwords = (nbytes + 3) / 4 + 2;
     for (int i = tid; i < nwords; i += PT) bitbuf[i] = 0u;
     __syncthreads();
 
+    // allocation of this channel's bands = 2 + highest granted level (tokens of a band are granted in level order)
+    {
+        const uint32_t* tn = reinterpret_cast<const uint32_t*>(io.rec + lb * (size_t)MRC_REC_BYTES + MRC_REC_TN);
+        const uint32_t* gm = io.gmask + lb * 32;
+        for (int j = tid; j < MRC_NSLOT; j += PT) {
+            const uint32_t t = tn[j];
+            if (t == 0xffffffffu || !((gm[j >> 5] >> (j & 31)) & 1u)) continue;
+            const int bb = (int)(t & 0xff), lvl = (int)((t >> 8) & 0xff);
+            if ((bb >= nb) == (ch != 0)) atomicMax(&s_alloc[bb - ch * nb], lvl + 2);
+        }
+    }
+    __syncthreads();
+    if (tid < nb)
+        s_sf[tid] = scale_factor_of((double)ho.bandmax[(lb * 2 + ch) * MRC_BSTRIDE + tid], cp.n_scale_bits, s_alloc[tid]);
+    __syncthreads();
+    if (taps.alloc != nullptr && tid < MRC_BSTRIDE) {
+        taps.alloc[(lb * 2 + ch) * MRC_BSTRIDE + tid] = (uint8_t)(tid < nb ? s_alloc[tid] : 0);
+        taps.sf[(lb * 2 + ch) * MRC_BSTRIDE + tid] = (uint8_t)(tid < nb ? s_sf[tid] : 0);
+    }
+
     const bool joint = cp.joint && !(cp.flush_nonjoint && s_b == s_nblk - 1);
-    const int table = qo.table[lb * 2 + ch];
+    const int table = cb.table[ch];
     const int band_hdr = cp.n_mant_size_bits + cp.n_scale_bits;
     int hdr_bits = 4 + 1 + 1;
     if (joint) hdr_bits += (ch == 0) ? 4 * cp.n_scale_bits + nb : 0;
@@ -68,17 +91,18 @@ pack_kernel(CodecParams cp, const HuffDev* __restrict__ huff, const int* __restr
 
     // per-line symbols: LPT consecutive lines per thread
     const int LPT = L / PT;                      // 1, 2, 4 or 8
-    const uint16_t* mant = qo.mant + (lb * 2 + ch) * L;
+    const T* __restrict__ lines = ho.lines + (lb * 2 + ch) * L;
     uint32_t sym[8];
     int slen[8];
     int local = 0;
     for (int i = 0; i < LPT; ++i) {
         const int k = tid * LPT + i;
-        const int Rb = s_alloc[line2band[k]];
-        const int m = mant[k];
-        int n = 0;
+        const int bd = line2band[k];
+        const int Rb = s_alloc[bd];
+        int n = 0, m = 0;
         uint32_t v = 0;
         if (Rb) {
+            m = mantissa_of((double)lines[k], s_sf[bd], cp.n_scale_bits, Rb);
             if (table == MRC_NO_TABLE) { n = Rb; v = (uint32_t)m; }
             else {
                 const int len = (m < MRC_HUFF_LUT) ? s_h.len[table][m] : 0;
@@ -86,6 +110,7 @@ pack_kernel(CodecParams cp, const HuffDev* __restrict__ huff, const int* __restr
                 else { n = s_h.esc_len[table] + Rb; v = ((uint32_t)s_h.esc_code[table] << Rb) | (uint32_t)m; }
             }
         }
+        if (taps.mant != nullptr) taps.mant[(lb * 2 + ch) * L + k] = (uint16_t)m;
         sym[i] = v;
         slen[i] = n;
         local += n;
@@ -117,17 +142,18 @@ pack_kernel(CodecParams cp, const HuffDev* __restrict__ huff, const int* __restr
         int p = 6;
         if (joint) {
             if (ch == 0) {
-                for (int i = 0; i < 4; ++i) { put(p, ovs[lb * 4 + i], cp.n_scale_bits); p += cp.n_scale_bits; }
-                const uint32_t ms = msv[lb];
+                for (int i = 0; i < 4; ++i) { put(p, ho.ovs[lb * 4 + i], cp.n_scale_bits); p += cp.n_scale_bits; }
+                const uint32_t ms = ho.ms[lb];
                 for (int bd = 0; bd < nb; ++bd) put(p + bd, (ms >> bd) & 1u, 1);
             }
         } else {
-            put(p, ovs[lb * 4 + ch], cp.n_scale_bits);
+            put(p, ho.ovs[lb * 4 + ch], cp.n_scale_bits);
         }
     }
     __syncthreads();
 
-    const long long dst_off = clip_base[s_clip] + qo.chunk_off[lb * 2 + ch];
+    if (out == nullptr) return;                   // taps only
+    const long long dst_off = clip_base[s_clip] + cb.chunk_off[ch];
     if (dst_off + 4 + nbytes > out_cap) {         // never write past the caller's buffer; the host reports NOSPACE
         if (tid == 0) *overflow_flag = 1;
         return;
@@ -183,12 +209,20 @@ void launch_clip_scan(cudaStream_t st, const int64_t* clip_bytes, int64_t* clip_
     clip_scan_kernel<<<1, 256, 0, st>>>(clip_bytes, clip_base, c0, n, running);
 }
 
-void launch_pack(cudaStream_t st, const CodecParams& cp, const HuffDev* huff, const int* band_lo, const int* band_n,
-                 const uint8_t* line2band, const ClipMap& cm, int g0, int nblk, QuantOut qo, const uint8_t* ovs,
-                 const uint32_t* ms, const int64_t* clip_base, uint8_t* out, long long out_cap,
-                 const uint8_t* header_template, int* overflow_flag) {
+template <typename T>
+void launch_pack(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
+                 const ClipMap& cm, int g0, int nblk, Handoff<T> ho, ChainIO io, PackTaps taps,
+                 const int64_t* clip_base, uint8_t* out, long long out_cap, const uint8_t* header_template,
+                 int* overflow_flag) {
     if (nblk <= 0) return;
     const size_t smem = (size_t)cp.L * 25 / 8 + 512;
-    pack_kernel<<<2 * nblk, PT, smem, st>>>(cp, huff, band_lo, band_n, line2band, cm, g0, qo, ovs, ms, clip_base,
-                                            out, out_cap, header_template, overflow_flag);
+    pack_kernel<T><<<2 * nblk, PT, smem, st>>>(tb, cp, huff, cm, g0, ho, io, taps, clip_base, out, out_cap,
+                                               header_template, overflow_flag);
 }
+
+template void launch_pack<double>(cudaStream_t, const DevTables<double>&, const CodecParams&, const HuffDev*,
+                                  const ClipMap&, int, int, Handoff<double>, ChainIO, PackTaps, const int64_t*,
+                                  uint8_t*, long long, const uint8_t*, int*);
+template void launch_pack<float>(cudaStream_t, const DevTables<float>&, const CodecParams&, const HuffDev*,
+                                 const ClipMap&, int, int, Handoff<float>, ChainIO, PackTaps, const int64_t*,
+                                 uint8_t*, long long, const uint8_t*, int*);
