@@ -225,6 +225,7 @@ def main():
             dev_ms += t["total_ms"]
             launches += t["launches"]
             maskers = t["maskers"]
+            work = {k: t[k] for k in ("general_pairs", "window_adds", "loud_maskers", "waves")}
             stage += np.array([t["analysis_ms"], t["cost_ms"], t["chain_ms"], t["pack_ms"]])
         barrier()
         wall = time.perf_counter() - t0
@@ -232,7 +233,7 @@ def main():
         tt = torch.tensor([wall, dev_ms / 1000.0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return dict(wall=float(tt[0]), dev=float(tt[1]), launches=launches, maskers=maskers, nbytes=nbytes,
+        return dict(wall=float(tt[0]), dev=float(tt[1]), launches=launches, maskers=maskers, nbytes=nbytes, work=work,
                     stage_ms=(stage / args.steps).tolist(), clocks=clocks)
 
     peaks = codec.measure_peaks()
@@ -284,6 +285,7 @@ def main():
                              "unit": "GB/s", "frac": alg_bytes / (an_ms * 1e-3) / 1e9 / hbm_peak,
                              "peak_source": hbm_src, "traffic": None},
             "pipe_peaks": peaks,
+            "executed_work": r_dev["work"],
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pcm, args.cpu_sample_seconds)

@@ -42,6 +42,10 @@ extern "C" {
 #define MRC_PRECISION_FP64 0 /* code-exact mode                                      */
 #define MRC_PRECISION_FP32 1 /* fast mode (MDCT/SMR within 1e-5 relative)            */
 
+/* Masker spreading (psychoac.py:68-78, :168) summed pair by pair in the reference's order: one 10**x per
+ * (masker, line) pair.  Default (flag clear) is the factorised evaluation of the same sum. */
+#define MRC_FLAG_SPREAD_SEQUENTIAL 1
+
 typedef struct mrc_ctx mrc_ctx;
 
 /* Mirrors the attribute bag the reference fills at pacfileThem.py:1105-1121. */
@@ -53,7 +57,7 @@ typedef struct mrc_config {
     int32_t n_mant_size_bits;       /* codingParams.nMantSizeBits (4)                                 */
     int32_t joint;                  /* 1: JointWriteDataBlock flow (M/S), 0: WriteDataBlock flow      */
     int32_t precision;              /* MRC_PRECISION_*                                                */
-    int32_t reserved0;
+    int32_t flags;                  /* MRC_FLAG_*                                                     */
     double target_bits_per_sample;  /* codingParams.targetBitsPerSample                               */
     int64_t reserved1[4];
 } mrc_config;
@@ -153,7 +157,9 @@ int32_t mrc_stage_alloc_quant(mrc_ctx* ctx, const int16_t* pcm, const int64_t* c
  * last encode/decode call: [0] analysis kernels, [1] chain (serial reservoir walk) kernels, [2] clip-offset scan +
  * quantise/pack kernels, [3] decode kernels, [4] H2D, [5] D2H, [6] whole call on the main stream, [7] cost kernels.
  * Analysis+cost of wave w+1 overlap chain+pack of wave w, so [0]+[7]+[1]+[2] can exceed [6].
- * counters [0] kernel launches, [1] sum over spectra of tonal maskers, [2] blocks, [4] waves. */
+ * counters [0] kernel launches, [1] sum over spectra of tonal maskers, [2] blocks, [4] waves, and the work the
+ * factorised spreading executed: [5] general (masker, line) pairs priced with one 10**x each, [6] plateau
+ * additions, [7] loud maskers (g > 0). */
 int32_t mrc_last_timing(const mrc_ctx* ctx, double* ms8, int64_t* counters8);
 /* Micro-benchmarks of this GPU's pipes, for the roofline denominators MEASURED_PEAKS.json does not carry:
  * out4[0] FP64 FMA TFLOP/s, [1] FP32 FMA TFLOP/s, [2] MUFU.EX2 Gop/s, [3] device copy GB/s (read+write). */

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_here, "libmrc.so")
 
 MRC_OK, MRC_E_INVALID, MRC_E_CUDA, MRC_E_NOSPACE, MRC_E_FORMAT, MRC_E_STATE = 0, -1, -2, -3, -4, -5
 PRECISION_FP64, PRECISION_FP32 = 0, 1
+FLAG_SPREAD_SEQUENTIAL = 1
 NO_TABLE = 15
 
 c_i16p = C.POINTER(C.c_int16)
@@ -21,7 +22,7 @@ c_f64p = C.POINTER(C.c_double)
 class MrcConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("sample_rate", C.c_int32), ("n_mdct_lines", C.c_int32),
                 ("n_scale_bits", C.c_int32), ("n_mant_size_bits", C.c_int32), ("joint", C.c_int32),
-                ("precision", C.c_int32), ("reserved0", C.c_int32), ("target_bits_per_sample", C.c_double),
+                ("precision", C.c_int32), ("flags", C.c_int32), ("target_bits_per_sample", C.c_double),
                 ("reserved1", C.c_int64 * 4)]
 
 

@@ -18,7 +18,7 @@ def _ptr(a):
 class Codec(object):
     def __init__(self, sample_rate=48000, n_mdct_lines=1024, n_scale_bits=4, n_mant_size_bits=4,
                  target_bits_per_sample=128000. / 48000., joint=True, precision="fp64", device=0,
-                 band_limits=None):
+                 band_limits=None, spreading="factorised"):
         self.lib = _lib.load()
         self.L = int(n_mdct_lines)
         self.sample_rate = int(sample_rate)
@@ -32,6 +32,7 @@ class Codec(object):
         cfg.n_mant_size_bits = int(n_mant_size_bits)
         cfg.joint = 1 if joint else 0
         cfg.precision = {"fp64": _lib.PRECISION_FP64, "fp32": _lib.PRECISION_FP32}[precision]
+        cfg.flags = {"factorised": 0, "sequential": _lib.FLAG_SPREAD_SEQUENTIAL}[spreading]
         cfg.target_bits_per_sample = float(target_bits_per_sample)
         self._ctx = C.c_void_p()
         rc = self.lib.mrc_create(C.byref(cfg), C.byref(self._ctx))
@@ -220,4 +221,4 @@ class Codec(object):
         self.lib.mrc_last_timing(self._ctx, _ptr(ms), _ptr(cnt))
         return dict(analysis_ms=ms[0], chain_ms=ms[1], pack_ms=ms[2], decode_ms=ms[3], h2d_ms=ms[4], d2h_ms=ms[5],
                     total_ms=ms[6], cost_ms=ms[7], launches=int(cnt[0]), maskers=int(cnt[1]), blocks=int(cnt[2]),
-                    waves=int(cnt[4]))
+                    waves=int(cnt[4]), general_pairs=int(cnt[5]), window_adds=int(cnt[6]), loud_maskers=int(cnt[7]))

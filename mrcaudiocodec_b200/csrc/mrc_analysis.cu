@@ -14,6 +14,8 @@
 //   bitalloc.py:106-155                       (order of grants only: the allocation itself needs the reservoir)
 //
 // One CTA = one block, NT = L/2 threads; thread t owns MDCT lines t and t+L/2.
+#include <algorithm>
+
 #include "mrc_internal.cuh"
 #include "mrc_math.cuh"
 
@@ -25,28 +27,50 @@ struct Smem {
     cpx<T>* buf;    // [L]      FFT work buffer
     T* lines;       // [4][L]   MDCT lines L,R,M,S
     T* xi;          // [L]      FFT intensity, later SMR-per-line scratch
-    T* pz;          // [L/2]    peak Bark position
-    T* ps15;        // [L/2]    peak SPL - 15
-    T* pg;          // [L/2]    0.37*max(SPL-40,0)
-    int* pbin;      // [L/2]
-    T* skey;        // [1024]   sort keys
+    // masker tables of the current spectrum, always double (Q = L/2 >= number of maskers)
+    double* mz;     // [Q]      Bark position
+    double* ms15;   // [Q]      SPL - 15
+    double* mg;     // [Q]      0.37*max(SPL-40,0)
+    double* mc;     // [Q]      10^((SPL-15-96)/10): intensity inside +-0.5 Bark
+    double* mU;     // [Q+1]    quiet maskers at or below i, decayed to z_i (upper slope, -27 dB/Bark)
+    double* mS;     // [Q+1]    maskers at or above i, decayed to z_i (lower slope, -27 dB/Bark)
+    int* pbin;      // [Q]
+    int* lcnt;      // [Q+1]    number of loud maskers (g > 0) below index i
+    uint16_t* lidx; // [Q]      their indices, ascending
+    T* skey;        // [1024]   sort keys        (aliases mc/mU/mS: the sort runs after the last spectrum)
     uint16_t* sid;  // [1024]   sort ids
+    double* etab;   // [64]     2^(j/64)
 };
 
 template <typename T>
 __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     Smem<T> s;
+    const int Q = L / 2;
     T* p = reinterpret_cast<T*>(raw);
     s.sx = p;            p += 4 * L;
     s.buf = reinterpret_cast<cpx<T>*>(p); p += 2 * L;
     s.lines = p;         p += 4 * L;
     s.xi = p;            p += L;
-    s.pz = p;            p += L / 2;
-    s.ps15 = p;          p += L / 2;
-    s.pg = p;            p += L / 2;
-    s.pbin = reinterpret_cast<int*>(p); p += L / 2;   // int fits in a T slot (sizeof(T) >= 4)
-    s.skey = p;          p += 1024;
-    s.sid = reinterpret_cast<uint16_t*>(p);
+    double* d = reinterpret_cast<double*>(p);
+    s.mz = d;            d += Q;
+    s.ms15 = d;          d += Q;
+    s.mg = d;            d += Q;
+    s.etab = d;          d += 64;
+    // mc, mU, mS (3Q+2 doubles) and, after the last spectrum, the sort keys (10 KB) share one region: the FFT
+    // work buffer when it is large enough (it is idle while maskers are spread), else a region of their own.
+    const size_t need = (size_t)((3 * Q + 2 > 1280) ? 3 * Q + 2 : 1280) * 8;
+    double* r;
+    if ((size_t)(2 * L) * sizeof(T) >= need) r = reinterpret_cast<double*>(s.buf);
+    else { r = d; d += need / 8; }
+    s.mc = r;
+    s.mU = r + Q;
+    s.mS = r + 2 * Q + 1;
+    s.skey = reinterpret_cast<T*>(r);
+    s.sid = reinterpret_cast<uint16_t*>(r + 1024);
+    int* ip = reinterpret_cast<int*>(d);
+    s.pbin = ip;         ip += Q;
+    s.lcnt = ip;         ip += Q + 1;
+    s.lidx = reinterpret_cast<uint16_t*>(ip);
     return s;
 }
 
@@ -94,6 +118,53 @@ __device__ __forceinline__ T tsample(const T* sx, int N, int c, int n) {
     return (l - r) / T(2);
 }
 
+// Masked threshold intensity at MDCT line k from the factorised masker tables (same mathematics as
+// psychoac.py:68-78 summed over all maskers, re-associated):
+//   maskers more than 0.5 Bark below the line   quiet ones (g = 0): one geometric tail U, decayed from the nearest
+//                                               loud ones (slope depends on their level): one 10**x each
+//   maskers within +-0.5 Bark                   their plateau intensities, summed directly
+//   maskers more than 0.5 Bark above the line   one geometric tail S, decayed from the nearest
+// The region of every (masker, line) pair is decided by the reference's own comparisons on dz = z_k - z_m.
+template <typename T>
+__device__ __forceinline__ double spread_line(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk,
+                                              unsigned& n_general, unsigned& n_window) {
+    const double zk = tb.bark_d[k];
+    double a = tb.quiet_d[k];
+    // m_lo = number of maskers with dz > 0.5 (a prefix: z_m ascends); m_hi = first masker with dz < -0.5
+    int lo = 0, hi = npk;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (zk - sm.mz[mid] > 0.5) lo = mid + 1; else hi = mid;
+    }
+    const int m_lo = lo;
+    hi = npk;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (zk - sm.mz[mid] < -0.5) hi = mid; else lo = mid + 1;
+    }
+    const int m_hi = lo;
+    if (m_lo > 0) a += sm.mU[m_lo - 1] * exp10(-2.7 * ((zk - sm.mz[m_lo - 1]) - 0.5));
+    const int nl = sm.lcnt[m_lo];
+    for (int j = 0; j < nl; ++j) {
+        const int m = sm.lidx[j];
+        const double t = __dadd_rn(__dadd_rn(zk, -sm.mz[m]), -0.5);
+        const double e = __dadd_rn(__dadd_rn(sm.ms15[m], __dmul_rn(-27.0, t)), __dmul_rn(sm.mg[m], t));
+        a += exp10_tab(div10(__dadd_rn(e, -96.0)), sm.etab);
+    }
+    {   // plateau intensities of the maskers within +-0.5 Bark: four running sums (the chain of dependent adds
+        // is what this loop waits for), combined pairwise at the end
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+        int m = m_lo;
+        for (; m + 4 <= m_hi; m += 4) { w0 += sm.mc[m]; w1 += sm.mc[m + 1]; w2 += sm.mc[m + 2]; w3 += sm.mc[m + 3]; }
+        for (; m < m_hi; ++m) w0 += sm.mc[m];
+        a += (w0 + w1) + (w2 + w3);
+    }
+    n_general += (unsigned)nl;
+    n_window += (unsigned)(m_hi - m_lo);
+    if (m_hi < npk) a += sm.mS[m_hi] * exp10(-2.7 * ((sm.mz[m_hi] - zk) - 0.5));
+    return a;
+}
+
 template <typename T, int LOGL>
 __global__ void __launch_bounds__(1 << (LOGL - 1))
 analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __restrict__ pcm,
@@ -111,8 +182,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ int s_scale[4];
     __shared__ unsigned int s_ms;
     __shared__ int s_wcnt[33];
+    __shared__ double s_scan[4][32];
     __shared__ int s_npk;
 
+    if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
     const int g = g0 + blockIdx.x;            // global block index
     const int lb = blockIdx.x;                // index inside this wave's hand-off buffers
     if (tid == 0) {
@@ -234,6 +307,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // ---- phase 4: psychoacoustic model per spectrum ------------------------------------------------------
     const T xi_den = T(N) * T(N) * T(0.375);
     int my_peaks = 0;
+    unsigned n_general = 0, n_window = 0, n_loud = 0;
     for (int c = 0; c < nspec; ++c) {
         // a. Hann window, real 2L-point FFT through an L-point complex FFT
         for (int n = tid; n < L; n += NT) {
@@ -280,36 +354,128 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             __syncthreads();
         }
         const int npk = s_npk;
-        // d. masker parameters (psychoac.py:163-165, :37-49)
-        for (int i = tid; i < npk; i += NT) {
-            const int p = sm.pbin[i];
-            const T x0 = sm.xi[p - 1], x1 = sm.xi[p], x2 = sm.xi[p + 1];
-            const T sum = (x0 + x1) + x2;
-            const T spl = fmax(T(96) + T(10) * m_log10(sum), T(-30));
-            const T num = (T(p - 1) * x0 + T(p) * x1) + T(p + 1) * x2;
-            const T f = (T(tb.fstep) * num) / sum;
-            const T fq = f / T(7500);
-            sm.pz[i] = T(13) * m_atan(T(0.76) * f / T(1000)) + T(3.5) * m_atan(fq * fq);
-            sm.ps15[i] = spl - T(15);
-            sm.pg[i] = T(0.37) * fmax(spl - T(40), T(0));
+        // d. masker parameters (psychoac.py:163-165, :37-49), in double in both modes
+        {
+            const int i = tid;                       // npk <= Q == NT: one masker per thread
+            double z = 0, s15 = 0, g = 0, cmid = 0;
+            bool loud = false;
+            if (i < npk) {
+                // products and sums kept unfused (__dmul_rn/__dadd_rn), in the reference's order
+                const int p = sm.pbin[i];
+                const double x0 = (double)sm.xi[p - 1], x1 = (double)sm.xi[p], x2 = (double)sm.xi[p + 1];
+                const double sum = __dadd_rn(__dadd_rn(x0, x1), x2);
+                const double spl = fmax(__dadd_rn(96.0, __dmul_rn(10.0, log10(sum))), -30.0);
+                const double num = __dadd_rn(__dadd_rn(__dmul_rn((double)(p - 1), x0), __dmul_rn((double)p, x1)),
+                                             __dmul_rn((double)(p + 1), x2));
+                const double f = __ddiv_rn(__dmul_rn((double)tb.fstep, num), sum);
+                const double fq = __ddiv_rn(f, 7500.0);
+                z = __dadd_rn(__dmul_rn(13.0, atan(__ddiv_rn(__dmul_rn(0.76, f), 1000.0))),
+                              __dmul_rn(3.5, atan(__dmul_rn(fq, fq))));
+                s15 = __dadd_rn(spl, -15.0);
+                g = __dmul_rn(0.37, fmax(__dadd_rn(spl, -40.0), 0.0));
+                loud = g > 0.0;
+                n_loud += loud ? 1u : 0u;
+                sm.mz[i] = z; sm.ms15[i] = s15; sm.mg[i] = g;
+                if (!cp.spread_seq) {
+                    cmid = exp10(div10(__dadd_rn(s15, -96.0)));
+                    sm.mc[i] = cmid;
+                }
+            }
+            if (tid == 0) my_peaks += npk;
+            if (!cp.spread_seq) {
+                // ordered list of the loud maskers (g > 0: their upper slope depends on their level)
+                const unsigned bal = __ballot_sync(0xffffffffu, loud);
+                if (lane == 0) s_wcnt[warp] = __popc(bal);
+                __syncthreads();                     // also publishes mz for the neighbour reads below
+                if (warp == 0) {
+                    int v = (lane < nwarp) ? s_wcnt[lane] : 0;
+                    int incl = v;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    s_wcnt[lane] = incl - v;
+                }
+                // decay between neighbouring maskers: rho(d) = 10^(-2.7 d), the -27 dB/Bark slope of both sides
+                double rU = 0.0, rS = 0.0;           // rU = rho(z_i - z_{i-1}); rS = rho(z_{i+1} - z_i)
+                if (i < npk) {
+                    if (i > 0) rU = exp10(-2.7 * (z - sm.mz[i - 1]));
+                    if (i + 1 < npk) rS = exp10(-2.7 * (sm.mz[i + 1] - z));
+                }
+                __syncthreads();
+                const int lpos = s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u));
+                if (i <= npk) sm.lcnt[i] = lpos;     // entry npk = total (threads >= npk are not loud)
+                if (loud) sm.lidx[lpos] = (uint16_t)i;
+                // two affine recurrences by warp scans:  U_i = cq_i + rU_i * U_{i-1}  (ascending, quiet maskers only)
+                //                                        S_i = c_i  + rS_i * S_{i+1}  (descending, all maskers)
+                // The descending one runs on the mirrored index j = npk-1-i, held by thread j.
+                double aU = rU, bU = (i < npk && !loud) ? cmid : 0.0;
+                // mirrored element for S: thread tid holds masker im = npk-1-tid
+                const int im = npk - 1 - tid;
+                double aS = 0.0, bS = 0.0;
+                // exchange through shared memory: stash (rS, c) of masker i, read those of masker im
+                sm.mU[i < npk ? i : npk] = rS;       // temporary use of mU/mS as exchange buffers
+                __syncthreads();
+                if (im >= 0) { aS = sm.mU[im]; bS = sm.mc[im]; }
+                __syncthreads();
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double alU = __shfl_up_sync(0xffffffffu, aU, o), blU = __shfl_up_sync(0xffffffffu, bU, o);
+                    const double alS = __shfl_up_sync(0xffffffffu, aS, o), blS = __shfl_up_sync(0xffffffffu, bS, o);
+                    if (lane >= o) {
+                        bU = fma(aU, blU, bU); aU = aU * alU;
+                        bS = fma(aS, blS, bS); aS = aS * alS;
+                    }
+                }
+                if (lane == 31) { s_scan[0][warp] = aU; s_scan[1][warp] = bU; s_scan[2][warp] = aS; s_scan[3][warp] = bS; }
+                __syncthreads();
+                if (warp == 0) {
+                    double a1 = (lane < nwarp) ? s_scan[0][lane] : 1.0, b1 = (lane < nwarp) ? s_scan[1][lane] : 0.0;
+                    double a2 = (lane < nwarp) ? s_scan[2][lane] : 1.0, b2 = (lane < nwarp) ? s_scan[3][lane] : 0.0;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double al1 = __shfl_up_sync(0xffffffffu, a1, o), bl1 = __shfl_up_sync(0xffffffffu, b1, o);
+                        const double al2 = __shfl_up_sync(0xffffffffu, a2, o), bl2 = __shfl_up_sync(0xffffffffu, b2, o);
+                        if (lane >= o) {
+                            b1 = fma(a1, bl1, b1); a1 = a1 * al1;
+                            b2 = fma(a2, bl2, b2); a2 = a2 * al2;
+                        }
+                    }
+                    if (lane < nwarp) { s_scan[1][lane] = b1; s_scan[3][lane] = b2; }
+                }
+                __syncthreads();
+                if (warp > 0) {                      // value carried in from the warps before
+                    bU = fma(aU, s_scan[1][warp - 1], bU);
+                    bS = fma(aS, s_scan[3][warp - 1], bS);
+                }
+                if (i < npk) sm.mU[i] = bU;
+                if (im >= 0) sm.mS[im] = bS;
+                if (tid == 0) { sm.mS[npk] = 0.0; }
+            }
         }
-        if (tid == 0) my_peaks += npk;
         __syncthreads();
-        // e. spreading: thread owns lines tid and tid+Q, maskers summed in ascending order (psychoac.py:68-78,168)
+        // e. masked threshold at the MDCT lines: thread owns lines tid and tid+Q
         {
             const int k0 = tid, k1 = tid + Q;
-            const T z0 = tb.bark[k0], z1 = tb.bark[k1];
-            T a0 = tb.quiet[k0], a1 = tb.quiet[k1];
-            for (int m = 0; m < npk; ++m) {
-                const T zm = sm.pz[m], s15 = sm.ps15[m], gg = sm.pg[m];
-                a0 += masker_intensity(z0 - zm, s15, gg);
-                a1 += masker_intensity(z1 - zm, s15, gg);
+            double a0, a1;
+            if (cp.spread_seq) {
+                // reference order (psychoac.py:68-78, :168): every masker onto every line, one 10**x per pair
+                const double z0 = tb.bark_d[k0], z1 = tb.bark_d[k1];
+                a0 = tb.quiet_d[k0]; a1 = tb.quiet_d[k1];
+                for (int m = 0; m < npk; ++m) {
+                    const double zm = sm.mz[m], s15 = sm.ms15[m], gg = sm.mg[m];
+                    a0 += masker_intensity(z0 - zm, s15, gg);
+                    a1 += masker_intensity(z1 - zm, s15, gg);
+                }
+            } else {
+                a0 = spread_line(sm, tb, k0, npk, n_general, n_window);
+                a1 = spread_line(sm, tb, k1, npk, n_general, n_window);
             }
             // f. SMR per line (psychoac.py:212-214)
             const T sc6 = T(6) * T(s_scale[c]);
             const T X0 = sm.lines[c * L + k0], X1 = sm.lines[c * L + k1];
-            const T thr0 = fmax(T(96) + T(10) * m_log10(a0), T(-30));
-            const T thr1 = fmax(T(96) + T(10) * m_log10(a1), T(-30));
+            const T thr0 = fmax(T(96) + T(10) * m_log10(T(a0)), T(-30));
+            const T thr1 = fmax(T(96) + T(10) * m_log10(T(a1)), T(-30));
             const T sp0 = fmax(T(96) + T(10) * m_log10((T(2) * (X0 * X0)) / T(0.5)), T(-30)) - sc6;
             const T sp1 = fmax(T(96) + T(10) * m_log10((T(2) * (X1 * X1)) / T(0.5)), T(-30)) - sc6;
             sm.xi[k0] = sp0 - thr0;
@@ -328,6 +494,17 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     }
     if (tid == 0) {
         if (peak_counter) atomicAdd(peak_counter, (unsigned long long)my_peaks);
+    }
+    if (peak_counter) {     // executed-work counters: [1] general (10**x) pairs, [2] plateau adds, [3] loud maskers
+        const unsigned g1 = __reduce_add_sync(0xffffffffu, n_general), g2 = __reduce_add_sync(0xffffffffu, n_window),
+                       g3 = __reduce_add_sync(0xffffffffu, n_loud);
+        if (lane == 0) {
+            atomicAdd(peak_counter + 1, (unsigned long long)g1);
+            atomicAdd(peak_counter + 2, (unsigned long long)g2);
+            atomicAdd(peak_counter + 3, (unsigned long long)g3);
+        }
+    }
+    if (tid == 0) {
         if (taps.npeaks != nullptr) for (int c = nspec; c < 4; ++c) taps.npeaks[lb * 4 + c] = 0;
     }
     if (taps.smr4 != nullptr) {
@@ -423,7 +600,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
 }  // namespace
 
 size_t analysis_smem_bytes(int L, int elem) {
-    return (size_t)(13 * L) * elem + 1024 * elem + 1024 * 2;
+    const size_t Q = L / 2;
+    size_t spread = std::max<size_t>(3 * Q + 2, 1280) * 8;             // mc, mU, mS (the sort aliases them)
+    if ((size_t)(2 * L) * elem >= spread) spread = 0;                  // ... living in the FFT work buffer
+    return (size_t)(11 * L) * elem + (3 * Q + 64) * 8 + spread + (2 * Q + 1) * 4 + Q * 2 + 16;
 }
 
 template <typename T>

@@ -21,7 +21,7 @@ struct Buf {
 };
 
 struct TablesDev {
-    Buf kbd, hann, tw_pre, tw_post, tw_fft, tw_rfft, bark, quiet;
+    Buf kbd, hann, tw_pre, tw_post, tw_fft, tw_rfft, bark, quiet, bark_d, quiet_d, exp_tab;
 };
 
 }  // namespace
@@ -126,7 +126,14 @@ cudaError_t upload_tables(mrc_ctx* c, TablesDev& d, DevTables<T>& tb, const mrc_
     if ((e = upload(d.tw_post, post, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.tw_fft, fft, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.tw_rfft, rfft, c->stream)) != cudaSuccess) return e;
+    std::vector<double> bark_d(t->bark, t->bark + L), quiet_d(t->quiet_intensity, t->quiet_intensity + L), etab(64);
+    for (int j = 0; j < 64; ++j) etab[j] = exp2(j / 64.0);       // correctly rounded by glibc
+    if ((e = upload(d.bark_d, bark_d, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.quiet_d, quiet_d, c->stream)) != cudaSuccess) return e;
+    if ((e = upload(d.exp_tab, etab, c->stream)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;   // host vectors die at scope exit
+    tb.bark_d = (const double*)d.bark_d.p; tb.quiet_d = (const double*)d.quiet_d.p;
+    tb.exp_tab = (const double*)d.exp_tab.p;
     tb.L = L; tb.logL = c->logL; tb.nb = c->nb; tb.sample_rate = c->cfg.sample_rate;
     tb.fstep = c->cfg.sample_rate / N;
     tb.kbd = (const T*)d.kbd.p; tb.hann = (const T*)d.hann.p;
@@ -201,12 +208,12 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     CK(ensure(ctx->clip_run, (size_t)(nc + 1) * 8));
     CK(ensure(ctx->running, 8));
     CK(ensure(ctx->overflow, 4));
-    CK(ensure(ctx->peakctr, 8));
+    CK(ensure(ctx->peakctr, 32));
     CK(cudaMemsetAsync(ctx->clip_bytes.p, 0, (size_t)(nc + 1) * 8, st));
     CK(cudaMemsetAsync(ctx->clip_base.p, 0, (size_t)(nc + 2) * 8, st));
     CK(cudaMemsetAsync(ctx->running.p, 0, 8, st));
     CK(cudaMemsetAsync(ctx->overflow.p, 0, 4, st));
-    CK(cudaMemsetAsync(ctx->peakctr.p, 0, 8, st));
+    CK(cudaMemsetAsync(ctx->peakctr.p, 0, 32, st));
     const int32_t* d_res_in = nullptr;
     int32_t* d_res_out = nullptr;
     if (job.h_res_in) {
@@ -387,8 +394,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     }
     // the analysis stream has nothing outstanding that the main stream does not already wait for (event 2 of the
     // last wave), so synchronising the main stream ends the call.
-    unsigned long long pk = 0;
-    CK(cudaMemcpyAsync(&pk, ctx->peakctr.p, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long pk[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(pk, ctx->peakctr.p, 32, cudaMemcpyDeviceToHost, st));
     if (job.h_res_out) CK(cudaMemcpyAsync(job.h_res_out, d_res_out, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
     int ovf = 0;
     if (job.d_out) {
@@ -409,7 +416,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     ctx->counters[0] = launches;
     ctx->counters[2] = nblk_total;
     ctx->counters[4] = nwaves;
-    ctx->counters[1] = (int64_t)pk;
+    ctx->counters[1] = (int64_t)pk[0];
+    ctx->counters[5] = (int64_t)pk[1]; ctx->counters[6] = (int64_t)pk[2]; ctx->counters[7] = (int64_t)pk[3];
     if (job.d_out && nblk_total == 0) for (int c = 0; c <= nc; ++c) job.h_clip_byte_off[c] = 0;
     if (ovf) return fail(ctx, MRC_E_NOSPACE, "output buffer too small for the encoded batch");
     return MRC_OK;
@@ -495,7 +503,8 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     Buf* all[] = {&ctx->td.kbd, &ctx->td.hann, &ctx->td.tw_pre, &ctx->td.tw_post, &ctx->td.tw_fft, &ctx->td.tw_rfft,
-                  &ctx->td.bark, &ctx->td.quiet, &ctx->tf.kbd, &ctx->tf.hann, &ctx->tf.tw_pre, &ctx->tf.tw_post,
+                  &ctx->td.bark, &ctx->td.quiet, &ctx->td.bark_d, &ctx->td.quiet_d, &ctx->td.exp_tab, &ctx->tf.bark_d,
+                  &ctx->tf.quiet_d, &ctx->tf.exp_tab, &ctx->tf.kbd, &ctx->tf.hann, &ctx->tf.tw_pre, &ctx->tf.tw_post,
                   &ctx->tf.tw_fft, &ctx->tf.tw_rfft, &ctx->tf.bark, &ctx->tf.quiet, &ctx->band_lo, &ctx->band_n,
                   &ctx->line2band, &ctx->huff, &ctx->header, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,
                   &ctx->clip_base, &ctx->running, &ctx->overflow, &ctx->peakctr, &ctx->res_in, &ctx->res_out,
@@ -585,6 +594,7 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     ctx->cp.n_scale_bits = c.n_scale_bits; ctx->cp.n_mant_size_bits = c.n_mant_size_bits;
     ctx->cp.max_mant_bits = std::min(16, 1 << c.n_mant_size_bits);
     ctx->cp.joint = c.joint; ctx->cp.flush_nonjoint = 1; ctx->cp.no_huff = 0;
+    ctx->cp.spread_seq = (c.flags & MRC_FLAG_SPREAD_SEQUENTIAL) ? 1 : 0;
     if (ctx->cp.max_mant_bits != 16) return fail(ctx, MRC_E_INVALID, "only n_mant_size_bits = 4 (16-bit cap) is supported");
     // .pac header template (pacfileThem.py:592-613); numSamples is patched per clip by the pack kernel
     uint8_t* hd = ctx->h_header;

@@ -59,6 +59,9 @@ struct DevTables {
     const cpx<T>* tw_rfft;                       // [L]    exp(-2*pi*j*k/(2L))
     const T* bark;                               // [L]
     const T* quiet;                              // [L]
+    const double* bark_d;                        // [L]   the same two tables in double (spreading is always fp64)
+    const double* quiet_d;                       // [L]
+    const double* exp_tab;                       // [64]  2^(j/64)
     const int* band_lo;                          // [nb]
     const int* band_n;                           // [nb]
     const uint8_t* line2band;                    // [L]
@@ -114,6 +117,7 @@ struct CodecParams {
     int L, nb, n_scale_bits, n_mant_size_bits, max_mant_bits, joint;
     int no_huff;                 // 1: EncodeNoHuff (codecThem.py:234-260): table 15, no reservoir credit
     int flush_nonjoint;          // 1: the last block of every clip is the non-joint Close() flush block (Q10)
+    int spread_seq;              // 1: masker spreading summed pair by pair in the reference's order (psychoac.py:168)
     double budget_joint;         // value of bitBudget just before `+= bitReservoir` (codecThem.py:381-391)
     double budget_single;        // value of bitBudget just before `+= bitReservoir` (codecThem.py:299-306)
     int header_bytes;            // .pac file header size

@@ -70,14 +70,44 @@ __device__ __forceinline__ double dequantize_of(int mant, int scale, int nScaleB
 
 // psychoac.py:68-78 for one (masker, line) pair: intensity of a tonal masker at Bark distance dz.
 //   s15 = SPL - 15, g = 0.37*max(SPL-40, 0)
-template <typename T>
-__device__ __forceinline__ T masker_intensity(T dz, T s15, T g) {
-    const T adz = fabs(dz);
-    const T t = adz - T(0.5);
-    T e = s15;
-    if (adz > T(0.5)) {
-        e = e + T(-27) * t;
-        if (dz > T(0.5)) e = e + g * t;
+__device__ __forceinline__ double masker_intensity(double dz, double s15, double g) {
+    const double adz = fabs(dz);
+    double e = s15;
+    if (adz > 0.5) {
+        const double t = __dadd_rn(adz, -0.5);
+        e = __dadd_rn(e, __dmul_rn(-27.0, t));
+        if (dz > 0.5) e = __dadd_rn(e, __dmul_rn(g, t));
     }
-    return m_exp10((e - T(96)) / T(10));
+    return exp10(__ddiv_rn(__dadd_rn(e, -96.0), 10.0));
+}
+
+// ---- psychoacoustic spreading helpers (double precision in both modes) -------------------------------------
+// q / 10 correctly rounded without the division routine: y0 = RN(q * RN(1/10)); r = q - 10*y0 is exact in an FMA;
+// y = RN(y0 + r * RN(1/10)) (Markstein's correction step).
+__device__ __forceinline__ double div10(double q) {
+    const double y0 = q * 0.1;
+    const double r = fma(-10.0, y0, q);
+    return fma(r, 0.1, y0);
+}
+
+// 10^y for y in about [-300, 300], < 1.5 ulp: y = n*log10(2)/64 + r with |r| <= log10(2)/128 (two-FMA reduction
+// against a hi/lo split of log10(2)/64), 10^r by a degree-6 Taylor polynomial in r (error < 1e-19 relative),
+// 2^(n mod 64 / 64) from a 64-entry table `tab` (shared memory), 2^(n div 64) added to the exponent field.
+__device__ __forceinline__ double exp10_tab(double y, const double* __restrict__ tab) {
+    const double magic = 6755399441055744.0;                       // 1.5 * 2^52: rint through the add
+    const double tn = fma(y, 212.60339807279118, magic);
+    const int n = __double2loint(tn);
+    const double nd = tn - magic;
+    double r = fma(nd, -0.004703593682222618, y);                  // hi part: 38 significant bits, nd*hi exact
+    r = fma(nd, -2.7088530630863833e-14, r);
+    double p = 0.2069958486968681;
+    p = fma(p, r, 0.5393829291955814);
+    p = fma(p, r, 1.171255148912267);
+    p = fma(p, r, 2.034678592293476);
+    p = fma(p, r, 2.650949055239199);
+    p = fma(p, r, 2.302585092994046);
+    p = p * r;
+    const double t = tab[n & 63];
+    const double v = fma(t, p, t);
+    return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
 }

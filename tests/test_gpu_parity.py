@@ -14,11 +14,11 @@ def codecs():
     from mrcaudiocodec_b200 import Codec
     cache = {}
 
-    def get(sr=48000, joint=True, tbps=128000. / 48000., precision="fp64", L=1024):
-        key = (sr, joint, tbps, precision, L)
+    def get(sr=48000, joint=True, tbps=128000. / 48000., precision="fp64", L=1024, spreading="factorised"):
+        key = (sr, joint, tbps, precision, L, spreading)
         if key not in cache:
             cache[key] = Codec(sample_rate=sr, joint=joint, target_bits_per_sample=tbps, precision=precision,
-                               n_mdct_lines=L)
+                               n_mdct_lines=L, spreading=spreading)
         return cache[key]
     yield get
     for c in cache.values():
@@ -71,6 +71,27 @@ def test_golden_decode_matches_reference_decoder(golden, codecs, name):
     d = np.abs(pcm.astype(np.int64) - g["decoded"].astype(np.int64))
     assert d.max() <= 1                                   # north_star: decoded PCM within 1 LSB
     assert np.count_nonzero(d) <= 2, "fp64 decode should reproduce the reference decoder almost everywhere"
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_sequential_spreading_mode(golden, codecs, name):
+    """MRC_FLAG_SPREAD_SEQUENTIAL sums the maskers pair by pair in the reference's order; the default factorised
+    evaluation is the same sum re-associated.  Both must give the reference's bytes, and their SMRs must agree
+    to 1e-11 dB (the golden SMRs are matched to 1e-9 dB by both)."""
+    g = golden(name)
+    sr, joint, tbps = _cfg(g)
+    cs = codecs(sr, joint, tbps, spreading="sequential")
+    cf = codecs(sr, joint, tbps)
+    assert cs.encode_clips([g["pcm"]])[0] == g["pac"].tobytes()
+    a_s = cs.stage_analysis([g["pcm"]])
+    a_f = cf.stage_analysis([g["pcm"]])
+    assert np.array_equal(a_s["n_peaks"], a_f["n_peaks"])
+    assert np.abs(a_s["smr"] - a_f["smr"]).max() <= 1e-11
+    n = g["mdct"].shape[0]
+    isj = g["isJoint"]
+    for i in range(n):
+        ns = 4 if isj[i] else 2
+        assert np.abs(a_s["smr"][i, :ns] - g["smr"][i, :ns]).max() <= 1e-9
 
 
 @pytest.mark.parametrize("joint", [True, False])
