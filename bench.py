@@ -225,7 +225,7 @@ def main():
             dev_ms += t["total_ms"]
             launches += t["launches"]
             maskers = t["maskers"]
-            work = {k: t[k] for k in ("general_pairs", "window_adds", "loud_maskers", "waves")}
+            work = {k: t[k] for k in ("general_pairs", "window_adds", "loud_maskers", "waves", "chain_iters")}
             stage += np.array([t["analysis_ms"], t["cost_ms"], t["chain_ms"], t["pack_ms"]])
         barrier()
         wall = time.perf_counter() - t0

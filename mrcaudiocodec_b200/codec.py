@@ -221,4 +221,4 @@ class Codec(object):
         self.lib.mrc_last_timing(self._ctx, _ptr(ms), _ptr(cnt))
         return dict(analysis_ms=ms[0], chain_ms=ms[1], pack_ms=ms[2], decode_ms=ms[3], h2d_ms=ms[4], d2h_ms=ms[5],
                     total_ms=ms[6], cost_ms=ms[7], launches=int(cnt[0]), maskers=int(cnt[1]), blocks=int(cnt[2]),
-                    waves=int(cnt[4]), general_pairs=int(cnt[5]), window_adds=int(cnt[6]), loud_maskers=int(cnt[7]))
+                    waves=int(cnt[4]), chain_iters=int(cnt[3]), general_pairs=int(cnt[5]), window_adds=int(cnt[6]), loud_maskers=int(cnt[7]))

@@ -44,7 +44,7 @@ struct mrc_ctx {
 
     // scratch (grow only)
     Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out;
-    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, gmask, cblk; } sets[2];
+    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk; } sets[2];
     Buf q_alloc, q_sf, q_mant;
     cudaStream_t stream2 = nullptr;
     std::vector<cudaEvent_t> evpool;
@@ -208,12 +208,12 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     CK(ensure(ctx->clip_run, (size_t)(nc + 1) * 8));
     CK(ensure(ctx->running, 8));
     CK(ensure(ctx->overflow, 4));
-    CK(ensure(ctx->peakctr, 32));
+    CK(ensure(ctx->peakctr, 64));
     CK(cudaMemsetAsync(ctx->clip_bytes.p, 0, (size_t)(nc + 1) * 8, st));
     CK(cudaMemsetAsync(ctx->clip_base.p, 0, (size_t)(nc + 2) * 8, st));
     CK(cudaMemsetAsync(ctx->running.p, 0, 8, st));
     CK(cudaMemsetAsync(ctx->overflow.p, 0, 4, st));
-    CK(cudaMemsetAsync(ctx->peakctr.p, 0, 32, st));
+    CK(cudaMemsetAsync(ctx->peakctr.p, 0, 64, st));
     const int32_t* d_res_in = nullptr;
     int32_t* d_res_out = nullptr;
     if (job.h_res_in) {
@@ -252,11 +252,14 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         CK(ensure(ws.ovs, W * 4));
         CK(ensure(ws.ms, W * 4));
         CK(ensure(ws.rec, W * MRC_REC_BYTES));
+        CK(ensure(ws.pw, W * MRC_PW_BYTES));
+        CK(ensure(ws.rsv, W * sizeof(int4)));
         CK(ensure(ws.gmask, W * 32 * 4));
         CK(ensure(ws.cblk, W * sizeof(ChainBlk)));
         ho[s].lines = (T*)ws.lines.p; ho[s].bandmax = (T*)ws.bandmax.p; ho[s].smr = nullptr;
         ho[s].tokens = (uint16_t*)ws.tokens.p; ho[s].ovs = (uint8_t*)ws.ovs.p; ho[s].ms = (uint32_t*)ws.ms.p;
-        io[s].rec = (const unsigned char*)ws.rec.p; io[s].gmask = (uint32_t*)ws.gmask.p;
+        io[s].rec = (const unsigned char*)ws.rec.p; io[s].pw = (const unsigned char*)ws.pw.p;
+        io[s].rsv = (int4*)ws.rsv.p; io[s].gmask = (uint32_t*)ws.gmask.p;
         io[s].cblk = (ChainBlk*)ws.cblk.p;
         io[s].clip_res = (int32_t*)ctx->clip_res.p; io[s].clip_run = (int64_t*)ctx->clip_run.p;
         io[s].clip_bytes = (int64_t*)ctx->clip_bytes.p;
@@ -305,7 +308,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         CK(cudaEventRecord(ev(w, 1), st2));
         ++launches;
         if (job.need_quant) {
-            launch_cost<T>(st2, tb, cp, (const HuffDev*)ctx->huff.p, cm, g0, nblk, ho[s], (unsigned char*)ctx->sets[s].rec.p);
+            launch_cost<T>(st2, tb, cp, (const HuffDev*)ctx->huff.p, cm, g0, nblk, ho[s], (unsigned char*)ctx->sets[s].rec.p,
+                           (unsigned char*)ctx->sets[s].pw.p);
             ++launches;
         }
         CK(cudaEventRecord(ev(w, 2), st2));
@@ -313,10 +317,16 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         CK(cudaStreamWaitEvent(st, ev(w, 2), 0));
         CK(cudaEventRecord(ev(w, 3), st));
         if (job.need_quant) {
-            launch_chain(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, min_nl, io[s], d_res_in, d_res_out);
+            launch_chain(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, min_nl, io[s], d_res_in, d_res_out,
+                         (unsigned long long*)ctx->peakctr.p + 4);
             ++launches;
         }
         CK(cudaEventRecord(ev(w, 4), st));
+        if (job.need_quant) {
+            launch_finish(st, cp, cm, g0, nblk, min_nl, io[s]);
+            launch_offsets(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, io[s]);
+            launches += 2;
+        }
         if (job.need_quant && (job.d_out || want_qtap)) {
             if (nfin > 0) {
                 launch_clip_scan(st, io[s].clip_bytes, (int64_t*)ctx->clip_base.p, c_lo, nfin, (int64_t*)ctx->running.p);
@@ -394,8 +404,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     }
     // the analysis stream has nothing outstanding that the main stream does not already wait for (event 2 of the
     // last wave), so synchronising the main stream ends the call.
-    unsigned long long pk[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(pk, ctx->peakctr.p, 32, cudaMemcpyDeviceToHost, st));
+    unsigned long long pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(pk, ctx->peakctr.p, 64, cudaMemcpyDeviceToHost, st));
     if (job.h_res_out) CK(cudaMemcpyAsync(job.h_res_out, d_res_out, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
     int ovf = 0;
     if (job.d_out) {
@@ -417,6 +427,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     ctx->counters[2] = nblk_total;
     ctx->counters[4] = nwaves;
     ctx->counters[1] = (int64_t)pk[0];
+    ctx->counters[3] = (int64_t)pk[4];
     ctx->counters[5] = (int64_t)pk[1]; ctx->counters[6] = (int64_t)pk[2]; ctx->counters[7] = (int64_t)pk[3];
     if (job.d_out && nblk_total == 0) for (int c = 0; c <= nc; ++c) job.h_clip_byte_off[c] = 0;
     if (ovf) return fail(ctx, MRC_E_NOSPACE, "output buffer too small for the encoded batch");
@@ -513,7 +524,7 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     for (Buf* b : all) release(*b);
     for (auto& b : ctx->dec) release(b);
     for (auto& ws : ctx->sets) {
-        Buf* wb[] = {&ws.lines, &ws.bandmax, &ws.tokens, &ws.ovs, &ws.ms, &ws.rec, &ws.gmask, &ws.cblk};
+        Buf* wb[] = {&ws.lines, &ws.bandmax, &ws.tokens, &ws.ovs, &ws.ms, &ws.rec, &ws.pw, &ws.rsv, &ws.gmask, &ws.cblk};
         for (Buf* b : wb) release(*b);
     }
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -589,6 +600,11 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
         B -= 1;
         B -= 1;
         ctx->cp.budget_single = B;
+    }
+    {   // integer form: bitBudget = k + frac + bitReservoir (the joint path's two blksw bits folded into k)
+        const double bj = ctx->cp.budget_joint - 1.0 - 1.0, bs = ctx->cp.budget_single;
+        ctx->cp.k_joint = (int)floor(bj);   ctx->cp.frac_joint = (bj - floor(bj)) > 0.0 ? 1 : 0;
+        ctx->cp.k_single = (int)floor(bs);  ctx->cp.frac_single = (bs - floor(bs)) > 0.0 ? 1 : 0;
     }
     ctx->cp.L = L; ctx->cp.nb = t->n_bands;
     ctx->cp.n_scale_bits = c.n_scale_bits; ctx->cp.n_mant_size_bits = c.n_mant_size_bits;

@@ -1,21 +1,28 @@
-// mrc_chain.cu -- K3b: the serial walk.  The only state the reference carries from block to block (and, for
-// independent channels, from channel to channel) is codingParams.bitReservoir, one int:
+// mrc_chain.cu -- K3b/K3c/K3d: the serial walk and its parallel replay.
+//
+// The only state the reference carries from block to block (and, for independent channels, from channel to
+// channel) is codingParams.bitReservoir, one int:
 //   bit budget + reservoir      codecThem.py:299-308 (single channel) / :381-396 (joint)
 //   water-filling allocation    bitalloc.py:106-155 -- here: how far down the presorted grant list the budget reaches
 //   reservoir = int(bitsLeft)   codecThem.py:332 / :503
 //   Huffman table choice        codecThem.py:136-203 (strict minimum below the raw size, ties -> lowest index)
 //   reservoir += bits_saved     codecThem.py:224 / :274
 //   chunk sizes                 pacfileThem.py:651-707 / :825-880
-// One warp per clip.  Per block it receives the cost kernel's 16.6 KB record through a TMA bulk copy
-// (cp.async.bulk + mbarrier, MRC_CHAIN_STAGES deep, so the next blocks are already in shared memory), finds the
-// first 32-token chunk the budget cannot fully pay with one ballot over the chunk maxima, resolves that chunk and
-// the tail with warp scans, and reads every total (bits spent, cost under each book) off the chunk checkpoint plus
-// a warp reduction.  Outputs: which tokens were granted (one 32-bit mask per chunk) and the ChainBlk record.
+//
+// chain_kernel   (serial, one warp per clip): computes nothing but the reservoir sequence.  Per block it receives
+//                the cost kernel's 18.5 KB record through a TMA bulk copy (cp.async.bulk + mbarrier, a ring of
+//                MRC_CHAIN_STAGES), finds the first refused token with two ballots (over the chunk maxima, then
+//                inside that chunk), reads the totals "everything before it granted" with two loads, resolves the
+//                short tail after the first refusal with warp scans, and updates the reservoir in integers.
+// finish_kernel  (parallel, one warp per block): replays the block from the reservoir the chain recorded and
+//                writes what the chain left out: grant masks, table ids, bits written, chunk sizes.
+// offsets_kernel (parallel, one warp per clip): chunk sizes -> byte offsets inside the clip's .pac.
 #include "mrc_internal.cuh"
 
 namespace {
 
 constexpr int MRC_CHAIN_STAGES = 4;
+constexpr unsigned INVALID_TOKEN = 0xffffffffu;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -43,9 +50,143 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  : "memory");
 }
 
+__device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ uint4 sub4(uint4 a, uint4 b) { return make_uint4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ uint4 redux4(uint4 a) {
+    return make_uint4(__reduce_add_sync(0xffffffffu, a.x), __reduce_add_sync(0xffffffffu, a.y),
+                      __reduce_add_sync(0xffffffffu, a.z), __reduce_add_sync(0xffffffffu, a.w));
+}
+
+// What one group (a joint block, or one channel of a non-joint block) comes to for budget B0 = k + reservoir.
+struct GroupTotals {
+    unsigned spent;     // bits spent, channel 0 | channel 1 << 16
+    uint4 cost;         // Huffman cost of the granted mantissas, {ch0 b0|b1<<16, ch0 b2|b3<<16, ch1 .., ch1 ..}
+    uint4 wbits;        // bits actually written (FULL only)
+};
+
+// The greedy allocation over the presorted grant tokens of chunks [k0, k0+nck) (bitalloc.py:131-149): a token is
+// granted iff its band's nLines <= bits left at its turn; the first grant of a band costs 2*nLines but checks only
+// nLines (Q5); bits left only decrease, so a refused band stays refused, which is the reference's exclusion.
+// All lanes return the same totals.  FULL also accumulates the written bits and the grant masks (lane k <-> chunk k).
+template <bool FULL>
+__device__ __forceinline__ GroupTotals walk_group(const uint32_t* tn, const uint32_t* cpre, const uint4* pc,
+                                                  const uint4* pw, const int32_t* mx, int k0, int nck, int B0,
+                                                  int min_nl, int lane, unsigned& gmask, unsigned& n_iter) {
+    GroupTotals g;
+    g.spent = 0u;
+    g.cost = make_uint4(0u, 0u, 0u, 0u);
+    g.wbits = make_uint4(0u, 0u, 0u, 0u);
+    if (B0 <= 0) return g;
+    // first refused token: the chunk from the running maxima, the lane from the stored prefix (no scan)
+    const int mxk = (lane < nck) ? mx[k0 + lane] : (int)0x80000000;
+    const unsigned fm = __ballot_sync(0xffffffffu, mxk > B0);
+    int k, f;
+    if (fm) {
+        k = __ffs(fm) - 1;
+        const int slot = (k0 + k) * 32 + lane;
+        const uint32_t t = tn[slot];
+        const uint32_t c = cpre[slot];
+        const int before = (int)((c & 0xffffu) + (c >> 16));
+        const unsigned f2 = __ballot_sync(0xffffffffu, t != INVALID_TOKEN && (int)(t >> 16) > B0 - before);
+        f = __ffs(f2) - 1;                           // f2 != 0: this chunk's maximum exceeded B0
+    } else {
+        k = nck - 1;                                 // everything granted: the group's last slot is never a token,
+        f = 31;                                      // so its prefix is the group total
+    }
+    const int jstar = (k0 + k) * 32 + f;
+    g.spent = cpre[jstar];
+    g.cost = pc[jstar];
+    if (FULL) {
+        g.wbits = pw[jstar];
+        if (lane >= k0 && lane < k0 + k) gmask = 0xffffffffu;
+        if (lane == k0 + k) gmask |= (1u << f) - 1u;
+    }
+    int rem = B0 - (int)((g.spent & 0xffffu) + (g.spent >> 16));
+    // tail: tokens after the first refusal that still fit (few: rem < nLines of the refused band)
+    unsigned active = ~((2u << f) - 1u);             // lanes after f
+    if (f == 31) { active = 0xffffffffu; ++k; }
+    unsigned a_spent = 0u;
+    uint4 a_cost = make_uint4(0u, 0u, 0u, 0u), a_w = make_uint4(0u, 0u, 0u, 0u);
+    bool any = false;
+    while (k < nck && rem >= min_nl) {
+        ++n_iter;
+        const int slot = (k0 + k) * 32 + lane;
+        const uint32_t t = tn[slot];
+        const int n = (int)(t >> 16);
+        const bool cand = t != INVALID_TOKEN && ((active >> lane) & 1u) && n <= rem;
+        const int cc = cand ? ((t & 0xff00u) ? n : 2 * n) : 0;      // level 0: 2 bits per line
+        int incl = cc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int excl = incl - cc;
+        const unsigned f2 = __ballot_sync(0xffffffffu, cand && n > rem - excl);
+        bool grant;
+        const int kk = k;
+        if (f2 == 0u) {
+            grant = cand;
+            rem -= __shfl_sync(0xffffffffu, incl, 31);
+            active = 0xffffffffu;
+            ++k;
+        } else {
+            const int ff = __ffs(f2) - 1;            // refused: that band is out from here on
+            grant = cand && lane < ff;
+            rem -= __shfl_sync(0xffffffffu, excl, ff);
+            if (ff == 31) { active = 0xffffffffu; ++k; }
+            else active &= ~((2u << ff) - 1u);       // resume this chunk after lane ff
+        }
+        if (FULL) {
+            const unsigned gb = __ballot_sync(0xffffffffu, grant);
+            if (lane == k0 + kk) gmask |= gb;
+        }
+        if (grant) {                                 // this token's own contribution = difference of the prefixes
+            any = true;
+            a_spent += cpre[slot + 1] - cpre[slot];
+            a_cost = add4(a_cost, sub4(pc[slot + 1], pc[slot]));
+            if (FULL) a_w = add4(a_w, sub4(pw[slot + 1], pw[slot]));
+        }
+    }
+    if (__any_sync(0xffffffffu, any)) {
+        g.spent += __reduce_add_sync(0xffffffffu, a_spent);
+        g.cost = add4(g.cost, redux4(a_cost));
+        if (FULL) g.wbits = add4(g.wbits, redux4(a_w));
+    }
+    return g;
+}
+
+// reservoir after the group: int(bitsLeft) truncates toward zero, then += bits_saved per channel
+__device__ __forceinline__ int reservoir_after(const GroupTotals& g, int B0, int fracpos, int no_huff, int* table,
+                                               int* wbits) {
+    const int left = B0 - (int)((g.spent & 0xffffu) + (g.spent >> 16));
+    int R = left >= 0 ? left : left + fracpos;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const int raw = (int)((g.spent >> (16 * ch)) & 0xffffu);
+        const unsigned c01 = ch ? g.cost.z : g.cost.x, c23 = ch ? g.cost.w : g.cost.y;
+        const int c[4] = {(int)(c01 & 0xffffu), (int)(c01 >> 16), (int)(c23 & 0xffffu), (int)(c23 >> 16)};
+        int best = raw, tb = MRC_NO_TABLE;
+        if (!no_huff) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (c[t] < best) { best = c[t]; tb = t; }
+        }
+        R += raw - best;
+        if (table) {
+            const unsigned w01 = ch ? g.wbits.z : g.wbits.x, w23 = ch ? g.wbits.w : g.wbits.y;
+            const int w[4] = {(int)(w01 & 0xffffu), (int)(w01 >> 16), (int)(w23 & 0xffffu), (int)(w23 >> 16)};
+            table[ch] = tb;
+            wbits[ch] = tb == MRC_NO_TABLE ? raw : w[tb];
+        }
+    }
+    return R;
+}
+
 __global__ void __launch_bounds__(32)
 chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_nl, ChainIO io,
-             const int32_t* __restrict__ reservoir_in, int32_t* __restrict__ reservoir_out) {
+             const int32_t* __restrict__ reservoir_in, int32_t* __restrict__ reservoir_out,
+             unsigned long long* __restrict__ iter_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[MRC_CHAIN_STAGES];
     const int lane = threadIdx.x;
@@ -53,8 +194,6 @@ chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_
     const int blk0 = cm.clip_blk0[clip], nblk_clip = cm.clip_blk0[clip + 1] - blk0;
     const int b_lo = max(blk0, g0) - blk0, b_hi = min(blk0 + nblk_clip, g0 + nblk_wave) - blk0;   // [b_lo, b_hi)
     if (b_hi <= b_lo) return;
-    const int nb = cp.nb;
-    const int band_hdr_bits = nb * (cp.n_mant_size_bits + cp.n_scale_bits);
 
     if (lane == 0) {
         for (int s = 0; s < MRC_CHAIN_STAGES; ++s) mbar_init(&s_bar[s], 1);
@@ -69,163 +208,154 @@ chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_
     if (lane == 0)
         for (int i = 0; i < MRC_CHAIN_STAGES && b_lo + i < b_hi; ++i) issue(b_lo + i, i);
 
-    int R;
-    long long running;
-    if (b_lo == 0) {
-        R = reservoir_in ? reservoir_in[clip] : 0;
-        running = cp.header_bytes;
-    } else {
-        R = io.clip_res[clip];
-        running = io.clip_run[clip];
-    }
+    int R = (b_lo == 0) ? (reservoir_in ? reservoir_in[clip] : 0) : io.clip_res[clip];
+    unsigned n_iter = 0, dummy = 0;
 
     for (int b = b_lo; b < b_hi; ++b) {
         const int it = b - b_lo, s = it % MRC_CHAIN_STAGES;
         mbar_wait(&s_bar[s], (unsigned)((it / MRC_CHAIN_STAGES) & 1));
         const unsigned char* st = smem_raw + (size_t)s * MRC_REC_BYTES;
         const uint32_t* tn = reinterpret_cast<const uint32_t*>(st + MRC_REC_TN);
-        const uint4* dd = reinterpret_cast<const uint4*>(st + MRC_REC_D);
-        const uint32_t* ck = reinterpret_cast<const uint32_t*>(st + MRC_REC_CK);
+        const uint32_t* cpre = reinterpret_cast<const uint32_t*>(st + MRC_REC_CP);
+        const uint4* pc = reinterpret_cast<const uint4*>(st + MRC_REC_PC);
         const int32_t* mx = reinterpret_cast<const int32_t*>(st + MRC_REC_MX);
-
         const bool joint = cp.joint && !(cp.flush_nonjoint && b == nblk_clip - 1);
-        const int ngroups = joint ? 1 : 2;
-        const int nck = joint ? MRC_NCHUNK : MRC_GROUP_CHUNKS;
-        unsigned gmask = 0u;                       // lane k: granted tokens of chunk k
-        int table[2] = {MRC_NO_TABLE, MRC_NO_TABLE}, wbits[2] = {0, 0};
-        for (int grp = 0; grp < ngroups; ++grp) {
-            const int k0 = grp * MRC_GROUP_CHUNKS;
-            double B;
-            if (joint) {
-                B = cp.budget_joint + (double)R;      // += bitReservoir
-                B -= 1.0;                             // -= blkswBitA
-                B -= 1.0;                             // -= blkswBitB
-            } else {
-                B = cp.budget_single + (double)R;     // blksw bits already subtracted, then += bitReservoir
-            }
-            unsigned acc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            int raw0 = 0, raw1 = 0;
-            if (B > 0.0) {
-                const int B0 = B >= 2147483647.0 ? 0x7fffffff : (int)floor(B);
-                const int mxk = (lane < nck) ? mx[k0 + lane] : (int)0x80000000;
-                const unsigned fm = __ballot_sync(0xffffffffu, mxk > B0);
-                const int ks = fm ? (__ffs(fm) - 1) : nck - 1;       // first chunk with a refusal (or the last chunk)
-                if (lane >= k0 && lane < k0 + ks) gmask = 0xffffffffu;
-                const uint32_t* c = ck + (k0 + ks) * MRC_CK_WORDS;
-                const int cr0 = (int)c[8], cr1 = (int)c[9];      // bits already spent by the chunks before ks
-                if (lane == 0) {                                 // checkpoint totals enter through lane 0
-                    const uint4 a = *reinterpret_cast<const uint4*>(c), b2 = *reinterpret_cast<const uint4*>(c + 4);
-                    acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w;
-                    acc[4] = b2.x; acc[5] = b2.y; acc[6] = b2.z; acc[7] = b2.w;
-                    raw0 = cr0; raw1 = cr1;
-                }
-                int rem = B0 - (cr0 + cr1);
-                int k = ks;
-                unsigned active = 0xffffffffu;
-                while (k < nck && rem >= min_nl) {
-                    const int slot = (k0 + k) * 32 + lane;
-                    const uint32_t t = tn[slot];
-                    const bool valid = t != 0xffffffffu;
-                    const int n = (int)(t >> 16), lvl = (int)((t >> 8) & 0xff), bb = (int)(t & 0xff);
-                    const bool cand = valid && ((active >> lane) & 1u) && n <= rem;
-                    const int cc = cand ? (lvl == 0 ? 2 * n : n) : 0;
-                    int incl = cc;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += v;
-                    }
-                    const int excl = incl - cc;
-                    const unsigned f2 = __ballot_sync(0xffffffffu, cand && n > rem - excl);
-                    bool grant;
-                    int kk = k;
-                    if (f2 == 0u) {
-                        grant = cand;
-                        rem -= __shfl_sync(0xffffffffu, incl, 31);
-                        active = 0xffffffffu;
-                        ++k;
-                    } else {
-                        const int f = __ffs(f2) - 1;              // first refusal: that band is out from here on
-                        grant = cand && lane < f;
-                        rem -= __shfl_sync(0xffffffffu, excl, f);
-                        if (f == 31) { active = 0xffffffffu; ++k; }
-                        else active &= ~((2u << f) - 1u);         // resume this chunk after lane f
-                    }
-                    const unsigned gb = __ballot_sync(0xffffffffu, grant);
-                    if (lane == k0 + kk) gmask |= gb;
-                    if (grant) {
-                        const uint4 d = dd[slot];
-                        const bool ch = bb >= nb;
-                        acc[0] += ch ? 0u : d.x; acc[1] += ch ? 0u : d.y; acc[2] += ch ? 0u : d.z; acc[3] += ch ? 0u : d.w;
-                        acc[4] += ch ? d.x : 0u; acc[5] += ch ? d.y : 0u; acc[6] += ch ? d.z : 0u; acc[7] += ch ? d.w : 0u;
-                        if (ch) raw1 += cc; else raw0 += cc;
-                    }
-                }
-            }
-            unsigned tot[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tot[i] = __reduce_add_sync(0xffffffffu, acc[i]);
-            const int r0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)raw0);
-            const int r1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)raw1);
-            const double left = B - (double)(r0 + r1);      // exact: both are integers-plus-a-fixed-fraction < 2^53
-            R = (int)left;                                  // int() truncates toward zero
-            const int ch_lo = joint ? 0 : grp, ch_hi = joint ? 2 : grp + 1;
-            for (int ch = ch_lo; ch < ch_hi; ++ch) {
-                const int raw = ch ? r1 : r0;
-                int best = raw, tb_ = MRC_NO_TABLE, bits = raw;
-                if (!cp.no_huff) {
-#pragma unroll
-                    for (int t = 0; t < MRC_N_HUFF_TABLES; ++t) {
-                        const int cost = (int)(tot[ch * 4 + t] & 0xffffu), wb = (int)(tot[ch * 4 + t] >> 16);
-                        if (cost < best) { best = cost; tb_ = t; bits = wb; }
-                    }
-                }
-                R += raw - best;                            // bitReservoir += bits_saved
-                table[ch] = tb_;
-                wbits[ch] = bits;
-            }
+        const int R0 = R;
+        int R1 = R;
+        if (joint) {
+            const int B0 = cp.k_joint + R;
+            const GroupTotals g = walk_group<false>(tn, cpre, pc, nullptr, mx, 0, MRC_NCHUNK, B0, min_nl, lane, dummy, n_iter);
+            R = reservoir_after(g, B0, cp.frac_joint, cp.no_huff, nullptr, nullptr);
+        } else {
+            int B0 = cp.k_single + R;
+            GroupTotals g = walk_group<false>(tn, cpre, pc, nullptr, mx, 0, MRC_GROUP_CHUNKS, B0, min_nl, lane, dummy, n_iter);
+            R = R1 = reservoir_after(g, B0, cp.frac_single, cp.no_huff, nullptr, nullptr);
+            B0 = cp.k_single + R;
+            g = walk_group<false>(tn, cpre, pc, nullptr, mx, MRC_GROUP_CHUNKS, MRC_GROUP_CHUNKS, B0, min_nl, lane, dummy, n_iter);
+            R = reservoir_after(g, B0, cp.frac_single, cp.no_huff, nullptr, nullptr);
         }
-        // ---- block outputs ----
-        const size_t lb = (size_t)(blk0 + b - g0);
-        io.gmask[lb * 32 + lane] = gmask;
-        if (lane == 0) {
-            ChainBlk o;
-            for (int ch = 0; ch < 2; ++ch) {
-                int bits = 4 + 1 + 1 + band_hdr_bits + wbits[ch];
-                if (joint) bits += (ch == 0) ? (4 * cp.n_scale_bits + nb) : 0;
-                else bits += cp.n_scale_bits;
-                const int nbytes = (bits + 7) >> 3;
-                o.chunk_off[ch] = running;
-                o.chunk_bytes[ch] = (unsigned)nbytes;
-                o.table[ch] = (unsigned char)table[ch];
-                running += 4 + nbytes;
-            }
-            o.reservoir = R;
-            o.pad[0] = o.pad[1] = 0;
-            io.cblk[lb] = o;
-        }
-        __syncwarp();
-        if (lane == 0 && b + MRC_CHAIN_STAGES < b_hi) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if (lane == 0) io.rsv[blk0 + b - g0] = make_int4(R0, R1, R, 0);
+        __syncwarp();                               // every lane is done reading stage s (generic-proxy reads need
+        if (lane == 0 && b + MRC_CHAIN_STAGES < b_hi)    // no proxy fence before the async-proxy overwrite)
             issue(b + MRC_CHAIN_STAGES, s);
-        }
     }
     if (lane == 0) {
+        if (iter_counter) atomicAdd(iter_counter, (unsigned long long)n_iter);
         io.clip_res[clip] = R;
-        io.clip_run[clip] = running;
-        if (b_hi == nblk_clip) {
-            io.clip_bytes[clip] = running;
-            if (reservoir_out) reservoir_out[clip] = R;
+        if (b_hi == nblk_clip && reservoir_out) reservoir_out[clip] = R;
+    }
+}
+
+constexpr int FIN_WARPS = 8;
+
+__global__ void __launch_bounds__(FIN_WARPS * 32)
+finish_kernel(CodecParams cp, ClipMap cm, int g0, int nblk, int min_nl, ChainIO io) {
+    const int lane = threadIdx.x & 31;
+    const int lb = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
+    if (lb >= nblk) return;
+    const int g = g0 + lb;
+    int lo = 0, hi = cm.n_clips;                     // clip of this block (every lane: uniform, cached loads)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cm.clip_blk0[mid] <= g) lo = mid; else hi = mid;
+    }
+    const bool joint = cp.joint && !(cp.flush_nonjoint && g == cm.clip_blk0[lo + 1] - 1);
+    const unsigned char* rec = io.rec + (size_t)lb * MRC_REC_BYTES;
+    const uint32_t* tn = reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN);
+    const uint32_t* cpre = reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP);
+    const uint4* pc = reinterpret_cast<const uint4*>(rec + MRC_REC_PC);
+    const int32_t* mx = reinterpret_cast<const int32_t*>(rec + MRC_REC_MX);
+    const uint4* pw = reinterpret_cast<const uint4*>(io.pw + (size_t)lb * MRC_PW_BYTES);
+    const int4 rs = io.rsv[lb];
+    unsigned gmask = 0u, n_iter = 0u;
+    int table[2] = {MRC_NO_TABLE, MRC_NO_TABLE}, wbits[2] = {0, 0};
+    if (joint) {
+        const int B0 = cp.k_joint + rs.x;
+        const GroupTotals gt = walk_group<true>(tn, cpre, pc, pw, mx, 0, MRC_NCHUNK, B0, min_nl, lane, gmask, n_iter);
+        reservoir_after(gt, B0, cp.frac_joint, cp.no_huff, table, wbits);
+    } else {
+        int t2[2], w2[2];
+        int B0 = cp.k_single + rs.x;
+        GroupTotals gt = walk_group<true>(tn, cpre, pc, pw, mx, 0, MRC_GROUP_CHUNKS, B0, min_nl, lane, gmask, n_iter);
+        reservoir_after(gt, B0, cp.frac_single, cp.no_huff, t2, w2);
+        table[0] = t2[0]; wbits[0] = w2[0];
+        B0 = cp.k_single + rs.y;
+        gt = walk_group<true>(tn, cpre, pc, pw, mx, MRC_GROUP_CHUNKS, MRC_GROUP_CHUNKS, B0, min_nl, lane, gmask, n_iter);
+        reservoir_after(gt, B0, cp.frac_single, cp.no_huff, t2, w2);
+        table[1] = t2[1]; wbits[1] = w2[1];
+    }
+    io.gmask[(size_t)lb * 32 + lane] = gmask;
+    if (lane == 0) {
+        const int nb = cp.nb;
+        ChainBlk o;
+        for (int ch = 0; ch < 2; ++ch) {
+            int bits = 4 + 1 + 1 + nb * (cp.n_mant_size_bits + cp.n_scale_bits) + wbits[ch];
+            if (joint) bits += (ch == 0) ? (4 * cp.n_scale_bits + nb) : 0;
+            else bits += cp.n_scale_bits;
+            o.chunk_off[ch] = 0;                     // filled by offsets_kernel
+            o.chunk_bytes[ch] = (unsigned)((bits + 7) >> 3);
+            o.table[ch] = (unsigned char)table[ch];
         }
+        o.reservoir = rs.z;
+        o.pad[0] = o.pad[1] = 0;
+        io.cblk[lb] = o;
+    }
+}
+
+// one warp per clip: running byte offset over the clip's blocks inside this wave (carried across waves in clip_run)
+__global__ void __launch_bounds__(32)
+offsets_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, ChainIO io) {
+    const int lane = threadIdx.x;
+    const int clip = c0 + blockIdx.x;
+    const int blk0 = cm.clip_blk0[clip], nblk_clip = cm.clip_blk0[clip + 1] - blk0;
+    const int b_lo = max(blk0, g0) - blk0, b_hi = min(blk0 + nblk_clip, g0 + nblk_wave) - blk0;
+    if (b_hi <= b_lo) return;
+    long long running = (b_lo == 0) ? (long long)cp.header_bytes : io.clip_run[clip];
+    for (int base = b_lo; base < b_hi; base += 32) {
+        const int b = base + lane;
+        const bool in = b < b_hi;
+        ChainBlk* cb = io.cblk + (blk0 + b - g0);
+        const unsigned s0 = in ? cb->chunk_bytes[0] : 0u, s1 = in ? cb->chunk_bytes[1] : 0u;
+        const long long sz = in ? (long long)(8u + s0 + s1) : 0ll;
+        long long incl = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (in) {
+            const long long off = running + incl - sz;
+            cb->chunk_off[0] = off;
+            cb->chunk_off[1] = off + 4 + s0;
+        }
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        io.clip_run[clip] = running;
+        if (b_hi == nblk_clip) io.clip_bytes[clip] = running;
     }
 }
 
 }  // namespace
 
 void launch_chain(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
-                  int min_nlines, ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out) {
+                  int min_nlines, ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out,
+                  unsigned long long* iter_counter) {
     if (nclips <= 0 || nblk <= 0) return;
     const size_t smem = (size_t)MRC_CHAIN_STAGES * MRC_REC_BYTES;
     cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    chain_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, min_nlines, io, reservoir_in, reservoir_out);
+    chain_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, min_nlines, io, reservoir_in, reservoir_out,
+                                           iter_counter);
+}
+
+void launch_finish(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int min_nlines,
+                   ChainIO io) {
+    if (nblk <= 0) return;
+    finish_kernel<<<(nblk + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, st>>>(cp, cm, g0, nblk, min_nlines, io);
+}
+
+void launch_offsets(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
+                    ChainIO io) {
+    if (nclips <= 0 || nblk <= 0) return;
+    offsets_kernel<<<nclips, 32, 0, st>>>(cp, cm, c0, g0, nblk, io);
 }

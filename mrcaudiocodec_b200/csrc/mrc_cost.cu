@@ -7,10 +7,10 @@
 // *stopping point* of the greedy loop depends on the reservoir: the order of the grants was fixed by the analysis
 // kernel (tokens).  So for every band and every possible allocation 2..16 this kernel quantises the band and
 // prices it under the four books (15 * 2L quantisations per block, integer-exact), and re-orders the result into
-// grant order as *deltas*: granting token j changes book t's cost of that channel by d_cost[j][t] and the bits
-// actually written by d_wbits[j][t] (they differ by quirk Q4: a mantissa equal to the escape value is priced at
-// the escape code's length but written as escape code + raw bits).  With exclusive prefix sums every 32 tokens
-// ("checkpoints") the chain kernel gets the totals for "all tokens before chunk k granted" in one load.
+// grant order as *prefix sums*: entry j holds, for "every token before j granted", the bits spent per channel, the
+// cost of each channel under each book, and the bits actually written (they differ from the cost by quirk Q4: a
+// mantissa equal to the escape value is priced at the escape code's length but written as escape code + raw
+// bits).  The chain kernel then reads every total at the first refused token with two loads.
 //
 // One CTA per block, 256 threads; thread <-> (band, level) pair, adjacent threads share a band (broadcast reads).
 #include "mrc_internal.cuh"
@@ -34,7 +34,7 @@ __device__ __forceinline__ unsigned long long splat16(unsigned v) {
 template <typename T>
 __global__ void __launch_bounds__(CT)
 cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, ClipMap cm, int g0, Handoff<T> ho,
-            unsigned char* __restrict__ rec) {
+            unsigned char* rec, unsigned char* pw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = tb.L, nb = tb.nb, nb2 = 2 * nb, npair = nb2 * MRC_MAX_LEVELS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -44,7 +44,7 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     __shared__ double s_bmax[2 * MRC_BSTRIDE];
     __shared__ uint16_t s_tok[MRC_TOK_STRIDE];
     __shared__ LutEntry s_lut[MRC_HUFF_LUT + 1];
-    __shared__ unsigned s_tot[MRC_NCHUNK][MRC_CK_WORDS];     // per chunk: acc[8], raw[2], bits total, local max
+    __shared__ unsigned s_tot[MRC_NCHUNK][10];     // per chunk: totals -> exclusive prefixes of the 9 words, local max
     __shared__ int s_joint;
     __shared__ int s_blo[MRC_BSTRIDE], s_bn[MRC_BSTRIDE];
     __shared__ unsigned long long s_esclen4;
@@ -109,12 +109,13 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     }
     __syncthreads();
 
-    // ---- phase 2: grant order, deltas, chunk totals -------------------------------------------------------
+    // ---- phase 2: grant order; per 32-token chunk: local exclusive prefix sums, totals, local maximum -------
     unsigned char* out = rec + lb * (size_t)MRC_REC_BYTES;
     uint32_t* o_tn = reinterpret_cast<uint32_t*>(out + MRC_REC_TN);
-    uint4* o_d = reinterpret_cast<uint4*>(out + MRC_REC_D);
-    uint32_t* o_ck = reinterpret_cast<uint32_t*>(out + MRC_REC_CK);
+    uint32_t* o_cp = reinterpret_cast<uint32_t*>(out + MRC_REC_CP);
+    uint4* o_pc = reinterpret_cast<uint4*>(out + MRC_REC_PC);
     int32_t* o_mx = reinterpret_cast<int32_t*>(out + MRC_REC_MX);
+    uint4* o_pw = reinterpret_cast<uint4*>(pw + lb * (size_t)MRC_PW_BYTES);
     const int per_group = nb * MRC_MAX_LEVELS;
     for (int k = warp; k < MRC_NCHUNK; k += CT / 32) {
         const int slot = k * 32 + lane;
@@ -125,76 +126,87 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
             if (i < per_group) src = grp * per_group + i;
         }
         uint32_t tn = 0xffffffffu;
-        uint4 d = make_uint4(0u, 0u, 0u, 0u);
-        unsigned acc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        int cost = 0, n = 0, raw0 = 0, raw1 = 0;
+        unsigned v[9] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // [0] bits (ch0 | ch1<<16), [1..4] cost, [5..8] written
+        int n = 0;
         const bool valid = src >= 0;
         if (valid) {
             const unsigned tok = s_tok[src];
             const int bb = tok & 0xff, lvl = tok >> 8;
             const int ch = bb >= nb, bd = bb - ch * nb;
             n = s_bn[bd];
-            cost = lvl == 0 ? 2 * n : n;
             tn = tok | ((uint32_t)n << 16);
+            v[0] = (unsigned)(lvl == 0 ? 2 * n : n) << (16 * ch);
             const int p = bb * MRC_MAX_LEVELS + lvl;
             const unsigned long long c1 = s_c4[p], w1 = s_w4[p];
             const unsigned long long c0 = lvl ? s_c4[p - 1] : 0ull, w0 = lvl ? s_w4[p - 1] : 0ull;
-            unsigned dv[4];
+            unsigned dc[4], dw[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const unsigned dc = (unsigned)((c1 >> (16 * t)) & 0xffff) - (unsigned)((c0 >> (16 * t)) & 0xffff);
-                const unsigned dw = (unsigned)((w1 >> (16 * t)) & 0xffff) - (unsigned)((w0 >> (16 * t)) & 0xffff);
-                dv[t] = dc + (dw << 16);                // = dc + 65536*dw (mod 2^32): sums decode while totals < 65536
-                acc[ch * 4 + t] = dv[t];
+                dc[t] = (unsigned)((c1 >> (16 * t)) & 0xffff) - (unsigned)((c0 >> (16 * t)) & 0xffff);
+                dw[t] = (unsigned)((w1 >> (16 * t)) & 0xffff) - (unsigned)((w0 >> (16 * t)) & 0xffff);
             }
-            d = make_uint4(dv[0], dv[1], dv[2], dv[3]);
-            if (ch) raw1 = cost; else raw0 = cost;
+            // two books per word: lo + 65536*hi (mod 2^32); a sum decodes field by field while every total < 65536
+            v[1 + 2 * ch] = dc[0] + (dc[1] << 16);
+            v[2 + 2 * ch] = dc[2] + (dc[3] << 16);
+            v[5 + 2 * ch] = dw[0] + (dw[1] << 16);
+            v[6 + 2 * ch] = dw[2] + (dw[3] << 16);
         }
-        o_tn[slot] = tn;
-        o_d[slot] = d;
-        int incl = cost;
+        unsigned inc[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) inc[i] = v[i];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, inc[i], o);
+                if (lane >= o) inc[i] += u;
+            }
         }
-        const int need = valid ? (incl - cost) + n : (int)0x80000000;     // bits spent before this token + nLines
+        o_tn[slot] = tn;
+        o_cp[slot] = inc[0] - v[0];                                       // chunk-local; offsets added in phase 3
+        o_pc[slot] = make_uint4(inc[1] - v[1], inc[2] - v[2], inc[3] - v[3], inc[4] - v[4]);
+        o_pw[slot] = make_uint4(inc[5] - v[5], inc[6] - v[6], inc[7] - v[7], inc[8] - v[8]);
+        const unsigned ex0 = inc[0] - v[0];
+        const int need = valid ? (int)((ex0 & 0xffffu) + (ex0 >> 16)) + n : (int)0x80000000;
         const int mxl = __reduce_max_sync(0xffffffffu, need);
-        unsigned tot[8];
+        if (lane == 31) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tot[i] = __reduce_add_sync(0xffffffffu, acc[i]);
-        const unsigned r0 = __reduce_add_sync(0xffffffffu, (unsigned)raw0);
-        const unsigned r1 = __reduce_add_sync(0xffffffffu, (unsigned)raw1);
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s_tot[k][i] = tot[i];
-            s_tot[k][8] = r0;
-            s_tot[k][9] = r1;
-            s_tot[k][10] = r0 + r1;
-            s_tot[k][11] = (unsigned)mxl;
+            for (int i = 0; i < 9; ++i) s_tot[k][i] = inc[i];
+            s_tot[k][9] = (unsigned)mxl;
         }
     }
     __syncthreads();
     // ---- phase 3: exclusive prefix over the chunks (restarting at the second group of a non-joint block) ---
-    if (tid < 10) {
+    if (tid < 9) {
         unsigned run = 0;
         for (int k = 0; k < MRC_NCHUNK; ++k) {
             if (k == MRC_GROUP_CHUNKS && !joint) run = 0;
-            o_ck[k * MRC_CK_WORDS + tid] = run;
-            run += s_tot[k][tid];
+            const unsigned t = s_tot[k][tid];
+            s_tot[k][tid] = run;
+            run += t;
         }
-    } else if (tid < 12) {
-        for (int k = 0; k < MRC_NCHUNK; ++k) o_ck[k * MRC_CK_WORDS + tid] = 0u;
-    } else if (tid == 32) {
-        int spent = 0, mx = (int)0x80000000;
+    }
+    __syncthreads();
+    if (tid == 32) {
+        int mx = (int)0x80000000;
         for (int k = 0; k < MRC_NCHUNK; ++k) {
-            if (k == MRC_GROUP_CHUNKS && !joint) { spent = 0; mx = (int)0x80000000; }
-            const int mxl = (int)s_tot[k][11];
-            if (mxl != (int)0x80000000) mx = max(mx, spent + mxl);
+            if (k == MRC_GROUP_CHUNKS && !joint) mx = (int)0x80000000;
+            const int mxl = (int)s_tot[k][9];
+            const unsigned sp = s_tot[k][0];
+            if (mxl != (int)0x80000000) mx = max(mx, (int)((sp & 0xffffu) + (sp >> 16)) + mxl);
             o_mx[k] = mx;
-            spent += (int)s_tot[k][10];
         }
         for (int k = MRC_NCHUNK; k < 32; ++k) o_mx[k] = 0x7fffffff;
+    }
+    for (int k = warp; k < MRC_NCHUNK; k += CT / 32) {      // same thread re-reads what it wrote above
+        const int slot = k * 32 + lane;
+        o_cp[slot] += s_tot[k][0];
+        uint4 a = o_pc[slot];
+        a.x += s_tot[k][1]; a.y += s_tot[k][2]; a.z += s_tot[k][3]; a.w += s_tot[k][4];
+        o_pc[slot] = a;
+        uint4 w = o_pw[slot];
+        w.x += s_tot[k][5]; w.y += s_tot[k][6]; w.z += s_tot[k][7]; w.w += s_tot[k][8];
+        o_pw[slot] = w;
     }
 }
 
@@ -202,14 +214,14 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
 
 template <typename T>
 void launch_cost(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
-                 const ClipMap& cm, int g0, int nblk, Handoff<T> ho, unsigned char* rec) {
+                 const ClipMap& cm, int g0, int nblk, Handoff<T> ho, unsigned char* rec, unsigned char* pw) {
     if (nblk <= 0) return;
     const size_t smem = (size_t)2 * tb.L * sizeof(double) + 2 * MRC_NSLOT * sizeof(unsigned long long);
     cudaFuncSetAttribute(cost_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cost_kernel<T><<<nblk, CT, smem, st>>>(tb, cp, huff, cm, g0, ho, rec);
+    cost_kernel<T><<<nblk, CT, smem, st>>>(tb, cp, huff, cm, g0, ho, rec, pw);
 }
 
 template void launch_cost<double>(cudaStream_t, const DevTables<double>&, const CodecParams&, const HuffDev*,
-                                  const ClipMap&, int, int, Handoff<double>, unsigned char*);
+                                  const ClipMap&, int, int, Handoff<double>, unsigned char*, unsigned char*);
 template void launch_cost<float>(cudaStream_t, const DevTables<float>&, const CodecParams&, const HuffDev*,
-                                 const ClipMap&, int, int, Handoff<float>, unsigned char*);
+                                 const ClipMap&, int, int, Handoff<float>, unsigned char*, unsigned char*);

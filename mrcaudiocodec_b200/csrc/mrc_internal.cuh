@@ -31,12 +31,15 @@
 #define MRC_GROUP_SLOTS 384
 #define MRC_NCHUNK (MRC_NSLOT / 32)
 #define MRC_GROUP_CHUNKS (MRC_GROUP_SLOTS / 32)
-#define MRC_CK_WORDS 12         // per chunk: acc[2 channels][4 books] (cost | wbits<<16, mod 2^32), raw bits[2], pad[2]
 #define MRC_REC_TN 0                                   // u32 [768]   token (band | level<<8) | nLines<<16
-#define MRC_REC_D (MRC_NSLOT * 4)                      // uint4 [768] per book: d(cost) + 65536*d(bits written)
-#define MRC_REC_CK (MRC_REC_D + MRC_NSLOT * 16)        // u32 [24][12] exclusive prefix at the start of each chunk
-#define MRC_REC_MX (MRC_REC_CK + MRC_NCHUNK * MRC_CK_WORDS * 4)   // i32 [32] running max of (prefix bits + nLines)
-#define MRC_REC_BYTES (MRC_REC_MX + 32 * 4)            // 16640, a multiple of 16
+#define MRC_REC_CP (MRC_NSLOT * 4)                     // u32 [768]   bits spent if every earlier token of the group is
+                                                       //             granted: channel 0 | channel 1 << 16
+#define MRC_REC_PC (MRC_REC_CP + MRC_NSLOT * 4)        // uint4 [768] Huffman cost of the four books under the same
+                                                       //             assumption: {ch0 b0|b1<<16, ch0 b2|b3<<16, ch1 .., ch1 ..}
+                                                       //             (sums of 16-bit fields carried mod 2^32)
+#define MRC_REC_MX (MRC_REC_PC + MRC_NSLOT * 16)       // i32 [32]    per 32-token chunk: running max of (bits spent + nLines)
+#define MRC_REC_BYTES (MRC_REC_MX + 32 * 4)            // 18560, a multiple of 16
+#define MRC_PW_BYTES (MRC_NSLOT * 16)                  // uint4 [768] like MRC_REC_PC for the bits actually written (Q4)
 
 struct ChainBlk {                // what the chain kernel decides per block (32 bytes)
     long long chunk_off[2];      // byte offset of each channel chunk (its <L prefix) inside the clip's .pac
@@ -100,6 +103,8 @@ struct AnalysisTaps {            // all nullable
 
 struct ChainIO {
     const unsigned char* rec;    // [nblk][MRC_REC_BYTES]   (wave-local)
+    const unsigned char* pw;     // [nblk][MRC_PW_BYTES]    (wave-local)
+    int4* rsv;                   // [nblk] reservoir before group 0, before group 1, after the block, - (wave-local)
     uint32_t* gmask;             // [nblk][32]              (wave-local)
     ChainBlk* cblk;              // [nblk]                  (wave-local)
     int32_t* clip_res;           // [n_clips] reservoir carried from wave to wave
@@ -120,6 +125,9 @@ struct CodecParams {
     int spread_seq;              // 1: masker spreading summed pair by pair in the reference's order (psychoac.py:168)
     double budget_joint;         // value of bitBudget just before `+= bitReservoir` (codecThem.py:381-391)
     double budget_single;        // value of bitBudget just before `+= bitReservoir` (codecThem.py:299-306)
+    // the same budgets as integers: bitBudget = k + frac + bitReservoir with 0 <= frac < 1 (the blksw bits of the
+    // joint path, subtracted after the reservoir is added, are folded into k_joint); frac_* = (frac > 0)
+    int k_joint, k_single, frac_joint, frac_single;
     int header_bytes;            // .pac file header size
 };
 
@@ -129,14 +137,22 @@ void launch_analysis(cudaStream_t st, const DevTables<T>& tb, const CodecParams&
                      const int16_t* pcm, const double* xin, int g0, int nblk, Handoff<T> ho, AnalysisTaps<T> taps,
                      unsigned long long* peak_counter);
 
-// cost of every (band, level) under the four books, re-ordered into grant order with chunk checkpoints
+// cost of every (band, level) under the four books, re-ordered into grant order as prefix sums
 template <typename T>
 void launch_cost(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
-                 const ClipMap& cm, int g0, int nblk, Handoff<T> ho, unsigned char* rec);
+                 const ClipMap& cm, int g0, int nblk, Handoff<T> ho, unsigned char* rec, unsigned char* pw);
 
-// one warp per clip c0 .. c0+nclips-1 walks the clip's blocks that lie in [g0, g0+nblk)
+// serial: one warp per clip c0 .. c0+nclips-1 walks the clip's blocks that lie in [g0, g0+nblk) and records the
+// reservoir each block starts with
 void launch_chain(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
-                  int min_nlines, ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out);
+                  int min_nlines, ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out,
+                  unsigned long long* iter_counter);
+// parallel: one warp per block replays the block from its recorded reservoir: grant masks, table ids, chunk sizes
+void launch_finish(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int min_nlines,
+                   ChainIO io);
+// parallel: one warp per clip turns the chunk sizes into byte offsets inside the clip's .pac
+void launch_offsets(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
+                    ChainIO io);
 
 template <typename T>
 void launch_pack(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
