@@ -1,0 +1,81 @@
+"""world_size-2 test of the multi-GPU bookkeeping on CPU (gloo): sharding of a clip batch and the one collective of the
+path, the all-gather of per-clip bitstream lengths -> global byte offsets (mrcaudiocodec_b200/dist.py).  The encoder is
+replaced by a stand-in that returns deterministic byte strings, because the product encoder needs a GPU; what is under
+test is the host logic around it.  The same functions run over NCCL in bench.py / on the GPU box."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _FakeCodec(object):
+    """stands in for Codec.encode_clips: clip -> bytes whose length and content depend only on the clip"""
+
+    def encode_clips(self, clips):
+        out = []
+        for c in clips:
+            n = 76 + 3 * int(c.shape[0] % 1000) + int(c[0, 0]) % 7
+            out.append(bytes([int(c[0, 0]) % 251]) * n)
+        return out
+
+
+def _make_clips(n):
+    rng = np.random.default_rng(7)
+    return [rng.integers(-3000, 3000, size=(int(rng.integers(1, 5000)), 2)).astype(np.int16) for _ in range(n)]
+
+
+def _worker(rank, world, port, n_clips, tmp):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from mrcaudiocodec_b200 import dist as mdist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    clips = _make_clips(n_clips)
+    lo, hi = mdist.shard_range(n_clips, rank, world)
+    blobs, offsets = mdist.encode_sharded(_FakeCodec(), clips[lo:hi], n_clips)
+    path = os.path.join(tmp, "all.pac")
+    if rank == 0:
+        with open(path, "wb") as fh:
+            fh.truncate(int(offsets[-1]))
+    dist.barrier()
+    mdist.write_concatenated(path, blobs, offsets, rank, world)
+    dist.barrier()
+    np.save(os.path.join(tmp, "off%d.npy" % rank), offsets)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_clips", [7, 2, 1])
+def test_sharded_encode_bookkeeping_world2(tmp_path, n_clips):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n_clips, str(tmp_path)), nprocs=2, join=True)
+    ref = _FakeCodec().encode_clips(_make_clips(n_clips))
+    want = b"".join(ref)
+    got = open(os.path.join(str(tmp_path), "all.pac"), "rb").read()
+    assert got == want
+    o0 = np.load(os.path.join(str(tmp_path), "off0.npy"))
+    o1 = np.load(os.path.join(str(tmp_path), "off1.npy"))
+    assert np.array_equal(o0, o1)
+    assert np.array_equal(np.diff(o0), [len(b) for b in ref])
+
+
+def test_shard_range_partitions():
+    from mrcaudiocodec_b200 import dist as mdist
+    for n in (0, 1, 5, 8, 4096, 4097):
+        for w in (1, 2, 3, 4, 8):
+            r = [mdist.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1

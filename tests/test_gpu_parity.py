@@ -139,6 +139,24 @@ def test_ragged_batch_and_edge_clips(codecs):
             assert np.abs(d.astype(np.int64) - od.astype(np.int64)).max() <= 1, "clip %d" % i
 
 
+def test_sharded_batch_equals_single_context(codecs):
+    """multi-GPU sharding (mrcaudiocodec_b200/dist.py) emulated in one process: three 'ranks' encode their
+    contiguous clip ranges with their own contexts; bytes and global offsets equal the single-context batch."""
+    from mrcaudiocodec_b200 import Codec, synth, dist as mdist
+    clips = [synth.synth_short(60 + i, 0.1 + 0.05 * (i % 4)) for i in range(10)]
+    whole = codecs(48000, True).encode_clips(clips)
+    world = 3
+    sizes = []
+    for r in range(world):
+        lo, hi = mdist.shard_range(len(clips), r, world)
+        c = Codec()
+        blobs = c.encode_clips(clips[lo:hi])
+        c.close()
+        assert blobs == whole[lo:hi], r
+        sizes += [len(b) for b in blobs]
+    assert sizes == [len(b) for b in whole]
+
+
 def test_reference_seam_drop_in(golden):
     """The reference-style PACFile loop of the oracle, with its `codec` module swapped for codec_gpu
     (the monkey-patch INTEGRATION.md describes), writes the reference's bytes."""
