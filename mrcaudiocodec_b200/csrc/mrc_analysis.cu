@@ -21,6 +21,8 @@
 
 namespace {
 
+constexpr int MRC_NEAR_LOUD = 4;     // loud maskers included in the pass-1 bound of a line's threshold
+
 template <typename T>
 struct Smem {
     T* sx;          // [2][2L]  time samples L, R
@@ -32,8 +34,9 @@ struct Smem {
     double* ms15;   // [Q]      SPL - 15
     double* mg;     // [Q]      0.37*max(SPL-40,0)
     double* mc;     // [Q]      10^((SPL-15-96)/10): intensity inside +-0.5 Bark
-    double* mU;     // [Q+1]    quiet maskers at or below i, decayed to z_i (upper slope, -27 dB/Bark)
-    double* mS;     // [Q+1]    maskers at or above i, decayed to z_i (lower slope, -27 dB/Bark)
+    double* mU;     // [Q]      quiet maskers at or below i, decayed to z_i (upper slope, -27 dB/Bark)
+    double* mS;     // [Q]      maskers at or above i, decayed to z_i (lower slope, -27 dB/Bark); [npk] = 0
+    double* mP;     // [Q]      sum of mc below i ([npk] = total); only for the pass-1 bound (npk < Q always)
     int* pbin;      // [Q]
     int* lcnt;      // [Q+1]    number of loud maskers (g > 0) below index i
     uint16_t* lidx; // [Q]      their indices, ascending
@@ -56,15 +59,16 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     s.ms15 = d;          d += Q;
     s.mg = d;            d += Q;
     s.etab = d;          d += 64;
-    // mc, mU, mS (3Q+2 doubles) and, after the last spectrum, the sort keys (10 KB) share one region: the FFT
-    // work buffer when it is large enough (it is idle while maskers are spread), else a region of their own.
-    const size_t need = (size_t)((3 * Q + 2 > 1280) ? 3 * Q + 2 : 1280) * 8;
+    // mc, mU, mS, mP (4Q doubles) and, after the last spectrum, the grant-order tables (10 KB) share one region:
+    // the FFT work buffer when it is large enough (it is idle while maskers are spread), else a region of their own.
+    const size_t need = (size_t)((4 * Q > 1280) ? 4 * Q : 1280) * 8;
     double* r;
     if ((size_t)(2 * L) * sizeof(T) >= need) r = reinterpret_cast<double*>(s.buf);
     else { r = d; d += need / 8; }
     s.mc = r;
     s.mU = r + Q;
-    s.mS = r + 2 * Q + 1;
+    s.mS = r + 2 * Q;
+    s.mP = r + 3 * Q;
     s.skey = reinterpret_cast<T*>(r);
     s.sid = reinterpret_cast<uint16_t*>(r + 1024);
     int* ip = reinterpret_cast<int*>(d);
@@ -118,6 +122,41 @@ __device__ __forceinline__ T tsample(const T* sx, int N, int c, int n) {
     return (l - r) / T(2);
 }
 
+// position of line k among the maskers: m_lo = number of maskers with dz > 0.5 (a prefix: z_m ascends),
+// m_hi = first masker with dz < -0.5, dz = z_k - z_m as the reference computes it
+template <typename T>
+__device__ __forceinline__ void masker_range(const Smem<T>& sm, double zk, int npk, int& m_lo, int& m_hi) {
+    int lo = 0, hi = npk;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (zk - sm.mz[mid] > 0.5) lo = mid + 1; else hi = mid;
+    }
+    m_lo = lo;
+    hi = npk;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (zk - sm.mz[mid] < -0.5) hi = mid; else lo = mid + 1;
+    }
+    m_hi = lo;
+}
+
+// one loud masker (index m) onto a line more than 0.5 Bark above it: the reference's exponent, unfused
+template <typename T>
+__device__ __forceinline__ double loud_term(const Smem<T>& sm, double zk, int m) {
+    const double t = __dadd_rn(__dadd_rn(zk, -sm.mz[m]), -0.5);
+    const double e = __dadd_rn(__dadd_rn(sm.ms15[m], __dmul_rn(-27.0, t)), __dmul_rn(sm.mg[m], t));
+    return exp10_tab(div10(__dadd_rn(e, -96.0)), sm.etab);
+}
+
+// the two geometric tails at line k
+template <typename T>
+__device__ __forceinline__ double tail_terms(const Smem<T>& sm, double zk, int npk, int m_lo, int m_hi) {
+    double a = 0.0;
+    if (m_lo > 0) a += sm.mU[m_lo - 1] * exp10_tab(-2.7 * ((zk - sm.mz[m_lo - 1]) - 0.5), sm.etab);
+    if (m_hi < npk) a += sm.mS[m_hi] * exp10_tab(-2.7 * ((sm.mz[m_hi] - zk) - 0.5), sm.etab);
+    return a;
+}
+
 // Masked threshold intensity at MDCT line k from the factorised masker tables (same mathematics as
 // psychoac.py:68-78 summed over all maskers, re-associated):
 //   maskers more than 0.5 Bark below the line   quiet ones (g = 0): one geometric tail U, decayed from the nearest
@@ -125,48 +164,45 @@ __device__ __forceinline__ T tsample(const T* sx, int N, int c, int n) {
 //   maskers within +-0.5 Bark                   their plateau intensities, summed directly
 //   maskers more than 0.5 Bark above the line   one geometric tail S, decayed from the nearest
 // The region of every (masker, line) pair is decided by the reference's own comparisons on dz = z_k - z_m.
+//
+// spread_line_bound: a LOWER bound of that threshold, cheap enough for every line: only the MRC_NEAR_LOUD nearest
+// loud maskers, and the plateau sum as a difference of prefix sums minus its worst-case rounding error.
 template <typename T>
-__device__ __forceinline__ double spread_line(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk,
-                                              unsigned& n_general, unsigned& n_window) {
+__device__ __forceinline__ double spread_line_bound(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk,
+                                                    unsigned& n_general) {
     const double zk = tb.bark_d[k];
-    double a = tb.quiet_d[k];
-    // m_lo = number of maskers with dz > 0.5 (a prefix: z_m ascends); m_hi = first masker with dz < -0.5
-    int lo = 0, hi = npk;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (zk - sm.mz[mid] > 0.5) lo = mid + 1; else hi = mid;
-    }
-    const int m_lo = lo;
-    hi = npk;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (zk - sm.mz[mid] < -0.5) hi = mid; else lo = mid + 1;
-    }
-    const int m_hi = lo;
-    if (m_lo > 0) a += sm.mU[m_lo - 1] * exp10(-2.7 * ((zk - sm.mz[m_lo - 1]) - 0.5));
+    int m_lo, m_hi;
+    masker_range(sm, zk, npk, m_lo, m_hi);
+    double a = tb.quiet_d[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
     const int nl = sm.lcnt[m_lo];
-    for (int j = 0; j < nl; ++j) {
-        const int m = sm.lidx[j];
-        const double t = __dadd_rn(__dadd_rn(zk, -sm.mz[m]), -0.5);
-        const double e = __dadd_rn(__dadd_rn(sm.ms15[m], __dmul_rn(-27.0, t)), __dmul_rn(sm.mg[m], t));
-        a += exp10_tab(div10(__dadd_rn(e, -96.0)), sm.etab);
-    }
-    {   // plateau intensities of the maskers within +-0.5 Bark: four running sums (the chain of dependent adds
-        // is what this loop waits for), combined pairwise at the end
-        double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
-        int m = m_lo;
-        for (; m + 4 <= m_hi; m += 4) { w0 += sm.mc[m]; w1 += sm.mc[m + 1]; w2 += sm.mc[m + 2]; w3 += sm.mc[m + 3]; }
-        for (; m < m_hi; ++m) w0 += sm.mc[m];
-        a += (w0 + w1) + (w2 + w3);
-    }
-    n_general += (unsigned)nl;
-    n_window += (unsigned)(m_hi - m_lo);
-    if (m_hi < npk) a += sm.mS[m_hi] * exp10(-2.7 * ((sm.mz[m_hi] - zk) - 0.5));
+    const int j0 = nl > MRC_NEAR_LOUD ? nl - MRC_NEAR_LOUD : 0;
+    for (int j = nl - 1; j >= j0; --j) a += loud_term(sm, zk, sm.lidx[j]);
+    n_general += (unsigned)(nl - j0);
+    const double w = (sm.mP[m_hi] - sm.mP[m_lo]) - 1.4210854715202004e-14 * sm.mP[npk];     // 2^-46 of the total
+    return a + fmax(w, 0.0);
+}
+
+// The same threshold, complete, evaluated by a whole warp: lanes stride over the plateau maskers and the loud
+// maskers, lane 0 adds the threshold in quiet and the two tails, then a butterfly sum.  All lanes return it.
+template <typename T>
+__device__ __forceinline__ double spread_line_warp(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk, int lane,
+                                                   unsigned& n_general, unsigned& n_window) {
+    const double zk = tb.bark_d[k];
+    int m_lo, m_hi;
+    masker_range(sm, zk, npk, m_lo, m_hi);
+    double a = 0.0;
+    if (lane == 0) a = tb.quiet_d[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
+    for (int m = m_lo + lane; m < m_hi; m += 32) a += sm.mc[m];
+    const int nl = sm.lcnt[m_lo];
+    for (int j = lane; j < nl; j += 32) a += loud_term(sm, zk, sm.lidx[j]);
+    if (lane == 0) { n_general += (unsigned)nl; n_window += (unsigned)(m_hi - m_lo); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     return a;
 }
 
 template <typename T, int LOGL>
-__global__ void __launch_bounds__(1 << (LOGL - 1))
+__global__ void __launch_bounds__(1 << (LOGL - 1), (LOGL <= 10) ? 2 : 1)
 analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __restrict__ pcm,
                 const double* __restrict__ xin, int g0, Handoff<T> ho, AnalysisTaps<T> taps,
                 unsigned long long* peak_counter) {
@@ -182,7 +218,9 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ int s_scale[4];
     __shared__ unsigned int s_ms;
     __shared__ int s_wcnt[33];
-    __shared__ double s_scan[4][32];
+    __shared__ double s_scan[5][32];
+    __shared__ T s_seg_smr[MRC_MAX_SEGS], s_seg_rho[MRC_MAX_SEGS];
+    __shared__ int s_seg_k[MRC_MAX_SEGS];
     __shared__ int s_npk;
 
     if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
@@ -410,6 +448,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 //                                        S_i = c_i  + rS_i * S_{i+1}  (descending, all maskers)
                 // The descending one runs on the mirrored index j = npk-1-i, held by thread j.
                 double aU = rU, bU = (i < npk && !loud) ? cmid : 0.0;
+                double pP = (i < npk) ? cmid : 0.0;          // plain running sum of the plateau intensities
                 // mirrored element for S: thread tid holds masker im = npk-1-tid
                 const int im = npk - 1 - tid;
                 double aS = 0.0, bS = 0.0;
@@ -422,72 +461,153 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 for (int o = 1; o < 32; o <<= 1) {
                     const double alU = __shfl_up_sync(0xffffffffu, aU, o), blU = __shfl_up_sync(0xffffffffu, bU, o);
                     const double alS = __shfl_up_sync(0xffffffffu, aS, o), blS = __shfl_up_sync(0xffffffffu, bS, o);
+                    const double plP = __shfl_up_sync(0xffffffffu, pP, o);
                     if (lane >= o) {
                         bU = fma(aU, blU, bU); aU = aU * alU;
                         bS = fma(aS, blS, bS); aS = aS * alS;
+                        pP += plP;
                     }
                 }
-                if (lane == 31) { s_scan[0][warp] = aU; s_scan[1][warp] = bU; s_scan[2][warp] = aS; s_scan[3][warp] = bS; }
+                if (lane == 31) {
+                    s_scan[0][warp] = aU; s_scan[1][warp] = bU; s_scan[2][warp] = aS; s_scan[3][warp] = bS;
+                    s_scan[4][warp] = pP;
+                }
                 __syncthreads();
                 if (warp == 0) {
                     double a1 = (lane < nwarp) ? s_scan[0][lane] : 1.0, b1 = (lane < nwarp) ? s_scan[1][lane] : 0.0;
                     double a2 = (lane < nwarp) ? s_scan[2][lane] : 1.0, b2 = (lane < nwarp) ? s_scan[3][lane] : 0.0;
+                    double p3 = (lane < nwarp) ? s_scan[4][lane] : 0.0;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const double al1 = __shfl_up_sync(0xffffffffu, a1, o), bl1 = __shfl_up_sync(0xffffffffu, b1, o);
                         const double al2 = __shfl_up_sync(0xffffffffu, a2, o), bl2 = __shfl_up_sync(0xffffffffu, b2, o);
+                        const double pl3 = __shfl_up_sync(0xffffffffu, p3, o);
                         if (lane >= o) {
                             b1 = fma(a1, bl1, b1); a1 = a1 * al1;
                             b2 = fma(a2, bl2, b2); a2 = a2 * al2;
+                            p3 += pl3;
                         }
                     }
-                    if (lane < nwarp) { s_scan[1][lane] = b1; s_scan[3][lane] = b2; }
+                    if (lane < nwarp) { s_scan[1][lane] = b1; s_scan[3][lane] = b2; s_scan[4][lane] = p3; }
                 }
                 __syncthreads();
                 if (warp > 0) {                      // value carried in from the warps before
                     bU = fma(aU, s_scan[1][warp - 1], bU);
                     bS = fma(aS, s_scan[3][warp - 1], bS);
+                    pP += s_scan[4][warp - 1];
                 }
                 if (i < npk) sm.mU[i] = bU;
                 if (im >= 0) sm.mS[im] = bS;
-                if (tid == 0) { sm.mS[npk] = 0.0; }
+                if (tid == 0) { sm.mS[npk] = 0.0; sm.mP[0] = 0.0; }
+                if (i < npk) sm.mP[i + 1] = pP;          // inclusive sum up to i = sum below i+1
             }
         }
         __syncthreads();
-        // e. masked threshold at the MDCT lines: thread owns lines tid and tid+Q
-        {
+        // e. masked threshold at the MDCT lines, f. SMR per line (psychoac.py:212-214), band maxima (:215-219)
+        const T sc6 = T(6) * T(s_scale[c]);
+        auto line_spl = [&](int k) -> T {           // SPL of the (scaled) MDCT line, scale undone
+            const T X = sm.lines[c * L + k];
+            return fmax(T(96) + T(10) * m_log10((T(2) * (X * X)) / T(0.5)), T(-30)) - sc6;
+        };
+        auto thr_of = [&](double a) -> T { return fmax(T(96) + T(10) * m_log10(T(a)), T(-30)); };
+        if (cp.spread_seq) {
+            // reference order (psychoac.py:68-78, :168): every masker onto every line, one 10**x per pair
             const int k0 = tid, k1 = tid + Q;
-            double a0, a1;
-            if (cp.spread_seq) {
-                // reference order (psychoac.py:68-78, :168): every masker onto every line, one 10**x per pair
-                const double z0 = tb.bark_d[k0], z1 = tb.bark_d[k1];
-                a0 = tb.quiet_d[k0]; a1 = tb.quiet_d[k1];
-                for (int m = 0; m < npk; ++m) {
-                    const double zm = sm.mz[m], s15 = sm.ms15[m], gg = sm.mg[m];
-                    a0 += masker_intensity(z0 - zm, s15, gg);
-                    a1 += masker_intensity(z1 - zm, s15, gg);
-                }
-            } else {
-                a0 = spread_line(sm, tb, k0, npk, n_general, n_window);
-                a1 = spread_line(sm, tb, k1, npk, n_general, n_window);
+            const double z0 = tb.bark_d[k0], z1 = tb.bark_d[k1];
+            double a0 = tb.quiet_d[k0], a1 = tb.quiet_d[k1];
+            for (int m = 0; m < npk; ++m) {
+                const double zm = sm.mz[m], s15 = sm.ms15[m], gg = sm.mg[m];
+                a0 += masker_intensity(z0 - zm, s15, gg);
+                a1 += masker_intensity(z1 - zm, s15, gg);
             }
-            // f. SMR per line (psychoac.py:212-214)
-            const T sc6 = T(6) * T(s_scale[c]);
-            const T X0 = sm.lines[c * L + k0], X1 = sm.lines[c * L + k1];
-            const T thr0 = fmax(T(96) + T(10) * m_log10(T(a0)), T(-30));
-            const T thr1 = fmax(T(96) + T(10) * m_log10(T(a1)), T(-30));
-            const T sp0 = fmax(T(96) + T(10) * m_log10((T(2) * (X0 * X0)) / T(0.5)), T(-30)) - sc6;
-            const T sp1 = fmax(T(96) + T(10) * m_log10((T(2) * (X1 * X1)) / T(0.5)), T(-30)) - sc6;
-            sm.xi[k0] = sp0 - thr0;
-            sm.xi[k1] = sp1 - thr1;
-        }
-        __syncthreads();
-        for (int bd = warp; bd < nb; bd += nwarp) {
-            const int lo = tb.band_lo[bd], n = tb.band_n[bd];
-            T v = -INFINITY;
-            for (int i = lane; i < n; i += 32) v = fmax(v, sm.xi[lo + i]);
-            v = warp_max(v);
-            if (lane == 0) s_smr[c][bd] = v;
+            sm.xi[k0] = line_spl(k0) - thr_of(a0);
+            sm.xi[k1] = line_spl(k1) - thr_of(a1);
+            __syncthreads();
+            for (int bd = warp; bd < nb; bd += nwarp) {
+                const int lo = tb.band_lo[bd], n = tb.band_n[bd];
+                T v = -INFINITY;
+                for (int i = lane; i < n; i += 32) v = fmax(v, sm.xi[lo + i]);
+                v = warp_max(v);
+                if (lane == 0) s_smr[c][bd] = v;
+            }
+        } else {
+            // The band SMR is a maximum over lines, so only lines that can be the maximum need their complete
+            // threshold.  With both clamps of psychoac.py:12 folded in, a line's SMR is 10 log10(rho) - 6 scale,
+            // rho = max(4 X^2, floor) / max(threshold intensity, floor): monotone in rho.
+            //   pass 1 (thread per line): rho from a LOWER bound of the threshold = an upper bound of the line's rho;
+            //   pass 2a (warp per segment of <= 64 lines of one band): complete threshold (warp-cooperative) of the
+            //           segment's line with the highest bound -> its true rho and SMR;
+            //   pass 2b: every other line whose bound reaches the band's best true rho so far (less 1e-9) gets its
+            //           complete threshold too; lines whose bound stays below cannot be the maximum.
+            // The band SMR is the maximum of the completely evaluated lines' SMRs: exact.
+            const double FLOOR = 2.5118864315095823e-13;        // 10^((-30-96)/10): where SPL() clamps
+            auto x2c = [&](int k) -> double {
+                const double X = (double)sm.lines[c * L + k];
+                return fmax((2.0 * (X * X)) / 0.5, FLOOR);
+            };
+            {
+                const int k0 = tid, k1 = tid + Q;
+                const double a0 = spread_line_bound(sm, tb, k0, npk, n_general);
+                const double a1 = spread_line_bound(sm, tb, k1, npk, n_general);
+                sm.xi[k0] = T(x2c(k0) / fmax(a0, FLOOR));
+                sm.xi[k1] = T(x2c(k1) / fmax(a1, FLOOR));
+            }
+            __syncthreads();
+            const T slack = sizeof(T) == 8 ? T(1.0 - 1e-9) : T(1.0 - 1e-4);   // bound vs true value: rounding only
+            auto complete = [&](int k, T& smr, T& rho) {         // whole warp; all lanes get the results
+                const double a = spread_line_warp(sm, tb, k, npk, lane, n_general, n_window);
+                smr = line_spl(k) - thr_of(a);
+                rho = T(x2c(k) / fmax(a, FLOOR));
+            };
+            for (int sg = warp; sg < tb.nseg; sg += nwarp) {     // pass 2a
+                const int lo = tb.seg_lo[sg], n = tb.seg_n[sg];
+                T ubest = T(-1);
+                int kbest = lo;
+                for (int i = lane; i < n; i += 32) {
+                    const T v = sm.xi[lo + i];
+                    if (v > ubest) { ubest = v; kbest = lo + i; }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const T ov = __shfl_xor_sync(0xffffffffu, ubest, o);
+                    const int ok = __shfl_xor_sync(0xffffffffu, kbest, o);
+                    if (ov > ubest || (ov == ubest && ok < kbest)) { ubest = ov; kbest = ok; }
+                }
+                T smr, rho;
+                complete(kbest, smr, rho);
+                if (lane == 0) { s_seg_smr[sg] = smr; s_seg_rho[sg] = rho; s_seg_k[sg] = kbest; }
+            }
+            __syncthreads();
+            for (int sg = warp; sg < tb.nseg; sg += nwarp) {     // pass 2b
+                const int lo = tb.seg_lo[sg], n = tb.seg_n[sg], bd = tb.seg_band[sg];
+                T rbest = T(0);                                  // best true rho of the band so far
+                for (int s2 = tb.band_seg0[bd]; s2 < tb.band_seg0[bd + 1]; ++s2) rbest = fmax(rbest, s_seg_rho[s2]);
+                T best = s_seg_smr[sg];
+                const int kdone = s_seg_k[sg];
+                for (int base = 0; base < n; base += 32) {
+                    const int i = base + lane;
+                    const T ub = (i < n) ? sm.xi[lo + i] : T(-1);
+                    unsigned bal = __ballot_sync(0xffffffffu, i < n && lo + i != kdone && ub >= rbest * slack);
+                    while (bal) {
+                        const int l = __ffs(bal) - 1;
+                        bal &= bal - 1;
+                        const T ubl = __shfl_sync(0xffffffffu, ub, l);
+                        if (ubl >= rbest * slack) {              // rbest may have risen since the ballot
+                            T smr, rho;
+                            complete(lo + base + l, smr, rho);
+                            best = fmax(best, smr);
+                            rbest = fmax(rbest, rho);
+                        }
+                    }
+                }
+                if (lane == 0) s_seg_smr[sg] = best;
+            }
+            __syncthreads();
+            if (tid < nb) {
+                T v = -INFINITY;
+                for (int s2 = tb.band_seg0[tid]; s2 < tb.band_seg0[tid + 1]; ++s2) v = fmax(v, s_seg_smr[s2]);
+                s_smr[c][tid] = v;
+            }
         }
         __syncthreads();
         if (taps.npeaks != nullptr && tid == 0) taps.npeaks[lb * 4 + c] = npk;
@@ -546,52 +666,54 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // Each band's SMR trajectory (smr, -12, -6, -6, ...) is independent of the other bands, so the greedy
     // arg-max visits the (band, level) tokens in globally sorted order: key descending, first (lowest) band on
     // ties.  Joint blocks sort 2*nb bands together; non-joint blocks sort each channel on its own.
+    // The order is found by counting instead of sorting: a token's position = number of tokens that come before
+    // it = its own level + for every other band of its group the number of that band's keys (a descending run of
+    // 15, searched in 4 steps) that beat its key.  No barriers inside, and the comparisons are on exactly the
+    // values the reference's `smr[i] -= 12.0 / 6.0` updates produce.
     {
-        const int ntok = 2 * nb * MRC_MAX_LEVELS;
-        for (int i = tid; i < 1024; i += NT) {
-            T key = -INFINITY;
-            uint16_t id = 0xffffu;
-            if (i < ntok) {
-                const int bb = i / MRC_MAX_LEVELS, lvl = i - bb * MRC_MAX_LEVELS;     // bb in [0, 2nb)
-                const int ch = bb / nb, bd = bb - ch * nb;
-                const bool m = (ms >> bd) & 1u;
-                T v = s_smr[(m ? 2 : 0) + ch][bd];
-                if (lvl >= 1) v -= T(12);
-                for (int q = 1; q < lvl; ++q) v -= T(6);
-                key = v;
-                id = (uint16_t)(bb | (lvl << 8));
+        const int nbb = 2 * nb, ntok = nbb * MRC_MAX_LEVELS;
+        T* ktab = sm.skey;                               // [2nb][16]: keys of each band by level, [15] = -inf
+        int* s_rank = reinterpret_cast<int*>(sm.xi);     // [768] (xi is idle by now)
+        for (int i = tid; i < nbb * 16; i += NT) {
+            const int bb = i >> 4, lvl = i & 15;
+            const int ch = bb / nb, bd = bb - ch * nb;
+            const bool m = (ms >> bd) & 1u;
+            T v = s_smr[(m ? 2 : 0) + ch][bd];
+            if (lvl >= 1) v -= T(12);
+            for (int q = 1; q < lvl; ++q) v -= T(6);
+            ktab[i] = (lvl < MRC_MAX_LEVELS) ? v : T(-INFINITY);
+        }
+        for (int i = tid; i < MRC_TOK_STRIDE; i += NT) { s_rank[i] = 0; sm.sid[i] = 0xffffu; }
+        __syncthreads();
+        const int gsz = joint ? nbb : nb;                // bands per group
+        const int hsz = (gsz + 1) >> 1;
+        for (int w = tid; w < 2 * ntok; w += NT) {       // work item = (token, half of the group's bands)
+            const int tok = w >> 1, half = w & 1;
+            const int bb = tok / MRC_MAX_LEVELS, lvl = tok - bb * MRC_MAX_LEVELS;
+            const int g0b = joint ? 0 : (bb / nb) * nb;
+            const int b_lo = g0b + half * hsz, b_hi = min(g0b + gsz, b_lo + hsz);
+            const T v = ktab[bb * 16 + lvl];
+            int cnt = 0;
+            for (int b2 = b_lo; b2 < b_hi; ++b2) {
+                if (b2 == bb) { cnt += lvl; continue; }
+                const T* kk = ktab + b2 * 16;
+                const bool lower = b2 < bb;              // ties go to the lower band (first maximum wins)
+                int pos = 0;
+                { const T x = kk[7]; if (x > v || (x == v && lower)) pos = 8; }
+                { const T x = kk[pos + 3]; if (x > v || (x == v && lower)) pos += 4; }
+                { const T x = kk[pos + 1]; if (x > v || (x == v && lower)) pos += 2; }
+                { const T x = kk[pos]; if (x > v || (x == v && lower)) pos += 1; }
+                cnt += pos;
             }
-            sm.skey[i] = key;
-            sm.sid[i] = id;
+            atomicAdd(&s_rank[tok], cnt);
         }
         __syncthreads();
-        const int split = joint ? 0x7fffffff : nb;      // non-joint: channel 1 bands (>= nb) sort after channel 0
-        auto before = [&](T ka, uint16_t ia, T kb, uint16_t ib) -> bool {
-            const int ba = ia & 0xff, bbb = ib & 0xff;
-            if (ia == 0xffffu || ib == 0xffffu) return ib == 0xffffu && ia != 0xffffu;
-            const int ca = ba >= split, cb = bbb >= split;
-            if (ca != cb) return ca < cb;
-            if (ka != kb) return ka > kb;
-            if (ba != bbb) return ba < bbb;
-            return ia < ib;
-        };
-        for (int k = 2; k <= 1024; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < 512; t += NT) {
-                    const int i = ((t / j) * 2 * j) + (t % j);
-                    const int ixj = i + j;
-                    const bool up = ((i & k) == 0);
-                    const T ka = sm.skey[i], kb = sm.skey[ixj];
-                    const uint16_t ia = sm.sid[i], ib = sm.sid[ixj];
-                    const bool sw = up ? before(kb, ib, ka, ia) : before(ka, ia, kb, ib);
-                    if (sw) {
-                        sm.skey[i] = kb; sm.skey[ixj] = ka;
-                        sm.sid[i] = ib;  sm.sid[ixj] = ia;
-                    }
-                }
-                __syncthreads();
-            }
+        for (int tok = tid; tok < ntok; tok += NT) {
+            const int bb = tok / MRC_MAX_LEVELS, lvl = tok - bb * MRC_MAX_LEVELS;
+            const int base = (!joint && bb >= nb) ? nb * MRC_MAX_LEVELS : 0;
+            sm.sid[base + s_rank[tok]] = (uint16_t)(bb | (lvl << 8));
         }
+        __syncthreads();
         uint16_t* ot = ho.tokens + (size_t)lb * MRC_TOK_STRIDE;
         for (int i = tid; i < MRC_TOK_STRIDE; i += NT) ot[i] = sm.sid[i];
     }
@@ -601,7 +723,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
 
 size_t analysis_smem_bytes(int L, int elem) {
     const size_t Q = L / 2;
-    size_t spread = std::max<size_t>(3 * Q + 2, 1280) * 8;             // mc, mU, mS (the sort aliases them)
+    size_t spread = std::max<size_t>(4 * Q, 1280) * 8;                 // mc, mU, mS, mP (the grant order aliases them)
     if ((size_t)(2 * L) * elem >= spread) spread = 0;                  // ... living in the FFT work buffer
     return (size_t)(11 * L) * elem + (3 * Q + 64) * 8 + spread + (2 * Q + 1) * 4 + Q * 2 + 16;
 }

@@ -34,7 +34,8 @@ struct mrc_ctx {
     std::string err;
 
     TablesDev td, tf;                 // double and float copies
-    Buf band_lo, band_n, line2band, huff, header;
+    Buf band_lo, band_n, line2band, huff, header, seg_lo, seg_n, seg_band, band_seg0;
+    int nseg = 0;
     DevTables<double> tbd;
     DevTables<float> tbf;
     HuffDev h_huff;
@@ -142,6 +143,9 @@ cudaError_t upload_tables(mrc_ctx* c, TablesDev& d, DevTables<T>& tb, const mrc_
     tb.bark = (const T*)d.bark.p; tb.quiet = (const T*)d.quiet.p;
     tb.band_lo = (const int*)c->band_lo.p; tb.band_n = (const int*)c->band_n.p;
     tb.line2band = (const uint8_t*)c->line2band.p;
+    tb.nseg = c->nseg;
+    tb.seg_lo = (const int*)c->seg_lo.p; tb.seg_n = (const int*)c->seg_n.p;
+    tb.seg_band = (const int*)c->seg_band.p; tb.band_seg0 = (const int*)c->band_seg0.p;
     return cudaSuccess;
 }
 
@@ -517,7 +521,7 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
                   &ctx->td.bark, &ctx->td.quiet, &ctx->td.bark_d, &ctx->td.quiet_d, &ctx->td.exp_tab, &ctx->tf.bark_d,
                   &ctx->tf.quiet_d, &ctx->tf.exp_tab, &ctx->tf.kbd, &ctx->tf.hann, &ctx->tf.tw_pre, &ctx->tf.tw_post,
                   &ctx->tf.tw_fft, &ctx->tf.tw_rfft, &ctx->tf.bark, &ctx->tf.quiet, &ctx->band_lo, &ctx->band_n,
-                  &ctx->line2band, &ctx->huff, &ctx->header, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,
+                  &ctx->line2band, &ctx->huff, &ctx->header, &ctx->seg_lo, &ctx->seg_n, &ctx->seg_band, &ctx->band_seg0, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,
                   &ctx->clip_base, &ctx->running, &ctx->overflow, &ctx->peakctr, &ctx->res_in, &ctx->res_out,
                   &ctx->clip_res, &ctx->clip_run, &ctx->q_alloc, &ctx->q_sf, &ctx->q_mant,
                   &ctx->tap_lines, &ctx->tap_smr, &ctx->tap_npk, &ctx->pcm_dev, &ctx->out_dev, &ctx->xin_dev};
@@ -561,6 +565,24 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     CK(upload(ctx->band_lo, ctx->h_band_lo, ctx->stream));
     CK(upload(ctx->band_n, ctx->h_band_n, ctx->stream));
     CK(upload(ctx->line2band, l2b, ctx->stream));
+    {   // segments of at most MRC_SEG_LINES lines, never straddling a band
+        std::vector<int> slo, sn, sb, b0(t->n_bands + 1, 0);
+        for (int b = 0; b < t->n_bands; ++b) {
+            b0[b] = (int)slo.size();
+            const int n = ctx->h_band_n[b], parts = (n + MRC_SEG_LINES - 1) / MRC_SEG_LINES;
+            for (int q = 0; q < parts; ++q) {
+                const int a0 = (int)((long long)n * q / parts), a1 = (int)((long long)n * (q + 1) / parts);
+                slo.push_back(ctx->h_band_lo[b] + a0); sn.push_back(a1 - a0); sb.push_back(b);
+            }
+        }
+        b0[t->n_bands] = (int)slo.size();
+        if ((int)slo.size() > MRC_MAX_SEGS) return fail(ctx, MRC_E_INVALID, "too many band segments");
+        ctx->nseg = (int)slo.size();
+        CK(upload(ctx->seg_lo, slo, ctx->stream));
+        CK(upload(ctx->seg_n, sn, ctx->stream));
+        CK(upload(ctx->seg_band, sb, ctx->stream));
+        CK(upload(ctx->band_seg0, b0, ctx->stream));
+    }
     // Huffman LUTs
     HuffDev& h = ctx->h_huff;
     memset(&h, 0, sizeof h);

@@ -21,6 +21,8 @@
 #define MRC_TOK_STRIDE 768      // >= 2*25*15 grant tokens per block
 #define MRC_MAX_LEVELS 15       // grants per band: 0->2, then +1 up to 16 bits
 #define MRC_BSTRIDE 32          // band stride in per-band arrays
+#define MRC_SEG_LINES 64
+#define MRC_MAX_SEGS 96        // >= nb + L / MRC_SEG_LINES for L <= 2048 ... 4096
 #define MRC_CODED_BANDS 25      // most bands per channel the grant-token machinery holds (25 * 15 <= MRC_GROUP_SLOTS)
 
 // ---- per-block record the cost kernel hands to the chain kernel (one TMA bulk copy per block) ---------------
@@ -68,6 +70,12 @@ struct DevTables {
     const int* band_lo;                          // [nb]
     const int* band_n;                           // [nb]
     const uint8_t* line2band;                    // [L]
+    // bands cut into segments of <= MRC_SEG_LINES lines: the work items of the band-maximum search
+    int nseg;
+    const int* seg_lo;                           // [nseg] first line
+    const int* seg_n;                            // [nseg] lines
+    const int* seg_band;                         // [nseg]
+    const int* band_seg0;                        // [nb+1] first segment of each band
 };
 
 struct HuffDev {
