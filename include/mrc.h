@@ -45,6 +45,9 @@ extern "C" {
 /* Masker spreading (psychoac.py:68-78, :168) summed pair by pair in the reference's order: one 10**x per
  * (masker, line) pair.  Default (flag clear) is the factorised evaluation of the same sum. */
 #define MRC_FLAG_SPREAD_SEQUENTIAL 1
+/* Never tabulate the per-block reservoir maps (the single-stream fast path of the serial walk); results are the
+ * same either way, the flag exists for cross-checking and timing. */
+#define MRC_FLAG_NO_CHAIN_TABLES 2
 
 typedef struct mrc_ctx mrc_ctx;
 

@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(_here, "libmrc.so")
 MRC_OK, MRC_E_INVALID, MRC_E_CUDA, MRC_E_NOSPACE, MRC_E_FORMAT, MRC_E_STATE = 0, -1, -2, -3, -4, -5
 PRECISION_FP64, PRECISION_FP32 = 0, 1
 FLAG_SPREAD_SEQUENTIAL = 1
+FLAG_NO_CHAIN_TABLES = 2
 NO_TABLE = 15
 
 c_i16p = C.POINTER(C.c_int16)

@@ -18,7 +18,7 @@ def _ptr(a):
 class Codec(object):
     def __init__(self, sample_rate=48000, n_mdct_lines=1024, n_scale_bits=4, n_mant_size_bits=4,
                  target_bits_per_sample=128000. / 48000., joint=True, precision="fp64", device=0,
-                 band_limits=None, spreading="factorised"):
+                 band_limits=None, spreading="factorised", chain_tables=True):
         self.lib = _lib.load()
         self.L = int(n_mdct_lines)
         self.sample_rate = int(sample_rate)
@@ -33,6 +33,8 @@ class Codec(object):
         cfg.joint = 1 if joint else 0
         cfg.precision = {"fp64": _lib.PRECISION_FP64, "fp32": _lib.PRECISION_FP32}[precision]
         cfg.flags = {"factorised": 0, "sequential": _lib.FLAG_SPREAD_SEQUENTIAL}[spreading]
+        if not chain_tables:
+            cfg.flags |= _lib.FLAG_NO_CHAIN_TABLES
         cfg.target_bits_per_sample = float(target_bits_per_sample)
         self._ctx = C.c_void_p()
         rc = self.lib.mrc_create(C.byref(cfg), C.byref(self._ctx))

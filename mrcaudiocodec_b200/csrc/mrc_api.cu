@@ -2,6 +2,7 @@
 // declared in include/mrc.h.  No CPU implementation of any codec stage lives here: every stage is a kernel.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -45,9 +46,11 @@ struct mrc_ctx {
 
     // scratch (grow only)
     Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out;
-    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk; } sets[2];
+    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab; } sets[2];
     Buf q_alloc, q_sf, q_mant;
     cudaStream_t stream2 = nullptr;
+    bool no_tables = false;          // MRC_FLAG_NO_CHAIN_TABLES
+    int tab_min_blocks = 512;        // blocks per clip in a wave from which the reservoir maps are tabulated
     std::vector<cudaEvent_t> evpool;
     Buf tap_lines, tap_smr, tap_npk;
     Buf pcm_dev, out_dev, xin_dev;
@@ -237,8 +240,10 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     cp.joint = job.joint;
     cp.flush_nonjoint = job.flush_nonjoint ? 1 : 0;
     cp.no_huff = job.no_huff;
-    int min_nl = 0x7fffffff;
-    for (int b = 0; b < nb; ++b) min_nl = std::min(min_nl, ctx->h_band_n[b]);
+    int min_nl = 0x7fffffff, max_nl = 0;
+    for (int b = 0; b < nb; ++b) { min_nl = std::min(min_nl, ctx->h_band_n[b]); max_nl = std::max(max_nl, ctx->h_band_n[b]); }
+    // reservoir-map tables of the single-stream fast path: R_in in [r_lo, r_lo + ntab)
+    const int r_lo = -((max_nl + 1 + 31) / 32 * 32), ntab = -r_lo + 640, tabw = (ntab + 2 + 3) / 4 * 4;
 
     // ---- buffer sets ----
     const bool want_atap = job.t_lines || job.t_smr || job.t_npk;
@@ -316,13 +321,25 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
                            (unsigned char*)ctx->sets[s].pw.p);
             ++launches;
         }
+        // long stretches of one clip in the wave: the serial walk is the critical path, tabulate the reservoir maps
+        const bool use_tab = job.need_quant && !ctx->no_tables && nblk / (c_hi - c_lo + 1) >= ctx->tab_min_blocks;
+        if (use_tab) {
+            CK(ensure(ctx->sets[s].tab, W * 2 * (size_t)tabw * 4));
+            launch_table(st2, cp, cm, g0, nblk, min_nl, io[s], r_lo, ntab, tabw, (int*)ctx->sets[s].tab.p);
+            ++launches;
+        }
         CK(cudaEventRecord(ev(w, 2), st2));
         // ---- main stream: chain -> clip offsets -> quantise + pack ----
         CK(cudaStreamWaitEvent(st, ev(w, 2), 0));
         CK(cudaEventRecord(ev(w, 3), st));
         if (job.need_quant) {
-            launch_chain(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, min_nl, io[s], d_res_in, d_res_out,
-                         (unsigned long long*)ctx->peakctr.p + 4);
+            if (use_tab)
+                launch_chain_table(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, min_nl, io[s], r_lo, ntab, tabw,
+                                   (const int*)ctx->sets[s].tab.p, d_res_in, d_res_out,
+                                   (unsigned long long*)ctx->peakctr.p + 4);
+            else
+                launch_chain(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, min_nl, io[s], d_res_in, d_res_out,
+                             (unsigned long long*)ctx->peakctr.p + 4);
             ++launches;
         }
         CK(cudaEventRecord(ev(w, 4), st));
@@ -499,11 +516,15 @@ int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out) {
     ctx->cfg = *cfg;
     ctx->L = cfg->n_mdct_lines;
     ctx->logL = logL;
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    // The main stream carries the serial reservoir walk: highest priority, so that its one CTA is placed as soon as
+    // an SM can take it instead of queueing behind the next wave's thousands of analysis CTAs (stream2, lowest).
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) {
+    if ((e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
         return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
@@ -528,7 +549,7 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     for (Buf* b : all) release(*b);
     for (auto& b : ctx->dec) release(b);
     for (auto& ws : ctx->sets) {
-        Buf* wb[] = {&ws.lines, &ws.bandmax, &ws.tokens, &ws.ovs, &ws.ms, &ws.rec, &ws.pw, &ws.rsv, &ws.gmask, &ws.cblk};
+        Buf* wb[] = {&ws.lines, &ws.bandmax, &ws.tokens, &ws.ovs, &ws.ms, &ws.rec, &ws.pw, &ws.rsv, &ws.gmask, &ws.cblk, &ws.tab};
         for (Buf* b : wb) release(*b);
     }
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -633,6 +654,8 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     ctx->cp.max_mant_bits = std::min(16, 1 << c.n_mant_size_bits);
     ctx->cp.joint = c.joint; ctx->cp.flush_nonjoint = 1; ctx->cp.no_huff = 0;
     ctx->cp.spread_seq = (c.flags & MRC_FLAG_SPREAD_SEQUENTIAL) ? 1 : 0;
+    ctx->no_tables = (c.flags & MRC_FLAG_NO_CHAIN_TABLES) != 0;
+    if (const char* e = getenv("MRC_CHAIN_TABLE_MIN_BLOCKS")) ctx->tab_min_blocks = std::max(1, atoi(e));   // test knob
     if (ctx->cp.max_mant_bits != 16) return fail(ctx, MRC_E_INVALID, "only n_mant_size_bits = 4 (16-bit cap) is supported");
     // .pac header template (pacfileThem.py:592-613); numSamples is patched per clip by the pack kernel
     uint8_t* hd = ctx->h_header;

@@ -246,6 +246,173 @@ chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_
     }
 }
 
+// ---- single-stream fast path -------------------------------------------------------------------------------
+// When a wave holds long stretches of one clip the serial walk above is the critical path of the whole encode.
+// table_kernel (parallel, one CTA per block) then tabulates the block's reservoir map R_in -> R_out for every
+// R_in in [r_lo, r_lo + ntab): one thread per R_in walks the grant tokens serially from the first token the
+// smallest budget refuses (everything before it is granted for every larger budget as well).  r_lo = -(largest
+// band + 1, rounded up): int(bitsLeft) cannot go lower (Q5 overspends by at most nLines), and savings push R_in up,
+// not down.  Two more entries give the closed form for "every token granted" (silence: R grows without bound).
+// chain_table_kernel then needs one shared-memory load per block; budgets outside the table and not all-granting
+// (rare: the blocks right after a Huffman table wins big) take the complete walk on the global record.
+constexpr int TAB_THREADS = 256;
+
+__global__ void __launch_bounds__(TAB_THREADS)
+table_kernel(CodecParams cp, ClipMap cm, int g0, int min_nl, ChainIO io, int r_lo, int ntab, int tabw, int* __restrict__ tab) {
+    __shared__ uint32_t s_tn[MRC_NSLOT];
+    __shared__ uint32_t s_dsp[MRC_NSLOT];
+    __shared__ uint4 s_dpc[MRC_NSLOT];
+    __shared__ int s_mx[32];
+    __shared__ int s_joint;
+    const int tid = threadIdx.x;
+    const size_t lb = blockIdx.x;
+    const int g = g0 + (int)lb;
+    const unsigned char* rec = io.rec + lb * (size_t)MRC_REC_BYTES;
+    const uint32_t* tn = reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN);
+    const uint32_t* cpre = reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP);
+    const uint4* pc = reinterpret_cast<const uint4*>(rec + MRC_REC_PC);
+    const int32_t* mx = reinterpret_cast<const int32_t*>(rec + MRC_REC_MX);
+    if (tid == 0) {
+        int lo = 0, hi = cm.n_clips;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cm.clip_blk0[mid] <= g) lo = mid; else hi = mid;
+        }
+        s_joint = cp.joint && !(cp.flush_nonjoint && g == cm.clip_blk0[lo + 1] - 1);
+    }
+    if (tid < 32) s_mx[tid] = mx[tid];
+    for (int j = tid; j < MRC_NSLOT; j += TAB_THREADS) {
+        s_tn[j] = tn[j];
+        const int j1 = (j + 1 < MRC_NSLOT) ? j + 1 : j;          // the last slot is never a token
+        s_dsp[j] = cpre[j1] - cpre[j];
+        s_dpc[j] = sub4(pc[j1], pc[j]);
+    }
+    __syncthreads();
+    const bool joint = s_joint != 0;
+    const int ngroups = joint ? 1 : 2, nck = joint ? MRC_NCHUNK : MRC_GROUP_CHUNKS;
+    const int K = joint ? cp.k_joint : cp.k_single, frac = joint ? cp.frac_joint : cp.frac_single;
+    int* out = tab + lb * (size_t)(2 * tabw);
+    for (int grp = 0; grp < 2; ++grp) {
+        int* o = out + grp * tabw;
+        if (grp >= ngroups) {                    // unused second table of a joint block
+            for (int i = tid; i < tabw; i += TAB_THREADS) o[i] = 0;
+            continue;
+        }
+        const int k0 = grp * MRC_GROUP_CHUNKS;
+        // first chunk the smallest budget cannot fully pay
+        const int b0min = K + r_lo;
+        int klo = nck - 1;
+        for (int k = nck - 1; k >= 0; --k)
+            if (s_mx[k0 + k] > b0min) klo = k;
+        const int j0 = (k0 + klo) * 32, jend = (k0 + nck) * 32;
+        const unsigned sp0 = cpre[j0];
+        const uint4 pc0 = pc[j0];
+        for (int base = 0; base < ntab; base += TAB_THREADS) {
+            const int idx = base + tid;
+            const int B0 = K + r_lo + idx;
+            GroupTotals gt;
+            gt.spent = sp0; gt.cost = pc0; gt.wbits = make_uint4(0u, 0u, 0u, 0u);
+            int rem = B0 - (int)((sp0 & 0xffffu) + (sp0 >> 16));
+            for (int jb = j0; jb < jend; jb += 16) {
+                if (__all_sync(0xffffffffu, rem < min_nl)) break;
+#pragma unroll 4
+                for (int j = jb; j < jb + 16; ++j) {
+                    const uint32_t t = s_tn[j];
+                    if (t == INVALID_TOKEN) continue;
+                    const int n = (int)(t >> 16);
+                    if (n <= rem) {
+                        rem -= (t & 0xff00u) ? n : 2 * n;
+                        gt.spent += s_dsp[j];
+                        gt.cost = add4(gt.cost, s_dpc[j]);
+                    }
+                }
+            }
+            if (idx < ntab) {
+                if (B0 <= 0) { gt.spent = 0u; gt.cost = make_uint4(0u, 0u, 0u, 0u); }
+                o[idx] = reservoir_after(gt, B0, frac, cp.no_huff, nullptr, nullptr);
+            }
+        }
+        if (tid == 0) {                          // every token granted: R_out = B0 + o[ntab] once B0 >= o[ntab+1]
+            GroupTotals gt;
+            gt.spent = cpre[jend - 1]; gt.cost = pc[jend - 1]; gt.wbits = make_uint4(0u, 0u, 0u, 0u);
+            const int big = 1 << 28;
+            o[ntab] = reservoir_after(gt, big, frac, cp.no_huff, nullptr, nullptr) - big;
+            o[ntab + 1] = s_mx[k0 + nck - 1];
+            for (int i = ntab + 2; i < tabw; ++i) o[i] = 0;
+        }
+    }
+}
+
+constexpr int TAB_STAGES = 6;
+
+__global__ void __launch_bounds__(32)
+chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_nl, ChainIO io, int r_lo,
+                   int ntab, int tabw, const int* __restrict__ tab, const int32_t* __restrict__ reservoir_in,
+                   int32_t* __restrict__ reservoir_out, unsigned long long* __restrict__ iter_counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[TAB_STAGES];
+    const int lane = threadIdx.x;
+    const int clip = c0 + blockIdx.x;
+    const int blk0 = cm.clip_blk0[clip], nblk_clip = cm.clip_blk0[clip + 1] - blk0;
+    const int b_lo = max(blk0, g0) - blk0, b_hi = min(blk0 + nblk_clip, g0 + nblk_wave) - blk0;
+    if (b_hi <= b_lo) return;
+    // a stage = the block's table (for the common case) followed by its full record (for the complete walk)
+    const unsigned tbytes = (unsigned)(2 * tabw * 4), sbytes = tbytes + MRC_REC_BYTES;
+    if (lane == 0) {
+        for (int s = 0; s < TAB_STAGES; ++s) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int b, int s) {          // lane 0 only
+        unsigned char* dst = smem_raw + (size_t)s * sbytes;
+        mbar_expect_tx(&s_bar[s], sbytes);
+        bulk_g2s(dst, tab + (size_t)(blk0 + b - g0) * (2 * tabw), tbytes, &s_bar[s]);
+        bulk_g2s(dst + tbytes, io.rec + (size_t)(blk0 + b - g0) * MRC_REC_BYTES, MRC_REC_BYTES, &s_bar[s]);
+    };
+    if (lane == 0)
+        for (int i = 0; i < TAB_STAGES && b_lo + i < b_hi; ++i) issue(b_lo + i, i);
+    int R = (b_lo == 0) ? (reservoir_in ? reservoir_in[clip] : 0) : io.clip_res[clip];
+    unsigned n_slow = 0, dummy = 0;
+    int s = 0;
+    unsigned parity = 0;
+    for (int b = b_lo; b < b_hi; ++b) {
+        mbar_wait(&s_bar[s], parity);
+        const unsigned char* stg = smem_raw + (size_t)s * sbytes;
+        const int* T0 = reinterpret_cast<const int*>(stg);
+        const bool joint = cp.joint && !(cp.flush_nonjoint && b == nblk_clip - 1);
+        const int K = joint ? cp.k_joint : cp.k_single, frac = joint ? cp.frac_joint : cp.frac_single;
+        const int R0 = R;
+        int R1 = R;
+        const int ngroups = joint ? 1 : 2;
+        for (int grp = 0; grp < ngroups; ++grp) {
+            const int* T = T0 + grp * tabw;
+            const int B0 = K + R;
+            const int idx = R - r_lo;
+            if ((unsigned)idx < (unsigned)ntab) R = T[idx];
+            else if (B0 >= T[ntab + 1]) R = B0 + T[ntab];
+            else {                               // outside the table and not all-granting: the complete walk
+                const unsigned char* rec = stg + tbytes;
+                const GroupTotals gt = walk_group<false>(
+                    reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN), reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP),
+                    reinterpret_cast<const uint4*>(rec + MRC_REC_PC), nullptr, reinterpret_cast<const int32_t*>(rec + MRC_REC_MX),
+                    grp * MRC_GROUP_CHUNKS, joint ? MRC_NCHUNK : MRC_GROUP_CHUNKS, B0, min_nl, lane, dummy, dummy);
+                R = reservoir_after(gt, B0, frac, cp.no_huff, nullptr, nullptr);
+                ++n_slow;
+            }
+            if (grp == 0) R1 = R;
+        }
+        if (lane == 0) io.rsv[blk0 + b - g0] = make_int4(R0, R1, R, 0);
+        __syncwarp();
+        if (lane == 0 && b + TAB_STAGES < b_hi) issue(b + TAB_STAGES, s);
+        if (++s == TAB_STAGES) { s = 0; parity ^= 1u; }
+    }
+    if (lane == 0) {
+        if (iter_counter) atomicAdd(iter_counter, (unsigned long long)n_slow);
+        io.clip_res[clip] = R;
+        if (b_hi == nblk_clip && reservoir_out) reservoir_out[clip] = R;
+    }
+}
+
 constexpr int FIN_WARPS = 8;
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
@@ -358,4 +525,20 @@ void launch_offsets(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, i
                     ChainIO io) {
     if (nclips <= 0 || nblk <= 0) return;
     offsets_kernel<<<nclips, 32, 0, st>>>(cp, cm, c0, g0, nblk, io);
+}
+
+void launch_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int min_nlines,
+                  ChainIO io, int r_lo, int ntab, int tabw, int* tab) {
+    if (nblk <= 0) return;
+    table_kernel<<<nblk, TAB_THREADS, 0, st>>>(cp, cm, g0, min_nlines, io, r_lo, ntab, tabw, tab);
+}
+
+void launch_chain_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0,
+                        int nblk, int min_nlines, ChainIO io, int r_lo, int ntab, int tabw, const int* tab,
+                        const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter) {
+    if (nclips <= 0 || nblk <= 0) return;
+    const size_t smem = (size_t)TAB_STAGES * ((size_t)2 * tabw * 4 + MRC_REC_BYTES);
+    cudaFuncSetAttribute(chain_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    chain_table_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, min_nlines, io, r_lo, ntab, tabw, tab,
+                                                 reservoir_in, reservoir_out, iter_counter);
 }

@@ -25,6 +25,9 @@ def test_one_hour_stream_properties():
     blob = c.encode_clips([pcm])[0]
     blob2 = c.encode_clips([pcm])[0]
     assert blob == blob2, "encode is not deterministic"
+    c2 = Codec(chain_tables=False)                      # serial walk without the tabulated fast path: same bytes
+    assert c2.encode_clips([pcm])[0] == blob
+    c2.close()
     h = pacfile.parse_header(blob)
     assert h["nMDCTLines"] == 1024 and h["nBands"] == 25 and h["sampleRate"] == 48000
     nblk = c.n_blocks(pcm.shape[0])

@@ -139,6 +139,27 @@ def test_ragged_batch_and_edge_clips(codecs):
             assert np.abs(d.astype(np.int64) - od.astype(np.int64)).max() <= 1, "clip %d" % i
 
 
+def test_chain_table_fast_path_vs_oracle(monkeypatch):
+    """The single-stream fast path (tabulated reservoir maps, mrc_chain.cu) forced on for short clips: bytes equal
+    the oracle's, for joint and independent channels, including silence (reservoir far outside the table: closed
+    form) and the blocks after it (complete walk)."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import Codec, synth
+    monkeypatch.setenv("MRC_CHAIN_TABLE_MIN_BLOCKS", "1")
+    pcm = synth.synth_short(77, 0.8)
+    for joint in (True, False):
+        c = Codec(joint=joint)
+        blob = c.encode_clips([pcm])[0]
+        assert c.last_timing()["launches"] >= 8          # table + chain_table were launched
+        c.close()
+        ob, _ = o.driver.encode_pcm(pcm, joint=joint)
+        assert blob == ob, joint
+    c = Codec(target_bits_per_sample=64000. / 48000.)
+    ob, _ = o.driver.encode_pcm(pcm, joint=True, targetBitsPerSample=64000. / 48000.)
+    assert c.encode_clips([pcm])[0] == ob
+    c.close()
+
+
 def test_sharded_batch_equals_single_context(codecs):
     """multi-GPU sharding (mrcaudiocodec_b200/dist.py) emulated in one process: three 'ranks' encode their
     contiguous clip ranges with their own contexts; bytes and global offsets equal the single-context batch."""
