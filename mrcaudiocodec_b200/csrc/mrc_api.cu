@@ -48,7 +48,7 @@ struct mrc_ctx {
     Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out;
     struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab; } sets[2];
     Buf q_alloc, q_sf, q_mant;
-    cudaStream_t stream2 = nullptr;
+    cudaStream_t stream2 = nullptr, stream3 = nullptr;    // analysis stream, H2D copy stream
     bool no_tables = false;          // MRC_FLAG_NO_CHAIN_TABLES
     int tab_min_blocks = 512;        // blocks per clip in a wave from which the reservoir maps are tabulated
     std::vector<cudaEvent_t> evpool;
@@ -155,6 +155,7 @@ cudaError_t upload_tables(mrc_ctx* c, TablesDev& d, DevTables<T>& tb, const mrc_
 struct EncodeJob {
     // inputs (exactly one of d_pcm / d_xin)
     const int16_t* d_pcm = nullptr;
+    const int16_t* h_pcm = nullptr;        // when set: frames are uploaded into d_pcm wave by wave on the copy stream
     const double* d_xin = nullptr;
     const int64_t* h_clip_off = nullptr;   // [n_clips+1]
     int n_clips = 0;
@@ -291,8 +292,9 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     }
 
     const int nwaves = (nblk_total + WAVE_BLOCKS - 1) / WAVE_BLOCKS;
-    // events per wave: 0 analysis start, 1 analysis end, 2 cost end, 3 chain start, 4 chain end, 5 pack end
-    constexpr int EPW = 6;
+    // events per wave: 0 analysis start, 1 analysis end, 2 cost end, 3 chain start, 4 chain end, 5 pack end,
+    // 6 PCM of the wave uploaded
+    constexpr int EPW = 7;
     for (int i = 0; i < nwaves * EPW; ++i) pool_event(ctx, (size_t)i);
     auto ev = [&](int w, int k) { return ctx->evpool[(size_t)w * EPW + k]; };
     // everything queued on `st` so far (tables of this call, PCM upload) must precede the first analysis
@@ -302,6 +304,9 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     int launches = 0;
     std::vector<unsigned char> hb;     // host bounce buffer for taps
     int c_lo = 0;
+    int64_t uploaded = 0;              // frames of job.h_pcm already queued for upload
+    cudaStream_t st3 = ctx->stream3;
+    if (job.h_pcm) CK(cudaStreamWaitEvent(st3, ctx->ev[0], 0));
     for (int w = 0; w < nwaves; ++w) {
         const int s = w % nsets;
         const int g0 = w * WAVE_BLOCKS, nblk = std::min(WAVE_BLOCKS, nblk_total - g0);
@@ -309,6 +314,20 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         int c_hi = c_lo;
         while (blk0[c_hi + 1] < g0 + nblk) ++c_hi;                 // clip holding block g0+nblk-1
         const int nfin = (blk0[c_hi + 1] <= g0 + nblk) ? c_hi - c_lo + 1 : c_hi - c_lo;   // clips ending in this wave
+        if (job.h_pcm) {
+            // frames this wave reads: up to the end of its last block (or of that clip); everything before was needed
+            // by earlier blocks, so the upload front only moves forward.  The copy stream runs ahead of the kernels.
+            const long long b_last = (long long)(g0 + nblk - 1) - blk0[c_hi];
+            const int64_t fr_hi = job.h_clip_off[c_hi + 1] - job.h_clip_off[c_hi];
+            const int64_t need = job.h_clip_off[c_hi] + std::min<int64_t>(fr_hi, (b_last + 1) * (int64_t)L);
+            if (need > uploaded) {
+                CK(cudaMemcpyAsync((int16_t*)job.d_pcm + uploaded * 2, job.h_pcm + uploaded * 2,
+                                   (size_t)(need - uploaded) * 4, cudaMemcpyHostToDevice, st3));
+                uploaded = need;
+            }
+            CK(cudaEventRecord(ev(w, 6), st3));
+            CK(cudaStreamWaitEvent(st2, ev(w, 6), 0));
+        }
         // ---- stream 2: analysis + cost (needs buffer set s free: pack of wave w-nsets done) ----
         if (w >= nsets) CK(cudaStreamWaitEvent(st2, ev(w - nsets, 5), 0));
         CK(cudaEventRecord(ev(w, 0), st2));
@@ -529,6 +548,12 @@ int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out) {
         delete ctx;
         return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        cudaStreamDestroy(ctx->stream2);
+        delete ctx;
+        return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     *out = ctx;
     return MRC_OK;
@@ -556,6 +581,8 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     for (auto& ev : ctx->evpool) if (ev) cudaEventDestroy(ev);
     cudaStreamSynchronize(ctx->stream2);
     cudaStreamDestroy(ctx->stream2);
+    cudaStreamSynchronize(ctx->stream3);
+    cudaStreamDestroy(ctx->stream3);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MRC_OK;
@@ -715,10 +742,10 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
     for (int attempt = 0; attempt < 2; ++attempt) {
         CK(ensure(ctx->out_dev, (size_t)cap));
         CK(cudaEventRecord(ctx->ev[4], st));
-        if (frames > 0) CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)frames * 4, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(ctx->ev[6], st));
         EncodeJob job;
         job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
+        job.h_pcm = frames > 0 ? pcm : nullptr;             // uploaded wave by wave, overlapped with the kernels
         job.joint = ctx->cfg.joint; job.flush_nonjoint = true;
         job.d_out = (uint8_t*)ctx->out_dev.p; job.out_cap = cap; job.h_clip_byte_off = clip_byte_offsets;
         const int rc = run_encode(ctx, job);
