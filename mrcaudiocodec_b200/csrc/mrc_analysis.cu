@@ -21,6 +21,7 @@
 
 namespace {
 
+constexpr int MRC_ZLUT = 832;         // cells of 1/32 Bark: Bark(24 kHz) = 24.6
 constexpr int MRC_NEAR_LOUD = 4;     // loud maskers included in the pass-1 bound of a line's threshold
 
 template <typename T>
@@ -37,11 +38,12 @@ struct Smem {
     double* mU;     // [Q]      quiet maskers at or below i, decayed to z_i (upper slope, -27 dB/Bark)
     double* mS;     // [Q]      maskers at or above i, decayed to z_i (lower slope, -27 dB/Bark); [npk] = 0
     double* mP;     // [Q]      sum of mc below i ([npk] = total); only for the pass-1 bound (npk < Q always)
-    int* pbin;      // [Q]
+    int* pbin;      // [Q]      peak bins; once the masker tables are built the same words hold zlut
+    uint16_t* zlut; // [MRC_ZLUT+1] number of maskers with z < g/32 Bark (only when Q ints can hold it)
     int* lcnt;      // [Q+1]    number of loud maskers (g > 0) below index i
     uint16_t* lidx; // [Q]      their indices, ascending
-    T* skey;        // [1024]   sort keys        (aliases mc/mU/mS: the sort runs after the last spectrum)
-    uint16_t* sid;  // [1024]   sort ids
+    T* mkey;        // [2][1024] merge buffers of the grant order (alias `lines` when it is large enough)
+    uint16_t* mid;  // [2][1024]
     double* etab;   // [64]     2^(j/64)
 };
 
@@ -59,9 +61,9 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     s.ms15 = d;          d += Q;
     s.mg = d;            d += Q;
     s.etab = d;          d += 64;
-    // mc, mU, mS, mP (4Q doubles) and, after the last spectrum, the grant-order tables (10 KB) share one region:
-    // the FFT work buffer when it is large enough (it is idle while maskers are spread), else a region of their own.
-    const size_t need = (size_t)((4 * Q > 1280) ? 4 * Q : 1280) * 8;
+    // mc, mU, mS, mP (4Q doubles) live in the FFT work buffer when it is large enough (it is idle while maskers
+    // are spread), else in a region of their own.
+    const size_t need = (size_t)(4 * Q) * 8;
     double* r;
     if ((size_t)(2 * L) * sizeof(T) >= need) r = reinterpret_cast<double*>(s.buf);
     else { r = d; d += need / 8; }
@@ -69,12 +71,18 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     s.mU = r + Q;
     s.mS = r + 2 * Q;
     s.mP = r + 3 * Q;
-    s.skey = reinterpret_cast<T*>(r);
-    s.sid = reinterpret_cast<uint16_t*>(r + 1024);
     int* ip = reinterpret_cast<int*>(d);
     s.pbin = ip;         ip += Q;
+    s.zlut = (Q * 4 >= (MRC_ZLUT + 2) * 2) ? reinterpret_cast<uint16_t*>(s.pbin) : nullptr;
     s.lcnt = ip;         ip += Q + 1;
     s.lidx = reinterpret_cast<uint16_t*>(ip);
+    const size_t mbytes = 2048 * sizeof(T) + 2048 * 2;
+    if ((size_t)(4 * L) * sizeof(T) >= mbytes) s.mkey = s.lines;
+    else {
+        const size_t a = (reinterpret_cast<size_t>(s.lidx) + (size_t)Q * 2 + 15) & ~(size_t)15;
+        s.mkey = reinterpret_cast<T*>(a);
+    }
+    s.mid = reinterpret_cast<uint16_t*>(s.mkey + 2048);
     return s;
 }
 
@@ -126,6 +134,22 @@ __device__ __forceinline__ T tsample(const T* sx, int N, int c, int n) {
 // m_hi = first masker with dz < -0.5, dz = z_k - z_m as the reference computes it
 template <typename T>
 __device__ __forceinline__ void masker_range(const Smem<T>& sm, double zk, int npk, int& m_lo, int& m_hi) {
+    if (sm.zlut != nullptr) {
+        // start from the count table (maskers per 1/32 Bark cell, prefix-summed), then settle with the exact
+        // comparisons: a cell holds two or three maskers at most
+        int g = (int)((zk - 0.5) * 32.0);
+        int m = sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)];
+        while (m > 0 && !(zk - sm.mz[m - 1] > 0.5)) --m;
+        while (m < npk && zk - sm.mz[m] > 0.5) ++m;
+        m_lo = m;
+        g = (int)((zk + 0.5) * 32.0) + 1;
+        m = sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)];
+        if (m < m_lo) m = m_lo;
+        while (m > m_lo && zk - sm.mz[m - 1] < -0.5) --m;
+        while (m < npk && !(zk - sm.mz[m] < -0.5)) ++m;
+        m_hi = m;
+        return;
+    }
     int lo = 0, hi = npk;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -415,7 +439,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 n_loud += loud ? 1u : 0u;
                 sm.mz[i] = z; sm.ms15[i] = s15; sm.mg[i] = g;
                 if (!cp.spread_seq) {
-                    cmid = exp10(div10(__dadd_rn(s15, -96.0)));
+                    cmid = exp10_tab(div10(__dadd_rn(s15, -96.0)), sm.etab);
                     sm.mc[i] = cmid;
                 }
             }
@@ -437,8 +461,8 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 // decay between neighbouring maskers: rho(d) = 10^(-2.7 d), the -27 dB/Bark slope of both sides
                 double rU = 0.0, rS = 0.0;           // rU = rho(z_i - z_{i-1}); rS = rho(z_{i+1} - z_i)
                 if (i < npk) {
-                    if (i > 0) rU = exp10(-2.7 * (z - sm.mz[i - 1]));
-                    if (i + 1 < npk) rS = exp10(-2.7 * (sm.mz[i + 1] - z));
+                    if (i > 0) rU = exp10_tab(-2.7 * (z - sm.mz[i - 1]), sm.etab);
+                    if (i + 1 < npk) rS = exp10_tab(-2.7 * (sm.mz[i + 1] - z), sm.etab);
                 }
                 __syncthreads();
                 const int lpos = s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u));
@@ -500,6 +524,33 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (im >= 0) sm.mS[im] = bS;
                 if (tid == 0) { sm.mS[npk] = 0.0; sm.mP[0] = 0.0; }
                 if (i < npk) sm.mP[i + 1] = pP;          // inclusive sum up to i = sum below i+1
+            }
+        }
+        if (!cp.spread_seq && sm.zlut != nullptr) {
+            // count table over Bark cells for masker_range (the peak bins in these words are no longer needed)
+            __syncthreads();
+            unsigned* z32 = reinterpret_cast<unsigned*>(sm.zlut);
+            for (int i = tid; i < (MRC_ZLUT + 2) / 2; i += NT) z32[i] = 0u;
+            __syncthreads();
+            if (tid < npk) {
+                int cell = (int)(sm.mz[tid] * 32.0) + 1;             // counted from cell+1 on: z < g/32 for g > z*32
+                cell = cell < 1 ? 1 : (cell > MRC_ZLUT ? MRC_ZLUT : cell);
+                atomicAdd(&z32[cell >> 1], 1u << (16 * (cell & 1)));
+            }
+            __syncthreads();
+            if (warp == 0) {                                         // inclusive prefix over the 833 cells
+                constexpr int PER = (MRC_ZLUT + 1 + 31) / 32;        // 27 cells per lane
+                const int c0 = lane * PER;
+                int run = 0;
+                for (int i = 0; i < PER; ++i) if (c0 + i <= MRC_ZLUT) run += sm.zlut[c0 + i];
+                int incl = run;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int acc = incl - run;
+                for (int i = 0; i < PER; ++i)
+                    if (c0 + i <= MRC_ZLUT) { acc += sm.zlut[c0 + i]; sm.zlut[c0 + i] = (uint16_t)acc; }
             }
         }
         __syncthreads();
@@ -666,56 +717,77 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // Each band's SMR trajectory (smr, -12, -6, -6, ...) is independent of the other bands, so the greedy
     // arg-max visits the (band, level) tokens in globally sorted order: key descending, first (lowest) band on
     // ties.  Joint blocks sort 2*nb bands together; non-joint blocks sort each channel on its own.
-    // The order is found by counting instead of sorting: a token's position = number of tokens that come before
-    // it = its own level + for every other band of its group the number of that band's keys (a descending run of
-    // 15, searched in 4 steps) that beat its key.  No barriers inside, and the comparisons are on exactly the
-    // values the reference's `smr[i] -= 12.0 / 6.0` updates produce.
+    // The 2*nb bands give 2*nb runs of 15 keys that are already in order, so the order is a merge: runs padded to 64
+    // runs of 16, then 6 rounds of pairwise merging in which every element finds its place by a binary search in
+    // the partner run (stable: ties in key go to the lower band, then to the run that came first).  Non-joint
+    // blocks keep their two channels in separate halves and skip the last round.  All comparisons are on exactly
+    // the values the reference's `smr[i] -= 12.0 / 6.0` updates produce.
     {
-        const int nbb = 2 * nb, ntok = nbb * MRC_MAX_LEVELS;
-        T* ktab = sm.skey;                               // [2nb][16]: keys of each band by level, [15] = -inf
-        int* s_rank = reinterpret_cast<int*>(sm.xi);     // [768] (xi is idle by now)
-        for (int i = tid; i < nbb * 16; i += NT) {
-            const int bb = i >> 4, lvl = i & 15;
-            const int ch = bb / nb, bd = bb - ch * nb;
-            const bool m = (ms >> bd) & 1u;
-            T v = s_smr[(m ? 2 : 0) + ch][bd];
-            if (lvl >= 1) v -= T(12);
-            for (int q = 1; q < lvl; ++q) v -= T(6);
-            ktab[i] = (lvl < MRC_MAX_LEVELS) ? v : T(-INFINITY);
-        }
-        for (int i = tid; i < MRC_TOK_STRIDE; i += NT) { s_rank[i] = 0; sm.sid[i] = 0xffffu; }
-        __syncthreads();
-        const int gsz = joint ? nbb : nb;                // bands per group
-        const int hsz = (gsz + 1) >> 1;
-        for (int w = tid; w < 2 * ntok; w += NT) {       // work item = (token, half of the group's bands)
-            const int tok = w >> 1, half = w & 1;
-            const int bb = tok / MRC_MAX_LEVELS, lvl = tok - bb * MRC_MAX_LEVELS;
-            const int g0b = joint ? 0 : (bb / nb) * nb;
-            const int b_lo = g0b + half * hsz, b_hi = min(g0b + gsz, b_lo + hsz);
-            const T v = ktab[bb * 16 + lvl];
-            int cnt = 0;
-            for (int b2 = b_lo; b2 < b_hi; ++b2) {
-                if (b2 == bb) { cnt += lvl; continue; }
-                const T* kk = ktab + b2 * 16;
-                const bool lower = b2 < bb;              // ties go to the lower band (first maximum wins)
-                int pos = 0;
-                { const T x = kk[7]; if (x > v || (x == v && lower)) pos = 8; }
-                { const T x = kk[pos + 3]; if (x > v || (x == v && lower)) pos += 4; }
-                { const T x = kk[pos + 1]; if (x > v || (x == v && lower)) pos += 2; }
-                { const T x = kk[pos]; if (x > v || (x == v && lower)) pos += 1; }
-                cnt += pos;
+        __syncthreads();                                 // phase 5 is done reading sm.lines: the merge buffers alias it
+        T* const key0 = sm.mkey;
+        T* const key1 = sm.mkey + 1024;
+        uint16_t* const id0 = sm.mid;
+        uint16_t* const id1 = sm.mid + 1024;
+        for (int e = tid; e < 1024; e += NT) {
+            const int run = e >> 4, lvl = e & 15;
+            // joint: run = band of the 2nb-band list; non-joint: channel 0 in runs 0..31, channel 1 in runs 32..63
+            int bb = -1;
+            if (joint) { if (run < 2 * nb) bb = run; }
+            else { const int ch = run >> 5, bd = run & 31; if (bd < nb) bb = ch * nb + bd; }
+            T v = -INFINITY;
+            uint16_t id = 0xffffu;
+            if (bb >= 0 && lvl < MRC_MAX_LEVELS) {
+                const int ch = bb / nb, bd = bb - ch * nb;
+                const bool m = (ms >> bd) & 1u;
+                v = s_smr[(m ? 2 : 0) + ch][bd];
+                if (lvl >= 1) v -= T(12);
+                for (int q = 1; q < lvl; ++q) v -= T(6);
+                id = (uint16_t)((bb << 4) | lvl);        // band-major: ties in key go to the lower band
             }
-            atomicAdd(&s_rank[tok], cnt);
+            key0[e] = v;
+            id0[e] = id;
         }
         __syncthreads();
-        for (int tok = tid; tok < ntok; tok += NT) {
-            const int bb = tok / MRC_MAX_LEVELS, lvl = tok - bb * MRC_MAX_LEVELS;
-            const int base = (!joint && bb >= nb) ? nb * MRC_MAX_LEVELS : 0;
-            sm.sid[base + s_rank[tok]] = (uint16_t)(bb | (lvl << 8));
+        int cur = 0;
+        const int last_w = joint ? 512 : 256;
+        for (int w = 16; w <= last_w; w <<= 1) {
+            const T* ks = cur ? key1 : key0;
+            const uint16_t* is = cur ? id1 : id0;
+            T* kd = cur ? key0 : key1;
+            uint16_t* idd = cur ? id0 : id1;
+            for (int e = tid; e < 1024; e += NT) {
+                const int q = e / w, i = e - q * w;
+                const T v = ks[e];
+                const uint16_t id = is[e];
+                const int pbase = (q ^ 1) * w;           // partner run
+                const bool first = (q & 1) == 0;         // elements of the first run win ties
+                int lo = 0, hi = w;
+                while (lo < hi) {                        // number of partner elements that go before this one
+                    const int mid = (lo + hi) >> 1;
+                    const T x = ks[pbase + mid];
+                    const uint16_t xi = is[pbase + mid];
+                    const bool x_before = (x > v) || (x == v && (xi < id || (xi == id && !first)));
+                    if (x_before) lo = mid + 1; else hi = mid;
+                }
+                const int dst = (q >> 1) * 2 * w + i + lo;
+                kd[dst] = v;
+                idd[dst] = id;
+            }
+            __syncthreads();
+            cur ^= 1;
         }
-        __syncthreads();
+        const uint16_t* fin = cur ? id1 : id0;
         uint16_t* ot = ho.tokens + (size_t)lb * MRC_TOK_STRIDE;
-        for (int i = tid; i < MRC_TOK_STRIDE; i += NT) ot[i] = sm.sid[i];
+        const int per_group = nb * MRC_MAX_LEVELS;
+        for (int i = tid; i < MRC_TOK_STRIDE; i += NT) {
+            int src = -1;
+            if (joint) { if (i < 2 * per_group) src = i; }
+            else if (i < per_group) src = i;
+            else if (i < 2 * per_group) src = 512 + (i - per_group);
+            uint16_t o = 0xffffu;
+            if (src >= 0) { const uint16_t id = fin[src]; o = (uint16_t)((id >> 4) | ((id & 15) << 8)); }
+            ot[i] = o;
+        }
     }
 }
 
@@ -723,9 +795,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
 
 size_t analysis_smem_bytes(int L, int elem) {
     const size_t Q = L / 2;
-    size_t spread = std::max<size_t>(4 * Q, 1280) * 8;                 // mc, mU, mS, mP (the grant order aliases them)
+    size_t spread = (size_t)(4 * Q) * 8;                               // mc, mU, mS, mP
     if ((size_t)(2 * L) * elem >= spread) spread = 0;                  // ... living in the FFT work buffer
-    return (size_t)(11 * L) * elem + (3 * Q + 64) * 8 + spread + (2 * Q + 1) * 4 + Q * 2 + 16;
+    size_t merge = (size_t)2048 * elem + 2048 * 2;                     // merge buffers of the grant order
+    if ((size_t)(4 * L) * elem >= merge) merge = 0;                    // ... living in `lines`
+    return (size_t)(11 * L) * elem + (3 * Q + 64) * 8 + spread + (2 * Q + 1) * 4 + Q * 2 + 32 + merge;
 }
 
 template <typename T>
