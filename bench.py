@@ -42,6 +42,11 @@ def parse():
                     help="masker spreading: factorised (default) or pair by pair in the reference's order")
     ap.add_argument("--no-sequential-sample", action="store_true",
                     help="skip the short pair-by-pair run that is reported as roofline_sequential")
+    ap.add_argument("--workload", default="stream", choices=["stream", "batch"],
+                    help="stream: one clip of --seconds per GPU (BASELINE configs[1]); batch: the same audio cut into "
+                         "independent clips of --clip-seconds (configs[3] shape)")
+    ap.add_argument("--clip-seconds", type=float, default=30.0)
+    ap.add_argument("--decode", action="store_true", help="also time the decode mirror path on the encoded stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=1.5)
     return ap.parse_args()
@@ -182,10 +187,15 @@ def main():
     threads = max(1, min(16, (os.cpu_count() or 8) // max(world, 1)))
     pcm = synth.synth_clip(rank, seconds, threads=threads, fast=True)            # [frames, 2] int16
     frames = pcm.shape[0]
-    off = np.array([0, frames], dtype=np.int64)
+    if args.workload == "batch":
+        cf = int(round(args.clip_seconds * SR))
+        off = np.unique(np.append(np.arange(0, frames, cf), frames)).astype(np.int64)
+    else:
+        off = np.array([0, frames], dtype=np.int64)
+    n_clips = len(off) - 1
     codec = Codec(device=local, precision=args.precision, spreading=args.spreading)
     L = codec.L
-    nblk = codec.n_blocks(frames)
+    nblk = int(sum(codec.n_blocks(f) for f in np.diff(off)))
 
     # device-resident buffers (torch is plumbing: device memory + NCCL)
     d_pcm = torch.from_numpy(pcm).to(dev)
@@ -197,19 +207,22 @@ def main():
     lens = torch.zeros(1, dtype=torch.int64, device=dev)
     gathered = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
 
+    last_boff = [None]
+
     def step_device():
         boff = codec.encode_batch_device(d_pcm.data_ptr(), off, d_out.data_ptr(), cap)
         if world > 1:                    # the path's only collective: per-shard bitstream lengths -> offsets
-            lens[0] = int(boff[1])
+            lens[0] = int(boff[-1])
             dist.all_gather(gathered, lens)
-        return int(boff[1])
+        return int(boff[-1])
 
     def step_e2e():
         out, boff = codec.encode_batch(h_pcm_np, off, out=h_out_np)
+        last_boff[0] = boff
         if world > 1:
-            lens[0] = int(boff[1])
+            lens[0] = int(boff[-1])
             dist.all_gather(gathered, lens)
-        return int(boff[1])
+        return int(boff[-1])
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,7 +273,7 @@ def main():
             except Exception:
                 pass
         an_ms = r_dev["stage_ms"][0]
-        flops = algorithmic_flops(nblk - 1, 1, r_dev["maskers"], L)
+        flops = algorithmic_flops(nblk - n_clips, n_clips, r_dev["maskers"], L)
         is64 = args.precision == "fp64"
         peak_tf = peaks["fp64_tflops"] if is64 else peaks["fp32_tflops"]
         ach_tf = flops / (an_ms * 1e-3) / 1e12
@@ -269,8 +282,12 @@ def main():
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * r_dev["wall"] / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is64 else "f32", "data": "synthetic",
-            "config": {"workload": "%.0f s synthetic 48 kHz stereo 16-bit stream per GPU (BASELINE configs[1] = 1 h), "
-                                   "joint M/S, 128 kb/s/ch, %s mode, long blocks N=2048" % (seconds, args.precision),
+            "config": {"workload": ("%.0f s synthetic 48 kHz stereo 16-bit stream per GPU (BASELINE configs[1] = 1 h), "
+                                    "joint M/S, 128 kb/s/ch, %s mode, long blocks N=2048" % (seconds, args.precision))
+                       if args.workload == "stream" else
+                       ("%d independent clips of %.0f s (%.0f s of synthetic 48 kHz stereo audio per GPU, BASELINE "
+                        "configs[3] shape), joint M/S, 128 kb/s/ch, %s mode" % (n_clips, args.clip_seconds, seconds,
+                                                                                 args.precision)),
                        "l2": "input %.0f MB per step > 126 MB L2, no flush needed" % (frames * 4 / 1e6),
                        "blocks_per_step": nblk, "bitstream_bytes": r_dev["nbytes"]},
             "device_ms_per_step": 1000.0 * r_dev["dev"] / args.steps,
@@ -312,6 +329,23 @@ def main():
                                            "sample": "first %.0f s of the stream, 1 launch" % sample_s,
                                            "avg_launch_ms": ts["analysis_ms"]}
             cs.close()
+        if args.decode:
+            # the mirror path (rows a14-a17): .pac bytes in pinned host memory -> int16 PCM in host memory
+            nbytes = int(last_boff[0][-1])
+            pac = h_out_np[:nbytes]
+            pcm_out = np.empty((nblk * L, 2), dtype=np.int16)
+            for _ in range(2):
+                codec.decode_batch(pac, last_boff[0], pcm_out=pcm_out)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                codec.decode_batch(pac, last_boff[0], pcm_out=pcm_out)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            td = codec.last_timing()
+            line["decode"] = {"e2e_value": seconds / dt, "unit": "audio-s/s", "ms_per_step": 1000.0 * dt,
+                              "kernel_ms": td["decode_ms"], "h2d_bytes_per_step": nbytes,
+                              "d2h_bytes_per_step": int(pcm_out.nbytes)}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pcm, args.cpu_sample_seconds)
         print(json.dumps(line))

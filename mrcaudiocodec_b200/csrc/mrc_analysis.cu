@@ -765,8 +765,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 while (lo < hi) {                        // number of partner elements that go before this one
                     const int mid = (lo + hi) >> 1;
                     const T x = ks[pbase + mid];
-                    const uint16_t xi = is[pbase + mid];
-                    const bool x_before = (x > v) || (x == v && (xi < id || (xi == id && !first)));
+                    bool x_before = x > v;
+                    if (x == v) {                        // rare: only ties look at the ids
+                        const uint16_t xi = is[pbase + mid];
+                        x_before = xi < id || (xi == id && !first);
+                    }
                     if (x_before) lo = mid + 1; else hi = mid;
                 }
                 const int dst = (q >> 1) * 2 * w + i + lo;

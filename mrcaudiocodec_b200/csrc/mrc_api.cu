@@ -176,7 +176,8 @@ struct EncodeJob {
     bool need_quant = true;
 };
 
-constexpr int WAVE_BLOCKS = 1 << 15;   // blocks per wave: ~1.8 GB of hand-off per buffer set in fp64
+constexpr int WAVE_BLOCKS = 1 << 14;   // blocks per wave: ~0.9 GB of hand-off per buffer set in fp64; the serial walk of
+                                       // the last wave is the un-overlapped tail of a call, so waves are kept short
 constexpr int NSETS = 2;               // buffer sets: wave w+1 is analysed while wave w is chained and packed
 
 cudaEvent_t pool_event(mrc_ctx* ctx, size_t i) {
