@@ -15,17 +15,19 @@ fi
 if [ "$WHAT" = all ] || [ "$WHAT" = bench ]; then
     timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
     echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json
-    timeout 600 python bench.py --steps 3 --warmup 3 --precision fp32 --no-cpu-baseline > gpurun_out/${TAG}_bench_fp32.json 2>> gpurun_out/${TAG}_bench.err
-    cat gpurun_out/${TAG}_bench_fp32.json
+    timeout 600 python bench.py --steps 3 --warmup 3 --precision fp32 --no-cpu-baseline --no-sequential-sample > gpurun_out/${TAG}_bench_fp32.json 2>> gpurun_out/${TAG}_bench.err
+    timeout 600 python bench.py --steps 3 --warmup 3 --workload batch --decode --no-cpu-baseline --no-sequential-sample > gpurun_out/${TAG}_bench_batch.json 2>> gpurun_out/${TAG}_bench.err
+    timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
+    tail -c 600 gpurun_out/${TAG}_bench_reference.json
 fi
 if [ "$WHAT" = all ] || [ "$WHAT" = ncu ]; then
-    CMD="python bench.py --steps 2 --warmup 1 --seconds 600 --no-cpu-baseline"
+    CMD="python bench.py --steps 2 --warmup 1 --seconds 600 --no-cpu-baseline --no-sequential-sample"
     $CMD > gpurun_out/${TAG}_ncu_plain.log 2>&1 &&
     ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
     echo "launch list rc=$?"
-    CMD2="python bench.py --steps 1 --warmup 1 --seconds 120 --no-cpu-baseline"
+    CMD2="python bench.py --steps 1 --warmup 1 --seconds 120 --no-cpu-baseline --no-sequential-sample"
     $CMD2 > gpurun_out/${TAG}_ncu_plain2.log 2>&1 &&
-    ncu --set full --clock-control none --import-source on -k regex:'analysis_kernel|quant_kernel|cost_kernel|chain_kernel|pack_kernel' -s 4 -c 4 -f -o gpurun_out/${TAG}_prof $CMD2 > gpurun_out/${TAG}_ncu_full.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:'analysis_kernel|cost_kernel|table_kernel|chain_kernel|chain_table_kernel|finish_kernel|offsets_kernel|clip_scan_kernel|pack_kernel' -s 8 -c 8 -f -o gpurun_out/${TAG}_prof $CMD2 > gpurun_out/${TAG}_ncu_full.log 2>&1
     echo "full capture rc=$?"
     ls -la gpurun_out/
 fi
