@@ -92,6 +92,26 @@ template <typename T>
 __device__ __forceinline__ void fft_dit(cpx<T>* a, int logn, int lt, int nthr, const cpx<T>* __restrict__ tw,
                                         int logLtab) {
     const int nb = 1 << (logn - 1);
+    if (nthr == nb) {
+        // one butterfly per thread and stage: the twiddle of the next stage is fetched before the barrier (with two
+        // CTAs' worth of shared memory carved out there is next to no L1 left, so table reads come from L2)
+        const int i = lt;
+        cpx<T> w = tw[0];                                   // stage 1: j = 0
+        for (int s = 1; s <= logn; ++s) {
+            const int half = 1 << (s - 1);
+            const int j = i & (half - 1);
+            const int base = ((i >> (s - 1)) << s) + j;
+            const cpx<T> u = a[base];
+            const cpx<T> v = a[base + half];
+            const T vx = v.x * w.x - v.y * w.y;
+            const T vy = v.x * w.y + v.y * w.x;
+            if (s < logn) w = tw[(i & (2 * half - 1)) << (logLtab - s - 1)];
+            a[base].x = u.x + vx;          a[base].y = u.y + vy;
+            a[base + half].x = u.x - vx;   a[base + half].y = u.y - vy;
+            __syncthreads();
+        }
+        return;
+    }
     for (int s = 1; s <= logn; ++s) {
         const int half = 1 << (s - 1);
         for (int i = lt; i < nb; i += nthr) {
