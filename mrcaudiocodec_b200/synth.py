@@ -78,3 +78,35 @@ def synth_short(seed, seconds, sample_rate=48000):
     b = min(a + int(0.2 * sample_rate), n)
     x[a:b] *= 10 ** (-70 / 20.0) / 0.2
     return np.round(np.clip(x, -0.999, 0.999) * 32767.0).astype(np.int16)
+
+
+def synth_music(seed, seconds, sample_rate=48000):
+    """Music-like test material (dense loud tonal maskers, unlike synth_clip's sparse tones over a noise floor): a
+    new chord every 0.4 s of three to five notes, each a fundamental with a dozen decaying harmonics and a slow
+    vibrato, panned individually, under an exponentially decaying attack envelope, plus a little noise; peaks around
+    -3 dBFS.  Exercises the loud-masker path of the spreading (levels above 40 dB SPL) on most of the spectrum."""
+    rng = np.random.default_rng([int(seed), 777])
+    n = int(round(seconds * sample_rate))
+    t = np.arange(n, dtype=np.float64) / sample_rate
+    x = np.zeros((n, 2), dtype=np.float64)
+    seg = int(0.4 * sample_rate)
+    for s0 in range(0, n, seg):
+        s1 = min(s0 + seg, n)
+        tt = t[s0:s1] - t[s0]
+        env = np.exp(-3.0 * tt) * (1.0 - np.exp(-400.0 * tt))
+        for _ in range(int(rng.integers(3, 6))):
+            f0 = 55.0 * 2.0 ** (rng.integers(0, 48) / 12.0) * (1.0 + 0.003 * rng.standard_normal())
+            pan = rng.uniform(0.1, 0.9)
+            vib = 1.0 + 0.004 * np.sin(2 * np.pi * rng.uniform(4, 7) * tt)
+            ph = 2 * np.pi * f0 * np.cumsum(vib) / sample_rate
+            note = np.zeros_like(tt)
+            for h in range(1, 13):
+                if f0 * h > 0.45 * sample_rate:
+                    break
+                note += (0.5 ** (0.5 * (h - 1))) * np.sin(h * ph + rng.uniform(0, 2 * np.pi))
+            note *= env * rng.uniform(0.08, 0.25)
+            x[s0:s1, 0] += note * np.sqrt(1.0 - pan)
+            x[s0:s1, 1] += note * np.sqrt(pan)
+    x += 0.002 * rng.standard_normal((n, 2))
+    np.clip(x, -0.999, 0.999, out=x)
+    return np.round(x * 32767.0).astype(np.int16)

@@ -61,3 +61,19 @@ def test_batch_of_clips_equals_singles():
     for i, b in enumerate(batch):
         assert b == singles[i % 8], i
     c.close()
+
+
+def test_factorised_equals_sequential_at_scale():
+    """Ten minutes of music-like material and ten of the bench signal: the factorised evaluation of the masker
+    spreading (default) and the pair-by-pair evaluation in the reference's order give the same bytes."""
+    from mrcaudiocodec_b200 import Codec, synth
+    minutes = min(MINUTES, 10.0)
+    clips = [np.concatenate([synth.synth_music(100 + i, 30.0) for i in range(int(2 * minutes))], axis=0),
+             synth.synth_clip(7, 60 * minutes, threads=8, fast=True)]
+    cf, cs = Codec(), Codec(spreading="sequential")
+    bf = cf.encode_clips(clips)
+    bs = cs.encode_clips(clips)
+    assert [len(b) for b in bf] == [len(b) for b in bs]
+    assert bf == bs
+    cf.close()
+    cs.close()

@@ -160,6 +160,21 @@ def test_chain_table_fast_path_vs_oracle(monkeypatch):
     c.close()
 
 
+def test_music_like_material_vs_oracle(codecs):
+    """dense loud tonal maskers (most peaks above 40 dB SPL): the loud-masker branch of the factorised spreading and
+    the band-maximum search, against the oracle; joint and independent channels."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import synth
+    pcm = synth.synth_music(5, 0.9)
+    for joint in (True, False):
+        ob, _ = o.driver.encode_pcm(pcm, joint=joint)
+        assert codecs(48000, joint).encode_clips([pcm])[0] == ob, joint
+        assert codecs(48000, joint, spreading="sequential").encode_clips([pcm])[0] == ob, joint
+    od = o.driver.decode_pac(ob, joint=False)
+    gd = codecs(48000, False).decode_clips([ob])[0]
+    assert np.abs(gd.astype(np.int64) - od.astype(np.int64)).max() <= 1
+
+
 def test_sharded_batch_equals_single_context(codecs):
     """multi-GPU sharding (mrcaudiocodec_b200/dist.py) emulated in one process: three 'ranks' encode their
     contiguous clip ranges with their own contexts; bytes and global offsets equal the single-context batch."""
@@ -276,3 +291,21 @@ def test_bitrate_sweep_vs_oracle(codecs):
         tbps = kbps * 1000. / 48000.
         ob, _ = o.driver.encode_pcm(pcm, joint=True, targetBitsPerSample=tbps)
         assert codecs(48000, True, tbps).encode_clips([pcm])[0] == ob, kbps
+
+
+def test_cli_wav_roundtrip(tmp_path):
+    """in.wav -> in.pac -> in_decoded.wav through the command line front end; the .pac equals the
+    oracle's file for the same PCM and the decoded WAV equals the oracle decoder's PCM within 1 LSB."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import cli, synth
+    pcm = synth.synth_short(91, 0.4, sample_rate=44100)
+    wav = str(tmp_path / "x.wav")
+    cli.write_wav(wav, 44100, pcm)
+    cli.main(["roundtrip", wav, "--kbps", "96"])
+    blob = open(str(tmp_path / "x.pac"), "rb").read()
+    ob, _ = o.driver.encode_pcm(pcm, joint=True, sampleRate=44100, targetBitsPerSample=96000. / 44100.)
+    assert blob == ob
+    sr, dec = cli.read_wav(str(tmp_path / "x_decoded.wav"))
+    od = o.driver.decode_pac(ob, joint=True)
+    assert sr == 44100 and dec.shape == od.shape
+    assert np.abs(dec.astype(np.int64) - od.astype(np.int64)).max() <= 1
