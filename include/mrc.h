@@ -155,6 +155,19 @@ int32_t mrc_stage_alloc_quant(mrc_ctx* ctx, const int16_t* pcm, const int64_t* c
                               int32_t n_clips, int32_t* bit_alloc, int32_t* scale_factor, int32_t* mantissa,
                               int32_t* huff_table, int32_t* reservoir, int32_t* chunk_bytes);
 
+/* ---- Huffman table training front end (huffman_training_script.py:33-66) ----------------------
+ * Encodes the clips block by block like the script's loop -- independent channels (the context must have joint = 0),
+ * EncodeNoHuff (codecThem.py:234-260), reservoir starting at 0 per file, no flush block -- and runs every channel's
+ * compacted mantissa vector through calculateFrequencies (huffman.py:56-71), including that function's reset quirk:
+ * the first never-seen (hence record-high) value of a call zeroes the counts of all smaller values.
+ * prior_max : largest mantissa value counted by earlier calls (-1 for the first call)
+ * hist      : [65536] counts accumulated in THIS call since its last reset (or since its start if it had none)
+ * max_out   : largest value seen so far (prior_max included);  reset_out : 1 if a reset happened in this call (the
+ *             caller then replaces its running table by hist instead of adding to it)
+ * At most 16384 blocks per call.                                                                                */
+int32_t mrc_mantissa_histogram(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
+                               int32_t prior_max, int64_t* hist, int32_t* max_out, int32_t* reset_out);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the stream each kernel is launched on, summed over waves) of the stages of the
  * last encode/decode call: [0] analysis kernels, [1] chain (serial reservoir walk) kernels, [2] clip-offset scan +

@@ -42,7 +42,7 @@ class MrcError(RuntimeError):
 EXPORTS = ["mrc_version", "mrc_last_error", "mrc_create", "mrc_destroy", "mrc_set_tables", "mrc_host_alloc",
            "mrc_host_free", "mrc_encode_batch", "mrc_encode_batch_device", "mrc_decode_batch",
            "mrc_decode_batch_device", "mrc_encode_block", "mrc_decode_block", "mrc_stage_analysis",
-           "mrc_stage_alloc_quant", "mrc_last_timing", "mrc_measure_peaks"]
+           "mrc_stage_alloc_quant", "mrc_mantissa_histogram", "mrc_last_timing", "mrc_measure_peaks"]
 
 _lib = None
 

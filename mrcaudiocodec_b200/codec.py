@@ -211,6 +211,18 @@ class Codec(object):
                                               _ptr(ms), _ptr(out)))
         return out
 
+    # ---- Huffman table training front end ------------------------------------------
+    def mantissa_histogram(self, clips, prior_max=-1):
+        """calculateFrequencies over the EncodeNoHuff mantissas of `clips` (at most 16384 blocks per call).
+        Returns (hist int64 [65536] since the last reset inside the call, largest value so far, reset flag)."""
+        pcm, off = self._concat(clips)
+        hist = np.zeros(65536, np.int64)
+        mx = np.zeros(1, np.int32)
+        rs = np.zeros(1, np.int32)
+        self._check(self.lib.mrc_mantissa_histogram(self._ctx, _ptr(pcm), _ptr(off), len(clips), int(prior_max),
+                                                    _ptr(hist), _ptr(mx), _ptr(rs)))
+        return hist, int(mx[0]), bool(rs[0])
+
     def measure_peaks(self):
         out = np.zeros(4, np.float64)
         self._check(self.lib.mrc_measure_peaks(self._ctx, _ptr(out)))

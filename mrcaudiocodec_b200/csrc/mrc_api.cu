@@ -174,6 +174,7 @@ struct EncodeJob {
     int32_t* t_alloc = nullptr; int32_t* t_sf = nullptr; int32_t* t_mant = nullptr; int32_t* t_table = nullptr;
     int32_t* t_res = nullptr; int32_t* t_cbytes = nullptr;
     bool need_quant = true;
+    bool dev_qtaps = false;                // leave alloc / mantissa taps of the (single) wave in q_alloc / q_mant
 };
 
 constexpr int WAVE_BLOCKS = 1 << 14;   // blocks per wave: ~0.9 GB of hand-off per buffer set in fp64; the serial walk of
@@ -249,8 +250,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
 
     // ---- buffer sets ----
     const bool want_atap = job.t_lines || job.t_smr || job.t_npk;
-    const bool want_qtap = job.t_alloc || job.t_sf || job.t_mant;
-    const bool any_tap = want_atap || want_qtap || job.t_ovs || job.t_ms || job.t_table || job.t_res || job.t_cbytes;
+    const bool want_qtap = job.t_alloc || job.t_sf || job.t_mant || job.dev_qtaps;
+    const bool any_tap = want_atap || job.t_alloc || job.t_sf || job.t_mant || job.t_ovs || job.t_ms || job.t_table || job.t_res || job.t_cbytes;
     const size_t W = (size_t)std::max(std::min(nblk_total, WAVE_BLOCKS), 1);
     const int nsets = (nblk_total > WAVE_BLOCKS) ? NSETS : 1;
     Handoff<T> ho[NSETS];
@@ -521,8 +522,8 @@ int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out) {
     while ((1 << logL) < cfg->n_mdct_lines) ++logL;
     if ((1 << logL) != cfg->n_mdct_lines || logL < 8 || logL > 11)
         return fail(nullptr, MRC_E_INVALID, "n_mdct_lines must be 256, 512, 1024 or 2048");
-    if (cfg->n_scale_bits < 1 || cfg->n_scale_bits > 4 || cfg->n_mant_size_bits < 1 || cfg->n_mant_size_bits > 4)
-        return fail(nullptr, MRC_E_INVALID, "n_scale_bits and n_mant_size_bits must be in 1..4");
+    if (cfg->n_scale_bits < 1 || cfg->n_scale_bits > 4 || cfg->n_mant_size_bits < 4 || cfg->n_mant_size_bits > 5)
+        return fail(nullptr, MRC_E_INVALID, "n_scale_bits must be in 1..4 and n_mant_size_bits 4 or 5 (16-bit mantissa cap)");
     if (cfg->precision != MRC_PRECISION_FP64 && cfg->precision != MRC_PRECISION_FP32)
         return fail(nullptr, MRC_E_INVALID, "unknown precision");
     int ndev = 0;
@@ -684,7 +685,7 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     ctx->cp.spread_seq = (c.flags & MRC_FLAG_SPREAD_SEQUENTIAL) ? 1 : 0;
     ctx->no_tables = (c.flags & MRC_FLAG_NO_CHAIN_TABLES) != 0;
     if (const char* e = getenv("MRC_CHAIN_TABLE_MIN_BLOCKS")) ctx->tab_min_blocks = std::max(1, atoi(e));   // test knob
-    if (ctx->cp.max_mant_bits != 16) return fail(ctx, MRC_E_INVALID, "only n_mant_size_bits = 4 (16-bit cap) is supported");
+    if (ctx->cp.max_mant_bits != 16) return fail(ctx, MRC_E_INVALID, "only a 16-bit mantissa cap is supported");
     // .pac header template (pacfileThem.py:592-613); numSamples is patched per clip by the pack kernel
     uint8_t* hd = ctx->h_header;
     memset(hd, 0, sizeof ctx->h_header);
@@ -820,6 +821,54 @@ int32_t mrc_encode_block(mrc_ctx* ctx, const double* data, int32_t joint, int32_
     const int rc = run_encode(ctx, job);
     if (rc == MRC_OK) *reservoir = res_out;
     return rc;
+}
+
+int32_t mrc_mantissa_histogram(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
+                               int32_t prior_max, int64_t* hist, int32_t* max_out, int32_t* reset_out) {
+    if (!ctx) return MRC_E_INVALID;
+    if (!clip_frame_offsets || n_clips < 0 || !hist || !max_out || !reset_out) return fail(ctx, MRC_E_INVALID, "bad argument");
+    if (ctx->cfg.joint) return fail(ctx, MRC_E_INVALID, "the training front end encodes independent channels: create the context with joint = 0");
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    const int L = ctx->L;
+    const int64_t frames = clip_frame_offsets[n_clips];
+    int64_t nblk = 0;
+    for (int c = 0; c < n_clips; ++c) nblk += (clip_frame_offsets[c + 1] - clip_frame_offsets[c] + L - 1) / L;
+    if (nblk > WAVE_BLOCKS) return fail(ctx, MRC_E_INVALID, "too many blocks in one histogram call (split the corpus)");
+    memset(hist, 0, 65536 * sizeof(int64_t));
+    *max_out = prior_max;
+    *reset_out = 0;
+    if (nblk == 0) return MRC_OK;
+    CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(frames, 1) * 4));
+    CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)frames * 4, cudaMemcpyHostToDevice, st));
+    EncodeJob job;
+    job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
+    job.joint = 0; job.no_huff = 1; job.flush_nonjoint = false;       // the script counts the blocks of its own loop only
+    job.dev_qtaps = true;
+    const int rc = run_encode(ctx, job);
+    if (rc != MRC_OK) return rc;
+    const int ncalls = (int)nblk * 2;
+    const size_t cmax_bytes = ((size_t)ncalls * 4 + 15) & ~(size_t)15;
+    CK(ensure(ctx->dec[15], cmax_bytes + 65536 * 8));
+    int32_t* d_cmax = (int32_t*)ctx->dec[15].p;
+    unsigned long long* d_hist = (unsigned long long*)((char*)ctx->dec[15].p + cmax_bytes);
+    launch_callmax(st, L, ncalls, (const uint8_t*)ctx->q_alloc.p, (const uint16_t*)ctx->q_mant.p,
+                   (const uint8_t*)ctx->line2band.p, d_cmax);
+    std::vector<int32_t> cmax(ncalls);
+    CK(cudaMemcpyAsync(cmax.data(), d_cmax, (size_t)ncalls * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // the last call whose maximum is a new record: its first record-breaking mantissa resets all smaller counts
+    int gmax = prior_max, first_call = 0, thr = -2;
+    for (int c = 0; c < ncalls; ++c)
+        if (cmax[c] > gmax) { first_call = c; thr = gmax; gmax = cmax[c]; *reset_out = 1; }
+    CK(cudaMemsetAsync(d_hist, 0, 65536 * 8, st));
+    launch_hist(st, L, ncalls, first_call, thr, (const uint8_t*)ctx->q_alloc.p, (const uint16_t*)ctx->q_mant.p,
+                (const uint8_t*)ctx->line2band.p, d_hist);
+    CK(cudaMemcpyAsync(hist, d_hist, 65536 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *max_out = gmax;
+    return MRC_OK;
 }
 
 int32_t mrc_measure_peaks(mrc_ctx* ctx, double* out4) {

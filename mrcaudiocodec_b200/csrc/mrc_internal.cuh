@@ -181,5 +181,11 @@ void launch_clip_scan(cudaStream_t st, const int64_t* clip_bytes, int64_t* clip_
 
 size_t analysis_smem_bytes(int L, int elem);
 
+// mrc_train.cu
+void launch_callmax(cudaStream_t st, int L, int ncalls, const uint8_t* alloc, const uint16_t* mant,
+                    const uint8_t* line2band, int32_t* cmax);
+void launch_hist(cudaStream_t st, int L, int ncalls, int first_call, int thr, const uint8_t* alloc, const uint16_t* mant,
+                 const uint8_t* line2band, unsigned long long* hist);
+
 // mrc_peaks.cu
 int measure_peaks(cudaStream_t st, double* out);
