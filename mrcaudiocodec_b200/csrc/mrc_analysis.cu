@@ -390,7 +390,18 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     const T xi_den = T(N) * T(N) * T(0.375);
     int my_peaks = 0;
     unsigned n_general = 0, n_window = 0, n_loud = 0;
+    // OverallSMRs (ms_stereo.py:70-81) keeps, per band, the SMRs of (M, S) where ms_switch is set and of (L, R) where
+    // it is not, and drops the other pair.  So a spectrum's SMR is only needed in the bands that select it: the
+    // others are not evaluated (all of the spectrum's model when no band selects it).  The stage taps and the
+    // reference-order mode evaluate everything.
+    const bool all_bands = !joint || cp.spread_seq || taps.smr4 != nullptr || taps.npeaks != nullptr;
+    const unsigned band_mask = (nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u);
     for (int c = 0; c < nspec; ++c) {
+        const unsigned need = all_bands ? band_mask : ((c < 2 ? ~s_ms : s_ms) & band_mask);
+        if (need == 0u) {
+            if (tid < nb) s_smr[c][tid] = T(0);
+            continue;                                    // uniform: s_ms is shared
+        }
         // a. Hann window, real 2L-point FFT through an L-point complex FFT
         for (int n = tid; n < L; n += NT) {
             const int r = (int)(__brev((unsigned)n) >> (32 - logL));
@@ -618,10 +629,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             };
             {
                 const int k0 = tid, k1 = tid + Q;
-                const double a0 = spread_line_bound(sm, tb, k0, npk, n_general);
-                const double a1 = spread_line_bound(sm, tb, k1, npk, n_general);
-                sm.xi[k0] = T(x2c(k0) / fmax(a0, FLOOR));
-                sm.xi[k1] = T(x2c(k1) / fmax(a1, FLOOR));
+                T r0 = T(-1), r1 = T(-1);                // lines of bands that do not select this spectrum: never candidates
+                if ((need >> tb.line2band[k0]) & 1u) r0 = T(x2c(k0) / fmax(spread_line_bound(sm, tb, k0, npk, n_general), FLOOR));
+                if ((need >> tb.line2band[k1]) & 1u) r1 = T(x2c(k1) / fmax(spread_line_bound(sm, tb, k1, npk, n_general), FLOOR));
+                sm.xi[k0] = r0;
+                sm.xi[k1] = r1;
             }
             __syncthreads();
             const T slack = sizeof(T) == 8 ? T(1.0 - 1e-9) : T(1.0 - 1e-4);   // bound vs true value: rounding only
@@ -631,6 +643,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 rho = T(x2c(k) / fmax(a, FLOOR));
             };
             for (int sg = warp; sg < tb.nseg; sg += nwarp) {     // pass 2a
+                if (!((need >> tb.seg_band[sg]) & 1u)) continue;
                 const int lo = tb.seg_lo[sg], n = tb.seg_n[sg];
                 T ubest = T(-1);
                 int kbest = lo;
@@ -651,6 +664,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             __syncthreads();
             for (int sg = warp; sg < tb.nseg; sg += nwarp) {     // pass 2b
                 const int lo = tb.seg_lo[sg], n = tb.seg_n[sg], bd = tb.seg_band[sg];
+                if (!((need >> bd) & 1u)) continue;
                 T rbest = T(0);                                  // best true rho of the band so far
                 for (int s2 = tb.band_seg0[bd]; s2 < tb.band_seg0[bd + 1]; ++s2) rbest = fmax(rbest, s_seg_rho[s2]);
                 T best = s_seg_smr[sg];
@@ -675,8 +689,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             }
             __syncthreads();
             if (tid < nb) {
-                T v = -INFINITY;
-                for (int s2 = tb.band_seg0[tid]; s2 < tb.band_seg0[tid + 1]; ++s2) v = fmax(v, s_seg_smr[s2]);
+                T v = T(0);                              // bands that do not select this spectrum: value never used
+                if ((need >> tid) & 1u) {
+                    v = -INFINITY;
+                    for (int s2 = tb.band_seg0[tid]; s2 < tb.band_seg0[tid + 1]; ++s2) v = fmax(v, s_seg_smr[s2]);
+                }
                 s_smr[c][tid] = v;
             }
         }
