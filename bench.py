@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 SR = 48000
 TBPS = 128000.0 / 48000.0
 METRIC = "encoded audio-seconds/sec, 48 kHz stereo 128 kb/s/ch"
+NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK = 12767.0      # (23.57 + 48.26) MB / 5626 blocks, profiles/r01u_ncu_full_summary.csv
 
 
 def parse():
@@ -300,15 +301,20 @@ def main():
             "clocks": r_dev["clocks"],
             "roofline": {"kernel": "analysis_kernel (MDCT + psychoacoustics, fused)",
                          "bound": "fp64" if is64 else "fp32", "achieved": ach_tf, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
+                         # dram__bytes_read + dram__bytes_write of one analysis launch, from the committed ncu capture
+                         # (profiles/*_ncu_full_summary.csv: 71.8 MB for 5626 blocks), scaled to this run's launch size
+                         "traffic": NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK * nblk / max(r_dev["work"]["waves"], 1),
                          "peak_source": "mrc_measure_peaks (FMA chain on this GPU, this run)",
                          "work": "SURVEY 8d reference formulation (40 FLOP per masker-line pair), %d maskers measured; "
                                  "the %s evaluation executes the work listed under executed_work" %
                                  (r_dev["maskers"], args.spreading),
-                         "avg_launch_ms": an_ms},
+                         "launches_per_step": r_dev["work"]["waves"],
+                         "avg_launch_ms": an_ms / max(r_dev["work"]["waves"], 1), "ms_per_step": an_ms},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (an_ms * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": alg_bytes / (an_ms * 1e-3) / 1e9 / hbm_peak,
-                             "peak_source": hbm_src, "traffic": None},
+                             "peak_source": hbm_src,
+                             "traffic": NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK * nblk / max(r_dev["work"]["waves"], 1)},
             "pipe_peaks": peaks,
             "executed_work": r_dev["work"],
         }
