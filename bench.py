@@ -339,7 +339,8 @@ def main():
             # the mirror path (rows a14-a17): .pac bytes in pinned host memory -> int16 PCM in host memory
             nbytes = int(last_boff[0][-1])
             pac = h_out_np[:nbytes]
-            pcm_out = np.empty((nblk * L, 2), dtype=np.int16)
+            h_dec = torch.empty((nblk * L, 2), dtype=torch.int16).pin_memory()
+            pcm_out = h_dec.numpy()
             for _ in range(2):
                 codec.decode_batch(pac, last_boff[0], pcm_out=pcm_out)
             torch.cuda.synchronize()

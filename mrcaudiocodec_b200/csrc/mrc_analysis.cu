@@ -18,6 +18,7 @@
 
 #include "mrc_internal.cuh"
 #include "mrc_math.cuh"
+#include "mrc_fft.cuh"
 
 namespace {
 
@@ -84,61 +85,6 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     }
     s.mid = reinterpret_cast<uint16_t*>(s.mkey + 2048);
     return s;
-}
-
-// Position of input element n of a size-2^logn FFT for fft_r4 below: the digits of n reversed, in radix 4 with one
-// innermost radix-2 digit when logn is odd (n = t0 + 4 t1 + ... + 4^(m-1) t_(m-1) + 4^m u  ->  u + 2 (t_(m-1) + 4 t_(m-2)
-// + ... + 4^(m-1) t0)).
-__device__ __forceinline__ int fft_r4_pos(int n, int logn) {
-    const int m2 = logn & ~1;                                  // bits of the radix-4 digits
-    const unsigned t = (unsigned)n & ((1u << m2) - 1u);
-    unsigned b = m2 ? (__brev(t) >> (32 - m2)) : 0u;           // bits reversed ...
-    b = ((b & 0xaaaaaaaau) >> 1) | ((b & 0x55555555u) << 1);   // ... and swapped back inside every digit
-    return (logn & 1) ? (int)(((unsigned)n >> m2) | (b << 1)) : (int)b;
-}
-
-// In-place decimation-in-time FFT of size 2^logn on input placed by fft_r4_pos: one radix-2 stage first when logn is
-// odd, then radix-4 stages (half as many barriers and 0.4 x the instructions of radix 2).  `nthr` threads of this group
-// (local id lt); a radix-4 stage has n/4 butterflies.  tw[k] = exp(-2*pi*j*k/Ltab), k < Ltab/2, Ltab = 2^logLtab >= n.
-template <typename T>
-__device__ __forceinline__ void fft_r4(cpx<T>* a, int logn, int lt, int nthr, const cpx<T>* __restrict__ tw,
-                                       int logLtab) {
-    const int n = 1 << logn;
-    int h = 1;
-    if (logn & 1) {
-        for (int q = lt; q < (n >> 1); q += nthr) {
-            const cpx<T> u = a[2 * q], v = a[2 * q + 1];
-            a[2 * q].x = u.x + v.x;      a[2 * q].y = u.y + v.y;
-            a[2 * q + 1].x = u.x - v.x;  a[2 * q + 1].y = u.y - v.y;
-        }
-        __syncthreads();
-        h = 2;
-    }
-    const int half_tab = 1 << (logLtab - 1);
-    for (; 4 * h <= n; h <<= 2) {
-        const int logh = 31 - __clz(h);
-        for (int bi = lt; bi < (n >> 2); bi += nthr) {
-            const int j = bi & (h - 1);
-            const int base = ((bi >> logh) << (logh + 2)) + j;
-            const int k1 = j << (logLtab - logh - 2);          // W_(4h)^j = tw[j * Ltab / (4h)]
-            const cpx<T> w1 = tw[k1], w2 = tw[2 * k1];
-            const int k3 = 3 * k1;
-            cpx<T> w3;
-            if (k3 >= half_tab) { w3 = tw[k3 - half_tab]; w3.x = -w3.x; w3.y = -w3.y; }
-            else w3 = tw[k3];
-            const cpx<T> x0 = a[base], x1 = a[base + h], x2 = a[base + 2 * h], x3 = a[base + 3 * h];
-            const T t1x = x1.x * w1.x - x1.y * w1.y, t1y = x1.x * w1.y + x1.y * w1.x;
-            const T t2x = x2.x * w2.x - x2.y * w2.y, t2y = x2.x * w2.y + x2.y * w2.x;
-            const T t3x = x3.x * w3.x - x3.y * w3.y, t3y = x3.x * w3.y + x3.y * w3.x;
-            const T s02x = x0.x + t2x, s02y = x0.y + t2y, d02x = x0.x - t2x, d02y = x0.y - t2y;
-            const T s13x = t1x + t3x, s13y = t1y + t3y, d13x = t1x - t3x, d13y = t1y - t3y;
-            a[base].x = s02x + s13x;          a[base].y = s02y + s13y;
-            a[base + h].x = d02x + d13y;      a[base + h].y = d02y - d13x;          // d02 - j d13
-            a[base + 2 * h].x = s02x - s13x;  a[base + 2 * h].y = s02y - s13y;
-            a[base + 3 * h].x = d02x - d13y;  a[base + 3 * h].y = d02y + d13x;      // d02 + j d13
-        }
-        __syncthreads();
-    }
 }
 
 template <typename T>

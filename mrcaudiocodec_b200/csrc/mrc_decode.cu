@@ -10,29 +10,9 @@
 // switching bits set, unknown table id) raises the error flag and decodes as silence instead of reading on.
 #include "mrc_decode.cuh"
 #include "mrc_math.cuh"
+#include "mrc_fft.cuh"
 
 namespace {
-
-template <typename T>
-__device__ __forceinline__ void fft_dit_d(cpx<T>* a, int logn, int lt, int nthr, const cpx<T>* __restrict__ tw,
-                                          int logLtab) {
-    const int nb = 1 << (logn - 1);
-    for (int s = 1; s <= logn; ++s) {
-        const int half = 1 << (s - 1);
-        for (int i = lt; i < nb; i += nthr) {
-            const int j = i & (half - 1);
-            const int base = ((i >> (s - 1)) << s) + j;
-            const cpx<T> w = tw[j << (logLtab - s)];
-            const cpx<T> u = a[base];
-            const cpx<T> v = a[base + half];
-            const T vx = v.x * w.x - v.y * w.y;
-            const T vy = v.x * w.y + v.y * w.x;
-            a[base].x = u.x + vx;          a[base].y = u.y + vy;
-            a[base + half].x = u.x - vx;   a[base + half].y = u.y - vy;
-        }
-        __syncthreads();
-    }
-}
 
 struct BitReader {
     const uint32_t* w;       // big-endian words in shared memory
@@ -114,12 +94,12 @@ __device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecPa
         for (int n = lt; n < Q; n += gthr) {
             const T re = X[2 * n], im = X[L - 1 - 2 * n];
             const cpx<T> w = tb.tw_pre[n];
-            const int r = (int)(__brev((unsigned)n) >> (32 - (LOGL - 1)));
+            const int r = fft_r4_pos(n, LOGL - 1);
             a[r].x = re * w.x - im * w.y;
             a[r].y = re * w.y + im * w.x;
         }
         __syncthreads();
-        fft_dit_d<T>(a, LOGL - 1, lt, gthr, tb.tw_fft, LOGL);
+        fft_r4<T>(a, LOGL - 1, lt, gthr, tb.tw_fft, LOGL);
         T* v = sm.v + grp * L;
         for (int k = lt; k < Q; k += gthr) {
             const cpx<T> w = tb.tw_post[k];
@@ -153,6 +133,7 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
     __shared__ unsigned s_ms;
     __shared__ int s_bad, s_joint;
     __shared__ int s_esc[MRC_N_HUFF_TABLES];
+    __shared__ int s_boff[2 * MRC_BSTRIDE], s_raw[2];
 
     const int lp = blockIdx.x, p = p0 + lp;
     if (tid == 0) {
@@ -216,7 +197,10 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
             if (!ba) continue;
             const int lo = tb.band_lo[bd], n = tb.band_n[bd];
             if (table == MRC_NO_TABLE) {
-                for (int j = 0; j < n; ++j) mant[lo + j] = (int)br.read(ba);
+                // raw mantissas: fixed width, so only their position is recorded here; all threads extract them below
+                s_boff[ch * MRC_BSTRIDE + bd] = br.pos;
+                if (br.pos + n * ba > br.nbits) { br.bad = true; break; }
+                br.pos += n * ba;
             } else {
                 const uint16_t* lut = hdec->lut[table];
                 const int esc = s_esc[table];
@@ -231,12 +215,27 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
                 }
             }
         }
+        s_raw[ch] = (table == MRC_NO_TABLE);
         if (br.bad) {
             s_bad = 1;
             for (int bd = 0; bd < nb; ++bd) s_alloc[ch * MRC_BSTRIDE + bd] = 0;
         }
     }
     __syncthreads();
+    if (!s_bad) {
+        for (int i = tid; i < 2 * L; i += NT) {
+            const int ch = i / L, k = i - ch * L;
+            if (!s_raw[ch]) continue;
+            const int bd = tb.line2band[k];
+            const int ba = s_alloc[ch * MRC_BSTRIDE + bd];
+            if (!ba) continue;
+            BitReader br;
+            br.w = sm.cw + ch * cwords;
+            br.pos = s_boff[ch * MRC_BSTRIDE + bd] + (k - tb.band_lo[bd]) * ba;
+            sm.mant[i] = (int)br.peek(ba);
+        }
+        __syncthreads();
+    }
     if (s_bad) {
         if (tid == 0) atomicExch(error_flag, 1);
         if (tid < 2 * nb) s_alloc[(tid / nb) * MRC_BSTRIDE + tid % nb] = 0;
