@@ -77,3 +77,24 @@ def test_factorised_equals_sequential_at_scale():
     assert bf == bs
     cf.close()
     cs.close()
+
+
+def test_many_tiny_clips():
+    """2000 clips of 0..3000 frames in one call (clips straddle waves, many clips per wave): a sample of them equals
+    the single-clip encode, every clip has the chunk structure its length implies, and the batch decodes."""
+    from mrcaudiocodec_b200 import Codec, synth, pacfile
+    rng = np.random.default_rng(3)
+    base = synth.synth_clip(11, 40, fast=True)
+    lens = rng.integers(0, 3001, size=2000)
+    starts = rng.integers(0, base.shape[0] - 3001, size=2000)
+    clips = [base[s:s + n] for s, n in zip(starts, lens)]
+    c = Codec()
+    blobs = c.encode_clips(clips)
+    assert len(blobs) == 2000
+    for i in range(0, 2000, 97):
+        assert c.encode_clips([clips[i]])[0] == blobs[i], i
+    for i in range(0, 2000, 13):
+        assert len(pacfile.chunk_index(blobs[i])) == 2 * c.n_blocks(len(clips[i])), i
+    dec = c.decode_clips(blobs)
+    assert [d.shape[0] for d in dec] == [c.n_blocks(len(x)) * 1024 for x in clips]
+    c.close()
