@@ -1,6 +1,14 @@
 // mrc_analysis.cu -- K1/K2: framing + PCM conversion + M/S + KBD window + MDCT (N/4-point complex FFT) +
-// Hann-windowed FFT + tonal masker detection + Bark-domain spreading + SMR + grant-order sort, fused in one CTA
-// per 2L-sample block, everything staged in shared memory.
+// Hann-windowed FFT + tonal masker detection + Bark-domain spreading + SMR + grant order, fused in one CTA per
+// 2L-sample block, everything staged in shared memory (two CTAs per SM: <= 64 registers, ~114 KB each at L = 1024).
+//
+// How the psychoacoustic part differs from a literal transcription (same results):
+//   * masker spreading is the reference's sum re-associated (geometric tails by affine warp scans, plateau sums,
+//     one 10**x only for loud maskers below a line); MRC_FLAG_SPREAD_SEQUENTIAL keeps the pair-by-pair loop;
+//   * the band SMR is a maximum over lines: lines are ranked by a cheap upper bound and only those that can be the
+//     maximum get their complete threshold (warp-cooperatively);
+//   * a spectrum is only evaluated in the bands whose SMR OverallSMRs would keep (L/R vs M/S per band);
+//   * the grant order of the water-filling is a merge of the per-band runs, not a loop over arg-maxima.
 //
 // Reference path restated here (file:line in laser55/mrcAudioCodec):
 //   pcmfile.py:87-101 + quantize.py:90-111   int16 -> signed fraction (Q1: -32768 -> 0.0)

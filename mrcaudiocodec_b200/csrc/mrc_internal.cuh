@@ -1,16 +1,18 @@
 // mrc_internal.cuh -- shared declarations for the libmrc.so kernels (sm_100a).
 //
-// Data layout in HBM (per encode wave of nblk blocks, L = n_mdct_lines, NB = n_bands <= 32):
+// Data layout in HBM (per encode wave of nblk blocks, L = n_mdct_lines, NB = n_bands <= 25):
 //   analysis kernel -> hand-off      lines   [nblk][2][L]   real  selected (M|L, S|R per band), scaled by 2^overall
 //                                    bandmax [nblk][2][32]  real  max |line| per band of the selected lines
-//                                    smr     [nblk][2][32]  real  selected SMRs (tap / token source)
 //                                    tokens  [nblk][768]    u16   water-filling grant order (band | level<<8)
 //                                    ovs     [nblk][4]      u8    overall scale factors L,R,M,S
 //                                    ms      [nblk]         u32   ms_switch bit mask
-//   cost kernel -> chain kernel      rec     [nblk][MRC_REC_BYTES]  per grant token (in grant order): band/level/
-//                                    nLines, Huffman cost deltas of the four books; per 32-token chunk: exclusive
-//                                    prefix sums ("checkpoints") and the running maximum of (bits spent + nLines)
-//   chain kernel -> pack             gmask   [nblk][32] u32  granted tokens per 32-token chunk
+//   cost kernel -> chain / finish    rec     [nblk][MRC_REC_BYTES]  per grant token (in grant order): band/level/
+//                                    nLines and, as prefix sums over the order, bits spent and Huffman cost under
+//                                    the four books; per 32-token chunk the running maximum of (bits spent + nLines)
+//                                    pw      [nblk][MRC_PW_BYTES]   the same prefix sums for the bits actually written
+//   table kernel -> chain            tab     [nblk][2][tabw] i32    reservoir map R_in -> R_out (single-stream path)
+//   chain kernel -> finish           rsv     [nblk] int4            reservoir before group 0 / group 1 / after
+//   finish, offsets -> pack          gmask   [nblk][32] u32  granted tokens per 32-token chunk
 //                                    cblk    [nblk] ChainBlk  table ids, chunk sizes and offsets, reservoir
 //   pack kernel (taps only)          alloc,sf [nblk][2][32] u8 ; mant [nblk][2][L] u16
 #pragma once
