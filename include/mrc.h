@@ -48,6 +48,12 @@ extern "C" {
 /* Never tabulate the per-block reservoir maps (the single-stream fast path of the serial walk); results are the
  * same either way, the flag exists for cross-checking and timing. */
 #define MRC_FLAG_NO_CHAIN_TABLES 2
+/* Block switching: mrc_encode_batch follows the reference's `__main__` loop (pacfileThem.py
+ * :1142-1215) instead of the plain per-block loop: a transient detector with one block of look-ahead decides, per
+ * n_mdct_lines-frame block, between one long block and eight 128-sample short blocks.  Needs
+ * mrc_set_switch_tables, joint = 1 and n_mdct_lines = 1024.  Decoding never needs the flag: the block sizes are in
+ * every chunk header. */
+#define MRC_FLAG_BLOCK_SWITCHING 4
 
 typedef struct mrc_ctx mrc_ctx;
 
@@ -83,12 +89,33 @@ typedef struct mrc_tables {
     const uint16_t* huff_code;             /* [n_huff_tables][MRC_HUFF_LUT] code bits (right aligned)    */
 } mrc_tables;
 
+/* One block geometry of block switching: window halves a (the previous block's size) and b (this block's), each
+ * n_mdct_lines or 128.  window = TransitionWindow(ones, a, b) window.py:104-121; hann_window window.py:36-42 at
+ * a+b points; bark / quiet_intensity at the (a+b)/2 line frequencies; band_nlines = AssignMDCTLinesFromFreqLimits
+ * ((a+b)/2, sampleRate, the 9-band short table) pacfileThem.py:213-219. */
+typedef struct mrc_block_tables {
+    int32_t a, b;
+    int32_t n_bands;
+    const int32_t* band_nlines;            /* [n_bands], sums to (a+b)/2                                 */
+    const double* window;                  /* [a+b]                                                      */
+    const double* hann_window;             /* [a+b]                                                      */
+    const double* bark;                    /* [(a+b)/2]                                                  */
+    const double* quiet_intensity;         /* [(a+b)/2]                                                  */
+} mrc_block_tables;
+
 int32_t mrc_version(void);
 const char* mrc_last_error(const mrc_ctx* ctx);   /* ctx may be NULL: message of the last failed mrc_create */
 
 int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out);
 int32_t mrc_destroy(mrc_ctx* ctx);
 int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t);
+
+/* Block switching tables, after mrc_set_tables: t3 = the geometries (L,128), (128,L), (128,128) in this order;
+ * sos = the transient detector's high-pass as n_sections rows of b0 b1 b2 a0 a1 a2 with a0 = 1 (the reference
+ * designs it with scipy.signal.cheby2(20, 40, 9000./sampleRate, 'high') + tf2sos, pacfileThem.py:1146-1147);
+ * t0, t1 = the thresholds T (pacfileThem.py:1154: 0.1, 0.075). */
+int32_t mrc_set_switch_tables(mrc_ctx* ctx, const mrc_block_tables* t3, const double* sos, int32_t n_sections,
+                              double t0, double t1);
 
 /* Pinned host memory for PCM / bitstream buffers (optional; pageable memory works but copies slower). */
 int32_t mrc_host_alloc(void** p, int64_t bytes);
@@ -134,6 +161,24 @@ int32_t mrc_decode_batch_device(mrc_ctx* ctx, const uint8_t* d_pac, const uint8_
 int32_t mrc_encode_block(mrc_ctx* ctx, const double* data, int32_t joint, int32_t* reservoir,
                          int32_t* scale_factor, int32_t* bit_alloc, int32_t* mantissa, int32_t* overall_scale,
                          int32_t* ms_switch, int32_t* huff_table, int32_t* chunk_bytes);
+/* The same seam for any block geometry of block switching (codingParams.a, codingParams.b): data is
+ * [2][a+b], scale_factor / bit_alloc / ms_switch have that geometry's band count (9 unless a = b = n_mdct_lines),
+ * mantissa is [2][(a+b)/2].  Needs mrc_set_switch_tables unless a = b = n_mdct_lines. */
+int32_t mrc_encode_block_ab(mrc_ctx* ctx, const double* data, int32_t a, int32_t b, int32_t joint, int32_t* reservoir,
+                            int32_t* scale_factor, int32_t* bit_alloc, int32_t* mantissa, int32_t* overall_scale,
+                            int32_t* ms_switch, int32_t* huff_table, int32_t* chunk_bytes);
+int32_t mrc_decode_block_ab(mrc_ctx* ctx, int32_t a, int32_t b, int32_t joint, const int32_t* scale_factor,
+                            const int32_t* bit_alloc, const int32_t* mantissa, const int32_t* overall_scale,
+                            const int32_t* ms_switch, double* data_out);
+
+/* TransientDetector (pacfileThem.py:1021-1056) over whole clips plus the look-ahead decision (:1192), as
+ * mrc_encode_batch applies them under MRC_FLAG_BLOCK_SWITCHING.  All outputs may be NULL.
+ * flags [sum over clips of ceil(frames/L)]: bit 0 = a transient in the block's first 128 samples, bit 1 = one later
+ * in the block.  block_ab [block_cap][2]: (a, b) of every block the encoder writes, flush blocks included;
+ * clip_block_offsets [n_clips+1]: first written block of every clip (written even on MRC_E_NOSPACE). */
+int32_t mrc_detect_transients(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
+                              uint8_t* flags, int32_t* block_ab, int32_t block_cap, int32_t* clip_block_offsets);
+
 /* mrc_decode_block = codecThem.Decode x2 (joint=0) / JointDecode (joint=1): returns the windowed IMDCT output
  * [2][2*n_mdct_lines] (before overlap-add), like the reference functions. */
 int32_t mrc_decode_block(mrc_ctx* ctx, int32_t joint, const int32_t* scale_factor, const int32_t* bit_alloc,

@@ -10,6 +10,7 @@ MRC_OK, MRC_E_INVALID, MRC_E_CUDA, MRC_E_NOSPACE, MRC_E_FORMAT, MRC_E_STATE = 0,
 PRECISION_FP64, PRECISION_FP32 = 0, 1
 FLAG_SPREAD_SEQUENTIAL = 1
 FLAG_NO_CHAIN_TABLES = 2
+FLAG_BLOCK_SWITCHING = 4
 NO_TABLE = 15
 
 c_i16p = C.POINTER(C.c_int16)
@@ -33,6 +34,11 @@ class MrcTables(C.Structure):
                 ("huff_escape", c_i32p), ("huff_len", c_u8p), ("huff_code", c_u16p)]
 
 
+class MrcBlockTables(C.Structure):
+    _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("n_bands", C.c_int32), ("band_nlines", c_i32p),
+                ("window", c_f64p), ("hann_window", c_f64p), ("bark", c_f64p), ("quiet_intensity", c_f64p)]
+
+
 class MrcError(RuntimeError):
     def __init__(self, code, msg):
         RuntimeError.__init__(self, "libmrc error %d: %s" % (code, msg))
@@ -42,7 +48,8 @@ class MrcError(RuntimeError):
 EXPORTS = ["mrc_version", "mrc_last_error", "mrc_create", "mrc_destroy", "mrc_set_tables", "mrc_host_alloc",
            "mrc_host_free", "mrc_encode_batch", "mrc_encode_batch_device", "mrc_decode_batch",
            "mrc_decode_batch_device", "mrc_encode_block", "mrc_decode_block", "mrc_stage_analysis",
-           "mrc_stage_alloc_quant", "mrc_mantissa_histogram", "mrc_last_timing", "mrc_measure_peaks"]
+           "mrc_stage_alloc_quant", "mrc_mantissa_histogram", "mrc_last_timing", "mrc_measure_peaks",
+           "mrc_set_switch_tables", "mrc_encode_block_ab", "mrc_decode_block_ab", "mrc_detect_transients"]
 
 _lib = None
 
@@ -73,6 +80,10 @@ def load():
     lib.mrc_decode_block.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp]
     lib.mrc_stage_analysis.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.mrc_stage_alloc_quant.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+    lib.mrc_set_switch_tables.argtypes = [vp, C.POINTER(MrcBlockTables), vp, C.c_int32, C.c_double, C.c_double]
+    lib.mrc_encode_block_ab.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.mrc_decode_block_ab.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
+    lib.mrc_detect_transients.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp]
     lib.mrc_last_timing.argtypes = [vp, vp, vp]
     lib.mrc_measure_peaks.argtypes = [vp, vp]
     for name in EXPORTS:

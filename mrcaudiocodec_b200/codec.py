@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .tables import Tables
+from .tables import Tables, BlockTables, transient_sos, TRANSIENT_THRESHOLDS, N_SHORT
 
 
 def _ptr(a):
@@ -18,7 +18,13 @@ def _ptr(a):
 class Codec(object):
     def __init__(self, sample_rate=48000, n_mdct_lines=1024, n_scale_bits=4, n_mant_size_bits=4,
                  target_bits_per_sample=128000. / 48000., joint=True, precision="fp64", device=0,
-                 band_limits=None, spreading="factorised", chain_tables=True):
+                 band_limits=None, spreading="factorised", chain_tables=True, block_switching=False,
+                 switch_tables=None, transient_sos_sections=None):
+        """block_switching=True: encode_batch follows the reference's `__main__` loop (transient detector, one
+        block of look-ahead, eight 128-sample short blocks around transients; pacfileThem.py:1142-1215).
+        switch_tables=True (implied by block_switching) only loads the extra block geometries, which is what
+        decoding a switched stream and the per-block seam with a != b need.  transient_sos_sections overrides the
+        detector's filter (default: designed with scipy exactly like the reference)."""
         self.lib = _lib.load()
         self.L = int(n_mdct_lines)
         self.sample_rate = int(sample_rate)
@@ -35,6 +41,9 @@ class Codec(object):
         cfg.flags = {"factorised": 0, "sequential": _lib.FLAG_SPREAD_SEQUENTIAL}[spreading]
         if not chain_tables:
             cfg.flags |= _lib.FLAG_NO_CHAIN_TABLES
+        if block_switching:
+            cfg.flags |= _lib.FLAG_BLOCK_SWITCHING
+        self.block_switching = bool(block_switching)
         cfg.target_bits_per_sample = float(target_bits_per_sample)
         self._ctx = C.c_void_p()
         rc = self.lib.mrc_create(C.byref(cfg), C.byref(self._ctx))
@@ -55,6 +64,48 @@ class Codec(object):
         t.huff_code = T.huff_code.ctypes.data_as(_lib.c_u16p)
         self._check(self.lib.mrc_set_tables(self._ctx, C.byref(t)))
         self.n_bands = T.n_bands
+        self.block_tables = {(self.L, self.L): None}
+        if block_switching or switch_tables:
+            self._set_switch_tables(transient_sos_sections)
+
+    def _set_switch_tables(self, sos=None):
+        L = self.L
+        geos = [(L, N_SHORT), (N_SHORT, L), (N_SHORT, N_SHORT)]
+        arr = (_lib.MrcBlockTables * 3)()
+        for i, (a, b) in enumerate(geos):
+            bt = BlockTables(a, b, L, self.sample_rate)
+            self.block_tables[(a, b)] = bt
+            arr[i].a, arr[i].b, arr[i].n_bands = a, b, bt.n_bands
+            arr[i].band_nlines = bt.band_nlines.ctypes.data_as(_lib.c_i32p)
+            arr[i].window = bt.window.ctypes.data_as(_lib.c_f64p)
+            arr[i].hann_window = bt.hann.ctypes.data_as(_lib.c_f64p)
+            arr[i].bark = bt.bark.ctypes.data_as(_lib.c_f64p)
+            arr[i].quiet_intensity = bt.quiet.ctypes.data_as(_lib.c_f64p)
+        self.sos = np.ascontiguousarray(transient_sos(self.sample_rate) if sos is None else sos, dtype=np.float64)
+        self._check(self.lib.mrc_set_switch_tables(self._ctx, arr, _ptr(self.sos), int(self.sos.shape[0]),
+                                                   float(TRANSIENT_THRESHOLDS[0]), float(TRANSIENT_THRESHOLDS[1])))
+
+    def geometry(self, a, b):
+        """(n_lines, n_bands, band_nlines, band_lower) of the block geometry (a, b)."""
+        bt = self.block_tables.get((int(a), int(b)))
+        if bt is None:
+            if (int(a), int(b)) != (self.L, self.L):
+                raise ValueError("block geometry (%d, %d) not loaded: create the Codec with switch_tables=True" % (a, b))
+            return self.L, self.n_bands, self.tables.band_nlines, self.tables.band_lower
+        return bt.n_lines, bt.n_bands, bt.band_nlines, bt.band_lower
+
+    def detect_transients(self, clips):
+        """TransientDetector + look-ahead decision over whole clips: (flags per n_mdct_lines-frame block, list of
+        per-clip [(a, b), ...] of the blocks the encoder writes, flush block included)."""
+        pcm, off = self._concat(clips)
+        nsb = int(np.sum((np.diff(off) + self.L - 1) // self.L))
+        flags = np.zeros(max(nsb, 1), np.uint8)
+        cap = 8 * nsb + len(clips) + 1
+        ab = np.zeros((cap, 2), np.int32)
+        boff = np.zeros(len(clips) + 1, np.int32)
+        self._check(self.lib.mrc_detect_transients(self._ctx, _ptr(pcm), _ptr(off), len(clips), _ptr(flags), _ptr(ab),
+                                                   cap, _ptr(boff)))
+        return flags[:nsb], [[tuple(int(v) for v in r) for r in ab[boff[i]:boff[i + 1]]] for i in range(len(clips))]
 
     # ------------------------------------------------------------------------------------------------
     def _check(self, rc):
@@ -87,7 +138,7 @@ class Codec(object):
     def nominal_capacity(self, frame_offsets):
         fr = np.diff(frame_offsets)
         nblk = (fr + self.L - 1) // self.L + 1
-        return int(np.sum(256 + nblk * (2 * 1.5 * self.L * 16 // 8 // 4 + 256)))
+        return int(np.sum(256 + nblk * (2 * 1.5 * self.L * 16 // 8 // 4 + 256 + (256 if self.block_switching else 0))))
 
     # ---- batch encode ----------------------------------------------------------------------------
     def encode_batch(self, pcm, frame_offsets, out=None):
@@ -181,34 +232,40 @@ class Codec(object):
         return dict(bitAlloc=ba, scaleFactor=sf, mantissa=mant, huffTable=ht, reservoir=res, chunkBytes=cb)
 
     # ---- per-block seam ------------------------------------------------------------------------------
-    def encode_block(self, data, joint, reservoir):
-        """data: float64 [2, 2L].  Returns dict + new reservoir."""
-        data = np.ascontiguousarray(data, dtype=np.float64).reshape(2, 2 * self.L)
+    def encode_block(self, data, joint, reservoir, a=None, b=None):
+        """data: float64 [2, a+b] (a = b = L by default).  Returns dict + new reservoir."""
+        a = self.L if a is None else int(a)
+        b = self.L if b is None else int(b)
+        nl, nbands, _, _ = self.geometry(a, b)
+        data = np.ascontiguousarray(data, dtype=np.float64).reshape(2, a + b)
         res = np.array([int(reservoir)], dtype=np.int32)
-        sf = np.zeros((2, self.n_bands), np.int32)
-        ba = np.zeros((2, self.n_bands), np.int32)
-        mant = np.zeros((2, self.L), np.int32)
+        sf = np.zeros((2, nbands), np.int32)
+        ba = np.zeros((2, nbands), np.int32)
+        mant = np.zeros((2, nl), np.int32)
         ovs = np.zeros(4, np.int32)
-        ms = np.zeros(self.n_bands, np.int32)
+        ms = np.zeros(nbands, np.int32)
         ht = np.zeros(2, np.int32)
         cb = np.zeros(2, np.int32)
-        self._check(self.lib.mrc_encode_block(self._ctx, _ptr(data), 1 if joint else 0, _ptr(res), _ptr(sf), _ptr(ba),
-                                              _ptr(mant), _ptr(ovs), _ptr(ms), _ptr(ht), _ptr(cb)))
+        self._check(self.lib.mrc_encode_block_ab(self._ctx, _ptr(data), a, b, int(joint), _ptr(res), _ptr(sf),
+                                                 _ptr(ba), _ptr(mant), _ptr(ovs), _ptr(ms), _ptr(ht), _ptr(cb)))
         return dict(scaleFactor=sf, bitAlloc=ba, mantissa=mant, overallScale=ovs, ms_switch=ms, huffTable=ht,
                     chunkBytes=cb), int(res[0])
 
-    def decode_block(self, joint, scaleFactor, bitAlloc, mantissa, overallScale, ms_switch=None):
-        sf = np.ascontiguousarray(scaleFactor, dtype=np.int32).reshape(2, self.n_bands)
-        ba = np.ascontiguousarray(bitAlloc, dtype=np.int32).reshape(2, self.n_bands)
-        mant = np.ascontiguousarray(mantissa, dtype=np.int32).reshape(2, self.L)
+    def decode_block(self, joint, scaleFactor, bitAlloc, mantissa, overallScale, ms_switch=None, a=None, b=None):
+        a = self.L if a is None else int(a)
+        b = self.L if b is None else int(b)
+        nl, nbands, _, _ = self.geometry(a, b)
+        sf = np.ascontiguousarray(scaleFactor, dtype=np.int32).reshape(2, nbands)
+        ba = np.ascontiguousarray(bitAlloc, dtype=np.int32).reshape(2, nbands)
+        mant = np.ascontiguousarray(np.asarray(mantissa, dtype=np.int32)[:, :nl], dtype=np.int32).reshape(2, nl)
         ovs = np.zeros(4, np.int32)
         o = np.asarray(overallScale, dtype=np.int32).ravel()
         ovs[:o.size] = o
-        ms = np.zeros(self.n_bands, np.int32) if ms_switch is None else \
+        ms = np.zeros(nbands, np.int32) if ms_switch is None else \
             np.ascontiguousarray(ms_switch, dtype=np.int32)
-        out = np.zeros((2, 2 * self.L), np.float64)
-        self._check(self.lib.mrc_decode_block(self._ctx, 1 if joint else 0, _ptr(sf), _ptr(ba), _ptr(mant), _ptr(ovs),
-                                              _ptr(ms), _ptr(out)))
+        out = np.zeros((2, a + b), np.float64)
+        self._check(self.lib.mrc_decode_block_ab(self._ctx, a, b, 1 if joint else 0, _ptr(sf), _ptr(ba), _ptr(mant),
+                                                 _ptr(ovs), _ptr(ms), _ptr(out)))
         return out
 
     # ---- Huffman table training front end (SURVEY.md 8 f3) ------------------------------------------

@@ -15,9 +15,11 @@ so a reference-style PACFile can be pointed at the GPU with `pacfileThem.codec =
 mantissa[ch] is the compacted int32 array (table 15) or the list of "code" / "esccode/mantissa" strings
 (tables 0..3), exactly what calculateHuffmanGain returns (codecThem.py:178-203).
 
-Only long blocks (a == b == nMDCTLines) and two channels are served; anything else raises (block switching is
-SURVEY.md §8 f1, not built).  Every call is one round trip to the GPU: this layer is for parity and integration,
-the batch API in codec.py is the fast path."""
+Two channels only.  Block switching: codingParams.a / codingParams.b may each be nMDCTLines or
+128, as the reference's `__main__` loop sets them (pacfileThem.py:1193-1210); the band table follows a + b like
+pacfileThem.py:808-816 (25 bands for two long halves, else the 9-band short table), nMDCTLines must be 1024 then.
+Every call is one round trip to the GPU: this layer is for parity and integration, the batch API in codec.py is
+the fast path."""
 import json
 import os
 
@@ -40,27 +42,30 @@ def _huff():
 
 
 def _codec_for(cp, precision=None):
-    if cp.a != cp.b or cp.a != cp.nMDCTLines:
-        raise NotImplementedError("codec_gpu serves long blocks only (a == b == nMDCTLines)")
+    for v in (cp.a, cp.b):
+        if v != cp.nMDCTLines and v != 128:
+            raise NotImplementedError("codec_gpu serves window halves of nMDCTLines or 128 samples")
     if getattr(cp, "nChannels", 2) != 2:
         raise NotImplementedError("codec_gpu serves two-channel streams")
     precision = precision or getattr(cp, "precision", "fp64")
+    switched = not (cp.a == cp.b == cp.nMDCTLines)
     key = (int(cp.sampleRate), int(cp.nMDCTLines), int(cp.nScaleBits), int(cp.nMantSizeBits),
            float(getattr(cp, "targetBitsPerSample", 0.0)), precision, int(getattr(cp, "device", 0)))
     c = _ctx_cache.get(key)
-    if c is None:
+    if c is None or (switched and len(c.block_tables) == 1):
+        if c is not None:
+            c.close()
         c = Codec(sample_rate=key[0], n_mdct_lines=key[1], n_scale_bits=key[2], n_mant_size_bits=key[3],
-                  target_bits_per_sample=key[4], precision=precision, device=key[6])
+                  target_bits_per_sample=key[4], precision=precision, device=key[6], switch_tables=switched)
         _ctx_cache[key] = c
     return c
 
 
-def _compact(c, r, ch, as_codes=True):
+def _compact(c, r, ch, a, b, as_codes=True):
     """line-aligned mantissas -> what the reference returns for channel ch."""
-    lo = c.tables.band_lower
-    n = c.tables.band_nlines
+    _, nbands, n, lo = c.geometry(a, b)
     ba = r["bitAlloc"][ch]
-    parts = [r["mantissa"][ch][lo[b]:lo[b] + n[b]] for b in range(c.n_bands) if ba[b]]
+    parts = [r["mantissa"][ch][lo[k]:lo[k] + n[k]] for k in range(nbands) if ba[k]]
     m = np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
     t = int(r["huffTable"][ch])
     if t == 15 or not as_codes:
@@ -78,11 +83,12 @@ def _compact(c, r, ch, as_codes=True):
 def _encode(data, codingParams, joint, no_huff=False):
     c = _codec_for(codingParams)
     x = np.stack([np.asarray(data[0], dtype=np.float64), np.asarray(data[1], dtype=np.float64)])
-    r, res = c.encode_block(x, (1 if joint else 0) | (2 if no_huff else 0), int(codingParams.bitReservoir))
+    r, res = c.encode_block(x, (1 if joint else 0) | (2 if no_huff else 0), int(codingParams.bitReservoir),
+                            a=codingParams.a, b=codingParams.b)
     codingParams.bitReservoir = res
     S = [r["scaleFactor"][ch].astype(np.int32) for ch in range(2)]
     A = [r["bitAlloc"][ch].astype(int) for ch in range(2)]
-    M = [_compact(c, r, ch) for ch in range(2)]
+    M = [_compact(c, r, ch, codingParams.a, codingParams.b) for ch in range(2)]
     H = [int(r["huffTable"][ch]) for ch in range(2)]
     return c, r, S, A, M, H
 
@@ -104,13 +110,19 @@ def JointEncode(data, codingParams):
 
 def Decode(scaleFactor, bitAlloc, mantissa, overallScaleFactor, codingParams):
     c = _codec_for(codingParams)
-    z = np.zeros(c.n_bands, np.int32)
-    y = c.decode_block(False, [scaleFactor, z], [bitAlloc, z], [mantissa, np.zeros(c.L, np.int32)],
-                       [overallScaleFactor, 0])
+    a, b = codingParams.a, codingParams.b
+    nl, nbands, _, _ = c.geometry(a, b)
+    z = np.zeros(nbands, np.int32)
+    m = np.asarray(mantissa, dtype=np.int32)
+    y = c.decode_block(False, [scaleFactor, z], [bitAlloc, z], np.stack([m[:nl], np.zeros(nl, np.int32)]),
+                       [overallScaleFactor, 0], a=a, b=b)
     return y[0]
 
 
 def JointDecode(scaleFactor, bitAlloc, mantissa, overallScaleFactor, codingParams, ms_switch):
     c = _codec_for(codingParams)
-    y = c.decode_block(True, scaleFactor, bitAlloc, mantissa, overallScaleFactor, ms_switch)
+    a, b = codingParams.a, codingParams.b
+    nl = c.geometry(a, b)[0]
+    m = np.stack([np.asarray(mantissa[0], dtype=np.int32)[:nl], np.asarray(mantissa[1], dtype=np.int32)[:nl]])
+    y = c.decode_block(True, scaleFactor, bitAlloc, m, overallScaleFactor, ms_switch, a=a, b=b)
     return [y[0], y[1]]

@@ -21,7 +21,8 @@
 //   psychoac.py:176-219, ms_stereo.py:70-81   SMR per band and M/S vs L/R selection
 //   bitalloc.py:106-155                       (order of grants only: the allocation itself needs the reservoir)
 //
-// One CTA = one block, NT = L/2 threads; thread t owns MDCT lines t and t+L/2.
+// One CTA = one block, NT = L/2 threads; thread t owns MDCT lines t and t+L/2.  L = (a+b)/2 is a template parameter:
+// nMDCTLines for long blocks, 576 for the transition blocks of block switching (a+b = 1024+128), 128 for short ones.
 #include <algorithm>
 
 #include "mrc_internal.cuh"
@@ -211,13 +212,14 @@ __device__ __forceinline__ double spread_line_warp(const Smem<T>& sm, const DevT
     return a;
 }
 
-template <typename T, int LOGL>
-__global__ void __launch_bounds__(1 << (LOGL - 1), (LOGL <= 10) ? 2 : 1)
+template <typename T, int L_>
+__global__ void __launch_bounds__(L_ / 2, (L_ <= 1024) ? 2 : 1)
 analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __restrict__ pcm,
                 const double* __restrict__ xin, int g0, Handoff<T> ho, AnalysisTaps<T> taps,
                 unsigned long long* peak_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int L = 1 << LOGL, N = 2 * L, Q = L / 2, logL = LOGL, NT = Q, nwarp = NT >> 5;
+    constexpr int L = L_, N = 2 * L, Q = L / 2, NT = Q, nwarp = NT >> 5;
+    static_assert(NT % 32 == 0, "whole warps");
     const int nb = tb.nb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     Smem<T> sm = carve<T>(smem_raw, L);
@@ -234,8 +236,8 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ int s_npk;
 
     if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
-    const int g = g0 + blockIdx.x;            // global block index
-    const int lb = blockIdx.x;                // index inside this wave's hand-off buffers
+    const int lb = cm.list ? cm.list[blockIdx.x] : (int)blockIdx.x;   // index inside this wave's hand-off buffers
+    const int g = g0 + lb;                    // global block index
     if (tid == 0) {
         int lo = 0, hi = cm.n_clips;          // last clip whose first block <= g
         while (hi - lo > 1) {
@@ -259,7 +261,8 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     } else {
         const long long frames = cm.clip_off[s_clip + 1] - cm.clip_off[s_clip];
         const uint32_t* __restrict__ p32 = reinterpret_cast<const uint32_t*>(pcm) + cm.clip_off[s_clip];
-        const long long s0 = (long long)(b - 1) * L;
+        // the block's a "prior" samples then its b new ones (pacfileThem.py:799-802)
+        const long long s0 = cm.blk_start ? cm.blk_start[g] - tb.a : (long long)(b - 1) * L;
         for (int n = tid; n < N; n += NT) {
             const long long s = s0 + n;
             uint32_t w = 0;
@@ -280,7 +283,18 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             cpx<T>* a = sm.buf + grp * Q;
             for (int n = lt; n < Q; n += gthr) {
                 T re, im;
-                auto y = [&](int i) { return tb.kbd[i] * tsample(sm.sx, N, c, i); };
+                // n0 = (b+1)/2 (mdct.py:66) is the standard phase N/4 + 1/2 shifted by rot = (a-b)/4 samples: the
+                // transform of the sequence rotated by rot, wrapped samples negated (the kernel is antiperiodic)
+                auto y = [&](int i) {
+                    if constexpr (FftShape<L>::pow2) return tb.kbd[i] * tsample(sm.sx, N, c, i);     // a == b
+                    else {
+                        int j = i + tb.rot;
+                        T sg = T(1);
+                        if (j >= N) { j -= N; sg = T(-1); }
+                        else if (j < 0) { j += N; sg = T(-1); }
+                        return sg * (tb.kbd[j] * tsample(sm.sx, N, c, j));
+                    }
+                };
                 if (n < Q / 2) {
                     re = -y(3 * Q - 1 - 2 * n) - y(3 * Q + 2 * n);
                     im = y(Q - 1 - 2 * n) - y(Q + 2 * n);
@@ -289,12 +303,12 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                     im = -y(Q + 2 * n) - y(5 * Q - 1 - 2 * n);
                 }
                 const cpx<T> w = tb.tw_pre[n];
-                const int r = fft_r4_pos(n, logL - 1);
+                const int r = fft_pos<Q>(n);
                 a[r].x = re * w.x - im * w.y;
                 a[r].y = re * w.y + im * w.x;
             }
             __syncthreads();
-            fft_r4<T>(a, logL - 1, lt, gthr, tb.tw_fft, logL);
+            fft_any<T, Q>(a, lt, gthr, tb.tw_fft, tb.logLtab, tb.tw9, L, tb.w9);
             T* X = sm.lines + c * L;
             for (int k = lt; k < Q; k += gthr) {
                 const cpx<T> w = tb.tw_post[k];
@@ -307,8 +321,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     }
 
     if (taps.lines4 != nullptr) {
-        T* o = taps.lines4 + (size_t)lb * 4 * L;
-        for (int i = tid; i < 4 * L; i += NT) o[i] = (i < nspec * L) ? sm.lines[i] : T(0);
+        T* o = taps.lines4 + (size_t)lb * 4 * cp.Lmax;           // rows of Lmax, zero beyond this geometry's L
+        for (int i = tid; i < 4 * cp.Lmax; i += NT) {
+            const int c = i / cp.Lmax, k = i - c * cp.Lmax;
+            o[i] = (c < nspec && k < L) ? sm.lines[c * L + k] : T(0);
+        }
     }
 
     // ---- phase 2: ms_switch on the unscaled L/R lines (ms_stereo.py:5-27) -------------------------------
@@ -370,15 +387,15 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
         }
         // a. Hann window, real 2L-point FFT through an L-point complex FFT
         for (int n = tid; n < L; n += NT) {
-            const int r = fft_r4_pos(n, logL);
+            const int r = fft_pos<L>(n);
             sm.buf[r].x = tb.hann[2 * n] * tsample(sm.sx, N, c, 2 * n);
             sm.buf[r].y = tb.hann[2 * n + 1] * tsample(sm.sx, N, c, 2 * n + 1);
         }
         __syncthreads();
-        fft_r4<T>(sm.buf, logL, tid, NT, tb.tw_fft, logL);
+        fft_any<T, L>(sm.buf, tid, NT, tb.tw_fft, tb.logLtab, tb.tw9, L, tb.w9);
         // b. X[k] = E[k] + W^k O[k];  XI = 4|X|^2 / (N^2 * 3/8)   (psychoac.py:151)
         for (int k = tid; k < L; k += NT) {
-            const cpx<T> zk = sm.buf[k], zc = sm.buf[(L - k) & (L - 1)];
+            const cpx<T> zk = sm.buf[k], zc = sm.buf[k ? L - k : 0];
             const T ex = (zk.x + zc.x) * T(0.5), ey = (zk.y - zc.y) * T(0.5);
             const T dx = zk.x - zc.x, dy = zk.y + zc.y;           // D = Zk - conj(Zc)
             const T ox = dy * T(0.5), oy = -dx * T(0.5);          // O = D / (2j)
@@ -691,7 +708,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // ---- phase 5: per band pick (M,S) or (L,R) (ms_stereo.py:70-81; codecThem.py:509-559) ---------------
     const unsigned ms = s_ms;
     {
-        T* oA = ho.lines + (size_t)lb * 2 * L;
+        T* oA = ho.lines + (size_t)lb * 2 * cp.Lmax;     // [2][L] compact at a stride of 2*Lmax per block
         T* oB = oA + L;
         for (int k = tid; k < L; k += NT) {
             const bool m = (ms >> tb.line2band[k]) & 1u;
@@ -814,17 +831,18 @@ void launch_analysis(cudaStream_t st, const DevTables<T>& tb, const CodecParams&
                      unsigned long long* peak_counter) {
     if (nblk <= 0) return;
     const size_t smem = analysis_smem_bytes(tb.L, sizeof(T));
-#define MRC_LAUNCH_ANALYSIS(LG)                                                                                  \
-    case LG:                                                                                                     \
-        cudaFuncSetAttribute(analysis_kernel<T, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        analysis_kernel<T, LG><<<nblk, 1 << (LG - 1), smem, st>>>(tb, cp, cm, pcm, xin, g0, ho, taps,            \
-                                                                  peak_counter);                                 \
+#define MRC_LAUNCH_ANALYSIS(LL)                                                                                  \
+    case LL:                                                                                                     \
+        cudaFuncSetAttribute(analysis_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        analysis_kernel<T, LL><<<nblk, LL / 2, smem, st>>>(tb, cp, cm, pcm, xin, g0, ho, taps, peak_counter);     \
         break;
-    switch (tb.logL) {
-        MRC_LAUNCH_ANALYSIS(8)
-        MRC_LAUNCH_ANALYSIS(9)
-        MRC_LAUNCH_ANALYSIS(10)
-        MRC_LAUNCH_ANALYSIS(11)
+    switch (tb.L) {
+        MRC_LAUNCH_ANALYSIS(128)       // short blocks (128 + 128)
+        MRC_LAUNCH_ANALYSIS(256)
+        MRC_LAUNCH_ANALYSIS(512)
+        MRC_LAUNCH_ANALYSIS(576)       // transition blocks (1024 + 128, 128 + 1024)
+        MRC_LAUNCH_ANALYSIS(1024)
+        MRC_LAUNCH_ANALYSIS(2048)
         default: break;
     }
 #undef MRC_LAUNCH_ANALYSIS

@@ -22,7 +22,20 @@ struct Buf {
 };
 
 struct TablesDev {
-    Buf kbd, hann, tw_pre, tw_post, tw_fft, tw_rfft, bark, quiet, bark_d, quiet_d, exp_tab;
+    Buf kbd, hann, tw_pre, tw_post, tw_fft, tw_rfft, tw9, bark, quiet, bark_d, quiet_d, exp_tab;
+};
+
+// Everything that depends on the block geometry (window halves a, b): long blocks always; the transition and short
+// blocks of block switching once mrc_set_switch_tables has been called.
+struct GeoDev {
+    bool set = false;
+    int a = 0, b = 0, L = 0, nb = 0, nseg = 0;
+    TablesDev td, tf;                 // double and float copies
+    Buf band_lo, band_n, line2band, seg_lo, seg_n, seg_band, band_seg0;
+    DevTables<double> tbd;
+    DevTables<float> tbf;
+    CodecParams cp;
+    std::vector<int> h_band_lo, h_band_n;
 };
 
 }  // namespace
@@ -34,14 +47,17 @@ struct mrc_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
 
-    TablesDev td, tf;                 // double and float copies
-    Buf band_lo, band_n, line2band, huff, header, seg_lo, seg_n, seg_band, band_seg0;
-    int nseg = 0;
-    DevTables<double> tbd;
-    DevTables<float> tbf;
+    GeoDev geo[MRC_N_GEO];            // [MRC_GEO_LONG] is the context's own geometry (a = b = n_mdct_lines)
+    DevTables<double>& tbd = geo[0].tbd;
+    DevTables<float>& tbf = geo[0].tbf;
+    CodecParams& cp = geo[0].cp;
+    std::vector<int>& h_band_n = geo[0].h_band_n;
+    Buf huff, header;
     HuffDev h_huff;
-    CodecParams cp;
-    std::vector<int> h_band_lo, h_band_n;
+    // block switching
+    bool switch_set = false;          // mrc_set_switch_tables called: all four geometries are available
+    SosParams sos;
+    Buf sb0, peaks, flags, blk_start, blk_geom, blk_list;
     uint8_t h_header[4 + 18 + 4 + 2 * MRC_MAX_BANDS];
 
     // scratch (grow only)
@@ -101,21 +117,37 @@ cudaError_t upload(Buf& b, const std::vector<T>& v, cudaStream_t st) {
 }
 
 template <typename T>
-cudaError_t upload_tables(mrc_ctx* c, TablesDev& d, DevTables<T>& tb, const mrc_tables* t) {
-    const int L = c->L, N = 2 * L;
+cudaError_t upload_tables(mrc_ctx* c, GeoDev& g, TablesDev& d, DevTables<T>& tb, const double* window,
+                          const double* hann_w, const double* bark_t, const double* quiet_t) {
+    const int L = g.L, N = 2 * L;
     std::vector<T> kbd(N), hann(N), bark(L), quiet(L);
-    for (int i = 0; i < N; ++i) { kbd[i] = (T)t->kbd_window[i]; hann[i] = (T)t->hann_window[i]; }
-    for (int i = 0; i < L; ++i) { bark[i] = (T)t->bark[i]; quiet[i] = (T)t->quiet_intensity[i]; }
-    // twiddles: angles are exact dyadic fractions of pi, evaluated in double by the host libm
-    std::vector<cpx<T>> pre(L / 2), post(L / 2), fft(L / 2), rfft(L);
+    for (int i = 0; i < N; ++i) { kbd[i] = (T)window[i]; hann[i] = (T)hann_w[i]; }
+    for (int i = 0; i < L; ++i) { bark[i] = (T)bark_t[i]; quiet[i] = (T)quiet_t[i]; }
+    // twiddles: angles evaluated in double by the host libm
+    int logLtab = 0;                                       // largest power of two dividing L: L itself, or L/9
+    while (!((L >> logLtab) & 1)) ++logLtab;
+    const int Ltab = 1 << logLtab;
+    const bool pow2 = (Ltab == L);
+    std::vector<cpx<T>> pre(L / 2), post(L / 2), fft(std::max(Ltab / 2, 1)), rfft(L), tw9(pow2 ? 1 : L);
     const double pi = 3.14159265358979323846;
     for (int n = 0; n < L / 2; ++n) {
         const double a = -pi * (4.0 * n + 1.0) / (4.0 * L);
         pre[n].x = (T)cos(a); pre[n].y = (T)sin(a);
         const double b = -pi * n / (double)L;
         post[n].x = (T)cos(b); post[n].y = (T)sin(b);
-        const double f = -2.0 * pi * n / (double)L;
+    }
+    for (int n = 0; n < Ltab / 2; ++n) {
+        const double f = -2.0 * pi * n / (double)Ltab;
         fft[n].x = (T)cos(f); fft[n].y = (T)sin(f);
+    }
+    if (!pow2)
+        for (int m = 0; m < L; ++m) {
+            const double f = -2.0 * pi * m / (double)L;
+            tw9[m].x = (T)cos(f); tw9[m].y = (T)sin(f);
+        }
+    for (int m = 0; m < 9; ++m) {
+        const double f = -2.0 * pi * m / 9.0;
+        tb.w9[m].x = (T)cos(f); tb.w9[m].y = (T)sin(f);
     }
     for (int k = 0; k < L; ++k) {
         const double a = -2.0 * pi * k / (double)N;
@@ -130,7 +162,8 @@ cudaError_t upload_tables(mrc_ctx* c, TablesDev& d, DevTables<T>& tb, const mrc_
     if ((e = upload(d.tw_post, post, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.tw_fft, fft, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.tw_rfft, rfft, c->stream)) != cudaSuccess) return e;
-    std::vector<double> bark_d(t->bark, t->bark + L), quiet_d(t->quiet_intensity, t->quiet_intensity + L), etab(64);
+    if ((e = upload(d.tw9, tw9, c->stream)) != cudaSuccess) return e;
+    std::vector<double> bark_d(bark_t, bark_t + L), quiet_d(quiet_t, quiet_t + L), etab(64);
     for (int j = 0; j < 64; ++j) etab[j] = exp2(j / 64.0);       // correctly rounded by glibc
     if ((e = upload(d.bark_d, bark_d, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.quiet_d, quiet_d, c->stream)) != cudaSuccess) return e;
@@ -138,19 +171,105 @@ cudaError_t upload_tables(mrc_ctx* c, TablesDev& d, DevTables<T>& tb, const mrc_
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;   // host vectors die at scope exit
     tb.bark_d = (const double*)d.bark_d.p; tb.quiet_d = (const double*)d.quiet_d.p;
     tb.exp_tab = (const double*)d.exp_tab.p;
-    tb.L = L; tb.logL = c->logL; tb.nb = c->nb; tb.sample_rate = c->cfg.sample_rate;
+    tb.L = L; tb.logL = pow2 ? logLtab : 0; tb.nb = g.nb; tb.sample_rate = c->cfg.sample_rate;
     tb.fstep = c->cfg.sample_rate / N;
+    tb.a = g.a; tb.b = g.b; tb.geom = (g.a != c->L ? 2 : 0) | (g.b != c->L ? 1 : 0);
+    tb.rot = (g.a - g.b) / 4;
+    tb.logLtab = logLtab;
+    tb.tw9 = (const cpx<T>*)d.tw9.p;
     tb.kbd = (const T*)d.kbd.p; tb.hann = (const T*)d.hann.p;
     tb.tw_pre = (const cpx<T>*)d.tw_pre.p; tb.tw_post = (const cpx<T>*)d.tw_post.p;
     tb.tw_fft = (const cpx<T>*)d.tw_fft.p; tb.tw_rfft = (const cpx<T>*)d.tw_rfft.p;
     tb.bark = (const T*)d.bark.p; tb.quiet = (const T*)d.quiet.p;
-    tb.band_lo = (const int*)c->band_lo.p; tb.band_n = (const int*)c->band_n.p;
-    tb.line2band = (const uint8_t*)c->line2band.p;
-    tb.nseg = c->nseg;
-    tb.seg_lo = (const int*)c->seg_lo.p; tb.seg_n = (const int*)c->seg_n.p;
-    tb.seg_band = (const int*)c->seg_band.p; tb.band_seg0 = (const int*)c->band_seg0.p;
+    tb.band_lo = (const int*)g.band_lo.p; tb.band_n = (const int*)g.band_n.p;
+    tb.line2band = (const uint8_t*)g.line2band.p;
+    tb.nseg = g.nseg;
+    tb.seg_lo = (const int*)g.seg_lo.p; tb.seg_n = (const int*)g.seg_n.p;
+    tb.seg_band = (const int*)g.seg_band.p; tb.band_seg0 = (const int*)g.band_seg0.p;
     return cudaSuccess;
 }
+
+// band table of one geometry: lines per band, line -> band, segments of the band-maximum search
+int set_geo_bands(mrc_ctx* ctx, GeoDev& g, const int32_t* band_nlines, int n_bands) {
+    if (n_bands < 1 || n_bands > MRC_CODED_BANDS)
+        return fail(ctx, MRC_E_INVALID, "n_bands out of range (1..25: the reference's tables have 25 or 9 bands)");
+    g.nb = n_bands;
+    g.h_band_lo.assign(n_bands, 0);
+    g.h_band_n.assign(n_bands, 0);
+    int acc = 0;
+    for (int b = 0; b < n_bands; ++b) {
+        if (band_nlines[b] < 1)
+            return fail(ctx, MRC_E_INVALID, "empty scale factor band (the reference crashes on these too)");
+        g.h_band_lo[b] = acc;
+        g.h_band_n[b] = band_nlines[b];
+        acc += band_nlines[b];
+    }
+    if (acc != g.L) return fail(ctx, MRC_E_INVALID, "band_nlines must sum to the block's MDCT lines");
+    std::vector<uint8_t> l2b(g.L);
+    for (int b = 0; b < n_bands; ++b)
+        for (int i = 0; i < g.h_band_n[b]; ++i) l2b[g.h_band_lo[b] + i] = (uint8_t)b;
+    CK(upload(g.band_lo, g.h_band_lo, ctx->stream));
+    CK(upload(g.band_n, g.h_band_n, ctx->stream));
+    CK(upload(g.line2band, l2b, ctx->stream));
+    // segments of at most MRC_SEG_LINES lines, never straddling a band
+    std::vector<int> slo, sn, sb, b0(n_bands + 1, 0);
+    for (int b = 0; b < n_bands; ++b) {
+        b0[b] = (int)slo.size();
+        const int n = g.h_band_n[b], parts = (n + MRC_SEG_LINES - 1) / MRC_SEG_LINES;
+        for (int q = 0; q < parts; ++q) {
+            const int a0 = (int)((long long)n * q / parts), a1 = (int)((long long)n * (q + 1) / parts);
+            slo.push_back(g.h_band_lo[b] + a0); sn.push_back(a1 - a0); sb.push_back(b);
+        }
+    }
+    b0[n_bands] = (int)slo.size();
+    if ((int)slo.size() > MRC_MAX_SEGS) return fail(ctx, MRC_E_INVALID, "too many band segments");
+    g.nseg = (int)slo.size();
+    CK(upload(g.seg_lo, slo, ctx->stream));
+    CK(upload(g.seg_n, sn, ctx->stream));
+    CK(upload(g.seg_band, sb, ctx->stream));
+    CK(upload(g.band_seg0, b0, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MRC_OK;
+}
+
+// bit budgets of one geometry up to the point where the reservoir is added, in the reference's order of operations
+void set_geo_budgets(mrc_ctx* ctx, GeoDev& g) {
+    const mrc_config& c = ctx->cfg;
+    const int halfN = g.L, nb = g.nb;
+    CodecParams& cp = g.cp;
+    {   // codecThem.py:381-391
+        double B = c.target_bits_per_sample * halfN;
+        B -= c.n_scale_bits * nb;
+        B -= c.n_mant_size_bits * nb;
+        B += B;
+        B -= nb;
+        B -= c.n_scale_bits * 4;
+        cp.budget_joint = B;
+    }
+    {   // codecThem.py:299-306
+        double B = c.target_bits_per_sample * halfN;
+        B -= c.n_scale_bits * (nb + 1);
+        B -= c.n_mant_size_bits * nb;
+        B -= 1;
+        B -= 1;
+        cp.budget_single = B;
+    }
+    {   // integer form: bitBudget = k + frac + bitReservoir (the joint path's two blksw bits folded into k)
+        const double bj = cp.budget_joint - 1.0 - 1.0, bs = cp.budget_single;
+        cp.k_joint = (int)floor(bj);   cp.frac_joint = (bj - floor(bj)) > 0.0 ? 1 : 0;
+        cp.k_single = (int)floor(bs);  cp.frac_single = (bs - floor(bs)) > 0.0 ? 1 : 0;
+    }
+    cp.L = g.L; cp.nb = nb; cp.Lmax = ctx->L;
+    cp.n_scale_bits = c.n_scale_bits; cp.n_mant_size_bits = c.n_mant_size_bits;
+    cp.max_mant_bits = std::min(16, 1 << c.n_mant_size_bits);
+    cp.joint = c.joint; cp.flush_nonjoint = 1; cp.no_huff = 0;
+    cp.spread_seq = (c.flags & MRC_FLAG_SPREAD_SEQUENTIAL) ? 1 : 0;
+    cp.header_bytes = 26 + 2 * ctx->geo[0].nb;
+}
+
+template <typename T> DevTables<T>& tb_of(mrc_ctx* ctx, int q);
+template <> DevTables<double>& tb_of<double>(mrc_ctx* ctx, int q) { return ctx->geo[q].tbd; }
+template <> DevTables<float>& tb_of<float>(mrc_ctx* ctx, int q) { return ctx->geo[q].tbf; }
 
 struct EncodeJob {
     // inputs (exactly one of d_pcm / d_xin)
@@ -175,7 +294,72 @@ struct EncodeJob {
     int32_t* t_res = nullptr; int32_t* t_cbytes = nullptr;
     bool need_quant = true;
     bool dev_qtaps = false;                // leave alloc / mantissa taps of the (single) wave in q_alloc / q_mant
+    int geom = MRC_GEO_LONG;               // d_xin jobs: the geometry of every block (per-block seam with a, b given)
+    bool switching = false;                // d_pcm jobs: transient detector + look-ahead decide each block's geometry
 };
+
+// ---- block switching: which nMDCTLines-frame blocks are written as eight short blocks --------------------------
+// Runs the detector over all clips (PCM already on the device), brings the two flags per block back and lays out
+// the written blocks of every clip: the block at frames [kL, (k+1)L) is short iff it holds a transient after its
+// first 128 samples or the NEXT block holds one in its first 128 samples (pacfileThem.py:1192; the last block of a
+// clip has no look-ahead); a = the previous written block's b; the Close() flush block has b = nMDCTLines.
+int plan_switched_blocks(mrc_ctx* ctx, const int16_t* d_pcm, const int64_t* h_clip_off, int nc, cudaStream_t st,
+                         std::vector<int32_t>& blk0, std::vector<int64_t>& bstart, std::vector<uint8_t>& bgeom,
+                         std::vector<uint8_t>* flags_out) {
+    const int L = ctx->L, S = MRC_SHORT, nseg = L / S;
+    std::vector<int32_t> sb0(nc + 1);
+    long long nsb = 0;
+    for (int c = 0; c < nc; ++c) {
+        const long long fr = h_clip_off[c + 1] - h_clip_off[c];
+        if (fr < 0) return fail(ctx, MRC_E_INVALID, "clip_frame_offsets must be non-decreasing");
+        sb0[c] = (int32_t)nsb;
+        nsb += (fr + L - 1) / L;
+        if (nsb > 0x0fff0000ll) return fail(ctx, MRC_E_INVALID, "too many blocks in one call");
+    }
+    sb0[nc] = (int32_t)nsb;
+    std::vector<uint8_t> flags((size_t)nsb);
+    if (nsb > 0) {
+        std::vector<int64_t> coff(h_clip_off, h_clip_off + nc + 1);
+        CK(upload(ctx->clip_off, coff, st));
+        CK(upload(ctx->sb0, sb0, st));
+        CK(ensure(ctx->peaks, (size_t)nsb * 2 * nseg * 8));
+        CK(ensure(ctx->flags, (size_t)nsb));
+        launch_transient(st, ctx->sos, (const int64_t*)ctx->clip_off.p, (const int32_t*)ctx->sb0.p, nc, d_pcm, L,
+                         (int)nsb, (double*)ctx->peaks.p, (uint8_t*)ctx->flags.p);
+        CK(cudaMemcpyAsync(flags.data(), ctx->flags.p, (size_t)nsb, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+    }
+    if (flags_out) *flags_out = flags;
+    blk0.assign(nc + 1, 0);
+    bstart.clear();
+    bgeom.clear();
+    for (int c = 0; c < nc; ++c) {
+        blk0[c] = (int32_t)bstart.size();
+        const int n = sb0[c + 1] - sb0[c];
+        const uint8_t* f = flags.data() + sb0[c];
+        bool a_short = false;
+        for (int k = 0; k < n; ++k) {
+            const bool is_short = (f[k] & 2) || (k + 1 < n && (f[k + 1] & 1));
+            if (is_short) {
+                for (int i = 0; i < nseg; ++i) {
+                    bstart.push_back((int64_t)k * L + (int64_t)i * S);
+                    bgeom.push_back((uint8_t)((a_short ? 2 : 0) | 1));
+                    a_short = true;
+                }
+            } else {
+                bstart.push_back((int64_t)k * L);
+                bgeom.push_back((uint8_t)(a_short ? 2 : 0));
+                a_short = false;
+            }
+        }
+        bstart.push_back((int64_t)n * L);                     // Close(): nMDCTLines zeros, non-joint
+        bgeom.push_back((uint8_t)(a_short ? 2 : 0));
+        if (bstart.size() > 0x7fff0000ull) return fail(ctx, MRC_E_INVALID, "too many blocks in one call");
+    }
+    blk0[nc] = (int32_t)bstart.size();
+    return MRC_OK;
+}
 
 constexpr int WAVE_BLOCKS = 1 << 14;   // blocks per wave: ~0.9 GB of hand-off per buffer set in fp64; the serial walk of
                                        // the last wave is the un-overlapped tail of a call, so waves are kept short
@@ -195,20 +379,37 @@ cudaEvent_t pool_event(mrc_ctx* ctx, size_t i) {
 // chain walk, the clip-offset scan and quantise+pack of wave w.
 template <typename T>
 int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
-    const int L = ctx->L, nb = ctx->nb, nc = job.n_clips;
+    const int L = ctx->L, nc = job.n_clips;
+    // taps of a per-block-seam job are sized by that block's geometry
+    const int nb = ctx->geo[job.geom].nb, Lt = ctx->geo[job.geom].L;
     cudaStream_t st = ctx->stream, st2 = ctx->stream2;
     // ---- block map ----
     std::vector<int32_t> blk0(nc + 1);
-    long long tot = 0;
-    for (int c = 0; c < nc; ++c) {
-        const long long fr = job.h_clip_off[c + 1] - job.h_clip_off[c];
-        if (fr < 0) return fail(ctx, MRC_E_INVALID, "clip_frame_offsets must be non-decreasing");
-        blk0[c] = (int32_t)tot;
-        tot += job.d_xin ? fr / (2 * L) : (fr + L - 1) / L + (job.flush_nonjoint ? 1 : 0);
-        if (tot > 0x7fff0000ll) return fail(ctx, MRC_E_INVALID, "too many blocks in one call");
+    std::vector<int64_t> bstart;
+    std::vector<uint8_t> bgeom;
+    int64_t uploaded = 0;              // frames of job.h_pcm already queued for upload
+    if (job.switching) {
+        // the detector reads every clip before the first block can be laid out: upload all PCM first
+        if (job.h_pcm) {
+            const int64_t frames = job.h_clip_off[nc];
+            if (frames > 0)
+                CK(cudaMemcpyAsync((int16_t*)job.d_pcm, job.h_pcm, (size_t)frames * 4, cudaMemcpyHostToDevice, st));
+            uploaded = frames;
+        }
+        const int rc = plan_switched_blocks(ctx, job.d_pcm, job.h_clip_off, nc, st, blk0, bstart, bgeom, nullptr);
+        if (rc != MRC_OK) return rc;
+    } else {
+        long long tot = 0;
+        for (int c = 0; c < nc; ++c) {
+            const long long fr = job.h_clip_off[c + 1] - job.h_clip_off[c];
+            if (fr < 0) return fail(ctx, MRC_E_INVALID, "clip_frame_offsets must be non-decreasing");
+            blk0[c] = (int32_t)tot;
+            tot += job.d_xin ? fr / (2 * Lt) : (fr + L - 1) / L + (job.flush_nonjoint ? 1 : 0);
+            if (tot > 0x7fff0000ll) return fail(ctx, MRC_E_INVALID, "too many blocks in one call");
+        }
+        blk0[nc] = (int32_t)tot;
     }
-    blk0[nc] = (int32_t)tot;
-    const int nblk_total = (int)tot;
+    const int nblk_total = blk0[nc];
     std::vector<int64_t> coff(job.h_clip_off, job.h_clip_off + nc + 1);
     CK(upload(ctx->clip_off, coff, st));
     CK(upload(ctx->clip_blk0, blk0, st));
@@ -239,12 +440,39 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     cm.clip_off = (const int64_t*)ctx->clip_off.p;
     cm.clip_blk0 = (const int32_t*)ctx->clip_blk0.p;
     cm.n_clips = nc;
-    CodecParams cp = ctx->cp;
-    cp.joint = job.joint;
-    cp.flush_nonjoint = job.flush_nonjoint ? 1 : 0;
-    cp.no_huff = job.no_huff;
+    cm.blk_start = nullptr; cm.blk_geom = nullptr; cm.list = nullptr;
+    // geometries in play, their launch parameters, and (block switching) the per-wave block lists of each
+    const int q_lo = job.switching ? 0 : job.geom, q_hi = job.switching ? MRC_N_GEO - 1 : job.geom;
+    CodecParams cpq[MRC_N_GEO];
     int min_nl = 0x7fffffff, max_nl = 0;
-    for (int b = 0; b < nb; ++b) { min_nl = std::min(min_nl, ctx->h_band_n[b]); max_nl = std::max(max_nl, ctx->h_band_n[b]); }
+    for (int q = q_lo; q <= q_hi; ++q) {
+        cpq[q] = ctx->geo[q].cp;
+        cpq[q].joint = job.joint;
+        cpq[q].flush_nonjoint = job.flush_nonjoint ? 1 : 0;
+        cpq[q].no_huff = job.no_huff;
+        for (int v : ctx->geo[q].h_band_n) { min_nl = std::min(min_nl, v); max_nl = std::max(max_nl, v); }
+    }
+    const CodecParams& cp = cpq[q_lo];     // for the kernels that read only geometry-independent fields
+    const int nwaves = (nblk_total + WAVE_BLOCKS - 1) / WAVE_BLOCKS;
+    std::vector<int32_t> lists;            // [wave][geometry] wave-local indices, back to back
+    std::vector<int> list_off((size_t)nwaves * MRC_N_GEO + 1, 0);
+    if (job.switching) {
+        CK(upload(ctx->blk_start, bstart, st));
+        CK(upload(ctx->blk_geom, bgeom, st));
+        cm.blk_start = (const int64_t*)ctx->blk_start.p;
+        cm.blk_geom = (const uint8_t*)ctx->blk_geom.p;
+        lists.reserve((size_t)nblk_total);
+        for (int w = 0; w < nwaves; ++w) {
+            const int g0 = w * WAVE_BLOCKS, nblk = std::min(WAVE_BLOCKS, nblk_total - g0);
+            for (int q = 0; q < MRC_N_GEO; ++q) {
+                list_off[(size_t)w * MRC_N_GEO + q] = (int)lists.size();
+                for (int i = 0; i < nblk; ++i)
+                    if (bgeom[(size_t)g0 + i] == q) lists.push_back(i);
+            }
+        }
+        list_off[(size_t)nwaves * MRC_N_GEO] = (int)lists.size();
+        CK(upload(ctx->blk_list, lists, st));
+    }
     // reservoir-map tables of the single-stream fast path: R_in in [r_lo, r_lo + ntab)
     const int r_lo = -((max_nl + 1 + 31) / 32 * 32), ntab = -r_lo + 640, tabw = (ntab + 2 + 3) / 4 * 4;
 
@@ -293,7 +521,6 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         taps.lines4 = (T*)ctx->tap_lines.p; taps.smr4 = (T*)ctx->tap_smr.p; taps.npeaks = (int32_t*)ctx->tap_npk.p;
     }
 
-    const int nwaves = (nblk_total + WAVE_BLOCKS - 1) / WAVE_BLOCKS;
     // events per wave: 0 analysis start, 1 analysis end, 2 cost end, 3 chain start, 4 chain end, 5 pack end,
     // 6 PCM of the wave uploaded
     constexpr int EPW = 7;
@@ -306,7 +533,6 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     int launches = 0;
     std::vector<unsigned char> hb;     // host bounce buffer for taps
     int c_lo = 0;
-    int64_t uploaded = 0;              // frames of job.h_pcm already queued for upload
     cudaStream_t st3 = ctx->stream3;
     if (job.h_pcm) CK(cudaStreamWaitEvent(st3, ctx->ev[0], 0));
     for (int w = 0; w < nwaves; ++w) {
@@ -316,7 +542,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         int c_hi = c_lo;
         while (blk0[c_hi + 1] < g0 + nblk) ++c_hi;                 // clip holding block g0+nblk-1
         const int nfin = (blk0[c_hi + 1] <= g0 + nblk) ? c_hi - c_lo + 1 : c_hi - c_lo;   // clips ending in this wave
-        if (job.h_pcm) {
+        if (job.h_pcm && !job.switching) {
             // frames this wave reads: up to the end of its last block (or of that clip); everything before was needed
             // by earlier blocks, so the upload front only moves forward.  The copy stream runs ahead of the kernels.
             const long long b_last = (long long)(g0 + nblk - 1) - blk0[c_hi];
@@ -333,15 +559,29 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         // ---- stream 2: analysis + cost (needs buffer set s free: pack of wave w-nsets done) ----
         if (w >= nsets) CK(cudaStreamWaitEvent(st2, ev(w - nsets, 5), 0));
         CK(cudaEventRecord(ev(w, 0), st2));
-        launch_analysis<T>(st2, tb, cp, cm, job.d_pcm, job.d_xin, g0, nblk, ho[s], taps,
-                           (unsigned long long*)ctx->peakctr.p);
+        // one launch per geometry present in the wave (a single one unless block switching is on)
+        auto for_geos = [&](auto&& fn) {
+            for (int q = q_lo; q <= q_hi; ++q) {
+                ClipMap cmq = cm;
+                int n = nblk;
+                if (job.switching) {
+                    const int o = list_off[(size_t)w * MRC_N_GEO + q];
+                    n = list_off[(size_t)w * MRC_N_GEO + q + 1] - o;
+                    cmq.list = (const int32_t*)ctx->blk_list.p + o;
+                }
+                if (n > 0) { fn(q, cmq, n); ++launches; }
+            }
+        };
+        for_geos([&](int q, const ClipMap& cmq, int n) {
+            launch_analysis<T>(st2, tb_of<T>(ctx, q), cpq[q], cmq, job.d_pcm, job.d_xin, g0, n, ho[s], taps,
+                               (unsigned long long*)ctx->peakctr.p);
+        });
         CK(cudaEventRecord(ev(w, 1), st2));
-        ++launches;
-        if (job.need_quant) {
-            launch_cost<T>(st2, tb, cp, (const HuffDev*)ctx->huff.p, cm, g0, nblk, ho[s], (unsigned char*)ctx->sets[s].rec.p,
-                           (unsigned char*)ctx->sets[s].pw.p);
-            ++launches;
-        }
+        if (job.need_quant)
+            for_geos([&](int q, const ClipMap& cmq, int n) {
+                launch_cost<T>(st2, tb_of<T>(ctx, q), cpq[q], (const HuffDev*)ctx->huff.p, cmq, g0, n, ho[s],
+                               (unsigned char*)ctx->sets[s].rec.p, (unsigned char*)ctx->sets[s].pw.p);
+            });
         // long stretches of one clip in the wave: the serial walk is the critical path, tabulate the reservoir maps
         const bool use_tab = job.need_quant && !ctx->no_tables && nblk / (c_hi - c_lo + 1) >= ctx->tab_min_blocks;
         if (use_tab) {
@@ -374,10 +614,11 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
                 launch_clip_scan(st, io[s].clip_bytes, (int64_t*)ctx->clip_base.p, c_lo, nfin, (int64_t*)ctx->running.p);
                 ++launches;
             }
-            launch_pack<T>(st, tb, cp, (const HuffDev*)ctx->huff.p, cm, g0, nblk, ho[s], io[s], ptaps,
-                           (const int64_t*)ctx->clip_base.p, job.d_out, job.out_cap, (const uint8_t*)ctx->header.p,
-                           (int*)ctx->overflow.p);
-            ++launches;
+            for_geos([&](int q, const ClipMap& cmq, int n) {
+                launch_pack<T>(st, tb_of<T>(ctx, q), cpq[q], (const HuffDev*)ctx->huff.p, cmq, g0, n, ho[s], io[s], ptaps,
+                               (const int64_t*)ctx->clip_base.p, job.d_out, job.out_cap, (const uint8_t*)ctx->header.p,
+                               (int*)ctx->overflow.p);
+            });
         }
         CK(cudaEventRecord(ev(w, 5), st));
         CK(cudaGetLastError());
@@ -389,11 +630,12 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
             if (e != cudaSuccess) return e;
             return cudaStreamSynchronize(st);
         };
-        if (job.t_lines) {
+        if (job.t_lines) {          // device rows hold Lmax lines; the caller's hold the geometry's Lt
             CK(fetch(taps.lines4, (size_t)nblk * 4 * L * sizeof(T)));
             const T* src = (const T*)hb.data();
-            double* d = job.t_lines + (size_t)g0 * 4 * L;
-            for (size_t i = 0; i < (size_t)nblk * 4 * L; ++i) d[i] = (double)src[i];
+            double* d = job.t_lines + (size_t)g0 * 4 * Lt;
+            for (size_t r = 0; r < (size_t)nblk * 4; ++r)
+                for (int i = 0; i < Lt; ++i) d[r * Lt + i] = (double)src[r * L + i];
         }
         if (job.t_smr) {
             CK(fetch(taps.smr4, (size_t)nblk * 4 * MRC_BSTRIDE * sizeof(T)));
@@ -431,8 +673,9 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         if (job.t_mant) {
             CK(fetch(ptaps.mant, (size_t)nblk * 2 * L * 2));
             const uint16_t* src = (const uint16_t*)hb.data();
-            int32_t* d = job.t_mant + (size_t)g0 * 2 * L;
-            for (size_t i = 0; i < (size_t)nblk * 2 * L; ++i) d[i] = src[i];
+            int32_t* d = job.t_mant + (size_t)g0 * 2 * Lt;
+            for (size_t r = 0; r < (size_t)nblk * 2; ++r)
+                for (int i = 0; i < Lt; ++i) d[r * Lt + i] = src[r * L + i];
         }
         if (job.t_table || job.t_res || job.t_cbytes) {
             CK(fetch(io[s].cblk, (size_t)nblk * sizeof(ChainBlk)));
@@ -478,6 +721,10 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
 
 int run_encode(mrc_ctx* ctx, const EncodeJob& job) {
     if (!ctx->tables_set) return fail(ctx, MRC_E_STATE, "mrc_set_tables has not been called");
+    if ((job.switching || job.geom != MRC_GEO_LONG) && !ctx->switch_set)
+        return fail(ctx, MRC_E_STATE, "block switching needs mrc_set_switch_tables");
+    if (job.switching && !job.joint)
+        return fail(ctx, MRC_E_INVALID, "block switching follows the reference's loop, which is the joint flow: create the context with joint = 1");
     if (ctx->cfg.precision == MRC_PRECISION_FP32) return run_encode_t<float>(ctx, job, ctx->tbf);
     return run_encode_t<double>(ctx, job, ctx->tbd);
 }
@@ -490,6 +737,8 @@ int64_t worst_case_bytes(const mrc_ctx* ctx, const int64_t* off, int nc) {
     for (int c = 0; c < nc; ++c) {
         const int64_t fr = off[c + 1] - off[c];
         tot += (int64_t)sizeof(ctx->h_header) + ((fr + L - 1) / L + 1) * 2 * per_chunk;
+        if (ctx->cfg.flags & MRC_FLAG_BLOCK_SWITCHING)      // eight short blocks instead of one: 16 chunk headers
+            tot += ((fr + L - 1) / L + 1) * 16 * (int64_t)(4 + (6 + 4 * ctx->cfg.n_scale_bits + 9 + 9 * 8 + 7) / 8 + 1);
     }
     return tot;
 }
@@ -501,6 +750,7 @@ int64_t nominal_bytes(const mrc_ctx* ctx, const int64_t* off, int nc) {
         const int64_t fr = off[c + 1] - off[c];
         const int64_t nblk = (fr + L - 1) / L + 1;
         tot += 128 + nblk * (int64_t)(2.0 * ctx->cfg.target_bits_per_sample * L / 8.0 + 64);
+        if (ctx->cfg.flags & MRC_FLAG_BLOCK_SWITCHING) tot += nblk * 160;
     }
     return tot;
 }
@@ -565,14 +815,20 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     if (!ctx) return MRC_OK;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    Buf* all[] = {&ctx->td.kbd, &ctx->td.hann, &ctx->td.tw_pre, &ctx->td.tw_post, &ctx->td.tw_fft, &ctx->td.tw_rfft,
-                  &ctx->td.bark, &ctx->td.quiet, &ctx->td.bark_d, &ctx->td.quiet_d, &ctx->td.exp_tab, &ctx->tf.bark_d,
-                  &ctx->tf.quiet_d, &ctx->tf.exp_tab, &ctx->tf.kbd, &ctx->tf.hann, &ctx->tf.tw_pre, &ctx->tf.tw_post,
-                  &ctx->tf.tw_fft, &ctx->tf.tw_rfft, &ctx->tf.bark, &ctx->tf.quiet, &ctx->band_lo, &ctx->band_n,
-                  &ctx->line2band, &ctx->huff, &ctx->header, &ctx->seg_lo, &ctx->seg_n, &ctx->seg_band, &ctx->band_seg0, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,
+    for (GeoDev& g : ctx->geo) {
+        for (TablesDev* d : {&g.td, &g.tf}) {
+            Buf* tb[] = {&d->kbd, &d->hann, &d->tw_pre, &d->tw_post, &d->tw_fft, &d->tw_rfft, &d->tw9, &d->bark, &d->quiet,
+                         &d->bark_d, &d->quiet_d, &d->exp_tab};
+            for (Buf* b : tb) release(*b);
+        }
+        Buf* gb[] = {&g.band_lo, &g.band_n, &g.line2band, &g.seg_lo, &g.seg_n, &g.seg_band, &g.band_seg0};
+        for (Buf* b : gb) release(*b);
+    }
+    Buf* all[] = {&ctx->huff, &ctx->header, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,
                   &ctx->clip_base, &ctx->running, &ctx->overflow, &ctx->peakctr, &ctx->res_in, &ctx->res_out,
                   &ctx->clip_res, &ctx->clip_run, &ctx->q_alloc, &ctx->q_sf, &ctx->q_mant,
-                  &ctx->tap_lines, &ctx->tap_smr, &ctx->tap_npk, &ctx->pcm_dev, &ctx->out_dev, &ctx->xin_dev};
+                  &ctx->tap_lines, &ctx->tap_smr, &ctx->tap_npk, &ctx->pcm_dev, &ctx->out_dev, &ctx->xin_dev,
+                  &ctx->sb0, &ctx->peaks, &ctx->flags, &ctx->blk_start, &ctx->blk_geom, &ctx->blk_list};
     for (Buf* b : all) release(*b);
     for (auto& b : ctx->dec) release(b);
     for (auto& ws : ctx->sets) {
@@ -597,42 +853,13 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
         return fail(ctx, MRC_E_INVALID, "n_bands out of range (1..25: the reference's tables have 25 or 9 bands)");
     if (t->n_huff_tables != MRC_N_HUFF_TABLES) return fail(ctx, MRC_E_INVALID, "exactly four Huffman tables expected");
     const int L = ctx->L;
+    GeoDev& g0 = ctx->geo[MRC_GEO_LONG];
+    g0.a = g0.b = g0.L = L;
+    {
+        const int rc = set_geo_bands(ctx, g0, t->band_nlines, t->n_bands);
+        if (rc != MRC_OK) return rc;
+    }
     ctx->nb = t->n_bands;
-    ctx->h_band_lo.assign(t->n_bands, 0);
-    ctx->h_band_n.assign(t->n_bands, 0);
-    int acc = 0;
-    for (int b = 0; b < t->n_bands; ++b) {
-        if (t->band_nlines[b] < 1)
-            return fail(ctx, MRC_E_INVALID, "empty scale factor band (the reference crashes on these too)");
-        ctx->h_band_lo[b] = acc;
-        ctx->h_band_n[b] = t->band_nlines[b];
-        acc += t->band_nlines[b];
-    }
-    if (acc != L) return fail(ctx, MRC_E_INVALID, "band_nlines must sum to n_mdct_lines");
-    std::vector<uint8_t> l2b(L);
-    for (int b = 0; b < t->n_bands; ++b)
-        for (int i = 0; i < ctx->h_band_n[b]; ++i) l2b[ctx->h_band_lo[b] + i] = (uint8_t)b;
-    CK(upload(ctx->band_lo, ctx->h_band_lo, ctx->stream));
-    CK(upload(ctx->band_n, ctx->h_band_n, ctx->stream));
-    CK(upload(ctx->line2band, l2b, ctx->stream));
-    {   // segments of at most MRC_SEG_LINES lines, never straddling a band
-        std::vector<int> slo, sn, sb, b0(t->n_bands + 1, 0);
-        for (int b = 0; b < t->n_bands; ++b) {
-            b0[b] = (int)slo.size();
-            const int n = ctx->h_band_n[b], parts = (n + MRC_SEG_LINES - 1) / MRC_SEG_LINES;
-            for (int q = 0; q < parts; ++q) {
-                const int a0 = (int)((long long)n * q / parts), a1 = (int)((long long)n * (q + 1) / parts);
-                slo.push_back(ctx->h_band_lo[b] + a0); sn.push_back(a1 - a0); sb.push_back(b);
-            }
-        }
-        b0[t->n_bands] = (int)slo.size();
-        if ((int)slo.size() > MRC_MAX_SEGS) return fail(ctx, MRC_E_INVALID, "too many band segments");
-        ctx->nseg = (int)slo.size();
-        CK(upload(ctx->seg_lo, slo, ctx->stream));
-        CK(upload(ctx->seg_n, sn, ctx->stream));
-        CK(upload(ctx->seg_band, sb, ctx->stream));
-        CK(upload(ctx->band_seg0, b0, ctx->stream));
-    }
     // Huffman LUTs
     HuffDev& h = ctx->h_huff;
     memset(&h, 0, sizeof h);
@@ -651,38 +878,12 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     CK(ensure(ctx->huff, sizeof(HuffDev)));
     CK(cudaMemcpyAsync(ctx->huff.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(upload_tables<double>(ctx, ctx->td, ctx->tbd, t));
-    CK(upload_tables<float>(ctx, ctx->tf, ctx->tbf, t));
-    // bit budgets up to the point where the reservoir is added, in the reference's order of operations
+    CK(upload_tables<double>(ctx, g0, g0.td, g0.tbd, t->kbd_window, t->hann_window, t->bark, t->quiet_intensity));
+    CK(upload_tables<float>(ctx, g0, g0.tf, g0.tbf, t->kbd_window, t->hann_window, t->bark, t->quiet_intensity));
+    set_geo_budgets(ctx, g0);
+    g0.set = true;
+    ctx->switch_set = false;         // geometries 1..3 were derived for the previous tables
     const mrc_config& c = ctx->cfg;
-    const int halfN = L;
-    {   // codecThem.py:381-391
-        double B = c.target_bits_per_sample * halfN;
-        B -= c.n_scale_bits * t->n_bands;
-        B -= c.n_mant_size_bits * t->n_bands;
-        B += B;
-        B -= t->n_bands;
-        B -= c.n_scale_bits * 4;
-        ctx->cp.budget_joint = B;
-    }
-    {   // codecThem.py:299-306
-        double B = c.target_bits_per_sample * halfN;
-        B -= c.n_scale_bits * (t->n_bands + 1);
-        B -= c.n_mant_size_bits * t->n_bands;
-        B -= 1;
-        B -= 1;
-        ctx->cp.budget_single = B;
-    }
-    {   // integer form: bitBudget = k + frac + bitReservoir (the joint path's two blksw bits folded into k)
-        const double bj = ctx->cp.budget_joint - 1.0 - 1.0, bs = ctx->cp.budget_single;
-        ctx->cp.k_joint = (int)floor(bj);   ctx->cp.frac_joint = (bj - floor(bj)) > 0.0 ? 1 : 0;
-        ctx->cp.k_single = (int)floor(bs);  ctx->cp.frac_single = (bs - floor(bs)) > 0.0 ? 1 : 0;
-    }
-    ctx->cp.L = L; ctx->cp.nb = t->n_bands;
-    ctx->cp.n_scale_bits = c.n_scale_bits; ctx->cp.n_mant_size_bits = c.n_mant_size_bits;
-    ctx->cp.max_mant_bits = std::min(16, 1 << c.n_mant_size_bits);
-    ctx->cp.joint = c.joint; ctx->cp.flush_nonjoint = 1; ctx->cp.no_huff = 0;
-    ctx->cp.spread_seq = (c.flags & MRC_FLAG_SPREAD_SEQUENTIAL) ? 1 : 0;
     ctx->no_tables = (c.flags & MRC_FLAG_NO_CHAIN_TABLES) != 0;
     if (const char* e = getenv("MRC_CHAIN_TABLE_MIN_BLOCKS")) ctx->tab_min_blocks = std::max(1, atoi(e));   // test knob
     if (ctx->cp.max_mant_bits != 16) return fail(ctx, MRC_E_INVALID, "only a 16-bit mantissa cap is supported");
@@ -695,7 +896,6 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     put32(4, (uint32_t)c.sample_rate); put16(8, 2); put32(10, 0); put32(14, (uint32_t)L);
     put16(18, (uint32_t)c.n_scale_bits); put16(20, (uint32_t)c.n_mant_size_bits); put32(22, (uint32_t)t->n_bands);
     for (int b = 0; b < t->n_bands; ++b) put16(26 + 2 * b, (uint32_t)t->band_nlines[b]);
-    ctx->cp.header_bytes = 26 + 2 * t->n_bands;
     CK(ensure(ctx->header, sizeof ctx->h_header));
     CK(cudaMemcpyAsync(ctx->header.p, hd, sizeof ctx->h_header, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -718,6 +918,7 @@ int32_t mrc_encode_batch_device(mrc_ctx* ctx, const int16_t* d_pcm, const int64_
     EncodeJob job;
     job.d_pcm = d_pcm; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
     job.joint = ctx->cfg.joint; job.flush_nonjoint = true;
+    job.switching = (ctx->cfg.flags & MRC_FLAG_BLOCK_SWITCHING) != 0;
     job.d_out = d_out; job.out_cap = out_cap; job.h_clip_byte_off = clip_byte_offsets;
     cudaEventRecord(ctx->ev[4], ctx->stream);
     const int rc = run_encode(ctx, job);
@@ -749,6 +950,7 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
         job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
         job.h_pcm = frames > 0 ? pcm : nullptr;             // uploaded wave by wave, overlapped with the kernels
         job.joint = ctx->cfg.joint; job.flush_nonjoint = true;
+        job.switching = (ctx->cfg.flags & MRC_FLAG_BLOCK_SWITCHING) != 0;
         job.d_out = (uint8_t*)ctx->out_dev.p; job.out_cap = cap; job.h_clip_byte_off = clip_byte_offsets;
         const int rc = run_encode(ctx, job);
         if (rc == MRC_E_NOSPACE && attempt == 0) {          // staging too small: retry once at the worst case
@@ -779,7 +981,7 @@ int32_t mrc_stage_analysis(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip
     const int64_t frames = clip_frame_offsets[n_clips];
     CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(frames, 1) * 4));
     if (frames > 0) CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)frames * 4, cudaMemcpyHostToDevice, ctx->stream));
-    EncodeJob job;
+    EncodeJob job;       // the whole-clip taps always follow the long-block flow (block counts are fixed up front)
     job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
     job.joint = ctx->cfg.joint; job.flush_nonjoint = true; job.need_quant = false;
     job.t_lines = mdct_lines; job.t_ovs = overall_scale; job.t_ms = ms_switch; job.t_smr = smr; job.t_npk = n_peaks;
@@ -802,18 +1004,23 @@ int32_t mrc_stage_alloc_quant(mrc_ctx* ctx, const int16_t* pcm, const int64_t* c
     return run_encode(ctx, job);
 }
 
-int32_t mrc_encode_block(mrc_ctx* ctx, const double* data, int32_t joint, int32_t* reservoir,
-                         int32_t* scale_factor, int32_t* bit_alloc, int32_t* mantissa, int32_t* overall_scale,
-                         int32_t* ms_switch, int32_t* huff_table, int32_t* chunk_bytes) {
+int32_t mrc_encode_block_ab(mrc_ctx* ctx, const double* data, int32_t a, int32_t b, int32_t joint, int32_t* reservoir,
+                            int32_t* scale_factor, int32_t* bit_alloc, int32_t* mantissa, int32_t* overall_scale,
+                            int32_t* ms_switch, int32_t* huff_table, int32_t* chunk_bytes) {
     if (!ctx || !data || !reservoir) return MRC_E_INVALID;
     cudaSetDevice(ctx->cfg.device);
-    const int N = 2 * ctx->L;
+    const int Lc = ctx->L;
+    if ((a != Lc && a != MRC_SHORT) || (b != Lc && b != MRC_SHORT))
+        return fail(ctx, MRC_E_INVALID, "window halves a and b must each be n_mdct_lines or 128");
+    const int q = (a != Lc ? 2 : 0) | (b != Lc ? 1 : 0);
+    const int N = a + b;
     CK(ensure(ctx->xin_dev, (size_t)2 * N * 8));
     CK(cudaMemcpyAsync(ctx->xin_dev.p, data, (size_t)2 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
     const int64_t off[2] = {0, N};
     int32_t res_in = *reservoir, res_out = 0;
     EncodeJob job;
     job.d_xin = (const double*)ctx->xin_dev.p; job.h_clip_off = off; job.n_clips = 1;
+    job.geom = q;
     job.joint = (joint & 1) ? 1 : 0; job.no_huff = (joint & 2) ? 1 : 0; job.flush_nonjoint = false;
     job.h_res_in = &res_in; job.h_res_out = &res_out;
     job.t_alloc = bit_alloc; job.t_sf = scale_factor; job.t_mant = mantissa; job.t_table = huff_table;
@@ -821,6 +1028,75 @@ int32_t mrc_encode_block(mrc_ctx* ctx, const double* data, int32_t joint, int32_
     const int rc = run_encode(ctx, job);
     if (rc == MRC_OK) *reservoir = res_out;
     return rc;
+}
+
+int32_t mrc_encode_block(mrc_ctx* ctx, const double* data, int32_t joint, int32_t* reservoir,
+                         int32_t* scale_factor, int32_t* bit_alloc, int32_t* mantissa, int32_t* overall_scale,
+                         int32_t* ms_switch, int32_t* huff_table, int32_t* chunk_bytes) {
+    if (!ctx) return MRC_E_INVALID;
+    return mrc_encode_block_ab(ctx, data, ctx->L, ctx->L, joint, reservoir, scale_factor, bit_alloc, mantissa,
+                               overall_scale, ms_switch, huff_table, chunk_bytes);
+}
+
+int32_t mrc_set_switch_tables(mrc_ctx* ctx, const mrc_block_tables* t3, const double* sos, int32_t n_sections,
+                              double t0, double t1) {
+    if (!ctx || !t3 || !sos) return MRC_E_INVALID;
+    if (!ctx->tables_set) return fail(ctx, MRC_E_STATE, "mrc_set_tables has not been called");
+    if (n_sections < 1 || n_sections > MRC_MAX_SOS) return fail(ctx, MRC_E_INVALID, "1..16 second-order sections");
+    if (ctx->L < 4 * MRC_SHORT) return fail(ctx, MRC_E_INVALID, "block switching needs n_mdct_lines >= 512");
+    if (ctx->L != 1024) return fail(ctx, MRC_E_INVALID, "block switching is built for n_mdct_lines = 1024 (transition blocks of 576 lines)");
+    cudaSetDevice(ctx->cfg.device);
+    const int Lc = ctx->L;
+    const int want[3][2] = {{Lc, MRC_SHORT}, {MRC_SHORT, Lc}, {MRC_SHORT, MRC_SHORT}};
+    for (int i = 0; i < 3; ++i) {
+        const mrc_block_tables& t = t3[i];
+        if (t.a != want[i][0] || t.b != want[i][1])
+            return fail(ctx, MRC_E_INVALID, "block tables must come in the order (L,128), (128,L), (128,128)");
+        GeoDev& g = ctx->geo[i + 1];
+        g.a = t.a; g.b = t.b; g.L = (t.a + t.b) / 2;
+        const int rc = set_geo_bands(ctx, g, t.band_nlines, t.n_bands);
+        if (rc != MRC_OK) return rc;
+        CK(upload_tables<double>(ctx, g, g.td, g.tbd, t.window, t.hann_window, t.bark, t.quiet_intensity));
+        CK(upload_tables<float>(ctx, g, g.tf, g.tbf, t.window, t.hann_window, t.bark, t.quiet_intensity));
+        set_geo_budgets(ctx, g);
+        g.set = true;
+    }
+    ctx->sos.n = n_sections;
+    ctx->sos.t0 = t0; ctx->sos.t1 = t1;
+    for (int s2 = 0; s2 < n_sections; ++s2) {
+        const double* r = sos + 6 * s2;
+        if (r[3] != 1.0) return fail(ctx, MRC_E_INVALID, "second-order sections must be normalised (a0 = 1)");
+        ctx->sos.c[s2][0] = r[0]; ctx->sos.c[s2][1] = r[1]; ctx->sos.c[s2][2] = r[2];
+        ctx->sos.c[s2][3] = r[4]; ctx->sos.c[s2][4] = r[5];
+    }
+    ctx->switch_set = true;
+    return MRC_OK;
+}
+
+int32_t mrc_detect_transients(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
+                              uint8_t* flags, int32_t* block_ab, int32_t block_cap, int32_t* clip_block_offsets) {
+    if (!ctx || !clip_frame_offsets || n_clips < 0) return MRC_E_INVALID;
+    if (!ctx->switch_set) return fail(ctx, MRC_E_STATE, "block switching needs mrc_set_switch_tables");
+    cudaSetDevice(ctx->cfg.device);
+    const int64_t frames = clip_frame_offsets[n_clips];
+    CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(frames, 1) * 4));
+    if (frames > 0) CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int32_t> blk0;
+    std::vector<int64_t> bstart;
+    std::vector<uint8_t> bgeom, fl;
+    const int rc = plan_switched_blocks(ctx, (const int16_t*)ctx->pcm_dev.p, clip_frame_offsets, n_clips, ctx->stream,
+                                        blk0, bstart, bgeom, &fl);
+    if (rc != MRC_OK) return rc;
+    if (flags) memcpy(flags, fl.data(), fl.size());
+    if (clip_block_offsets) memcpy(clip_block_offsets, blk0.data(), (size_t)(n_clips + 1) * 4);
+    if (block_ab) {
+        if ((int64_t)bgeom.size() > block_cap) return fail(ctx, MRC_E_NOSPACE, "block_ab too small (clip_block_offsets holds the counts)");
+        for (size_t i = 0; i < bgeom.size(); ++i) {
+            block_ab[2 * i] = (bgeom[i] & 2) ? MRC_SHORT : ctx->L;
+            block_ab[2 * i + 1] = (bgeom[i] & 1) ? MRC_SHORT : ctx->L;
+        }
+    }
+    return MRC_OK;
 }
 
 int32_t mrc_mantissa_histogram(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,
@@ -853,7 +1129,7 @@ int32_t mrc_mantissa_histogram(mrc_ctx* ctx, const int16_t* pcm, const int64_t* 
     int32_t* d_cmax = (int32_t*)ctx->dec[15].p;
     unsigned long long* d_hist = (unsigned long long*)((char*)ctx->dec[15].p + cmax_bytes);
     launch_callmax(st, L, ncalls, (const uint8_t*)ctx->q_alloc.p, (const uint16_t*)ctx->q_mant.p,
-                   (const uint8_t*)ctx->line2band.p, d_cmax);
+                   (const uint8_t*)ctx->geo[0].line2band.p, d_cmax);
     std::vector<int32_t> cmax(ncalls);
     CK(cudaMemcpyAsync(cmax.data(), d_cmax, (size_t)ncalls * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -863,7 +1139,7 @@ int32_t mrc_mantissa_histogram(mrc_ctx* ctx, const int16_t* pcm, const int64_t* 
         if (cmax[c] > gmax) { first_call = c; thr = gmax; gmax = cmax[c]; *reset_out = 1; }
     CK(cudaMemsetAsync(d_hist, 0, 65536 * 8, st));
     launch_hist(st, L, ncalls, first_call, thr, (const uint8_t*)ctx->q_alloc.p, (const uint16_t*)ctx->q_mant.p,
-                (const uint8_t*)ctx->line2band.p, d_hist);
+                (const uint8_t*)ctx->geo[0].line2band.p, d_hist);
     CK(cudaMemcpyAsync(hist, d_hist, 65536 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());

@@ -222,17 +222,18 @@ chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_
         const bool joint = cp.joint && !(cp.flush_nonjoint && b == nblk_clip - 1);
         const int R0 = R;
         int R1 = R;
+        const int K = mx[MRC_MX_K], frac = mx[MRC_MX_FRAC];      // this block's budget (its geometry's)
         if (joint) {
-            const int B0 = cp.k_joint + R;
+            const int B0 = K + R;
             const GroupTotals g = walk_group<false>(tn, cpre, pc, nullptr, mx, 0, MRC_NCHUNK, B0, min_nl, lane, dummy, n_iter);
-            R = reservoir_after(g, B0, cp.frac_joint, cp.no_huff, nullptr, nullptr);
+            R = reservoir_after(g, B0, frac, cp.no_huff, nullptr, nullptr);
         } else {
-            int B0 = cp.k_single + R;
+            int B0 = K + R;
             GroupTotals g = walk_group<false>(tn, cpre, pc, nullptr, mx, 0, MRC_GROUP_CHUNKS, B0, min_nl, lane, dummy, n_iter);
-            R = R1 = reservoir_after(g, B0, cp.frac_single, cp.no_huff, nullptr, nullptr);
-            B0 = cp.k_single + R;
+            R = R1 = reservoir_after(g, B0, frac, cp.no_huff, nullptr, nullptr);
+            B0 = K + R;
             g = walk_group<false>(tn, cpre, pc, nullptr, mx, MRC_GROUP_CHUNKS, MRC_GROUP_CHUNKS, B0, min_nl, lane, dummy, n_iter);
-            R = reservoir_after(g, B0, cp.frac_single, cp.no_huff, nullptr, nullptr);
+            R = reservoir_after(g, B0, frac, cp.no_huff, nullptr, nullptr);
         }
         if (lane == 0) io.rsv[blk0 + b - g0] = make_int4(R0, R1, R, 0);
         __syncwarp();                               // every lane is done reading stage s (generic-proxy reads need
@@ -290,7 +291,7 @@ table_kernel(CodecParams cp, ClipMap cm, int g0, int min_nl, ChainIO io, int r_l
     __syncthreads();
     const bool joint = s_joint != 0;
     const int ngroups = joint ? 1 : 2, nck = joint ? MRC_NCHUNK : MRC_GROUP_CHUNKS;
-    const int K = joint ? cp.k_joint : cp.k_single, frac = joint ? cp.frac_joint : cp.frac_single;
+    const int K = s_mx[MRC_MX_K], frac = s_mx[MRC_MX_FRAC];
     int* out = tab + lb * (size_t)(2 * tabw);
     for (int grp = 0; grp < 2; ++grp) {
         int* o = out + grp * tabw;
@@ -380,7 +381,8 @@ chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, in
         const unsigned char* stg = smem_raw + (size_t)s * sbytes;
         const int* T0 = reinterpret_cast<const int*>(stg);
         const bool joint = cp.joint && !(cp.flush_nonjoint && b == nblk_clip - 1);
-        const int K = joint ? cp.k_joint : cp.k_single, frac = joint ? cp.frac_joint : cp.frac_single;
+        const int32_t* mxs = reinterpret_cast<const int32_t*>(stg + tbytes + MRC_REC_MX);
+        const int K = mxs[MRC_MX_K], frac = mxs[MRC_MX_FRAC];
         const int R0 = R;
         int R1 = R;
         const int ngroups = joint ? 1 : 2;
@@ -436,24 +438,25 @@ finish_kernel(CodecParams cp, ClipMap cm, int g0, int nblk, int min_nl, ChainIO 
     const int4 rs = io.rsv[lb];
     unsigned gmask = 0u, n_iter = 0u;
     int table[2] = {MRC_NO_TABLE, MRC_NO_TABLE}, wbits[2] = {0, 0};
+    const int K = mx[MRC_MX_K], frac = mx[MRC_MX_FRAC];
     if (joint) {
-        const int B0 = cp.k_joint + rs.x;
+        const int B0 = K + rs.x;
         const GroupTotals gt = walk_group<true>(tn, cpre, pc, pw, mx, 0, MRC_NCHUNK, B0, min_nl, lane, gmask, n_iter);
-        reservoir_after(gt, B0, cp.frac_joint, cp.no_huff, table, wbits);
+        reservoir_after(gt, B0, frac, cp.no_huff, table, wbits);
     } else {
         int t2[2], w2[2];
-        int B0 = cp.k_single + rs.x;
+        int B0 = K + rs.x;
         GroupTotals gt = walk_group<true>(tn, cpre, pc, pw, mx, 0, MRC_GROUP_CHUNKS, B0, min_nl, lane, gmask, n_iter);
-        reservoir_after(gt, B0, cp.frac_single, cp.no_huff, t2, w2);
+        reservoir_after(gt, B0, frac, cp.no_huff, t2, w2);
         table[0] = t2[0]; wbits[0] = w2[0];
-        B0 = cp.k_single + rs.y;
+        B0 = K + rs.y;
         gt = walk_group<true>(tn, cpre, pc, pw, mx, MRC_GROUP_CHUNKS, MRC_GROUP_CHUNKS, B0, min_nl, lane, gmask, n_iter);
-        reservoir_after(gt, B0, cp.frac_single, cp.no_huff, t2, w2);
+        reservoir_after(gt, B0, frac, cp.no_huff, t2, w2);
         table[1] = t2[1]; wbits[1] = w2[1];
     }
     io.gmask[(size_t)lb * 32 + lane] = gmask;
     if (lane == 0) {
-        const int nb = cp.nb;
+        const int nb = mx[MRC_MX_NB];
         ChainBlk o;
         for (int ch = 0; ch < 2; ++ch) {
             int bits = 4 + 1 + 1 + nb * (cp.n_mant_size_bits + cp.n_scale_bits) + wbits[ch];

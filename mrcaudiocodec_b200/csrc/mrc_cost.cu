@@ -49,7 +49,7 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     __shared__ int s_blo[MRC_BSTRIDE], s_bn[MRC_BSTRIDE];
     __shared__ unsigned long long s_esclen4;
 
-    const size_t lb = blockIdx.x;
+    const size_t lb = cm.list ? (size_t)cm.list[blockIdx.x] : (size_t)blockIdx.x;
     const int g = g0 + (int)lb;
     if (tid == 0) {
         int lo = 0, hi = cm.n_clips;
@@ -76,7 +76,7 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     }
     if (tid < nb) { s_blo[tid] = tb.band_lo[tid]; s_bn[tid] = tb.band_n[tid]; }
     {
-        const T* gl = ho.lines + lb * 2 * L;
+        const T* gl = ho.lines + lb * 2 * cp.Lmax;
         for (int i = tid; i < 2 * L; i += CT) s_lines[i] = (double)gl[i];
         const T* gm = ho.bandmax + lb * 2 * MRC_BSTRIDE;
         if (tid < 2 * MRC_BSTRIDE) s_bmax[tid] = (double)gm[tid];
@@ -197,6 +197,10 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
             o_mx[k] = mx;
         }
         for (int k = MRC_NCHUNK; k < 32; ++k) o_mx[k] = 0x7fffffff;
+        // the block's own budget and band count travel with the record (they differ between block geometries)
+        o_mx[MRC_MX_K] = joint ? cp.k_joint : cp.k_single;
+        o_mx[MRC_MX_FRAC] = joint ? cp.frac_joint : cp.frac_single;
+        o_mx[MRC_MX_NB] = nb;
     }
     for (int k = warp; k < MRC_NCHUNK; k += CT / 32) {      // same thread re-reads what it wrote above
         const int slot = k * 32 + lane;

@@ -6,8 +6,10 @@
 //   IMDCT + window                  mdct.py:98-122 (here an L/2-point complex FFT DCT-IV), window.py:104-121
 //   overlap-add, first block drop   pacfileThem.py:312-314, :575-580, :1175-1177, :178-185
 //   PCM conversion                  pcmfile.py:164-174 with quantize.py:61-87 at 16 bits
-// One CTA per block pair (both channels), NT = L/2 threads.  A malformed chunk (reads past its nBytes, block
-// switching bits set, unknown table id) raises the error flag and decodes as silence instead of reading on.
+// One CTA per block pair (both channels), NT = L/2 threads, L = (a+b)/2 of the pair's geometry (block switching:
+// the host reads a and b from the chunk headers and launches each geometry over its own list of pairs).  A malformed
+// chunk (reads past its nBytes, block-size bits that differ from the pair's, unknown table id) raises the error flag
+// and decodes as silence instead of reading on.
 #include "mrc_decode.cuh"
 #include "mrc_math.cuh"
 #include "mrc_fft.cuh"
@@ -56,11 +58,11 @@ __device__ __forceinline__ DSmem<T> dcarve(unsigned char* raw, int L, int cwords
 }
 
 // dequantise + rescale + M/S + IMDCT + window; ints in shared memory.  Writes y[2][2L] to global.
-template <typename T, int LOGL>
+template <typename T, int L_>
 __device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecParams& cp, DSmem<T>& sm, bool joint,
                                            const int* s_alloc, const int* s_sf, const int* s_ovs, unsigned ms,
                                            T* __restrict__ yout) {
-    constexpr int L = 1 << LOGL, Q = L / 2, NT = Q;
+    constexpr int L = L_, Q = L / 2, NT = Q;
     const int tid = threadIdx.x, nb = tb.nb;
     // dequantise (codecThem.py:44-52 / :96-115) -- arithmetic in double in both precisions (a handful of ops)
     for (int i = tid; i < 2 * L; i += NT) {
@@ -94,12 +96,12 @@ __device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecPa
         for (int n = lt; n < Q; n += gthr) {
             const T re = X[2 * n], im = X[L - 1 - 2 * n];
             const cpx<T> w = tb.tw_pre[n];
-            const int r = fft_r4_pos(n, LOGL - 1);
+            const int r = fft_pos<Q>(n);
             a[r].x = re * w.x - im * w.y;
             a[r].y = re * w.y + im * w.x;
         }
         __syncthreads();
-        fft_r4<T>(a, LOGL - 1, lt, gthr, tb.tw_fft, LOGL);
+        fft_any<T, Q>(a, lt, gthr, tb.tw_fft, tb.logLtab, tb.tw9, L, tb.w9);
         T* v = sm.v + grp * L;
         for (int k = lt; k < Q; k += gthr) {
             const cpx<T> w = tb.tw_post[k];
@@ -109,24 +111,32 @@ __device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecPa
         }
         __syncthreads();
     }
-    // unfold (x[n] = 2 v_ext[n + L/2]) and window
+    // unfold (x[n] = 2 v_ext[n + L/2]) and window.  With a != b the phase n0 = (b+1)/2 (mdct.py:103) is the standard
+    // one shifted by rot = (a-b)/4 samples: output n is the standard output n - rot, negated where it wraps.
     for (int i = tid; i < 4 * L; i += NT) {
         const int ch = i / (2 * L), n = i - ch * 2 * L;
         const T* v = sm.v + ch * L;
+        int m = n;
+        T sg = T(2);
+        if constexpr (!FftShape<L>::pow2) {
+            m = n - tb.rot;
+            if (m < 0) { m += 2 * L; sg = T(-2); }
+            else if (m >= 2 * L) { m -= 2 * L; sg = T(-2); }
+        }
         T x;
-        if (n < Q) x = v[n + Q];
-        else if (n < 3 * Q) x = -v[3 * Q - 1 - n];
-        else x = -v[n - 3 * Q];
-        yout[i] = (T(2) * x) * tb.kbd[n];
+        if (m < Q) x = v[m + Q];
+        else if (m < 3 * Q) x = -v[3 * Q - 1 - m];
+        else x = -v[m - 3 * Q];
+        yout[i] = (sg * x) * tb.kbd[n];
     }
 }
 
-template <typename T, int LOGL>
-__global__ void __launch_bounds__(1 << (LOGL - 1))
+template <typename T, int L_>
+__global__ void __launch_bounds__(L_ / 2)
 decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, const HuffDecDev* __restrict__ hdec,
               DecodeMap dm, const uint8_t* __restrict__ pac, int p0, T* __restrict__ y, int* error_flag, int cwords) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int L = 1 << LOGL, NT = L / 2;
+    constexpr int L = L_, NT = L / 2;
     const int tid = threadIdx.x, nb = tb.nb;
     DSmem<T> sm = dcarve<T>(smem_raw, L, cwords);
     __shared__ int s_alloc[2 * MRC_BSTRIDE], s_sf[2 * MRC_BSTRIDE], s_ovs[4];
@@ -135,7 +145,7 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
     __shared__ int s_esc[MRC_N_HUFF_TABLES];
     __shared__ int s_boff[2 * MRC_BSTRIDE], s_raw[2];
 
-    const int lp = blockIdx.x, p = p0 + lp;
+    const int lp = dm.list ? dm.list[blockIdx.x] : (int)blockIdx.x, p = p0 + lp;
     if (tid == 0) {
         int lo = 0, hi = dm.n_clips;
         while (hi - lo > 1) {
@@ -176,7 +186,7 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
         br.bad = false;
         const int table = (int)br.read(4);
         const int swA = (int)br.read(1), swB = (int)br.read(1);
-        if (swA | swB) br.bad = true;                              // block switching is out of scope (§8 f1)
+        if (((swA << 1) | swB) != tb.geom) br.bad = true;          // both chunks of a pair carry the pair's geometry
         if (table != MRC_NO_TABLE && table >= MRC_N_HUFF_TABLES) br.bad = true;
         if (joint) {
             if (ch == 0) {
@@ -242,16 +252,16 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
         if (tid < 4) s_ovs[tid] = 0;
         __syncthreads();
     }
-    synthesize<T, LOGL>(tb, cp, sm, joint, s_alloc, s_sf, s_ovs, s_ms, y + (size_t)lp * 4 * L);
+    synthesize<T, L>(tb, cp, sm, joint, s_alloc, s_sf, s_ovs, s_ms, y + (size_t)lp * 4 * cp.Lmax);
 }
 
-template <typename T, int LOGL>
-__global__ void __launch_bounds__(1 << (LOGL - 1))
+template <typename T, int L_>
+__global__ void __launch_bounds__(L_ / 2)
 decode_ints_kernel(DevTables<T> tb, CodecParams cp, int joint, const int32_t* __restrict__ sf,
                    const int32_t* __restrict__ alloc, const int32_t* __restrict__ mant,
                    const int32_t* __restrict__ ovs, const int32_t* __restrict__ ms, T* __restrict__ y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int L = 1 << LOGL, NT = L / 2;
+    constexpr int L = L_, NT = L / 2;
     const int tid = threadIdx.x, nb = tb.nb, lp = blockIdx.x;
     DSmem<T> sm = dcarve<T>(smem_raw, L, 0);
     __shared__ int s_alloc[2 * MRC_BSTRIDE], s_sf[2 * MRC_BSTRIDE], s_ovs[4];
@@ -267,7 +277,7 @@ decode_ints_kernel(DevTables<T> tb, CodecParams cp, int joint, const int32_t* __
     if (tid < nb && ms[(size_t)lp * nb + tid]) atomicOr(&s_ms, 1u << tid);
     for (int i = tid; i < 2 * L; i += NT) sm.mant[i] = mant[(size_t)lp * 2 * L + i];
     __syncthreads();
-    synthesize<T, LOGL>(tb, cp, sm, joint != 0, s_alloc, s_sf, s_ovs, joint ? s_ms : 0u, y + (size_t)lp * 4 * L);
+    synthesize<T, L>(tb, cp, sm, joint != 0, s_alloc, s_sf, s_ovs, joint ? s_ms : 0u, y + (size_t)lp * 4 * L);
 }
 
 // pcmfile.py:164-174: sign/magnitude, |x|>=1 -> 32767 else trunc((65535|x|+1)/2)
@@ -281,7 +291,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ola_kernel(CodecParams cp, DecodeMap dm, int p0, const T* __restrict__ y, const int64_t* __restrict__ clip_frame_off,
            int16_t* __restrict__ pcm) {
-    const int L = cp.L, lp = blockIdx.x, p = p0 + lp, tid = threadIdx.x;
+    const int L = cp.Lmax, lp = blockIdx.x, p = p0 + lp, tid = threadIdx.x;
     __shared__ int s_clip, s_last;
     if (tid == 0) {
         int lo = 0, hi = dm.n_clips;
@@ -295,14 +305,25 @@ ola_kernel(CodecParams cp, DecodeMap dm, int p0, const T* __restrict__ y, const 
     __syncthreads();
     const int j = p - dm.clip_pair0[s_clip];
     const bool has_next = p < s_last;
-    const T* cur = y + (size_t)lp * 4 * L;           // [2][2L] of pair p
+    // this pair's window halves (a, b) and the next pair's; the saved tail (b samples) meets the next head (a' = b)
+    int a = L, b = L, n2 = 2 * L;
+    long long pos = (long long)j * L;
+    if (dm.pair_geom) {
+        const int q = dm.pair_geom[p];
+        a = (q & 2) ? MRC_SHORT : L;
+        b = (q & 1) ? MRC_SHORT : L;
+        pos = dm.pair_pos[p];
+        if (has_next) { const int q2 = dm.pair_geom[p + 1]; n2 = b + ((q2 & 1) ? MRC_SHORT : L); }
+    }
+    const int n1 = a + b;
+    const T* cur = y + (size_t)lp * 4 * L;            // [2][a+b] of pair p
     const T* nxt = cur + 4 * L;                       // pair p+1 (same wave: waves hold whole clips)
-    uint32_t* out = reinterpret_cast<uint32_t*>(pcm) + clip_frame_off[s_clip] + (long long)j * L;
-    for (int n = tid; n < L; n += blockDim.x) {
-        double l = (double)cur[L + n], r = (double)cur[2 * L + L + n];
+    uint32_t* out = reinterpret_cast<uint32_t*>(pcm) + clip_frame_off[s_clip] + pos;
+    for (int n = tid; n < b; n += blockDim.x) {
+        double l = (double)cur[a + n], r = (double)cur[n1 + a + n];
         if (has_next) {       // np.add(overlapAndAdd, decoded[:a]): saved tail first, then the new head
             l = l + (double)nxt[n];
-            r = r + (double)nxt[2 * L + n];
+            r = r + (double)nxt[n2 + n];
         }
         const int cl = fraction_to_pcm(l), cr = fraction_to_pcm(r);
         out[n] = ((uint32_t)(uint16_t)(int16_t)cl) | ((uint32_t)(uint16_t)(int16_t)cr << 16);
@@ -327,17 +348,18 @@ void launch_decode(cudaStream_t st, const DevTables<T>& tb, const CodecParams& c
     if (npairs <= 0) return;
     const int cw = chunk_words(cp);
     const size_t smem = decode_smem_bytes(tb.L, sizeof(T), cw);
-#define MRC_LAUNCH_DEC(LG)                                                                                     \
-    case LG:                                                                                                   \
-        cudaFuncSetAttribute(decode_kernel<T, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        decode_kernel<T, LG><<<npairs, 1 << (LG - 1), smem, st>>>(tb, cp, huff, hdec, dm, pac, p0, y,          \
-                                                                  error_flag, cw);                             \
+#define MRC_LAUNCH_DEC(LL)                                                                                     \
+    case LL:                                                                                                   \
+        cudaFuncSetAttribute(decode_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        decode_kernel<T, LL><<<npairs, LL / 2, smem, st>>>(tb, cp, huff, hdec, dm, pac, p0, y, error_flag, cw);  \
         break;
-    switch (tb.logL) {
-        MRC_LAUNCH_DEC(8)
-        MRC_LAUNCH_DEC(9)
-        MRC_LAUNCH_DEC(10)
-        MRC_LAUNCH_DEC(11)
+    switch (tb.L) {
+        MRC_LAUNCH_DEC(128)
+        MRC_LAUNCH_DEC(256)
+        MRC_LAUNCH_DEC(512)
+        MRC_LAUNCH_DEC(576)
+        MRC_LAUNCH_DEC(1024)
+        MRC_LAUNCH_DEC(2048)
         default: break;
     }
 #undef MRC_LAUNCH_DEC
@@ -349,16 +371,18 @@ void launch_decode_ints(cudaStream_t st, const DevTables<T>& tb, const CodecPara
                         const int32_t* ms, int npairs, T* y) {
     if (npairs <= 0) return;
     const size_t smem = decode_smem_bytes(tb.L, sizeof(T), 0);
-#define MRC_LAUNCH_DECI(LG)                                                                                    \
-    case LG:                                                                                                   \
-        cudaFuncSetAttribute(decode_ints_kernel<T, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        decode_ints_kernel<T, LG><<<npairs, 1 << (LG - 1), smem, st>>>(tb, cp, joint, sf, alloc, mant, ovs, ms, y); \
+#define MRC_LAUNCH_DECI(LL)                                                                                    \
+    case LL:                                                                                                   \
+        cudaFuncSetAttribute(decode_ints_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        decode_ints_kernel<T, LL><<<npairs, LL / 2, smem, st>>>(tb, cp, joint, sf, alloc, mant, ovs, ms, y);     \
         break;
-    switch (tb.logL) {
-        MRC_LAUNCH_DECI(8)
-        MRC_LAUNCH_DECI(9)
-        MRC_LAUNCH_DECI(10)
-        MRC_LAUNCH_DECI(11)
+    switch (tb.L) {
+        MRC_LAUNCH_DECI(128)
+        MRC_LAUNCH_DECI(256)
+        MRC_LAUNCH_DECI(512)
+        MRC_LAUNCH_DECI(576)
+        MRC_LAUNCH_DECI(1024)
+        MRC_LAUNCH_DECI(2048)
         default: break;
     }
 #undef MRC_LAUNCH_DECI

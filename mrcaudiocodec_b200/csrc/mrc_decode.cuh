@@ -13,6 +13,10 @@ struct DecodeMap {
     const uint32_t* chunk_len;   // [2*npairs]
     const int32_t* clip_pair0;   // [n_clips+1] first global pair of every clip
     int n_clips;
+    // block switching (null / unused for streams of long blocks only)
+    const uint8_t* pair_geom;    // [npairs] MRC_GEO_* from the chunk headers
+    const int64_t* pair_pos;     // [npairs] first output frame (relative to the clip) of tail(pair) + head(next pair)
+    const int32_t* list;         // wave-local pairs of the geometry being launched (null: all)
 };
 
 // parse + dequantise + M/S + IMDCT + window for pairs [p0, p0+npairs): writes y [npairs][2][2L] (head, tail)

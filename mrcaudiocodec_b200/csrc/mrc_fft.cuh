@@ -16,13 +16,14 @@ __device__ __forceinline__ int fft_r4_pos(int n, int logn) {
 // In-place decimation-in-time FFT of size 2^logn on input placed by fft_r4_pos: one radix-2 stage first when logn is
 // odd, then radix-4 stages (half as many barriers and 0.4 x the instructions of radix 2).  `nthr` threads of this group
 // (local id lt); a radix-4 stage has n/4 butterflies.  tw[k] = exp(-2*pi*j*k/Ltab), k < Ltab/2, Ltab = 2^logLtab >= n.
-template <typename T>
+// NB > 1: NB independent transforms of that size on the consecutive sub-arrays a + s*n, all stages in lock step.
+template <typename T, int NB = 1>
 __device__ __forceinline__ void fft_r4(cpx<T>* a, int logn, int lt, int nthr, const cpx<T>* __restrict__ tw,
                                        int logLtab) {
     const int n = 1 << logn;
     int h = 1;
     if (logn & 1) {
-        for (int q = lt; q < (n >> 1); q += nthr) {
+        for (int q = lt; q < NB * (n >> 1); q += nthr) {
             const cpx<T> u = a[2 * q], v = a[2 * q + 1];
             a[2 * q].x = u.x + v.x;      a[2 * q].y = u.y + v.y;
             a[2 * q + 1].x = u.x - v.x;  a[2 * q + 1].y = u.y - v.y;
@@ -33,9 +34,9 @@ __device__ __forceinline__ void fft_r4(cpx<T>* a, int logn, int lt, int nthr, co
     const int half_tab = 1 << (logLtab - 1);
     for (; 4 * h <= n; h <<= 2) {
         const int logh = 31 - __clz(h);
-        for (int bi = lt; bi < (n >> 2); bi += nthr) {
+        for (int bi = lt; bi < NB * (n >> 2); bi += nthr) {
             const int j = bi & (h - 1);
-            const int base = ((bi >> logh) << (logh + 2)) + j;
+            const int base = ((bi >> logh) << (logh + 2)) + j;     // sub-array s = bi / (n/4) lands at s*n by itself
             const int k1 = j << (logLtab - logh - 2);          // W_(4h)^j = tw[j * Ltab / (4h)]
             const cpx<T> w1 = tw[k1], w2 = tw[2 * k1];
             const int k3 = 3 * k1;
@@ -57,3 +58,71 @@ __device__ __forceinline__ void fft_r4(cpx<T>* a, int logn, int lt, int nthr, co
     }
 }
 
+
+// ---- transform sizes 2^p and 9 * 2^p (block switching: a + b = 1152 gives 288- and 576-point transforms) -------
+// n = 9 P, P = 2^p: input index i = 9 i1 + i2 goes to sub-array i2 (a P-point transform over i1), then one radix-9
+// pass:  X[k1 + P k2] = sum_{i2} ( W_n^(i2 k1) * Sub_i2[k1] ) * W_9^(i2 k2)   -- in place: column k1 in, column k1 out.
+template <int NFFT>
+struct FftShape {
+    static constexpr bool pow2 = (NFFT & (NFFT - 1)) == 0;
+    static constexpr int P = pow2 ? NFFT : NFFT / 9;
+    static constexpr int logP = (P == 1) ? 0 : (P == 2) ? 1 : (P == 4) ? 2 : (P == 8) ? 3 : (P == 16) ? 4 : (P == 32) ? 5 :
+                                (P == 64) ? 6 : (P == 128) ? 7 : (P == 256) ? 8 : (P == 512) ? 9 : (P == 1024) ? 10 :
+                                (P == 2048) ? 11 : -1;
+    static_assert(logP >= 0 && (pow2 || P * 9 == NFFT), "FFT size must be 2^p or 9 * 2^p");
+};
+
+template <int NFFT>
+__device__ __forceinline__ int fft_pos(int i) {
+    using S = FftShape<NFFT>;
+    if constexpr (S::pow2) return fft_r4_pos(i, S::logP);
+    else {
+        const int i1 = i / 9, i2 = i - 9 * i1;
+        return i2 * S::P + fft_r4_pos(i1, S::logP);
+    }
+}
+
+// tw9[m] = exp(-2*pi*j*m/n9), n9 a multiple of NFFT; w9[m] = exp(-2*pi*j*m/9).  Ends with a barrier.
+template <typename T, int NFFT>
+__device__ __forceinline__ void fft_any(cpx<T>* a, int lt, int nthr, const cpx<T>* __restrict__ tw, int logLtab,
+                                        const cpx<T>* __restrict__ tw9, int n9, const cpx<T>* w9) {
+    using S = FftShape<NFFT>;
+    if constexpr (S::pow2) {
+        fft_r4<T, 1>(a, S::logP, lt, nthr, tw, logLtab);
+    } else {
+        constexpr int P = S::P;
+        fft_r4<T, 9>(a, S::logP, lt, nthr, tw, logLtab);
+        // thread (k1, g) computes the outputs k2 = g, g+3, g+6 of column k1; all reads precede all writes
+        const int stride = n9 / NFFT;
+        const bool act = lt < 3 * P;
+        const int k1 = lt / 3, g = lt - 3 * k1;
+        cpx<T> o[3];
+        if (act) {
+            cpx<T> v[9];
+#pragma unroll
+            for (int i2 = 0; i2 < 9; ++i2) {
+                const cpx<T> x = a[i2 * P + k1], w = tw9[i2 * k1 * stride];
+                v[i2].x = x.x * w.x - x.y * w.y;
+                v[i2].y = x.x * w.y + x.y * w.x;
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int k2 = g + 3 * q;
+                T sx = v[0].x, sy = v[0].y;
+#pragma unroll
+                for (int i2 = 1; i2 < 9; ++i2) {
+                    const cpx<T> w = w9[(i2 * k2) % 9];
+                    sx += v[i2].x * w.x - v[i2].y * w.y;
+                    sy += v[i2].x * w.y + v[i2].y * w.x;
+                }
+                o[q].x = sx; o[q].y = sy;
+            }
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) a[k1 + P * (g + 3 * q)] = o[q];
+        }
+        __syncthreads();
+    }
+}

@@ -43,6 +43,11 @@
                                                        //             (sums of 16-bit fields carried mod 2^32)
 #define MRC_REC_MX (MRC_REC_PC + MRC_NSLOT * 16)       // i32 [32]    per 32-token chunk: running max of (bits spent + nLines)
 #define MRC_REC_BYTES (MRC_REC_MX + 32 * 4)            // 18560, a multiple of 16
+// words MRC_NCHUNK.. of the MX array carry the block's own geometry to the serial kernels (block switching: the
+// budget and the band count differ between long, transition and short blocks)
+#define MRC_MX_K 24                                    // integer part of the bit budget before the reservoir
+#define MRC_MX_FRAC 25                                 // 1 if the budget has a fractional part
+#define MRC_MX_NB 26                                   // scale factor bands of the block
 #define MRC_PW_BYTES (MRC_NSLOT * 16)                  // uint4 [768] like MRC_REC_PC for the bits actually written (Q4)
 
 struct ChainBlk {                // what the chain kernel decides per block (32 bytes)
@@ -55,10 +60,24 @@ struct ChainBlk {                // what the chain kernel decides per block (32 
 
 template <typename T> struct cpx { T x, y; };
 
+// Block geometries: window halves a (previous block) and b (this block), each nMDCTLines or 128.
+// geometry id = 2*(a short) + (b short) = the two blksw bits of the chunk header (pacfileThem.py:720-721).
+#define MRC_GEO_LONG 0
+#define MRC_GEO_START 1                          // (L, 128)
+#define MRC_GEO_STOP 2                           // (128, L)
+#define MRC_GEO_SHORT 3                          // (128, 128)
+#define MRC_N_GEO 4
+#define MRC_SHORT 128
+
 template <typename T>
 struct DevTables {
-    int L, logL, nb, sample_rate, fstep;         // fstep = sample_rate // (2L)   (Q2)
-    const T* kbd;                                // [2L]
+    int L, logL, nb, sample_rate, fstep;         // L = (a+b)/2 lines; fstep = sample_rate // (a+b)   (Q2)
+    int a, b, geom;
+    int rot;                                     // (a-b)/4: MDCT phase n0 = (b+1)/2 as a rotation of the standard one
+    int logLtab;                                 // tw_fft holds exp(-2*pi*j*k/2^logLtab), k < 2^(logLtab-1)
+    const cpx<T>* tw9;                           // [L]    exp(-2*pi*j*m/L) for the radix-9 pass (L = 9 * 2^p only)
+    cpx<T> w9[9];                                //        exp(-2*pi*j*m/9)
+    const T* kbd;                                // [2L]   TransitionWindow(a, b)
     const T* hann;                               // [2L]
     const cpx<T>* tw_pre;                        // [L/2]  exp(-j*pi*(4n+1)/(4L))
     const cpx<T>* tw_post;                       // [L/2]  exp(-j*pi*k/L)
@@ -92,6 +111,11 @@ struct ClipMap {
     const int64_t* clip_off;     // [n_clips+1] frame offsets into pcm            (device)
     const int32_t* clip_blk0;    // [n_clips+1] first global block of every clip   (device)
     int n_clips;
+    // block switching: blocks differ in size, so position and geometry are per block (null otherwise)
+    const int64_t* blk_start;    // [nblk_total] first frame of the block's new samples, relative to its clip
+    const uint8_t* blk_geom;     // [nblk_total] MRC_GEO_*
+    // the kernels of one geometry run over a list of wave-local block indices (null: all blocks of the wave)
+    const int32_t* list;
 };
 
 template <typename T>
@@ -130,6 +154,7 @@ struct PackTaps {                // all nullable (parity taps)
 
 struct CodecParams {
     int L, nb, n_scale_bits, n_mant_size_bits, max_mant_bits, joint;
+    int Lmax;                    // nMDCTLines: per-block stride of the hand-off buffers (L of a short block is smaller)
     int no_huff;                 // 1: EncodeNoHuff (codecThem.py:234-260): table 15, no reservoir credit
     int flush_nonjoint;          // 1: the last block of every clip is the non-joint Close() flush block (Q10)
     int spread_seq;              // 1: masker spreading summed pair by pair in the reference's order (psychoac.py:168)
@@ -182,6 +207,17 @@ void launch_clip_scan(cudaStream_t st, const int64_t* clip_bytes, int64_t* clip_
                       int64_t* running);
 
 size_t analysis_smem_bytes(int L, int elem);
+
+// mrc_transient.cu -- block switching: per nMDCTLines-frame block, flags bit 0 = transient in the first 128 samples,
+// bit 1 = transient later in the block (pacfileThem.py:1021-1056)
+#define MRC_MAX_SOS 16
+struct SosParams {
+    int n;                       // second-order sections
+    double t0, t1;               // thresholds T[0], T[1] (pacfileThem.py:1154)
+    double c[MRC_MAX_SOS][5];    // b0, b1, b2, a1, a2 (a0 = 1)
+};
+void launch_transient(cudaStream_t st, const SosParams& sp, const int64_t* clip_off, const int32_t* clip_sb0,
+                      int n_clips, const int16_t* pcm, int L, int nsb_total, double* peaks, uint8_t* flags);
 
 // mrc_train.cu
 void launch_callmax(cudaStream_t st, int L, int ncalls, const uint8_t* alloc, const uint16_t* mant,

@@ -24,7 +24,7 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     uint32_t* bitbuf = reinterpret_cast<uint32_t*>(smem_raw);
     const int L = cp.L, nb = cp.nb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t lb = blockIdx.x >> 1;
+    const size_t lb = cm.list ? (size_t)cm.list[blockIdx.x >> 1] : (size_t)(blockIdx.x >> 1);
     const int ch = blockIdx.x & 1;
     const int g = g0 + (int)lb;
     const uint8_t* __restrict__ line2band = tb.line2band;
@@ -68,6 +68,8 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     if (tid < nb)
         s_sf[tid] = scale_factor_of((double)ho.bandmax[(lb * 2 + ch) * MRC_BSTRIDE + tid], cp.n_scale_bits, s_alloc[tid]);
     __syncthreads();
+    if (taps.mant != nullptr)
+        for (int k = L + tid; k < cp.Lmax; k += PT) taps.mant[(lb * 2 + ch) * cp.Lmax + k] = 0;
     if (taps.alloc != nullptr && tid < MRC_BSTRIDE) {
         taps.alloc[(lb * 2 + ch) * MRC_BSTRIDE + tid] = (uint8_t)(tid < nb ? s_alloc[tid] : 0);
         taps.sf[(lb * 2 + ch) * MRC_BSTRIDE + tid] = (uint8_t)(tid < nb ? s_sf[tid] : 0);
@@ -90,13 +92,16 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     };
 
     // per-line symbols: LPT consecutive lines per thread
-    const int LPT = L / PT;                      // 1, 2, 4 or 8
-    const T* __restrict__ lines = ho.lines + (lb * 2 + ch) * L;
+    const int LPT = (L + PT - 1) / PT;           // 1 .. 8 (L = 576 -> 3: threads past the last line idle)
+    const T* __restrict__ lines = ho.lines + lb * 2 * cp.Lmax + (size_t)ch * L;
     uint32_t sym[8];
     int slen[8];
     int local = 0;
     for (int i = 0; i < LPT; ++i) {
         const int k = tid * LPT + i;
+        sym[i] = 0u;
+        slen[i] = 0;
+        if (k >= L) continue;
         const int bd = line2band[k];
         const int Rb = s_alloc[bd];
         int n = 0, m = 0;
@@ -110,7 +115,7 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
                 else { n = s_h.esc_len[table] + Rb; v = ((uint32_t)s_h.esc_code[table] << Rb) | (uint32_t)m; }
             }
         }
-        if (taps.mant != nullptr) taps.mant[(lb * 2 + ch) * L + k] = (uint16_t)m;
+        if (taps.mant != nullptr) taps.mant[(lb * 2 + ch) * cp.Lmax + k] = (uint16_t)m;
         sym[i] = v;
         slen[i] = n;
         local += n;
@@ -128,6 +133,7 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     int pos = woff + incl - local;               // mantissa bits before this thread's first line
     for (int i = 0; i < LPT; ++i) {
         const int k = tid * LPT + i;
+        if (k >= L) break;
         const int bd = line2band[k];
         const int p = hdr_bits + band_hdr * (bd + 1) + pos;
         if (k == band_lo[bd]) {                   // first line of a band also writes the band header
@@ -138,7 +144,8 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
         pos += slen[i];
     }
     if (tid == 0) {
-        put(0, (uint32_t)table, 4);               // huffTable(4); blkswA, blkswB = 0 for long blocks
+        put(0, (uint32_t)table, 4);               // huffTable(4)
+        put(4, (uint32_t)(tb.geom & 3), 2);       // blkswA, blkswB: 1 = that window half is short (pacfileThem.py:720-721)
         int p = 6;
         if (joint) {
             if (ch == 0) {
@@ -168,7 +175,7 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
         __syncthreads();
         if (tid == 0) {
             long long ns = cm.clip_off[s_clip + 1] - cm.clip_off[s_clip];
-            if (ns % L == 0) ns += L;             // Q9: bumped only when already a multiple
+            if (ns % cp.Lmax == 0) ns += cp.Lmax; // Q9: bumped only when already a multiple
             for (int i = 0; i < 4; ++i) h[10 + i] = (uint8_t)((unsigned long long)ns >> (8 * i));
         }
     }
@@ -215,7 +222,7 @@ void launch_pack(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp,
                  const int64_t* clip_base, uint8_t* out, long long out_cap, const uint8_t* header_template,
                  int* overflow_flag) {
     if (nblk <= 0) return;
-    const size_t smem = (size_t)cp.L * 25 / 8 + 512;
+    const size_t smem = (size_t)cp.Lmax * 25 / 8 + 512;
     pack_kernel<T><<<2 * nblk, PT, smem, st>>>(tb, cp, huff, cm, g0, ho, io, taps, clip_base, out, out_cap,
                                                header_template, overflow_flag);
 }

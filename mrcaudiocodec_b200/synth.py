@@ -110,3 +110,34 @@ def synth_music(seed, seconds, sample_rate=48000):
     x += 0.002 * rng.standard_normal((n, 2))
     np.clip(x, -0.999, 0.999, out=x)
     return np.round(x * 32767.0).astype(np.int16)
+
+
+def synth_percussive(seed, seconds, sample_rate=48000, hits_per_second=5.0):
+    """Castanet-like material for block switching: a quiet tonal bed (two sines, -35 dBFS noise floor) under sharp
+    hits at random times -- 2 ms attacks of band-limited noise decaying over 5..30 ms, random level and panning --
+    so that the transient detector (pacfileThem.py:1021-1056) fires in varying 128-sample segments, in one or both
+    channels, sometimes in consecutive blocks."""
+    rng = np.random.default_rng([int(seed), 4242])
+    n = int(round(seconds * sample_rate))
+    t = np.arange(n, dtype=np.float64) / sample_rate
+    x = np.zeros((n, 2), dtype=np.float64)
+    for k in range(2):
+        f = float(np.exp(rng.uniform(np.log(100.0), np.log(3000.0))))
+        x[:, 0] += 0.05 * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28))
+        x[:, 1] += 0.05 * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28))
+    x += 0.004 * rng.standard_normal((n, 2))
+    nhits = int(rng.poisson(hits_per_second * seconds)) + 1
+    for _ in range(nhits):
+        s0 = int(rng.integers(0, max(n - 1, 1)))
+        dur = int(rng.uniform(0.005, 0.03) * sample_rate)
+        m = min(dur, n - s0)
+        if m <= 0:
+            continue
+        tt = np.arange(m) / float(sample_rate)
+        env = np.exp(-tt / (dur / (5.0 * sample_rate)))
+        burst = rng.standard_normal(m) * env * rng.uniform(0.05, 0.7)
+        pan = rng.uniform(0.0, 1.0)
+        x[s0:s0 + m, 0] += burst * np.sqrt(1.0 - pan)
+        x[s0:s0 + m, 1] += burst * np.sqrt(pan)
+    np.clip(x, -0.999, 0.999, out=x)
+    return np.round(x * 32767.0).astype(np.int16)

@@ -8,6 +8,8 @@ them on every call (so the values, including their last bits, are the reference'
   Thresh(f)       psychoac.py:23-25,  Intensity psychoac.py:18
   band table      psychoac.py:82-105 (25 Zwicker critical bands) / pacfileThem.py:216 (9-band short table)
   Huffman books   training_data/*_table.pkl, alphabetical order, shipped as huffman_tables.json
+  block switching window.py:104-121 (TransitionWindow(a, b)), pacfileThem.py:213-219 (9 bands unless a+b = 2L),
+                  :1146-1147 (transient detector's high-pass, scipy.signal like the reference), :1154 (thresholds)
 """
 import json
 import os
@@ -34,6 +36,11 @@ def kbd_window(N, alpha=4.0):
     top = np.sqrt(np.divide(np.dot(np.tril(np.ones((h, h))), v2[0:h]), denom))
     bot = np.sqrt(np.divide(np.dot(np.triu(np.ones((h, h))), v2[1:h + 1]), denom))
     return np.concatenate((top, bot))
+
+
+def transition_window(a, b):
+    """window.py:112-119: left half of KBD(2a) then right half of KBD(2b)."""
+    return np.append(kbd_window(2 * a)[:a], kbd_window(2 * b)[b:])
 
 
 def hann_window(N):
@@ -106,4 +113,35 @@ class Tables(object):
         self.huff_len = np.ascontiguousarray(self.huff_len)
         self.huff_code = np.ascontiguousarray(self.huff_code)
         self.n_bands = int(len(self.band_nlines))
+        self.band_lower = np.concatenate(([0], np.cumsum(self.band_nlines)[:-1])).astype(np.int64)
+
+
+N_SHORT = 128                       # pacfileThem.py:1114
+TRANSIENT_THRESHOLDS = (0.1, 0.075)  # pacfileThem.py:1154
+
+
+def transient_sos(sample_rate):
+    """pacfileThem.py:1146-1147, the reference's own scipy calls (scipy is the reference's dependency for exactly
+    this).  tf2sos factors a 20th-order polynomial, so the sections' last bits depend on the LAPACK build; callers
+    that need a bit-exact match with a stream encoded elsewhere pass that encoder's sections instead."""
+    from scipy import signal
+    b, a = signal.cheby2(20, 40, 9000. / sample_rate, 'high')
+    return np.ascontiguousarray(signal.tf2sos(b, a), dtype=np.float64)
+
+
+class BlockTables(object):
+    """Tables of one block geometry of block switching: window halves a, b (each n_mdct_lines or 128)."""
+
+    def __init__(self, a, b, n_mdct_lines, sample_rate):
+        self.a, self.b = int(a), int(b)
+        half = (self.a + self.b) // 2
+        limits = None if self.a + self.b == 2 * n_mdct_lines else SHORT_FREQ_LIMITS      # pacfileThem.py:208-219
+        self.band_nlines = np.ascontiguousarray(band_lines(half, sample_rate, limits), dtype=np.int32)
+        self.window = np.ascontiguousarray(transition_window(self.a, self.b), dtype=np.float64)
+        self.hann = np.ascontiguousarray(hann_window(self.a + self.b), dtype=np.float64)
+        f = mdct_freqs(half, sample_rate)
+        self.bark = np.ascontiguousarray(bark(f), dtype=np.float64)
+        self.quiet = np.ascontiguousarray(intensity(thresh(f)), dtype=np.float64)
+        self.n_bands = int(len(self.band_nlines))
+        self.n_lines = half
         self.band_lower = np.concatenate(([0], np.cumsum(self.band_nlines)[:-1])).astype(np.int64)

@@ -140,6 +140,46 @@ def run_case(name):
           (name, nB, len(blob), tabs_used, res.min(), res.max(), t1 - t0, t2 - t1))
 
 
+SWITCHED_CASES = {
+    # name: (generator, seed, seconds, sampleRate, kbps per channel or None -> reference default 2.86 b/sample)
+    "switched48k_128": ("percussive", 11, 1.0, 48000, 128),
+    "switched44k_default": ("short", 12, 0.8, 44100, None),
+}
+
+
+def run_switched_case(name):
+    """Block switching: the reference's own TransientDetector / JointWriteDataBlock / Close driven
+    by its `__main__` loop (ref_driver.ref_encode_switched).  Stored: the canonical stream (last block written,
+    Close with b = nMDCTLines), the stream exactly as the shipped loop writes it (last block dropped, Q11), the
+    (a, b) of every written block, the detector's output per PCM block, the filter sections used (their last bits
+    depend on the LAPACK build behind tf2sos), and the reference decoder's PCM for the canonical stream."""
+    from scipy import signal
+    gen, seed, seconds, sr, kbps = SWITCHED_CASES[name]
+    pcm = synth.synth_percussive(seed, seconds, sr) if gen == "percussive" else synth.synth_short(seed, seconds, sr)
+    tbps = 2.86 if kbps is None else kbps * 1000.0 / sr
+    t0 = time.time()
+    blob, geom, dets = ref_driver.ref_encode_switched(pcm, sampleRate=sr, targetBitsPerSample=tbps)
+    blob_shipped, geom_shipped, _ = ref_driver.ref_encode_switched(pcm, sampleRate=sr, targetBitsPerSample=tbps,
+                                                                   drop_last=True)
+    t1 = time.time()
+    dec = ref_driver.ref_decode(blob, joint=True)
+    b_, a_ = signal.cheby2(20, 40, 9000. / sr, 'high')
+    sos = signal.tf2sos(b_, a_)
+    flags = np.zeros(len(dets), np.uint8)
+    for i, d in enumerate(dets):
+        flags[i] = (1 if np.any(d == 1) else 0) | (2 if np.any(d > 1) else 0)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), pcm=pcm, sampleRate=sr, tbps=tbps,
+                        pac=np.frombuffer(blob, np.uint8), pac_shipped=np.frombuffer(blob_shipped, np.uint8),
+                        geom=np.array(geom, np.int32), geom_shipped=np.array(geom_shipped, np.int32), flags=flags,
+                        sos=sos, decoded=dec)
+    ns = sum(1 for g in geom if g[1] == 128)
+    print("%-20s pcm blocks %3d  written %3d (%d short)  pac %6d B  encode %.1fs" %
+          (name, len(dets), len(geom), ns, len(blob), t1 - t0))
+
+
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or list(CASES)):
-        run_case(n)
+    for n in (sys.argv[1:] or (list(CASES) + list(SWITCHED_CASES))):
+        if n in SWITCHED_CASES:
+            run_switched_case(n)
+        else:
+            run_case(n)

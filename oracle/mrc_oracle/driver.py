@@ -2,14 +2,17 @@
 nMDCTLines-frame PCM block (the last one zero padded, pcmfile.py:79-82), Close() = one extra NON-joint block
 of zeros.  Decode: (Joint)ReadDataBlock for every block pair but the last, ReadDataBlock for the flush pair,
 first decoded block dropped (pacfileThem.py:1175-1177), saved overlap returned once at EOF (:178-185).
-This is the plain per-block loop of audiofile.py:24-38, not the reference __main__ with its look-ahead /
-block-switching driver (out of scope)."""
+encode_pcm is the plain per-block loop of audiofile.py:24-38 (long blocks only); encode_pcm_switched is the
+reference's `__main__` loop with its transient detector and one-block look-ahead (pacfileThem.py:1142-1215,
+SURVEY.md §8 f1), made canonical in two places where the shipped loop is broken (Q11): the last block read is
+written too (with no look-ahead information), and the Close() flush block always has b = nMDCTLines."""
 from struct import unpack
 
 import numpy as np
 
 from .pacfile import CodingParams, PACWriter, PACReader
 from .pcm import pcm_to_fraction, fraction_to_pcm
+from . import transient
 
 
 def make_params(sampleRate=48000, nChannels=2, numSamples=0, nMDCTLines=1024, nScaleBits=4, nMantSizeBits=4,
@@ -52,6 +55,54 @@ def encode_pcm(pcm, joint=True, trace=False, **kw):
     if trace:
         blocks.append(r)
     return w.getvalue(), blocks
+
+
+def encode_pcm_switched(pcm, trace=False, sos=None, **kw):
+    """pacfileThem.py:1142-1215 with block switching: every nMDCTLines-frame block goes through TransientDetector;
+    block k is written as 8 short blocks (b = 128 each) iff wants_short(detection of k, detection of k+1), else as
+    one long block; a = the previous written block's b.  Always the joint flow, like the reference's loop.
+    Returns (pac bytes, per-written-block trace, list of (a, b) per written block incl. the flush block)."""
+    pcm = np.asarray(pcm, dtype=np.int16)
+    n, nCh = pcm.shape
+    cp = make_params(numSamples=n, nChannels=nCh, **kw)
+    w = PACWriter(cp)
+    L = cp.nMDCTLines
+    nSeg = L // cp.nSamplesShort
+    if sos is None:
+        sos = transient.design_sos(cp.sampleRate)
+    cp.P = np.zeros((nCh, 1 + nSeg))
+    nBlocks = (n + L - 1) // L
+    data, det = [], []
+    for b in range(nBlocks):
+        seg = pcm[b * L:(b + 1) * L]
+        if seg.shape[0] < L:
+            seg = np.concatenate((seg, np.zeros((L - seg.shape[0], nCh), dtype=np.int16)))
+        d = np.vstack([pcm_to_fraction(seg[:, c]) for c in range(nCh)])
+        data.append(d)
+        det.append(transient.TransientDetector(d, cp, sos, transient.THRESHOLDS))
+    blocks, geom = [], []
+    for b in range(nBlocks):
+        if transient.wants_short(det[b], det[b + 1] if b + 1 < nBlocks else None):
+            for i in range(nSeg):
+                cp.b = cp.nSamplesShort
+                r = w.JointWriteDataBlock([data[b][c][cp.b * i:cp.b * (i + 1)] for c in range(nCh)], cp)
+                geom.append((cp.a, cp.b))
+                cp.a = cp.b
+                if trace:
+                    blocks.append(r)
+        else:
+            cp.b = L
+            r = w.JointWriteDataBlock([data[b][c] for c in range(nCh)], cp)
+            geom.append((cp.a, cp.b))
+            cp.a = cp.b
+            if trace:
+                blocks.append(r)
+    cp.b = L
+    r = w.Close(cp)
+    geom.append((cp.a, cp.b))
+    if trace:
+        blocks.append(r)
+    return w.getvalue(), blocks, geom, det
 
 
 def count_block_pairs(blob, nChannels):

@@ -97,6 +97,79 @@ def ref_encode(pcm, sampleRate=48000, joint=True, nMDCTLines=1024, nScaleBits=4,
         return outF.fp.getvalue(), blocks
 
 
+def ref_encode_switched(pcm, sampleRate=48000, nMDCTLines=1024, nScaleBits=4, nMantSizeBits=4,
+                        targetBitsPerSample=128000. / 48000., drop_last=False):
+    """The reference's `__main__` encode loop with block switching (pacfileThem.py:1142-1226), restated around the
+    reference's OWN TransientDetector / JointWriteDataBlock / Close.  drop_last=True is the shipped behaviour
+    (the last block read is never written, Q11); drop_last=False is the canonical driver: the last block is
+    written with no look-ahead information and Close() runs with b = nMDCTLines.
+    Returns (pac bytes, [(a, b) per written block], [detections per PCM block])."""
+    from scipy import signal
+    m = ref_shim.load()
+    PCMFile, PACFile = m["pcmfile"].PCMFile, m["pacfileThem"].PACFile
+    TransientDetector = m["pacfileThem"].TransientDetector
+    with ref_shim.in_reference_cwd():
+        inF = PCMFile("<mem>.wav")
+        inF.fp = _MemFile(wav_bytes(pcm, sampleRate))
+        cp = inF.ReadFileHeader()
+        cp.nMDCTLines = nMDCTLines
+        cp.nScaleBits = nScaleBits
+        cp.nMantSizeBits = nMantSizeBits
+        cp.targetBitsPerSample = targetBitsPerSample
+        cp.nSamplesPerBlock = cp.nMDCTLines
+        cp.bitReservoir = 0
+        cp.nSamplesShort = 128
+        cp.a = cp.b = cp.nMDCTLines
+        cp.blkswBitA = cp.blkswBitB = 1
+        outF = PACFile("<mem>.pac")
+        outF.fp = _MemFile(mode="wb")
+        outF.WriteFileHeader(cp)
+        b_, a_ = signal.cheby2(20, 40, 9000. / cp.sampleRate, 'high')          # :1146-1147
+        sos = signal.tf2sos(b_, a_)
+        nSeg = cp.nSamplesPerBlock // cp.nSamplesShort
+        cp.P = np.zeros((cp.nChannels, 1 + nSeg))
+        T = np.array([0.1, 0.075])
+        geom, dets = [], []
+        blocky = 0
+        firstBlock = True
+        dataMem = blkswMem = None
+
+        def write(dataMem, blkswMem, blksw):
+            nonlocal blocky
+            if np.sum(blkswMem) > 1 or (blksw is not None and any(blksw == 1)):       # :1192
+                for i in range(nSeg):
+                    cp.b = cp.nSamplesShort
+                    outF.JointWriteDataBlock(dataMem[:, cp.b * i:cp.b * (i + 1)], cp, blocky)
+                    geom.append((cp.a, cp.b))
+                    cp.a = cp.b
+                    blocky += 1
+            else:
+                cp.b = cp.nSamplesPerBlock
+                outF.JointWriteDataBlock(dataMem, cp, blocky)
+                geom.append((cp.a, cp.b))
+                cp.a = cp.b
+                blocky += 1
+
+        while True:
+            data = inF.ReadDataBlock(cp, blocky)
+            if not data:
+                break
+            data = np.vstack(data)
+            blksw = TransientDetector(data, cp, sos, T)
+            dets.append(blksw)
+            if firstBlock:
+                dataMem, blkswMem, firstBlock = data, blksw, False
+                continue
+            write(dataMem, blkswMem, blksw)
+            dataMem, blkswMem = data, blksw
+        if not drop_last and dataMem is not None:
+            write(dataMem, blkswMem, None)
+            cp.b = cp.nMDCTLines
+        outF.Close(cp)
+        geom.append((cp.a, cp.b))
+        return outF.fp.getvalue(), geom, dets
+
+
 def ref_decode(blob, joint=True):
     m = ref_shim.load()
     PCMFile, PACFile = m["pcmfile"].PCMFile, m["pacfileThem"].PACFile

@@ -26,3 +26,4 @@ def golden():
 
 
 GOLDEN_CASES = ["joint48k_128", "joint48k_64", "indep48k_128", "joint44k_default", "indep48k_64"]
+SWITCHED_CASES = ["switched48k_128", "switched44k_default"]
