@@ -47,6 +47,9 @@ def parse():
                     help="stream: one clip of --seconds per GPU (BASELINE configs[1]); batch: the same audio cut into "
                          "independent clips of --clip-seconds (configs[3] shape)")
     ap.add_argument("--clip-seconds", type=float, default=30.0)
+    ap.add_argument("--block-switching", action="store_true",
+                    help="encode with the reference's transient detector / look-ahead loop (SURVEY 8 f1): eight "
+                         "128-sample short blocks around transients instead of long blocks only")
     ap.add_argument("--decode", action="store_true", help="also time the decode mirror path on the encoded stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=1.5)
@@ -194,7 +197,8 @@ def main():
     else:
         off = np.array([0, frames], dtype=np.int64)
     n_clips = len(off) - 1
-    codec = Codec(device=local, precision=args.precision, spreading=args.spreading)
+    codec = Codec(device=local, precision=args.precision, spreading=args.spreading,
+                  block_switching=args.block_switching)
     L = codec.L
     nblk = int(sum(codec.n_blocks(f) for f in np.diff(off)))
 
@@ -238,6 +242,7 @@ def main():
         sampler = ClockSampler(local)
         sampler.start()
         dev_ms, launches, maskers, stage = 0.0, 0, 0, np.zeros(4)
+        extra = {}
         t0 = time.perf_counter()
         for _ in range(args.steps):
             nbytes = fn()
@@ -247,6 +252,8 @@ def main():
             maskers = t["maskers"]
             work = {k: t[k] for k in ("general_pairs", "window_adds", "loud_maskers", "waves", "chain_iters")}
             stage += np.array([t["analysis_ms"], t["cost_ms"], t["chain_ms"], t["pack_ms"]])
+            extra["blocks_written"] = t["blocks"]
+            extra["transient_ms"] = t["decode_ms"]
         barrier()
         wall = time.perf_counter() - t0
         clocks = sampler.stop()
@@ -254,7 +261,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return dict(wall=float(tt[0]), dev=float(tt[1]), launches=launches, maskers=maskers, nbytes=nbytes, work=work,
-                    stage_ms=(stage / args.steps).tolist(), clocks=clocks)
+                    stage_ms=(stage / args.steps).tolist(), clocks=clocks, extra=extra)
 
     peaks = codec.measure_peaks()
     r_dev = timed(step_device)
@@ -318,7 +325,13 @@ def main():
             "pipe_peaks": peaks,
             "executed_work": r_dev["work"],
         }
-        if args.spreading == "factorised" and not args.no_sequential_sample:
+        if args.block_switching:
+            line["config"]["workload"] += (", BLOCK SWITCHING on (transient detector + look-ahead, short blocks of 128: "
+                                           "%d blocks written for %d blocks of 1024 frames)" %
+                                           (r_dev["extra"]["blocks_written"], nblk))
+            line["stage_ms_per_step"]["transient_detector"] = r_dev["extra"]["transient_ms"]
+            line["roofline"]["work"] += "; work formula evaluated on the long-block equivalent of the stream"
+        if args.spreading == "factorised" and not args.no_sequential_sample and not args.block_switching:
             # the same analysis kernel summing the maskers pair by pair in the reference's order, on a bounded
             # sample of the same stream: this is the kernel SURVEY 8d's 40-FLOP-per-pair work formula describes
             sample_s = min(seconds, 600.0)
@@ -339,7 +352,7 @@ def main():
             # the mirror path (rows a14-a17): .pac bytes in pinned host memory -> int16 PCM in host memory
             nbytes = int(last_boff[0][-1])
             pac = h_out_np[:nbytes]
-            h_dec = torch.empty((nblk * L, 2), dtype=torch.int16).pin_memory()
+            h_dec = torch.empty(((nblk + 8) * L, 2), dtype=torch.int16).pin_memory()
             pcm_out = h_dec.numpy()
             for _ in range(2):
                 codec.decode_batch(pac, last_boff[0], pcm_out=pcm_out)

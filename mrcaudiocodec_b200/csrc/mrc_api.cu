@@ -324,11 +324,16 @@ int plan_switched_blocks(mrc_ctx* ctx, const int16_t* d_pcm, const int64_t* h_cl
         CK(upload(ctx->sb0, sb0, st));
         CK(ensure(ctx->peaks, (size_t)nsb * 2 * nseg * 8));
         CK(ensure(ctx->flags, (size_t)nsb));
+        CK(cudaEventRecord(ctx->ev[1], st));
         launch_transient(st, ctx->sos, (const int64_t*)ctx->clip_off.p, (const int32_t*)ctx->sb0.p, nc, d_pcm, L,
                          (int)nsb, (double*)ctx->peaks.p, (uint8_t*)ctx->flags.p);
+        CK(cudaEventRecord(ctx->ev[2], st));
         CK(cudaMemcpyAsync(flags.data(), ctx->flags.p, (size_t)nsb, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
+        float t = 0;
+        cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2]);
+        ctx->ms[3] = t;
     }
     if (flags_out) *flags_out = flags;
     blk0.assign(nc + 1, 0);
@@ -708,6 +713,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         CK(cudaEventElapsedTime(&t, ev(w, 4), ev(w, 5))); t_pk += t;
     }
     ctx->ms[0] = t_an; ctx->ms[1] = t_chain; ctx->ms[2] = t_pk; ctx->ms[7] = t_cost;
+    if (!job.switching) ctx->ms[3] = 0;
+    else launches += 2;                // the two transient detector kernels
     ctx->counters[0] = launches;
     ctx->counters[2] = nblk_total;
     ctx->counters[4] = nwaves;

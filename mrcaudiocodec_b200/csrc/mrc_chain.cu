@@ -184,7 +184,7 @@ __device__ __forceinline__ int reservoir_after(const GroupTotals& g, int B0, int
 }
 
 __global__ void __launch_bounds__(32)
-chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_nl, ChainIO io,
+chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int /*min_nl: per block, from the record*/, ChainIO io,
              const int32_t* __restrict__ reservoir_in, int32_t* __restrict__ reservoir_out,
              unsigned long long* __restrict__ iter_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -223,6 +223,7 @@ chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_
         const int R0 = R;
         int R1 = R;
         const int K = mx[MRC_MX_K], frac = mx[MRC_MX_FRAC];      // this block's budget (its geometry's)
+        const int min_nl = mx[MRC_MX_MINNL];
         if (joint) {
             const int B0 = K + R;
             const GroupTotals g = walk_group<false>(tn, cpre, pc, nullptr, mx, 0, MRC_NCHUNK, B0, min_nl, lane, dummy, n_iter);
@@ -259,7 +260,7 @@ chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_
 constexpr int TAB_THREADS = 256;
 
 __global__ void __launch_bounds__(TAB_THREADS)
-table_kernel(CodecParams cp, ClipMap cm, int g0, int min_nl, ChainIO io, int r_lo, int ntab, int tabw, int* __restrict__ tab) {
+table_kernel(CodecParams cp, ClipMap cm, int g0, int /*min_nl*/, ChainIO io, int r_lo, int ntab, int tabw, int* __restrict__ tab) {
     __shared__ uint32_t s_tn[MRC_NSLOT];
     __shared__ uint32_t s_dsp[MRC_NSLOT];
     __shared__ uint4 s_dpc[MRC_NSLOT];
@@ -291,7 +292,7 @@ table_kernel(CodecParams cp, ClipMap cm, int g0, int min_nl, ChainIO io, int r_l
     __syncthreads();
     const bool joint = s_joint != 0;
     const int ngroups = joint ? 1 : 2, nck = joint ? MRC_NCHUNK : MRC_GROUP_CHUNKS;
-    const int K = s_mx[MRC_MX_K], frac = s_mx[MRC_MX_FRAC];
+    const int K = s_mx[MRC_MX_K], frac = s_mx[MRC_MX_FRAC], min_nl = s_mx[MRC_MX_MINNL];
     int* out = tab + lb * (size_t)(2 * tabw);
     for (int grp = 0; grp < 2; ++grp) {
         int* o = out + grp * tabw;
@@ -347,7 +348,7 @@ table_kernel(CodecParams cp, ClipMap cm, int g0, int min_nl, ChainIO io, int r_l
 constexpr int TAB_STAGES = 6;
 
 __global__ void __launch_bounds__(32)
-chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int min_nl, ChainIO io, int r_lo,
+chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int /*min_nl: per block, from the record*/, ChainIO io, int r_lo,
                    int ntab, int tabw, const int* __restrict__ tab, const int32_t* __restrict__ reservoir_in,
                    int32_t* __restrict__ reservoir_out, unsigned long long* __restrict__ iter_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -382,7 +383,7 @@ chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, in
         const int* T0 = reinterpret_cast<const int*>(stg);
         const bool joint = cp.joint && !(cp.flush_nonjoint && b == nblk_clip - 1);
         const int32_t* mxs = reinterpret_cast<const int32_t*>(stg + tbytes + MRC_REC_MX);
-        const int K = mxs[MRC_MX_K], frac = mxs[MRC_MX_FRAC];
+        const int K = mxs[MRC_MX_K], frac = mxs[MRC_MX_FRAC], min_nl = mxs[MRC_MX_MINNL];
         const int R0 = R;
         int R1 = R;
         const int ngroups = joint ? 1 : 2;
@@ -418,7 +419,7 @@ chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, in
 constexpr int FIN_WARPS = 8;
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-finish_kernel(CodecParams cp, ClipMap cm, int g0, int nblk, int min_nl, ChainIO io) {
+finish_kernel(CodecParams cp, ClipMap cm, int g0, int nblk, int /*min_nl*/, ChainIO io) {
     const int lane = threadIdx.x & 31;
     const int lb = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
     if (lb >= nblk) return;
@@ -438,7 +439,7 @@ finish_kernel(CodecParams cp, ClipMap cm, int g0, int nblk, int min_nl, ChainIO 
     const int4 rs = io.rsv[lb];
     unsigned gmask = 0u, n_iter = 0u;
     int table[2] = {MRC_NO_TABLE, MRC_NO_TABLE}, wbits[2] = {0, 0};
-    const int K = mx[MRC_MX_K], frac = mx[MRC_MX_FRAC];
+    const int K = mx[MRC_MX_K], frac = mx[MRC_MX_FRAC], min_nl = mx[MRC_MX_MINNL];
     if (joint) {
         const int B0 = K + rs.x;
         const GroupTotals gt = walk_group<true>(tn, cpre, pc, pw, mx, 0, MRC_NCHUNK, B0, min_nl, lane, gmask, n_iter);

@@ -201,6 +201,9 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
         o_mx[MRC_MX_K] = joint ? cp.k_joint : cp.k_single;
         o_mx[MRC_MX_FRAC] = joint ? cp.frac_joint : cp.frac_single;
         o_mx[MRC_MX_NB] = nb;
+        int mn = 0x7fffffff;
+        for (int b = 0; b < nb; ++b) mn = min(mn, s_bn[b]);
+        o_mx[MRC_MX_MINNL] = mn;
     }
     for (int k = warp; k < MRC_NCHUNK; k += CT / 32) {      // same thread re-reads what it wrote above
         const int slot = k * 32 + lane;

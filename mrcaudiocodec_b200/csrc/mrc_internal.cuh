@@ -48,6 +48,7 @@
 #define MRC_MX_K 24                                    // integer part of the bit budget before the reservoir
 #define MRC_MX_FRAC 25                                 // 1 if the budget has a fractional part
 #define MRC_MX_NB 26                                   // scale factor bands of the block
+#define MRC_MX_MINNL 27                                // lines of its narrowest band: no grant fits below that
 #define MRC_PW_BYTES (MRC_NSLOT * 16)                  // uint4 [768] like MRC_REC_PC for the bits actually written (Q4)
 
 struct ChainBlk {                // what the chain kernel decides per block (32 bytes)

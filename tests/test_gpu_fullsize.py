@@ -98,3 +98,60 @@ def test_many_tiny_clips():
     dec = c.decode_clips(blobs)
     assert [d.shape[0] for d in dec] == [c.n_blocks(len(x)) * 1024 for x in clips]
     c.close()
+
+
+def test_block_switching_at_scale():
+    """Ten minutes of the bench stream plus castanet-like material, encoded with the reference's transient
+    detector / look-ahead loop, several waves long.  Size-independent properties: the written
+    blocks are exactly the detector's plan and their sizes chain (a of a block = b of the one before); a stream
+    prefix is byte-exact against the oracle; clips in a batch equal their single encodes; the stream decodes to
+    the plan's length, and short blocks do buy what they are for: less pre-echo energy ahead of the hits."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import Codec, synth, pacfile
+    minutes = min(MINUTES, 10.0)
+    perc = np.concatenate([synth.synth_percussive(200 + i, 30.0) for i in range(int(2 * minutes))], axis=0)
+    stream = synth.synth_clip(3, 60 * minutes, threads=8, fast=True)
+    c = Codec(block_switching=True)
+    flags, plan = c.detect_transients([perc, stream])
+    blobs = c.encode_clips([perc, stream])
+    assert blobs[0] == c.encode_clips([perc])[0] and blobs[1] == c.encode_clips([stream])[0]
+    for blob, ab, pcm in zip(blobs, plan, (perc, stream)):
+        idx = pacfile.chunk_index(blob)
+        assert len(idx) == 2 * len(ab)
+        got = []
+        for k in range(0, len(idx), 2):
+            q = (blob[idx[k][0]] >> 2) & 3
+            assert ((blob[idx[k + 1][0]] >> 2) & 3) == q
+            got.append((128 if q & 2 else 1024, 128 if q & 1 else 1024))
+        assert got == ab
+        assert all(got[i][0] == got[i - 1][1] for i in range(1, len(got))) and got[0][0] == 1024
+        assert sum(b for _, b in ab) == (c.n_blocks(pcm.shape[0])) * 1024
+    n_short = sum(1 for a, b in plan[0] if b == 128)
+    assert n_short > 8 * 100, n_short                     # the castanets do switch, a lot
+    # prefix byte-exactness: the first 30 blocks of PCM decide the first blocks of the stream (one block of look-ahead)
+    n = 30
+    ob, _, geom, _ = o.driver.encode_pcm_switched(perc[:(n + 1) * 1024], sos=c.sos)
+    k = 0
+    frames = 0
+    while frames < n * 1024:                              # written blocks covering the first n PCM blocks
+        frames += geom[k][1]
+        k += 1
+    h = pacfile.parse_header(blobs[0])
+    o_idx, g_idx = pacfile.chunk_index(ob), pacfile.chunk_index(blobs[0])
+    assert blobs[0][h["headerBytes"]:g_idx[2 * k][0] - 4] == ob[h["headerBytes"]:o_idx[2 * k][0] - 4]
+    dec = c.decode_clips(blobs)
+    assert [d.shape[0] for d in dec] == [c.n_blocks(x.shape[0]) * 1024 for x in (perc, stream)]
+    plain = Codec()
+    dec_plain = plain.decode_clips(plain.encode_clips([perc]))[0]
+    plain.close()
+    # pre-echo: error energy in the 256 samples before each switched block's position, switched vs long-only
+    pos, e_sw, e_pl = 0, 0.0, 0.0
+    ref = perc.astype(np.float64)
+    for a, b in plan[0][:-1]:
+        if b == 128 and a == 1024 and pos >= 1024:
+            s = slice(pos - 256, pos)
+            e_sw += np.sum((dec[0][s] - ref[s]) ** 2)
+            e_pl += np.sum((dec_plain[s] - ref[s]) ** 2)
+        pos += b
+    assert e_sw < e_pl, (e_sw, e_pl)
+    c.close()
