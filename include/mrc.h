@@ -9,6 +9,8 @@
  *                      JointWriteDataBlock :793-972, Close :973-984, ReadFileHeader :130-158,
  *                      ReadDataBlock :161-319, JointReadDataBlock :321-585 and the PCM sample conversion of
  *                      PCMFile.ReadDataBlock pcmfile.py:68-102 / WriteDataBlock :156-185
+ *   block switching    the `__main__` encode loop pacfileThem.py:1142-1215 with TransientDetector :1021-1056
+ *                      (MRC_FLAG_BLOCK_SWITCHING, mrc_set_switch_tables, mrc_detect_transients, *_block_ab)
  *
  * Conventions: every entry point returns 0 on success or a negative MRC_E_* code; mrc_last_error(ctx) gives a
  * human-readable message.  No exceptions cross the boundary.  There is no CPU fallback: without a CUDA device

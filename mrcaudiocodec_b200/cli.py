@@ -2,11 +2,14 @@
 `python pacfileThem.py in.wav` (pacfileThem.py:1064-1231: encode pass, then decode pass).
 
     python -m mrcaudiocodec_b200.cli encode in.wav out.pac [--kbps 128] [--independent] [--precision fp64]
+                                                            [--block-switching]
     python -m mrcaudiocodec_b200.cli decode in.pac out.wav [--independent]
     python -m mrcaudiocodec_b200.cli roundtrip in.wav            # writes in.pac and in_decoded.wav next to it
 
 WAV handling is host plumbing (stdlib `wave`; 16-bit PCM, two channels: what pcmfile.py:34-66 accepts, minus mono).
-The .pac files are the reference's format: long blocks, last block pair non-joint (Q10), so
+--block-switching is the reference's own `__main__` loop (transient detector, one block of look-ahead, eight
+128-sample short blocks around transients; the decoder reads the block sizes from the chunk headers).
+The .pac files are the reference's format: last block pair non-joint (Q10), so
 `decode` needs to be told --independent only for files that were encoded that way (nothing in the file says so).
 Decoded WAVs hold (#block pairs) * nMDCTLines frames like the reference's decode loop: the input delayed by nothing
 (the first, all-delay block is dropped) and zero-padded to whole blocks plus the flush block."""
@@ -35,17 +38,18 @@ def write_wav(path, sr, pcm):
         w.writeframes(np.ascontiguousarray(pcm, dtype="<i2").tobytes())
 
 
-def _codec(sr, args, L=1024, tbps=None):
+def _codec(sr, args, L=1024, tbps=None, switching=False):
     from .codec import Codec
     if tbps is None:
         tbps = args.kbps * 1000.0 / sr
     return Codec(sample_rate=sr, n_mdct_lines=L, target_bits_per_sample=tbps, joint=not args.independent,
-                 precision=args.precision, device=args.device)
+                 precision=args.precision, device=args.device,
+                 block_switching=switching, switch_tables=(L == 1024))
 
 
 def cmd_encode(args):
     sr, pcm = read_wav(args.input)
-    c = _codec(sr, args)
+    c = _codec(sr, args, switching=bool(args.block_switching))
     blob = c.encode_clips([pcm])[0]
     c.close()
     with open(args.output, "wb") as fh:
@@ -86,6 +90,8 @@ def main(argv=None):
         p.add_argument("--independent", action="store_true", help="independent channels instead of joint M/S")
         p.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
         p.add_argument("--device", type=int, default=0)
+        p.add_argument("--block-switching", action="store_true",
+                       help="encode with the reference's transient detector and short blocks (joint flow only)")
         p.set_defaults(fn=fn)
     args = ap.parse_args(argv)
     args.fn(args)

@@ -14,4 +14,4 @@ mantissas, table ids, reservoir) for joint and independent-channel encodes, and 
 Each function cites the reference file:line it follows.  Quirks Q1-Q12 of SURVEY.md Appendix C are
 reproduced on purpose.
 """
-from . import window, mdct, psychoac, bitalloc, quantize, ms_stereo, bitpack, tables, codec, pacfile, pcm, driver, huffman_train  # noqa: F401
+from . import window, mdct, psychoac, bitalloc, quantize, ms_stereo, bitpack, tables, codec, pacfile, pcm, driver, huffman_train, transient  # noqa: F401

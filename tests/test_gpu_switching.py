@@ -218,3 +218,21 @@ def test_plain_context_rejects_switched_stream(golden):
         assert e.value.code == _lib.MRC_E_FORMAT
     finally:
         c.close()
+
+
+def test_cli_roundtrip_with_block_switching(tmp_path):
+    """`cli roundtrip in.wav --block-switching` = the reference's `python pacfileThem.py in.wav` flow: the .pac
+    equals the oracle's switched stream, the decoded WAV the oracle decoder's PCM within 1 LSB."""
+    from mrcaudiocodec_b200 import cli, synth, tables
+    from mrc_oracle import driver
+    pcm = synth.synth_percussive(77, 0.5)
+    wav = str(tmp_path / "p.wav")
+    cli.write_wav(wav, 48000, pcm)
+    cli.main(["roundtrip", wav, "--block-switching"])
+    blob = open(str(tmp_path / "p.pac"), "rb").read()
+    ob = driver.encode_pcm_switched(pcm, sos=tables.transient_sos(48000))[0]
+    assert blob == ob
+    sr, dec = cli.read_wav(str(tmp_path / "p_decoded.wav"))
+    od = driver.decode_pac(ob)
+    assert sr == 48000 and dec.shape == od.shape
+    assert np.abs(dec.astype(np.int64) - od.astype(np.int64)).max() <= 1

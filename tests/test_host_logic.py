@@ -47,6 +47,28 @@ def test_host_tables_equal_oracle_tables():
                 assert t.huff_len[i, v] == 0
 
 
+def test_block_switching_tables_equal_oracle_tables():
+    """the three extra block geometries: window, Hann, Bark, threshold in quiet and the 9-band table
+    as the oracle (= the reference) computes them for codingParams.a / .b"""
+    import mrc_oracle as o
+    from mrc_oracle.pacfile import CodingParams, sfbands_for
+    from mrcaudiocodec_b200.tables import BlockTables, transient_sos
+    for sr in (48000, 44100):
+        for a, b in ((1024, 128), (128, 1024), (128, 128), (1024, 1024)):
+            t = BlockTables(a, b, 1024, sr)
+            half = (a + b) // 2
+            assert np.array_equal(t.window, o.window.transition_coeffs(a, b))
+            assert np.array_equal(t.hann, o.window.hann_coeffs(a + b))
+            f = (np.arange(half) + 0.5) * ((float(sr) / half) / 2.)
+            assert np.array_equal(t.bark, o.psychoac.Bark(f))
+            assert np.array_equal(t.quiet, o.psychoac.Intensity(o.psychoac.Thresh(f)))
+            cp = CodingParams()
+            cp.a, cp.b, cp.nMDCTLines, cp.sampleRate = a, b, 1024, sr
+            assert np.array_equal(t.band_nlines, sfbands_for(cp).nLines.astype(np.int32))
+            assert t.n_bands == (25 if a == b == 1024 else 9)
+        assert np.array_equal(transient_sos(sr), o.transient.design_sos(sr))
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must raise, never compute on the CPU."""
     import torch
