@@ -234,6 +234,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ T s_seg_smr[MRC_MAX_SEGS], s_seg_rho[MRC_MAX_SEGS];
     __shared__ int s_seg_k[MRC_MAX_SEGS];
     __shared__ int s_npk;
+    __shared__ int s_next[2];         // next unclaimed segment of pass 2a / pass 2b (claimed largest first)
 
     if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
     const int lb = cm.list ? cm.list[blockIdx.x] : (int)blockIdx.x;   // index inside this wave's hand-off buffers
@@ -541,31 +542,21 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             }
         }
         if (!cp.spread_seq && sm.zlut != nullptr) {
-            // count table over Bark cells for masker_range (the peak bins in these words are no longer needed)
+            // count table over Bark cells for masker_range (the peak bins in these words are no longer needed):
+            // zlut[g] = number of maskers with z < g/32 Bark.  The maskers ascend in z, so the count is a step function
+            // of the cell: masker i raises it to i+1 from its own cell up to the next masker's -- every thread fills its
+            // stretch, no counting and no prefix sum.
             __syncthreads();
-            unsigned* z32 = reinterpret_cast<unsigned*>(sm.zlut);
-            for (int i = tid; i < (MRC_ZLUT + 2) / 2; i += NT) z32[i] = 0u;
-            __syncthreads();
+            auto cell_of = [&](int i) {
+                int cell = (int)(sm.mz[i] * 32.0) + 1;               // counted from cell+1 on: z < g/32 for g > z*32
+                return cell < 1 ? 1 : (cell > MRC_ZLUT ? MRC_ZLUT : cell);
+            };
             if (tid < npk) {
-                int cell = (int)(sm.mz[tid] * 32.0) + 1;             // counted from cell+1 on: z < g/32 for g > z*32
-                cell = cell < 1 ? 1 : (cell > MRC_ZLUT ? MRC_ZLUT : cell);
-                atomicAdd(&z32[cell >> 1], 1u << (16 * (cell & 1)));
+                const int c0 = cell_of(tid), c1 = (tid + 1 < npk) ? cell_of(tid + 1) : MRC_ZLUT + 1;
+                for (int g = c0; g < c1; ++g) sm.zlut[g] = (uint16_t)(tid + 1);
+                if (tid == 0) for (int g = 0; g < c0; ++g) sm.zlut[g] = 0;
             }
-            __syncthreads();
-            if (warp == 0) {                                         // inclusive prefix over the 833 cells
-                constexpr int PER = (MRC_ZLUT + 1 + 31) / 32;        // 27 cells per lane
-                const int c0 = lane * PER;
-                int run = 0;
-                for (int i = 0; i < PER; ++i) if (c0 + i <= MRC_ZLUT) run += sm.zlut[c0 + i];
-                int incl = run;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                int acc = incl - run;
-                for (int i = 0; i < PER; ++i)
-                    if (c0 + i <= MRC_ZLUT) { acc += sm.zlut[c0 + i]; sm.zlut[c0 + i] = (uint16_t)acc; }
-            }
+            if (npk == 0) for (int g = tid; g <= MRC_ZLUT; g += NT) sm.zlut[g] = 0;
         }
         __syncthreads();
         // e. masked threshold at the MDCT lines, f. SMR per line (psychoac.py:212-214), band maxima (:215-219)
@@ -610,6 +601,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 const double X = (double)sm.lines[c * L + k];
                 return fmax((2.0 * (X * X)) / 0.5, FLOOR);
             };
+            if (tid < 2) s_next[tid] = 0;                // read after the barrier below
             {
                 const int k0 = tid, k1 = tid + Q;
                 T r0 = T(-1), r1 = T(-1);                // lines of bands that do not select this spectrum: never candidates
@@ -625,7 +617,14 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 smr = line_spl(k) - thr_of(a);
                 rho = T(x2c(k) / fmax(a, FLOOR));
             };
-            for (int sg = warp; sg < tb.nseg; sg += nwarp) {     // pass 2a
+            // Segments cost very different amounts (4 .. 64 lines, and pass 2b from nothing to dozens of complete
+            // thresholds), so warps claim them one at a time, widest bands first, instead of striding over them.
+            auto claim = [&](int pass) {
+                int v = 0;
+                if (lane == 0) v = atomicAdd(&s_next[pass], 1);
+                return tb.nseg - 1 - __shfl_sync(0xffffffffu, v, 0);
+            };
+            for (int sg = claim(0); sg >= 0; sg = claim(0)) {    // pass 2a
                 if (!((need >> tb.seg_band[sg]) & 1u)) continue;
                 const int lo = tb.seg_lo[sg], n = tb.seg_n[sg];
                 T ubest = T(-1);
@@ -645,7 +644,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (lane == 0) { s_seg_smr[sg] = smr; s_seg_rho[sg] = rho; s_seg_k[sg] = kbest; }
             }
             __syncthreads();
-            for (int sg = warp; sg < tb.nseg; sg += nwarp) {     // pass 2b
+            for (int sg = claim(1); sg >= 0; sg = claim(1)) {    // pass 2b
                 const int lo = tb.seg_lo[sg], n = tb.seg_n[sg], bd = tb.seg_band[sg];
                 if (!((need >> bd) & 1u)) continue;
                 T rbest = T(0);                                  // best true rho of the band so far

@@ -17,18 +17,37 @@ __device__ __forceinline__ int fft_r4_pos(int n, int logn) {
 // odd, then radix-4 stages (half as many barriers and 0.4 x the instructions of radix 2).  `nthr` threads of this group
 // (local id lt); a radix-4 stage has n/4 butterflies.  tw[k] = exp(-2*pi*j*k/Ltab), k < Ltab/2, Ltab = 2^logLtab >= n.
 // NB > 1: NB independent transforms of that size on the consecutive sub-arrays a + s*n, all stages in lock step.
-template <typename T, int NB = 1>
+//
+// WL (warp-local stages): butterflies bi = 32m .. 32m+31 of a radix-4 stage with 4h <= 128 read and write exactly the
+// elements [128m, 128m+128), in every such stage, and one warp owns them in all stages (lt must be warp-aligned and
+// n >= 128) -- so those stages are separated by __syncwarp() only; a block barrier is needed before the first stage
+// whose butterflies reach across 128-element spans, and after the last stage.  The arithmetic is the same either way.
+template <typename T, int NB = 1, bool WL = false>
 __device__ __forceinline__ void fft_r4(cpx<T>* a, int logn, int lt, int nthr, const cpx<T>* __restrict__ tw,
                                        int logLtab) {
     const int n = 1 << logn;
     int h = 1;
     if (logn & 1) {
-        for (int q = lt; q < NB * (n >> 1); q += nthr) {
-            const cpx<T> u = a[2 * q], v = a[2 * q + 1];
-            a[2 * q].x = u.x + v.x;      a[2 * q].y = u.y + v.y;
-            a[2 * q + 1].x = u.x - v.x;  a[2 * q + 1].y = u.y - v.y;
+        if constexpr (WL) {
+            // two radix-2 butterflies per thread, laid out so that butterfly group m covers elements [128m, 128m+128)
+            for (int bi = lt; bi < NB * (n >> 2); bi += nthr) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int q = ((bi >> 5) << 6) + (bi & 31) + 32 * t;
+                    const cpx<T> u = a[2 * q], v = a[2 * q + 1];
+                    a[2 * q].x = u.x + v.x;      a[2 * q].y = u.y + v.y;
+                    a[2 * q + 1].x = u.x - v.x;  a[2 * q + 1].y = u.y - v.y;
+                }
+            }
+            __syncwarp();
+        } else {
+            for (int q = lt; q < NB * (n >> 1); q += nthr) {
+                const cpx<T> u = a[2 * q], v = a[2 * q + 1];
+                a[2 * q].x = u.x + v.x;      a[2 * q].y = u.y + v.y;
+                a[2 * q + 1].x = u.x - v.x;  a[2 * q + 1].y = u.y - v.y;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         h = 2;
     }
     const int half_tab = 1 << (logLtab - 1);
@@ -54,10 +73,11 @@ __device__ __forceinline__ void fft_r4(cpx<T>* a, int logn, int lt, int nthr, co
             a[base + 2 * h].x = s02x - s13x;  a[base + 2 * h].y = s02y - s13y;
             a[base + 3 * h].x = d02x - d13y;  a[base + 3 * h].y = d02y + d13x;      // d02 + j d13
         }
-        __syncthreads();
+        // the next stage (4h) stays inside the warp's 128-element span iff 16h <= 128
+        if (WL && 16 * h <= 128 && 16 * h <= n) __syncwarp();
+        else __syncthreads();
     }
 }
-
 
 // ---- transform sizes 2^p and 9 * 2^p (block switching: a + b = 1152 gives 288- and 576-point transforms) -------
 // n = 9 P, P = 2^p: input index i = 9 i1 + i2 goes to sub-array i2 (a P-point transform over i1), then one radix-9
@@ -88,7 +108,13 @@ __device__ __forceinline__ void fft_any(cpx<T>* a, int lt, int nthr, const cpx<T
                                         const cpx<T>* __restrict__ tw9, int n9, const cpx<T>* w9) {
     using S = FftShape<NFFT>;
     if constexpr (S::pow2) {
-        fft_r4<T, 1>(a, S::logP, lt, nthr, tw, logLtab);
+        // warp-local early stages: callers give whole warps a warp-aligned lt when the group size is a multiple of 32
+        if constexpr (NFFT >= 128) {
+            if ((nthr & 31) == 0) fft_r4<T, 1, true>(a, S::logP, lt, nthr, tw, logLtab);
+            else fft_r4<T, 1, false>(a, S::logP, lt, nthr, tw, logLtab);
+        } else {
+            fft_r4<T, 1, false>(a, S::logP, lt, nthr, tw, logLtab);
+        }
     } else {
         constexpr int P = S::P;
         fft_r4<T, 9>(a, S::logP, lt, nthr, tw, logLtab);
