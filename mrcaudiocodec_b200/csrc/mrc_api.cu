@@ -65,6 +65,9 @@ struct mrc_ctx {
     struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab; } sets[2];
     Buf q_alloc, q_sf, q_mant;
     cudaStream_t stream2 = nullptr, stream3 = nullptr;    // analysis stream, H2D copy stream
+    cudaStream_t stream4 = nullptr;                       // D2H copy stream (bitstream of finished waves)
+    int64_t* h_prog = nullptr;                            // pinned: per wave, how far the output is final
+    int h_prog_cap = 0;
     bool no_tables = false;          // MRC_FLAG_NO_CHAIN_TABLES
     int tab_min_blocks = 512;        // blocks per clip in a wave from which the reservoir maps are tabulated
     std::vector<cudaEvent_t> evpool;
@@ -287,6 +290,11 @@ struct EncodeJob {
     uint8_t* d_out = nullptr;
     int64_t out_cap = 0;
     int64_t* h_clip_byte_off = nullptr;    // [n_clips+1]
+    // when set: the bytes of finished waves are copied to h_out (host) on the D2H stream while later waves run;
+    // *h_copied = how many leading bytes of the output have been queued (the caller copies the rest and syncs stream4)
+    uint8_t* h_out = nullptr;
+    int64_t h_out_cap = 0;
+    int64_t* h_copied = nullptr;
     // taps to host, optional
     double* t_lines = nullptr; int32_t* t_ovs = nullptr; int32_t* t_ms = nullptr; double* t_smr = nullptr;
     int32_t* t_npk = nullptr;
@@ -479,7 +487,10 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         CK(upload(ctx->blk_list, lists, st));
     }
     // reservoir-map tables of the single-stream fast path: R_in in [r_lo, r_lo + ntab)
-    const int r_lo = -((max_nl + 1 + 31) / 32 * 32), ntab = -r_lo + 640, tabw = (ntab + 2 + 3) / 4 * 4;
+    int r_lo = -((max_nl + 1 + 31) / 32 * 32), r_hi = 640;
+    if (const char* e = getenv("MRC_CHAIN_TABLE_LO")) r_lo = -std::max(32, (atoi(e) + 31) / 32 * 32);     // tuning knobs: any
+    if (const char* e = getenv("MRC_CHAIN_TABLE_HI")) r_hi = std::max(32, (atoi(e) + 31) / 32 * 32);      // range is exact
+    const int ntab = -r_lo + r_hi, tabw = (ntab + 2 + 3) / 4 * 4;
 
     // ---- buffer sets ----
     const bool want_atap = job.t_lines || job.t_smr || job.t_npk;
@@ -536,6 +547,30 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     CK(cudaStreamWaitEvent(st2, ctx->ev[0], 0));
 
     int launches = 0;
+    int64_t copied = 0;                // leading output bytes already queued for the host
+    std::vector<char> wave_ended(nwaves, 0);
+    const bool stream_out = job.h_out != nullptr && job.d_out != nullptr && job.need_quant;
+    if (stream_out && ctx->h_prog_cap < 2 * nwaves) {
+        if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
+        ctx->h_prog = nullptr;
+        ctx->h_prog_cap = 0;
+        CK(cudaMallocHost((void**)&ctx->h_prog, (size_t)(2 * nwaves + 64) * 8));
+        ctx->h_prog_cap = 2 * nwaves + 64;
+    }
+    // Output bytes are final up to the end of the last block of a finished wave (clips are laid out in order, and a
+    // clip's base is known once its predecessors are complete).  After wave v+1 has been queued the host waits for
+    // wave v's pack, reads that position and queues the copy; the kernels of wave v+1 hide it.
+    auto drain = [&](int v) -> int {
+        CK(cudaEventSynchronize(ev(v, 5)));
+        int64_t done = ctx->h_prog[2 * v] + (wave_ended[v] ? 0 : ctx->h_prog[2 * v + 1]);
+        done = std::min(done, std::min(job.h_out_cap, job.out_cap));
+        if (done > copied) {
+            CK(cudaMemcpyAsync(job.h_out + copied, job.d_out + copied, (size_t)(done - copied), cudaMemcpyDeviceToHost,
+                               ctx->stream4));
+            copied = done;
+        }
+        return MRC_OK;
+    };
     std::vector<unsigned char> hb;     // host bounce buffer for taps
     int c_lo = 0;
     cudaStream_t st3 = ctx->stream3;
@@ -625,8 +660,17 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
                                (int*)ctx->overflow.p);
             });
         }
+        if (stream_out) {
+            const bool ended = blk0[c_hi + 1] <= g0 + nblk;      // the wave's last clip ends with the wave
+            wave_ended[w] = ended ? 1 : 0;
+            CK(cudaMemcpyAsync(&ctx->h_prog[2 * w], (const int64_t*)ctx->clip_base.p + (ended ? c_hi + 1 : c_hi), 8,
+                               cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&ctx->h_prog[2 * w + 1], (const int64_t*)ctx->clip_run.p + c_hi, 8,
+                               cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaEventRecord(ev(w, 5), st));
         CK(cudaGetLastError());
+        if (stream_out && w >= 1) { const int rc = drain(w - 1); if (rc != MRC_OK) return rc; }
         if (!any_tap) continue;
         // ---- taps of this wave to the host (parity runs only; synchronous) ----
         auto fetch = [&](const void* dsrc, size_t bytes) -> cudaError_t {
@@ -722,6 +766,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     ctx->counters[3] = (int64_t)pk[4];
     ctx->counters[5] = (int64_t)pk[1]; ctx->counters[6] = (int64_t)pk[2]; ctx->counters[7] = (int64_t)pk[3];
     if (job.d_out && nblk_total == 0) for (int c = 0; c <= nc; ++c) job.h_clip_byte_off[c] = 0;
+    if (job.h_copied) *job.h_copied = ovf ? 0 : copied;
     if (ovf) return fail(ctx, MRC_E_NOSPACE, "output buffer too small for the encoded batch");
     return MRC_OK;
 }
@@ -813,6 +858,13 @@ int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out) {
         delete ctx;
         return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream4, cudaStreamNonBlocking)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        cudaStreamDestroy(ctx->stream2);
+        cudaStreamDestroy(ctx->stream3);
+        delete ctx;
+        return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     *out = ctx;
     return MRC_OK;
@@ -848,6 +900,9 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     cudaStreamDestroy(ctx->stream2);
     cudaStreamSynchronize(ctx->stream3);
     cudaStreamDestroy(ctx->stream3);
+    cudaStreamSynchronize(ctx->stream4);
+    cudaStreamDestroy(ctx->stream4);
+    if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MRC_OK;
@@ -949,7 +1004,9 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
     // device staging for the bitstream: nominal size with head-room, never more than the worst case
     int64_t cap = std::min(worst_case_bytes(ctx, clip_frame_offsets, n_clips),
                            std::max<int64_t>(2 * nominal_bytes(ctx, clip_frame_offsets, n_clips), out_cap));
+    int64_t copied = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
+        copied = 0;
         CK(ensure(ctx->out_dev, (size_t)cap));
         CK(cudaEventRecord(ctx->ev[4], st));
         CK(cudaEventRecord(ctx->ev[6], st));
@@ -959,7 +1016,9 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
         job.joint = ctx->cfg.joint; job.flush_nonjoint = true;
         job.switching = (ctx->cfg.flags & MRC_FLAG_BLOCK_SWITCHING) != 0;
         job.d_out = (uint8_t*)ctx->out_dev.p; job.out_cap = cap; job.h_clip_byte_off = clip_byte_offsets;
+        job.h_out = out; job.h_out_cap = out ? out_cap : 0; job.h_copied = &copied;
         const int rc = run_encode(ctx, job);
+        cudaStreamSynchronize(ctx->stream4);                // whatever was queued for `out` has landed (or failed with rc)
         if (rc == MRC_E_NOSPACE && attempt == 0) {          // staging too small: retry once at the worst case
             cap = worst_case_bytes(ctx, clip_frame_offsets, n_clips);
             continue;
@@ -970,7 +1029,9 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
     const int64_t total = clip_byte_offsets[n_clips];
     if (total > out_cap) return fail(ctx, MRC_E_NOSPACE, "output buffer too small (clip_byte_offsets holds the sizes)");
     CK(cudaEventRecord(ctx->ev[7], st));
-    if (total > 0) CK(cudaMemcpyAsync(out, ctx->out_dev.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    if (total > copied)
+        CK(cudaMemcpyAsync(out + copied, (const uint8_t*)ctx->out_dev.p + copied, (size_t)(total - copied),
+                           cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
     float t = 0;
