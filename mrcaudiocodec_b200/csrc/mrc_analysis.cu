@@ -29,6 +29,32 @@
 #include "mrc_math.cuh"
 #include "mrc_fft.cuh"
 
+// -DMRC_PHASE_CLOCKS: development build that accumulates, per CTA, the cycles between phase boundaries (read by
+// scripts/phase_clocks.py through mrc_debug_phase_clocks); never defined in the shipped library.
+#ifdef MRC_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[32];
+#define MRC_CLK(i)                                                                                                  \
+    do {                                                                                                            \
+        if (threadIdx.x == 0) {                                                                                     \
+            const long long t_ = clock64();                                                                         \
+            atomicAdd(&g_phase_clk[i], (unsigned long long)(t_ - s_clk_last));                                      \
+            s_clk_last = t_;                                                                                        \
+        }                                                                                                           \
+    } while (0)
+// warp-level: cycles of lane 0 between consecutive marks inside spread_line_warp / complete()
+#define MRC_WCLK_BEGIN() long long wt_ = clock64()
+#define MRC_WCLK(i)                                                                                                 \
+    do {                                                                                                            \
+        const long long t_ = clock64();                                                                             \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_clk[i], (unsigned long long)(t_ - wt_));                     \
+        wt_ = t_;                                                                                                   \
+    } while (0)
+#else
+#define MRC_CLK(i)
+#define MRC_WCLK_BEGIN()
+#define MRC_WCLK(i)
+#endif
+
 namespace {
 
 constexpr int MRC_ZLUT = 832;         // cells of 1/32 Bark: Bark(24 kHz) = 24.6
@@ -198,17 +224,26 @@ __device__ __forceinline__ double spread_line_bound(const Smem<T>& sm, const Dev
 template <typename T>
 __device__ __forceinline__ double spread_line_warp(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk, int lane,
                                                    unsigned& n_general, unsigned& n_window) {
+    MRC_WCLK_BEGIN();
     const double zk = tb.bark_d[k];
     int m_lo, m_hi;
     masker_range(sm, zk, npk, m_lo, m_hi);
+    MRC_WCLK(16);
     double a = 0.0;
     if (lane == 0) a = tb.quiet_d[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
+    __syncwarp();
+    MRC_WCLK(17);
     for (int m = m_lo + lane; m < m_hi; m += 32) a += sm.mc[m];
+    __syncwarp();
+    MRC_WCLK(18);
     const int nl = sm.lcnt[m_lo];
     for (int j = lane; j < nl; j += 32) a += loud_term(sm, zk, sm.lidx[j]);
+    __syncwarp();
+    MRC_WCLK(19);
     if (lane == 0) { n_general += (unsigned)nl; n_window += (unsigned)(m_hi - m_lo); }
 #pragma unroll
     for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    MRC_WCLK(20);
     return a;
 }
 
@@ -234,7 +269,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ T s_seg_smr[MRC_MAX_SEGS], s_seg_rho[MRC_MAX_SEGS];
     __shared__ int s_seg_k[MRC_MAX_SEGS];
     __shared__ int s_npk;
-    __shared__ int s_next[2];         // next unclaimed segment of pass 2a / pass 2b (claimed largest first)
+#ifdef MRC_PHASE_CLOCKS
+    __shared__ long long s_clk_last;
+    if (threadIdx.x == 0) s_clk_last = clock64();
+#endif
 
     if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
     const int lb = cm.list ? cm.list[blockIdx.x] : (int)blockIdx.x;   // index inside this wave's hand-off buffers
@@ -274,6 +312,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
         }
     }
     __syncthreads();
+    MRC_CLK(0);
 
     // ---- phase 1: KBD window + MDCT, two spectra at a time (each an L/2-point complex FFT) --------------
     {
@@ -318,6 +357,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 X[L - 1 - 2 * k] = -two_over_n * (t.x * w.y + t.y * w.x);
             }
             __syncthreads();
+            MRC_CLK(1);
         }
     }
 
@@ -365,6 +405,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             if (lane == 0 && nspec == 2) s_scale[2] = s_scale[3] = 0;
         }
         __syncthreads();
+        MRC_CLK(2);
         for (int i = tid; i < L; i += NT)
             for (int c = 0; c < nspec; ++c) sm.lines[c * L + i] *= T(1 << s_scale[c]);
         // (no sync needed yet: the next reader of `lines` is after several barriers)
@@ -405,6 +446,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             sm.xi[k] = T(4) * (xr * xr + xim * xim) / xi_den;
         }
         __syncthreads();
+        MRC_CLK(3);
         // c. strict local maxima at bins 1 .. L-102, ascending order (psychoac.py:158-170)
         {
             int found = -1;
@@ -429,6 +471,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             __syncthreads();
             if (found >= 0) sm.pbin[s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u))] = found;
             __syncthreads();
+            MRC_CLK(4);
         }
         const int npk = s_npk;
         // d. masker parameters (psychoac.py:163-165, :37-49), in double in both modes
@@ -559,6 +602,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             if (npk == 0) for (int g = tid; g <= MRC_ZLUT; g += NT) sm.zlut[g] = 0;
         }
         __syncthreads();
+        MRC_CLK(5);
         // e. masked threshold at the MDCT lines, f. SMR per line (psychoac.py:212-214), band maxima (:215-219)
         const T sc6 = T(6) * T(s_scale[c]);
         auto line_spl = [&](int k) -> T {           // SPL of the (scaled) MDCT line, scale undone
@@ -601,7 +645,6 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 const double X = (double)sm.lines[c * L + k];
                 return fmax((2.0 * (X * X)) / 0.5, FLOOR);
             };
-            if (tid < 2) s_next[tid] = 0;                // read after the barrier below
             {
                 const int k0 = tid, k1 = tid + Q;
                 T r0 = T(-1), r1 = T(-1);                // lines of bands that do not select this spectrum: never candidates
@@ -611,21 +654,22 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 sm.xi[k1] = r1;
             }
             __syncthreads();
+            MRC_CLK(6);
             const T slack = sizeof(T) == 8 ? T(1.0 - 1e-9) : T(1.0 - 1e-4);   // bound vs true value: rounding only
             auto complete = [&](int k, T& smr, T& rho) {         // whole warp; all lanes get the results
                 const double a = spread_line_warp(sm, tb, k, npk, lane, n_general, n_window);
+                MRC_WCLK_BEGIN();
                 smr = line_spl(k) - thr_of(a);
                 rho = T(x2c(k) / fmax(a, FLOOR));
+                MRC_WCLK(21);
+#ifdef MRC_PHASE_CLOCKS
+                if (lane == 0) atomicAdd(&g_phase_clk[22], 1ull);
+#endif
             };
-            // Segments cost very different amounts (4 .. 64 lines, and pass 2b from nothing to dozens of complete
-            // thresholds), so warps claim them one at a time, widest bands first, instead of striding over them.
-            auto claim = [&](int pass) {
-                int v = 0;
-                if (lane == 0) v = atomicAdd(&s_next[pass], 1);
-                return tb.nseg - 1 - __shfl_sync(0xffffffffu, v, 0);
-            };
-            for (int sg = claim(0); sg >= 0; sg = claim(0)) {    // pass 2a
-                if (!((need >> tb.seg_band[sg]) & 1u)) continue;
+            // Which warp takes which segment is a static schedule balanced by the host (tb.seg_slot).
+            for (int p = warp; p < tb.nslot; p += nwarp) {       // pass 2a
+                const int sg = tb.seg_slot[p];
+                if (sg < 0 || !((need >> tb.seg_band[sg]) & 1u)) continue;
                 const int lo = tb.seg_lo[sg], n = tb.seg_n[sg];
                 T ubest = T(-1);
                 int kbest = lo;
@@ -644,7 +688,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (lane == 0) { s_seg_smr[sg] = smr; s_seg_rho[sg] = rho; s_seg_k[sg] = kbest; }
             }
             __syncthreads();
-            for (int sg = claim(1); sg >= 0; sg = claim(1)) {    // pass 2b
+            MRC_CLK(7);
+            for (int p = warp; p < tb.nslot; p += nwarp) {       // pass 2b
+                const int sg = tb.seg_slot[p];
+                if (sg < 0) continue;
                 const int lo = tb.seg_lo[sg], n = tb.seg_n[sg], bd = tb.seg_band[sg];
                 if (!((need >> bd) & 1u)) continue;
                 T rbest = T(0);                                  // best true rho of the band so far
@@ -670,6 +717,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (lane == 0) s_seg_smr[sg] = best;
             }
             __syncthreads();
+            MRC_CLK(8);
             if (tid < nb) {
                 T v = T(0);                              // bands that do not select this spectrum: value never used
                 if ((need >> tid) & 1u) {
@@ -680,6 +728,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             }
         }
         __syncthreads();
+        MRC_CLK(9);
         if (taps.npeaks != nullptr && tid == 0) taps.npeaks[lb * 4 + c] = npk;
     }
     if (tid == 0) {
@@ -743,6 +792,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // the values the reference's `smr[i] -= 12.0 / 6.0` updates produce.
     {
         __syncthreads();                                 // phase 5 is done reading sm.lines: the merge buffers alias it
+        MRC_CLK(10);
         T* const key0 = sm.mkey;
         T* const key1 = sm.mkey + 1024;
         uint16_t* const id0 = sm.mid;
@@ -767,6 +817,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             id0[e] = id;
         }
         __syncthreads();
+        MRC_CLK(11);
         int cur = 0;
         const int last_w = joint ? 512 : 256;
         for (int w = 16; w <= last_w; w <<= 1) {
@@ -811,9 +862,22 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             ot[i] = o;
         }
     }
+    MRC_CLK(12);
 }
 
 }  // namespace
+
+#ifdef MRC_PHASE_CLOCKS
+extern "C" int mrc_debug_phase_clocks(unsigned long long* out32, int reset) {
+    cudaDeviceSynchronize();
+    if (out32 && cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof g_phase_clk) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(g_phase_clk, z, sizeof z) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
 
 size_t analysis_smem_bytes(int L, int elem) {
     const size_t Q = L / 2;

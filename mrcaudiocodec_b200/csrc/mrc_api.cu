@@ -31,7 +31,8 @@ struct GeoDev {
     bool set = false;
     int a = 0, b = 0, L = 0, nb = 0, nseg = 0;
     TablesDev td, tf;                 // double and float copies
-    Buf band_lo, band_n, line2band, seg_lo, seg_n, seg_band, band_seg0;
+    Buf band_lo, band_n, line2band, seg_lo, seg_n, seg_band, band_seg0, seg_slot;
+    int nslot = 0;
     DevTables<double> tbd;
     DevTables<float> tbf;
     CodecParams cp;
@@ -189,6 +190,7 @@ cudaError_t upload_tables(mrc_ctx* c, GeoDev& g, TablesDev& d, DevTables<T>& tb,
     tb.nseg = g.nseg;
     tb.seg_lo = (const int*)g.seg_lo.p; tb.seg_n = (const int*)g.seg_n.p;
     tb.seg_band = (const int*)g.seg_band.p; tb.band_seg0 = (const int*)g.band_seg0.p;
+    tb.nslot = g.nslot; tb.seg_slot = (const int*)g.seg_slot.p;
     return cudaSuccess;
 }
 
@@ -231,6 +233,30 @@ int set_geo_bands(mrc_ctx* ctx, GeoDev& g, const int32_t* band_nlines, int n_ban
     CK(upload(g.seg_n, sn, ctx->stream));
     CK(upload(g.seg_band, sb, ctx->stream));
     CK(upload(g.band_seg0, b0, ctx->stream));
+    // Static schedule of the band-maximum search: one warp evaluates a segment, a CTA has L/64 warps.  A segment costs
+    // a complete threshold evaluation or more plus a scan of its lines; longest-processing-time-first onto the least
+    // loaded warp, then laid out round by round (slot k*nwarp + w).
+    {
+        const int nwarp = std::max(g.L / 64, 1), ns = (int)slo.size();
+        std::vector<int> order(ns), load(nwarp, 0);
+        std::vector<std::vector<int>> mine(nwarp);
+        for (int i = 0; i < ns; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sn[x] > sn[y]; });
+        for (int sidx : order) {
+            int w = 0;
+            for (int v = 1; v < nwarp; ++v) if (load[v] < load[w]) w = v;
+            mine[w].push_back(sidx);
+            load[w] += sn[sidx] + 48;
+        }
+        size_t rounds = 0;
+        for (auto& m : mine) rounds = std::max(rounds, m.size());
+        std::vector<int> slot(rounds * nwarp, -1);
+        for (int w = 0; w < nwarp; ++w)
+            for (size_t k = 0; k < mine[w].size(); ++k) slot[k * nwarp + w] = mine[w][k];
+        g.nslot = (int)slot.size();
+        CK(upload(g.seg_slot, slot, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return MRC_OK;
 }
@@ -880,7 +906,7 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
                          &d->bark_d, &d->quiet_d, &d->exp_tab};
             for (Buf* b : tb) release(*b);
         }
-        Buf* gb[] = {&g.band_lo, &g.band_n, &g.line2band, &g.seg_lo, &g.seg_n, &g.seg_band, &g.band_seg0};
+        Buf* gb[] = {&g.band_lo, &g.band_n, &g.line2band, &g.seg_lo, &g.seg_n, &g.seg_band, &g.band_seg0, &g.seg_slot};
         for (Buf* b : gb) release(*b);
     }
     Buf* all[] = {&ctx->huff, &ctx->header, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,

@@ -23,7 +23,7 @@
 #define MRC_TOK_STRIDE 768      // >= 2*25*15 grant tokens per block
 #define MRC_MAX_LEVELS 15       // grants per band: 0->2, then +1 up to 16 bits
 #define MRC_BSTRIDE 32          // band stride in per-band arrays
-#define MRC_SEG_LINES 64
+#define MRC_SEG_LINES 96       // 25 critical bands at 48 kHz / 1024 lines -> 30 segments: two per warp of the analysis CTA
 #define MRC_MAX_SEGS 96        // >= nb + L / MRC_SEG_LINES for L <= 2048 ... 4096
 #define MRC_CODED_BANDS 25      // most bands per channel the grant-token machinery holds (25 * 15 <= MRC_GROUP_SLOTS)
 
@@ -98,6 +98,9 @@ struct DevTables {
     const int* seg_n;                            // [nseg] lines
     const int* seg_band;                         // [nseg]
     const int* band_seg0;                        // [nb+1] first segment of each band
+    // which warp takes which segment: slot k*nwarp + w = the k-th segment of warp w (-1: none), balanced by the host
+    int nslot;
+    const int* seg_slot;                         // [nslot]
 };
 
 struct HuffDev {
