@@ -43,6 +43,7 @@ __device__ unsigned long long g_phase_clk[32];
     } while (0)
 // warp-level: cycles of lane 0 between consecutive marks inside spread_line_warp / complete()
 #define MRC_WCLK_BEGIN() long long wt_ = clock64()
+#define MRC_WSYNC() __syncwarp()        /* so that lane 0's clock sees the slowest lane of the step before */
 #define MRC_WCLK(i)                                                                                                 \
     do {                                                                                                            \
         const long long t_ = clock64();                                                                             \
@@ -52,6 +53,7 @@ __device__ unsigned long long g_phase_clk[32];
 #else
 #define MRC_CLK(i)
 #define MRC_WCLK_BEGIN()
+#define MRC_WSYNC()
 #define MRC_WCLK(i)
 #endif
 
@@ -231,14 +233,14 @@ __device__ __forceinline__ double spread_line_warp(const Smem<T>& sm, const DevT
     MRC_WCLK(16);
     double a = 0.0;
     if (lane == 0) a = tb.quiet_d[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
-    __syncwarp();
+    MRC_WSYNC();
     MRC_WCLK(17);
     for (int m = m_lo + lane; m < m_hi; m += 32) a += sm.mc[m];
-    __syncwarp();
+    MRC_WSYNC();
     MRC_WCLK(18);
     const int nl = sm.lcnt[m_lo];
     for (int j = lane; j < nl; j += 32) a += loud_term(sm, zk, sm.lidx[j]);
-    __syncwarp();
+    MRC_WSYNC();
     MRC_WCLK(19);
     if (lane == 0) { n_general += (unsigned)nl; n_window += (unsigned)(m_hi - m_lo); }
 #pragma unroll
