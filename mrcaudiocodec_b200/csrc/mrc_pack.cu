@@ -16,7 +16,7 @@ namespace {
 constexpr int PT = 256;
 
 template <typename T>
-__global__ void __launch_bounds__(PT)
+__global__ void __launch_bounds__(PT, 8)
 pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, ClipMap cm, int g0, Handoff<T> ho,
             ChainIO io, PackTaps taps, const int64_t* __restrict__ clip_base, uint8_t* __restrict__ out,
             long long out_cap, const uint8_t* __restrict__ header_template, int* overflow_flag) {

@@ -17,6 +17,7 @@ if [ "$WHAT" = all ] || [ "$WHAT" = bench ]; then
     echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json
     timeout 600 python bench.py --steps 3 --warmup 3 --precision fp32 --no-cpu-baseline --no-sequential-sample > gpurun_out/${TAG}_bench_fp32.json 2>> gpurun_out/${TAG}_bench.err
     timeout 600 python bench.py --steps 3 --warmup 3 --workload batch --decode --no-cpu-baseline --no-sequential-sample > gpurun_out/${TAG}_bench_batch.json 2>> gpurun_out/${TAG}_bench.err
+    timeout 600 python bench.py --steps 3 --warmup 3 --block-switching --decode --no-cpu-baseline > gpurun_out/${TAG}_bench_switching.json 2>> gpurun_out/${TAG}_bench.err
     timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
     tail -c 600 gpurun_out/${TAG}_bench_reference.json
 fi
@@ -29,6 +30,11 @@ if [ "$WHAT" = all ] || [ "$WHAT" = ncu ]; then
     $CMD2 > gpurun_out/${TAG}_ncu_plain2.log 2>&1 &&
     ncu --set full --clock-control none --import-source on -k regex:'analysis_kernel|cost_kernel|table_kernel|chain_kernel|chain_table_kernel|finish_kernel|offsets_kernel|clip_scan_kernel|pack_kernel' -s 8 -c 8 -f -o gpurun_out/${TAG}_prof $CMD2 > gpurun_out/${TAG}_ncu_full.log 2>&1
     echo "full capture rc=$?"
+    # block switching: launch list of one switched encode (transient detector + per-geometry launches)
+    CMD3="python bench.py --steps 1 --warmup 1 --seconds 300 --block-switching --no-cpu-baseline"
+    $CMD3 > gpurun_out/${TAG}_ncu_plain3.log 2>&1 &&
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_switching.csv $CMD3 > gpurun_out/${TAG}_ncu_launches3.log 2>&1
+    echo "switching launch list rc=$?"
     ls -la gpurun_out/
 fi
 exit $RC

@@ -17,8 +17,8 @@ for ln in txt:
     elif cur is not None:
         cur[1].append(ln)
 def short(name):
-    for k in ("analysis_kernelIdLi10", "analysis_kernelIfLi10", "cost_kernelId", "chain_table_kernel", "table_kernel", "chain_kernel",
-              "finish_kernel", "offsets_kernel", "pack_kernelId", "decode_kernelIdLi10", "ola_kernelId", "clip_scan_kernel"):
+    for k in ("analysis_kernelIdLi1024", "analysis_kernelIfLi1024", "cost_kernelId", "chain_table_kernel", "table_kernel", "chain_kernel",
+              "finish_kernel", "offsets_kernel", "pack_kernelId", "decode_kernelIdLi1024", "ola_kernelId", "clip_scan_kernel", "analysis_kernelIdLi576", "analysis_kernelIdLi128", "peaks_kernelILi10", "decide_kernel"):
         if k in name: return k
     return None
 hist_lines = ["kernel,instructions," + ",".join(["DFMA", "DADD", "DMUL", "DSETP", "MUFU", "LDS", "STS", "LDG", "STG", "SHFL", "BAR", "REDUX", "VOTE", "ATOMS", "UBLKCP", "SYNCS", "HMMA", "UTC"])]
@@ -36,7 +36,7 @@ for name, body in funcs:
     cols = ["DFMA", "DADD", "DMUL", "DSETP", "MUFU", "LDS", "STS", "LDG", "STG", "SHFL", "BAR", "REDUX", "VOTE", "ATOMS", "UBLKCP", "SYNCS", "HMMA"]
     utc = sum(v for k, v in ops.items() if k.startswith("UTC"))
     hist_lines.append("%s,%d,%s,%d" % (s, n, ",".join(str(ops[c]) for c in cols), utc))
-    if s in ("analysis_kernelIdLi10", "chain_table_kernel", "chain_kernel"):
+    if s in ("analysis_kernelIdLi1024", "chain_table_kernel", "chain_kernel"):
         keep[s] = body
 open('profiles/%s_sass_mnemonics.csv' % tag, 'w').write("\n".join(hist_lines) + "\n")
 for s, body in keep.items():
