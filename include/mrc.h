@@ -63,7 +63,7 @@ typedef struct mrc_ctx mrc_ctx;
 typedef struct mrc_config {
     int32_t device;                 /* CUDA device ordinal                                            */
     int32_t sample_rate;            /* codingParams.sampleRate (int, pcmfile.py:46)                   */
-    int32_t n_mdct_lines;           /* codingParams.nMDCTLines: 256, 512, 1024 or 2048 (long blocks)  */
+    int32_t n_mdct_lines;           /* codingParams.nMDCTLines: 128 .. 2048, a power of two           */
     int32_t n_scale_bits;           /* codingParams.nScaleBits  (4)                                   */
     int32_t n_mant_size_bits;       /* codingParams.nMantSizeBits (4)                                 */
     int32_t joint;                  /* 1: JointWriteDataBlock flow (M/S), 0: WriteDataBlock flow      */

@@ -848,8 +848,8 @@ int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out) {
     *out = nullptr;
     int logL = 0;
     while ((1 << logL) < cfg->n_mdct_lines) ++logL;
-    if ((1 << logL) != cfg->n_mdct_lines || logL < 8 || logL > 11)
-        return fail(nullptr, MRC_E_INVALID, "n_mdct_lines must be 256, 512, 1024 or 2048");
+    if ((1 << logL) != cfg->n_mdct_lines || logL < 7 || logL > 11)
+        return fail(nullptr, MRC_E_INVALID, "n_mdct_lines must be 128, 256, 512, 1024 or 2048");
     if (cfg->n_scale_bits < 1 || cfg->n_scale_bits > 4 || cfg->n_mant_size_bits < 4 || cfg->n_mant_size_bits > 5)
         return fail(nullptr, MRC_E_INVALID, "n_scale_bits must be in 1..4 and n_mant_size_bits 4 or 5 (16-bit mantissa cap)");
     if (cfg->precision != MRC_PRECISION_FP64 && cfg->precision != MRC_PRECISION_FP32)
