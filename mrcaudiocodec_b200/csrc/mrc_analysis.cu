@@ -317,6 +317,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     MRC_CLK(0);
 
     // ---- phase 1: KBD window + MDCT, two spectra at a time (each an L/2-point complex FFT) --------------
+    // The FFT twiddles are staged in `xi` (idle until the first intensities are written): three twiddle loads per
+    // butterfly and stage from shared memory instead of through the L1 the other tables compete for.
+    cpx<T>* const tws = reinterpret_cast<cpx<T>*>(sm.xi);
+    const int ntw = 1 << (tb.logLtab - 1);
+    for (int i = tid; i < ntw; i += NT) tws[i] = tb.tw_fft[i];       // published by the barrier before the first FFT
     {
         const int grp = tid / (NT / 2), lt = tid - grp * (NT / 2), gthr = NT / 2;
         const T two_over_n = T(2) / T(N);
@@ -350,7 +355,9 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 a[r].y = re * w.y + im * w.x;
             }
             __syncthreads();
-            fft_any<T, Q>(a, lt, gthr, tb.tw_fft, tb.logLtab, tb.tw9, L, tb.w9);
+            MRC_CLK(13);
+            fft_any<T, Q>(a, lt, gthr, tws, tb.logLtab, tb.tw9, L, tb.w9);
+            MRC_CLK(14);
             T* X = sm.lines + c * L;
             for (int k = lt; k < Q; k += gthr) {
                 const cpx<T> w = tb.tw_post[k];
@@ -430,13 +437,16 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             continue;                                    // uniform: s_ms is shared
         }
         // a. Hann window, real 2L-point FFT through an L-point complex FFT
+        for (int i = tid; i < ntw; i += NT) tws[i] = tb.tw_fft[i];   // xi held the previous spectrum's per-line scratch
         for (int n = tid; n < L; n += NT) {
             const int r = fft_pos<L>(n);
             sm.buf[r].x = tb.hann[2 * n] * tsample(sm.sx, N, c, 2 * n);
             sm.buf[r].y = tb.hann[2 * n + 1] * tsample(sm.sx, N, c, 2 * n + 1);
         }
         __syncthreads();
-        fft_any<T, L>(sm.buf, tid, NT, tb.tw_fft, tb.logLtab, tb.tw9, L, tb.w9);
+        MRC_CLK(15);
+        fft_any<T, L>(sm.buf, tid, NT, tws, tb.logLtab, tb.tw9, L, tb.w9);
+        MRC_CLK(23);
         // b. X[k] = E[k] + W^k O[k];  XI = 4|X|^2 / (N^2 * 3/8)   (psychoac.py:151)
         for (int k = tid; k < L; k += NT) {
             const cpx<T> zk = sm.buf[k], zc = sm.buf[k ? L - k : 0];
@@ -827,26 +837,42 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             const uint16_t* is = cur ? id1 : id0;
             T* kd = cur ? key0 : key1;
             uint16_t* idd = cur ? id0 : id1;
-            for (int e = tid; e < 1024; e += NT) {
-                const int q = e / w, i = e - q * w;
-                const T v = ks[e];
-                const uint16_t id = is[e];
-                const int pbase = (q ^ 1) * w;           // partner run
-                const bool first = (q & 1) == 0;         // elements of the first run win ties
-                int lo = 0, hi = w;
-                while (lo < hi) {                        // number of partner elements that go before this one
-                    const int mid = (lo + hi) >> 1;
-                    const T x = ks[pbase + mid];
-                    bool x_before = x > v;
-                    if (x == v) {                        // rare: only ties look at the ids
-                        const uint16_t xi = is[pbase + mid];
-                        x_before = xi < id || (xi == id && !first);
-                    }
-                    if (x_before) lo = mid + 1; else hi = mid;
+            // number of partner elements that go before an element: a fixed-step search (the predicate holds for a
+            // prefix of the sorted partner run), two elements per thread in lock step so that their dependent loads
+            // overlap
+            auto before = [&](int idx, T v, uint16_t id, bool first) -> bool {
+                const T x = ks[idx];
+                bool b = x > v;
+                if (x == v) {                            // rare: only ties look at the ids
+                    const uint16_t xi = is[idx];
+                    b = xi < id || (xi == id && !first);
                 }
-                const int dst = (q >> 1) * 2 * w + i + lo;
-                kd[dst] = v;
-                idd[dst] = id;
+                return b;
+            };
+            const int logw = 31 - __clz(w);
+            for (int e0 = tid; e0 < 1024; e0 += 2 * NT) {
+                const int e1 = e0 + NT;
+                const bool two = e1 < 1024;
+                const int q0 = e0 >> logw, i0 = e0 - (q0 << logw), q1 = two ? (e1 >> logw) : q0, i1 = two ? e1 - (q1 << logw) : i0;
+                const T v0 = ks[e0], v1 = ks[two ? e1 : e0];
+                const uint16_t d0 = is[e0], d1 = is[two ? e1 : e0];
+                const int b0 = (q0 ^ 1) << logw, b1 = (q1 ^ 1) << logw;          // partner runs
+                const bool f0 = (q0 & 1) == 0, f1 = (q1 & 1) == 0;              // elements of the first run win ties
+                int p0 = 0, p1 = 0;
+                for (int step = w >> 1; step >= 1; step >>= 1) {
+                    if (before(b0 + p0 + step - 1, v0, d0, f0)) p0 += step;
+                    if (before(b1 + p1 + step - 1, v1, d1, f1)) p1 += step;
+                }
+                if (before(b0 + p0, v0, d0, f0)) ++p0;
+                if (before(b1 + p1, v1, d1, f1)) ++p1;
+                const int dst0 = ((q0 >> 1) << (logw + 1)) + i0 + p0;
+                kd[dst0] = v0;
+                idd[dst0] = d0;
+                if (two) {
+                    const int dst1 = ((q1 >> 1) << (logw + 1)) + i1 + p1;
+                    kd[dst1] = v1;
+                    idd[dst1] = d1;
+                }
             }
             __syncthreads();
             cur ^= 1;

@@ -28,10 +28,13 @@ buf = np.zeros(32, np.uint64)
 lib.mrc_debug_phase_clocks(None, 1)
 c.encode_clips([pcm])
 lib.mrc_debug_phase_clocks(buf.ctypes.data_as(C.c_void_p), 0)
-tot = float(buf[:13].sum())
+tot = float(buf[:16].sum() + buf[23])
 nblk = c.n_blocks(pcm.shape[0])
 print("blocks %d, cycles per CTA %.0f" % (nblk, tot / nblk))
 for i, n in enumerate(NAMES):
+    print("%-44s %6.2f%%  %8.0f cycles/CTA" % (n, 100.0 * buf[i] / tot, buf[i] / nblk))
+for i, n in ((13, "  1a MDCT: window + pre-twiddle"), (14, "  1b MDCT: FFT (then 1 = post-twiddle)"), (15, "  3a scale / Hann window placement"),
+             (23, "  3b Hann FFT (then 3 = intensities)")):
     print("%-44s %6.2f%%  %8.0f cycles/CTA" % (n, 100.0 * buf[i] / tot, buf[i] / nblk))
 sub = ["16 masker_range", "17 quiet + two tails (lane 0)", "18 plateau sum", "19 loud maskers", "20 butterfly sum",
        "21 two log10 + division"]
