@@ -678,10 +678,28 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (lane == 0) atomicAdd(&g_phase_clk[22], 1ull);
 #endif
             };
-            // Which warp takes which segment is a static schedule balanced by the host (tb.seg_slot).
-            for (int p = warp; p < tb.nslot; p += nwarp) {       // pass 2a
-                const int sg = tb.seg_slot[p];
-                if (sg < 0 || !((need >> tb.seg_band[sg]) & 1u)) continue;
+            // Work list: the segments of the bands that select this spectrum, widest first (tb.seg_slot compacted with
+            // the band mask -- every warp does the same three ballots), dealt out round-robin: warp w takes the w-th,
+            // (w + nwarp)-th, ... needed segment.  Half of the bands select a spectrum on average, so most spectra need
+            // one round instead of two.
+            unsigned wl[3];
+            int wl_n[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int idx = ch * 32 + lane;
+                const int sgi = idx < tb.nslot ? tb.seg_slot[idx] : -1;
+                wl[ch] = __ballot_sync(0xffffffffu, sgi >= 0 && ((need >> tb.seg_band[sgi < 0 ? 0 : sgi]) & 1u));
+                wl_n[ch] = __popc(wl[ch]);
+            }
+            const int wl_total = wl_n[0] + wl_n[1] + wl_n[2];
+            auto wl_get = [&](int j) -> int {                    // j-th needed segment
+                int ch = 0;
+                if (j >= wl_n[0]) { j -= wl_n[0]; ch = 1; if (j >= wl_n[1]) { j -= wl_n[1]; ch = 2; } }
+                const unsigned m = ch == 0 ? wl[0] : (ch == 1 ? wl[1] : wl[2]);
+                return tb.seg_slot[ch * 32 + (int)__fns(m, 0, j + 1)];
+            };
+            for (int p = warp; p < wl_total; p += nwarp) {       // pass 2a
+                const int sg = wl_get(p);
                 const int lo = tb.seg_lo[sg], n = tb.seg_n[sg];
                 T ubest = T(-1);
                 int kbest = lo;
@@ -701,11 +719,9 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             }
             __syncthreads();
             MRC_CLK(7);
-            for (int p = warp; p < tb.nslot; p += nwarp) {       // pass 2b
-                const int sg = tb.seg_slot[p];
-                if (sg < 0) continue;
+            for (int p = warp; p < wl_total; p += nwarp) {       // pass 2b
+                const int sg = wl_get(p);
                 const int lo = tb.seg_lo[sg], n = tb.seg_n[sg], bd = tb.seg_band[sg];
-                if (!((need >> bd) & 1u)) continue;
                 T rbest = T(0);                                  // best true rho of the band so far
                 for (int s2 = tb.band_seg0[bd]; s2 < tb.band_seg0[bd + 1]; ++s2) rbest = fmax(rbest, s_seg_rho[s2]);
                 T best = s_seg_smr[sg];

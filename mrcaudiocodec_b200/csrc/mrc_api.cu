@@ -233,28 +233,15 @@ int set_geo_bands(mrc_ctx* ctx, GeoDev& g, const int32_t* band_nlines, int n_ban
     CK(upload(g.seg_n, sn, ctx->stream));
     CK(upload(g.seg_band, sb, ctx->stream));
     CK(upload(g.band_seg0, b0, ctx->stream));
-    // Static schedule of the band-maximum search: one warp evaluates a segment, a CTA has L/64 warps.  A segment costs
-    // a complete threshold evaluation or more plus a scan of its lines; longest-processing-time-first onto the least
-    // loaded warp, then laid out round by round (slot k*nwarp + w).
+    // Work list of the band-maximum search: the segments widest first.  A spectrum only evaluates the segments of the
+    // bands that select it; the kernel compacts this list with the spectrum's band mask and deals it out to its warps.
     {
-        const int nwarp = std::max(g.L / 64, 1), ns = (int)slo.size();
-        std::vector<int> order(ns), load(nwarp, 0);
-        std::vector<std::vector<int>> mine(nwarp);
+        const int ns = (int)slo.size();
+        std::vector<int> order(ns);
         for (int i = 0; i < ns; ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sn[x] > sn[y]; });
-        for (int sidx : order) {
-            int w = 0;
-            for (int v = 1; v < nwarp; ++v) if (load[v] < load[w]) w = v;
-            mine[w].push_back(sidx);
-            load[w] += sn[sidx] + 48;
-        }
-        size_t rounds = 0;
-        for (auto& m : mine) rounds = std::max(rounds, m.size());
-        std::vector<int> slot(rounds * nwarp, -1);
-        for (int w = 0; w < nwarp; ++w)
-            for (size_t k = 0; k < mine[w].size(); ++k) slot[k * nwarp + w] = mine[w][k];
-        g.nslot = (int)slot.size();
-        CK(upload(g.seg_slot, slot, ctx->stream));
+        g.nslot = ns;
+        CK(upload(g.seg_slot, order, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));

@@ -98,8 +98,8 @@ struct DevTables {
     const int* seg_n;                            // [nseg] lines
     const int* seg_band;                         // [nseg]
     const int* band_seg0;                        // [nb+1] first segment of each band
-    // which warp takes which segment: slot k*nwarp + w = the k-th segment of warp w (-1: none), balanced by the host
-    int nslot;
+    // the segments widest first: the work list the kernel compacts per spectrum and deals out to its warps
+    int nslot;                                   // = nseg
     const int* seg_slot;                         // [nslot]
 };
 
