@@ -268,8 +268,9 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ unsigned int s_ms;
     __shared__ int s_wcnt[33];
     __shared__ double s_scan[5][32];
-    __shared__ T s_seg_smr[MRC_MAX_SEGS], s_seg_rho[MRC_MAX_SEGS];
-    __shared__ int s_seg_k[MRC_MAX_SEGS];
+    __shared__ T s_seg_smr[MRC_MAX_SEGS];
+    __shared__ T s_band_smr[MRC_BSTRIDE], s_band_rho[MRC_BSTRIDE];
+    __shared__ int s_band_k[MRC_BSTRIDE];
     __shared__ int s_npk;
 #ifdef MRC_PHASE_CLOCKS
     __shared__ long long s_clk_last;
@@ -381,7 +382,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // ---- phase 2: ms_switch on the unscaled L/R lines (ms_stereo.py:5-27) -------------------------------
     if (joint) {
         for (int bd = warp; bd < nb; bd += nwarp) {
-            const int lo = tb.band_lo[bd], n = tb.band_n[bd];
+            const int lo = tb.c_band_lo[bd], n = tb.c_band_n[bd];
             T sd = 0, ss = 0;
             for (int i = lane; i < n; i += 32) {
                 const T l = sm.lines[lo + i], r = sm.lines[L + lo + i];
@@ -636,7 +637,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             sm.xi[k1] = line_spl(k1) - thr_of(a1);
             __syncthreads();
             for (int bd = warp; bd < nb; bd += nwarp) {
-                const int lo = tb.band_lo[bd], n = tb.band_n[bd];
+                const int lo = tb.c_band_lo[bd], n = tb.c_band_n[bd];
                 T v = -INFINITY;
                 for (int i = lane; i < n; i += 32) v = fmax(v, sm.xi[lo + i]);
                 v = warp_max(v);
@@ -647,10 +648,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             // threshold.  With both clamps of psychoac.py:12 folded in, a line's SMR is 10 log10(rho) - 6 scale,
             // rho = max(4 X^2, floor) / max(threshold intensity, floor): monotone in rho.
             //   pass 1 (thread per line): rho from a LOWER bound of the threshold = an upper bound of the line's rho;
-            //   pass 2a (warp per segment of <= 64 lines of one band): complete threshold (warp-cooperative) of the
-            //           segment's line with the highest bound -> its true rho and SMR;
-            //   pass 2b: every other line whose bound reaches the band's best true rho so far (less 1e-9) gets its
-            //           complete threshold too; lines whose bound stays below cannot be the maximum.
+            //   pass 2a (warp per band): complete threshold (warp-cooperative) of the band's line with the highest
+            //           bound -> its true rho and SMR;
+            //   pass 2b (warp per segment of a band): every other line whose bound reaches the best true rho seen so
+            //           far (less 1e-9) gets its complete threshold too; lines whose bound stays below cannot be the
+            //           maximum.
             // The band SMR is the maximum of the completely evaluated lines' SMRs: exact.
             const double FLOOR = 2.5118864315095823e-13;        // 10^((-30-96)/10): where SPL() clamps
             auto x2c = [&](int k) -> double {
@@ -678,17 +680,45 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (lane == 0) atomicAdd(&g_phase_clk[22], 1ull);
 #endif
             };
-            // Work list: the segments of the bands that select this spectrum, widest first (tb.seg_slot compacted with
-            // the band mask -- every warp does the same three ballots), dealt out round-robin: warp w takes the w-th,
-            // (w + nwarp)-th, ... needed segment.  Half of the bands select a spectrum on average, so most spectra need
-            // one round instead of two.
+            // pass 2a, one warp per BAND that selects this spectrum (about half of them do, so one round of the
+            // CTA's warps usually covers them): the band's line with the highest bound gets its complete threshold;
+            // its true rho is the bar the other lines have to reach.  Bands are dealt out from the top: their lines
+            // see the most loud maskers and take longest.
+            {
+                const unsigned bl = need & band_mask;
+                const int nbl = __popc(bl);
+                for (int p = warp; p < nbl; p += nwarp) {
+                    const int bd = 31 - (int)__fns(__brev(bl), 0, p + 1);     // p-th needed band from the top
+                    const int lo = tb.c_band_lo[bd], n = tb.c_band_n[bd];
+                    T ubest = T(-1);
+                    int kbest = lo;
+                    for (int i = lane; i < n; i += 32) {
+                        const T v = sm.xi[lo + i];
+                        if (v > ubest) { ubest = v; kbest = lo + i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        const T ov = __shfl_xor_sync(0xffffffffu, ubest, o);
+                        const int ok = __shfl_xor_sync(0xffffffffu, kbest, o);
+                        if (ov > ubest || (ov == ubest && ok < kbest)) { ubest = ov; kbest = ok; }
+                    }
+                    T smr, rho;
+                    complete(kbest, smr, rho);
+                    if (lane == 0) { s_band_smr[bd] = smr; s_band_rho[bd] = rho; s_band_k[bd] = kbest; }
+                }
+            }
+            __syncthreads();
+            MRC_CLK(7);
+            // pass 2b, one warp per SEGMENT (<= MRC_SEG_LINES lines) of those bands, widest first (tb.c_seg_slot
+            // compacted with the band mask -- every warp does the same three ballots -- and dealt out round-robin):
+            // every other line whose bound reaches the band's bar gets its complete threshold too.
             unsigned wl[3];
             int wl_n[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 const int idx = ch * 32 + lane;
-                const int sgi = idx < tb.nslot ? tb.seg_slot[idx] : -1;
-                wl[ch] = __ballot_sync(0xffffffffu, sgi >= 0 && ((need >> tb.seg_band[sgi < 0 ? 0 : sgi]) & 1u));
+                const int sgi = idx < tb.nslot ? tb.c_seg_slot[idx] : -1;
+                wl[ch] = __ballot_sync(0xffffffffu, sgi >= 0 && ((need >> tb.c_seg_band[sgi < 0 ? 0 : sgi]) & 1u));
                 wl_n[ch] = __popc(wl[ch]);
             }
             const int wl_total = wl_n[0] + wl_n[1] + wl_n[2];
@@ -696,36 +726,14 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 int ch = 0;
                 if (j >= wl_n[0]) { j -= wl_n[0]; ch = 1; if (j >= wl_n[1]) { j -= wl_n[1]; ch = 2; } }
                 const unsigned m = ch == 0 ? wl[0] : (ch == 1 ? wl[1] : wl[2]);
-                return tb.seg_slot[ch * 32 + (int)__fns(m, 0, j + 1)];
+                return tb.c_seg_slot[ch * 32 + (int)__fns(m, 0, j + 1)];
             };
-            for (int p = warp; p < wl_total; p += nwarp) {       // pass 2a
+            for (int p = warp; p < wl_total; p += nwarp) {
                 const int sg = wl_get(p);
-                const int lo = tb.seg_lo[sg], n = tb.seg_n[sg];
-                T ubest = T(-1);
-                int kbest = lo;
-                for (int i = lane; i < n; i += 32) {
-                    const T v = sm.xi[lo + i];
-                    if (v > ubest) { ubest = v; kbest = lo + i; }
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    const T ov = __shfl_xor_sync(0xffffffffu, ubest, o);
-                    const int ok = __shfl_xor_sync(0xffffffffu, kbest, o);
-                    if (ov > ubest || (ov == ubest && ok < kbest)) { ubest = ov; kbest = ok; }
-                }
-                T smr, rho;
-                complete(kbest, smr, rho);
-                if (lane == 0) { s_seg_smr[sg] = smr; s_seg_rho[sg] = rho; s_seg_k[sg] = kbest; }
-            }
-            __syncthreads();
-            MRC_CLK(7);
-            for (int p = warp; p < wl_total; p += nwarp) {       // pass 2b
-                const int sg = wl_get(p);
-                const int lo = tb.seg_lo[sg], n = tb.seg_n[sg], bd = tb.seg_band[sg];
-                T rbest = T(0);                                  // best true rho of the band so far
-                for (int s2 = tb.band_seg0[bd]; s2 < tb.band_seg0[bd + 1]; ++s2) rbest = fmax(rbest, s_seg_rho[s2]);
-                T best = s_seg_smr[sg];
-                const int kdone = s_seg_k[sg];
+                const int lo = tb.c_seg_lo[sg], n = tb.c_seg_n[sg], bd = tb.c_seg_band[sg];
+                T rbest = s_band_rho[bd];                        // best true rho of the band so far
+                T best = -INFINITY;
+                const int kdone = s_band_k[bd];
                 for (int base = 0; base < n; base += 32) {
                     const int i = base + lane;
                     const T ub = (i < n) ? sm.xi[lo + i] : T(-1);
@@ -749,8 +757,8 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             if (tid < nb) {
                 T v = T(0);                              // bands that do not select this spectrum: value never used
                 if ((need >> tid) & 1u) {
-                    v = -INFINITY;
-                    for (int s2 = tb.band_seg0[tid]; s2 < tb.band_seg0[tid + 1]; ++s2) v = fmax(v, s_seg_smr[s2]);
+                    v = s_band_smr[tid];
+                    for (int s2 = tb.c_band_seg0[tid]; s2 < tb.c_band_seg0[tid + 1]; ++s2) v = fmax(v, s_seg_smr[s2]);
                 }
                 s_smr[c][tid] = v;
             }
@@ -794,8 +802,8 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
         for (int w2 = warp; w2 < 2 * nb; w2 += nwarp) {
             const int ch = w2 / nb, bd = w2 - ch * nb;
             const bool m = (ms >> bd) & 1u;
-            const T* src = sm.lines + ((m ? 2 : 0) + ch) * L + tb.band_lo[bd];
-            const int n = tb.band_n[bd];
+            const T* src = sm.lines + ((m ? 2 : 0) + ch) * L + tb.c_band_lo[bd];
+            const int n = tb.c_band_n[bd];
             T v = 0;
             for (int i = lane; i < n; i += 32) v = fmax(v, fabs(src[i]));
             v = warp_max(v);

@@ -33,6 +33,7 @@ struct GeoDev {
     TablesDev td, tf;                 // double and float copies
     Buf band_lo, band_n, line2band, seg_lo, seg_n, seg_band, band_seg0, seg_slot;
     int nslot = 0;
+    std::vector<int> h_seg_lo, h_seg_n, h_seg_band, h_seg_slot, h_band_seg0;
     DevTables<double> tbd;
     DevTables<float> tbf;
     CodecParams cp;
@@ -191,6 +192,16 @@ cudaError_t upload_tables(mrc_ctx* c, GeoDev& g, TablesDev& d, DevTables<T>& tb,
     tb.seg_lo = (const int*)g.seg_lo.p; tb.seg_n = (const int*)g.seg_n.p;
     tb.seg_band = (const int*)g.seg_band.p; tb.band_seg0 = (const int*)g.band_seg0.p;
     tb.nslot = g.nslot; tb.seg_slot = (const int*)g.seg_slot.p;
+    memset(tb.c_band_lo, 0, sizeof tb.c_band_lo); memset(tb.c_band_n, 0, sizeof tb.c_band_n);
+    memset(tb.c_seg_lo, 0, sizeof tb.c_seg_lo); memset(tb.c_seg_n, 0, sizeof tb.c_seg_n);
+    memset(tb.c_seg_band, 0, sizeof tb.c_seg_band); memset(tb.c_seg_slot, 0, sizeof tb.c_seg_slot);
+    memset(tb.c_band_seg0, 0, sizeof tb.c_band_seg0);
+    for (int b = 0; b < g.nb; ++b) { tb.c_band_lo[b] = (uint16_t)g.h_band_lo[b]; tb.c_band_n[b] = (uint16_t)g.h_band_n[b]; }
+    for (int i = 0; i < g.nseg; ++i) {
+        tb.c_seg_lo[i] = (uint16_t)g.h_seg_lo[i]; tb.c_seg_n[i] = (uint8_t)g.h_seg_n[i];
+        tb.c_seg_band[i] = (uint8_t)g.h_seg_band[i]; tb.c_seg_slot[i] = (uint8_t)g.h_seg_slot[i];
+    }
+    for (int b = 0; b <= g.nb; ++b) tb.c_band_seg0[b] = (uint8_t)g.h_band_seg0[b];
     return cudaSuccess;
 }
 
@@ -243,6 +254,7 @@ int set_geo_bands(mrc_ctx* ctx, GeoDev& g, const int32_t* band_nlines, int n_ban
         g.nslot = ns;
         CK(upload(g.seg_slot, order, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        g.h_seg_lo = slo; g.h_seg_n = sn; g.h_seg_band = sb; g.h_seg_slot = order; g.h_band_seg0 = b0;
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return MRC_OK;

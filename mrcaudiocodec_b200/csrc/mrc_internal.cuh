@@ -101,6 +101,12 @@ struct DevTables {
     // the segments widest first: the work list the kernel compacts per spectrum and deals out to its warps
     int nslot;                                   // = nseg
     const int* seg_slot;                         // [nslot]
+    // the same small tables by value (kernel parameters live in the constant bank: a warp-uniform lookup costs a few
+    // cycles instead of a dependent trip to L2) -- used by the analysis kernel's per-band and per-segment loops
+    uint16_t c_band_lo[MRC_BSTRIDE], c_band_n[MRC_BSTRIDE];
+    uint16_t c_seg_lo[MRC_MAX_SEGS];
+    uint8_t c_seg_n[MRC_MAX_SEGS], c_seg_band[MRC_MAX_SEGS], c_seg_slot[MRC_MAX_SEGS];
+    uint8_t c_band_seg0[MRC_BSTRIDE + 4];
 };
 
 struct HuffDev {
