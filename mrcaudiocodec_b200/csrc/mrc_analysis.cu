@@ -60,7 +60,10 @@ __device__ unsigned long long g_phase_clk[32];
 namespace {
 
 constexpr int MRC_ZLUT = 832;         // cells of 1/32 Bark: Bark(24 kHz) = 24.6
-constexpr int MRC_NEAR_LOUD = 4;     // loud maskers included in the pass-1 bound of a line's threshold
+#ifndef MRC_NEAR_LOUD_N
+#define MRC_NEAR_LOUD_N 4
+#endif
+constexpr int MRC_NEAR_LOUD = MRC_NEAR_LOUD_N;     // loud maskers included in the pass-1 bound of a line's threshold
 
 template <typename T>
 struct Smem {
