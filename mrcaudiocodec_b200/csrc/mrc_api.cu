@@ -512,7 +512,9 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         CK(upload(ctx->blk_list, lists, st));
     }
     // reservoir-map tables of the single-stream fast path: R_in in [r_lo, r_lo + ntab)
-    int r_lo = -((max_nl + 1 + 31) / 32 * 32), r_hi = 640;
+    // [-128, 640): reservoirs below -128 are possible (down to -(largest band + 1)) but rare -- they take the complete
+    // walk like the ones above the table (profiles/r01z_chain_table_range.log)
+    int r_lo = -std::min(128, (max_nl + 1 + 31) / 32 * 32), r_hi = 640;
     if (const char* e = getenv("MRC_CHAIN_TABLE_LO")) r_lo = -std::max(32, (atoi(e) + 31) / 32 * 32);     // tuning knobs: any
     if (const char* e = getenv("MRC_CHAIN_TABLE_HI")) r_hi = std::max(32, (atoi(e) + 31) / 32 * 32);      // range is exact
     const int ntab = -r_lo + r_hi, tabw = (ntab + 2 + 3) / 4 * 4;

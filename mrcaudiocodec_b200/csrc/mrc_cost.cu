@@ -48,6 +48,10 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     __shared__ int s_joint;
     __shared__ int s_blo[MRC_BSTRIDE], s_bn[MRC_BSTRIDE];
     __shared__ unsigned long long s_esclen4;
+    // per allocation level (Rb = level + 2) and mantissa value: what the value costs under the four books (.x) and what
+    // is actually written (.y), one byte per book (<= 9 + 16 + 16) -- the inner loop below is one 8-byte load, four
+    // byte permutes and four adds per line
+    __shared__ uint2 s_lv[MRC_MAX_LEVELS][MRC_HUFF_LUT + 1];
 
     const size_t lb = cm.list ? (size_t)cm.list[blockIdx.x] : (size_t)blockIdx.x;
     const int g = g0 + (int)lb;
@@ -85,6 +89,19 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     }
     __syncthreads();
     const bool joint = s_joint != 0;
+    for (int q = tid; q < MRC_MAX_LEVELS * (MRC_HUFF_LUT + 1); q += CT) {
+        const int lvl = q / (MRC_HUFF_LUT + 1), m = q - lvl * (MRC_HUFF_LUT + 1), Rb = lvl + 2;
+        const LutEntry e = s_lut[m];
+        const unsigned long long rb4 = splat16((unsigned)Rb);
+        const unsigned long long c = e.key + (e.nk & (rb4 + s_esclen4));      // 16-bit fields, each < 256
+        const unsigned long long w = c + (e.esc & rb4);
+        auto pack8 = [](unsigned long long v) {
+            return (unsigned)(v & 0xff) | ((unsigned)((v >> 16) & 0xff) << 8) | ((unsigned)((v >> 32) & 0xff) << 16) |
+                   ((unsigned)((v >> 48) & 0xff) << 24);
+        };
+        s_lv[lvl][m] = make_uint2(pack8(c), pack8(w));
+    }
+    __syncthreads();
 
     // ---- phase 1: price every (band, level) ---------------------------------------------------------------
     for (int p = tid; p < npair; p += CT) {
@@ -92,20 +109,20 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
         const int ch = bb >= nb, bd = bb - ch * nb;
         const int Rb = lvl + 2;
         const int sf = scale_factor_of(s_bmax[ch * MRC_BSTRIDE + bd], cp.n_scale_bits, Rb);
-        const unsigned long long rb4 = splat16((unsigned)Rb);
-        const unsigned long long rbesc4 = rb4 + s_esclen4;                 // Rb + len(escape code), per book
         const double* x = s_lines + ch * L + s_blo[bd];
         const int n = s_bn[bd];
-        unsigned long long c4 = 0, w4 = 0;
+        const uint2* __restrict__ tabl = s_lv[lvl];
+        unsigned c01 = 0, c23 = 0, w01 = 0, w23 = 0;        // books 0|1 and 2|3 in 16-bit fields: sums < 363 * 41
         for (int i = 0; i < n; ++i) {
             const int m = mantissa_of(x[i], sf, cp.n_scale_bits, Rb);
-            const LutEntry e = s_lut[m < MRC_HUFF_LUT ? m : MRC_HUFF_LUT];
-            const unsigned long long c = e.key + (e.nk & rbesc4);
-            c4 += c;
-            w4 += c + (e.esc & rb4);
+            const uint2 e = tabl[m < MRC_HUFF_LUT ? m : MRC_HUFF_LUT];
+            c01 += __byte_perm(e.x, 0u, 0x4140);
+            c23 += __byte_perm(e.x, 0u, 0x4342);
+            w01 += __byte_perm(e.y, 0u, 0x4140);
+            w23 += __byte_perm(e.y, 0u, 0x4342);
         }
-        s_c4[p] = c4;
-        s_w4[p] = w4;
+        s_c4[p] = (unsigned long long)c01 | ((unsigned long long)c23 << 32);
+        s_w4[p] = (unsigned long long)w01 | ((unsigned long long)w23 << 32);
     }
     __syncthreads();
 

@@ -45,8 +45,7 @@ __device__ __forceinline__ int scale_factor_of(double ax, int nScaleBits, int nM
 __device__ __forceinline__ int mantissa_of(double x, int scale, int nScaleBits, int nMantBits) {
     const int cap = (1 << nScaleBits) - 1;
     const int nBits = cap + nMantBits;
-    int code = quant_mag_code(fabs(x), nBits);
-    if (x == 0.0) code = 0;
+    int code = quant_mag_code(fabs(x), nBits);      // x == 0 gives trunc(0.5) = 0 by itself
     if (scale != cap) code >>= (cap - scale);
     return code + ((x < 0.0) ? (1 << (nMantBits - 1)) : 0);
 }

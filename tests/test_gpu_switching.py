@@ -236,3 +236,24 @@ def test_cli_roundtrip_with_block_switching(tmp_path):
     od = driver.decode_pac(ob)
     assert sr == 48000 and dec.shape == od.shape
     assert np.abs(dec.astype(np.int64) - od.astype(np.int64)).max() <= 1
+
+
+def test_switched_stream_at_training_parameters():
+    """nScaleBits 3 / nMantSizeBits 5 / 2.27 bits per sample (huffman_training_script.py:39-42) with block switching,
+    at 44.1 kHz: other header widths, other budgets, other band tables for all four block geometries."""
+    from mrcaudiocodec_b200 import Codec, synth
+    from mrc_oracle import driver
+    pcm = synth.synth_percussive(51, 0.5, sample_rate=44100)
+    c = Codec(sample_rate=44100, n_scale_bits=3, n_mant_size_bits=5, target_bits_per_sample=2.27, joint=True,
+              block_switching=True)
+    try:
+        blob = c.encode_clips([pcm])[0]
+        blob_o, _, geom, _ = driver.encode_pcm_switched(pcm, sos=c.sos, sampleRate=44100, nScaleBits=3, nMantSizeBits=5,
+                                                        targetBitsPerSample=2.27)
+        assert any(b == 128 for _, b in geom)
+        assert blob == blob_o
+        dec = c.decode_clips([blob])[0]
+        ref = driver.decode_pac(blob_o)
+        assert dec.shape == ref.shape and np.abs(dec.astype(np.int64) - ref.astype(np.int64)).max() <= 1
+    finally:
+        c.close()
