@@ -218,12 +218,7 @@ __device__ __forceinline__ double spread_line_bound(const Smem<T>& sm, const Dev
     double a = tb.quiet_d[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
     const int nl = sm.lcnt[m_lo];
     const int j0 = nl > MRC_NEAR_LOUD ? nl - MRC_NEAR_LOUD : 0;
-    // the (at most MRC_NEAR_LOUD) terms are independent: evaluate them side by side, add them in the old order
-    double lt[MRC_NEAR_LOUD];
-#pragma unroll
-    for (int q = 0; q < MRC_NEAR_LOUD; ++q) lt[q] = (nl - 1 - q >= j0) ? loud_term(sm, zk, sm.lidx[nl - 1 - q]) : 0.0;
-#pragma unroll
-    for (int q = 0; q < MRC_NEAR_LOUD; ++q) a += lt[q];
+    for (int j = nl - 1; j >= j0; --j) a += loud_term(sm, zk, sm.lidx[j]);
     n_general += (unsigned)(nl - j0);
     const double w = (sm.mP[m_hi] - sm.mP[m_lo]) - 1.4210854715202004e-14 * sm.mP[npk];     // 2^-46 of the total
     return a + fmax(w, 0.0);
@@ -247,17 +242,7 @@ __device__ __forceinline__ double spread_line_warp(const Smem<T>& sm, const DevT
     MRC_WSYNC();
     MRC_WCLK(18);
     const int nl = sm.lcnt[m_lo];
-    {   // two maskers per lane and trip: their 10**x chains are independent and overlap
-        double a2 = 0.0;
-        int j = lane;
-        for (; j + 32 < nl; j += 64) {
-            const double t0 = loud_term(sm, zk, sm.lidx[j]), t1 = loud_term(sm, zk, sm.lidx[j + 32]);
-            a += t0;
-            a2 += t1;
-        }
-        if (j < nl) a += loud_term(sm, zk, sm.lidx[j]);
-        a += a2;
-    }
+    for (int j = lane; j < nl; j += 32) a += loud_term(sm, zk, sm.lidx[j]);
     MRC_WSYNC();
     MRC_WCLK(19);
     if (lane == 0) { n_general += (unsigned)nl; n_window += (unsigned)(m_hi - m_lo); }
