@@ -271,9 +271,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ unsigned int s_ms;
     __shared__ int s_wcnt[33];
     __shared__ double s_scan[5][32];
-    __shared__ T s_seg_smr[MRC_MAX_SEGS];
-    __shared__ T s_band_smr[MRC_BSTRIDE], s_band_rho[MRC_BSTRIDE];
-    __shared__ int s_band_k[MRC_BSTRIDE];
+    __shared__ T s_band_smr[MRC_BSTRIDE];
     __shared__ int s_npk;
 #ifdef MRC_PHASE_CLOCKS
     __shared__ long long s_clk_last;
@@ -651,11 +649,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             // threshold.  With both clamps of psychoac.py:12 folded in, a line's SMR is 10 log10(rho) - 6 scale,
             // rho = max(4 X^2, floor) / max(threshold intensity, floor): monotone in rho.
             //   pass 1 (thread per line): rho from a LOWER bound of the threshold = an upper bound of the line's rho;
-            //   pass 2a (warp per band): complete threshold (warp-cooperative) of the band's line with the highest
-            //           bound -> its true rho and SMR;
-            //   pass 2b (warp per segment of a band): every other line whose bound reaches the best true rho seen so
-            //           far (less 1e-9) gets its complete threshold too; lines whose bound stays below cannot be the
-            //           maximum.
+            //   pass 2 (warp per band): complete threshold (warp-cooperative) of the band's line with the highest
+            //           bound -> its true rho and SMR; then every other line of the band whose bound reaches the best
+            //           true rho seen so far (less 1e-9) gets its complete threshold too; lines whose bound stays
+            //           below cannot be the maximum.
             // The band SMR is the maximum of the completely evaluated lines' SMRs: exact.
             const double FLOOR = 2.5118864315095823e-13;        // 10^((-30-96)/10): where SPL() clamps
             auto x2c = [&](int k) -> double {
@@ -683,10 +680,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (lane == 0) atomicAdd(&g_phase_clk[22], 1ull);
 #endif
             };
-            // pass 2a, one warp per BAND that selects this spectrum (about half of them do, so one round of the
-            // CTA's warps usually covers them): the band's line with the highest bound gets its complete threshold;
-            // its true rho is the bar the other lines have to reach.  Bands are dealt out from the top: their lines
-            // see the most loud maskers and take longest.
+            // pass 2, one warp per BAND that selects this spectrum (about half of them do, so one round of the CTA's
+            // warps usually covers them; bands are dealt out from the top: their lines see the most loud maskers and
+            // take longest): the band's line with the highest bound gets its complete threshold; its true rho is the
+            // bar every other line of the band has to reach with its bound to be evaluated as well (rare: the bounds
+            // are tight, about one extra line per block).
             {
                 const unsigned bl = need & band_mask;
                 const int nbl = __popc(bl);
@@ -705,64 +703,33 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                         const int ok = __shfl_xor_sync(0xffffffffu, kbest, o);
                         if (ov > ubest || (ov == ubest && ok < kbest)) { ubest = ov; kbest = ok; }
                     }
-                    T smr, rho;
-                    complete(kbest, smr, rho);
-                    if (lane == 0) { s_band_smr[bd] = smr; s_band_rho[bd] = rho; s_band_k[bd] = kbest; }
+                    T best, rbest;
+                    complete(kbest, best, rbest);
+                    for (int base = 0; base < n; base += 32) {
+                        const int i = base + lane;
+                        const T ub = (i < n) ? sm.xi[lo + i] : T(-1);
+                        unsigned bal = __ballot_sync(0xffffffffu, i < n && lo + i != kbest && ub >= rbest * slack);
+                        while (bal) {
+                            const int l = __ffs(bal) - 1;
+                            bal &= bal - 1;
+                            const T ubl = __shfl_sync(0xffffffffu, ub, l);
+                            if (ubl >= rbest * slack) {          // rbest may have risen since the ballot
+                                T smr, rho;
+                                complete(lo + base + l, smr, rho);
+                                best = fmax(best, smr);
+                                rbest = fmax(rbest, rho);
+                            }
+                        }
+                    }
+                    if (lane == 0) s_band_smr[bd] = best;
                 }
             }
             __syncthreads();
             MRC_CLK(7);
-            // pass 2b, one warp per SEGMENT (<= MRC_SEG_LINES lines) of those bands, widest first (tb.c_seg_slot
-            // compacted with the band mask -- every warp does the same three ballots -- and dealt out round-robin):
-            // every other line whose bound reaches the band's bar gets its complete threshold too.
-            unsigned wl[3];
-            int wl_n[3];
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const int idx = ch * 32 + lane;
-                const int sgi = idx < tb.nslot ? tb.c_seg_slot[idx] : -1;
-                wl[ch] = __ballot_sync(0xffffffffu, sgi >= 0 && ((need >> tb.c_seg_band[sgi < 0 ? 0 : sgi]) & 1u));
-                wl_n[ch] = __popc(wl[ch]);
-            }
-            const int wl_total = wl_n[0] + wl_n[1] + wl_n[2];
-            auto wl_get = [&](int j) -> int {                    // j-th needed segment
-                int ch = 0;
-                if (j >= wl_n[0]) { j -= wl_n[0]; ch = 1; if (j >= wl_n[1]) { j -= wl_n[1]; ch = 2; } }
-                const unsigned m = ch == 0 ? wl[0] : (ch == 1 ? wl[1] : wl[2]);
-                return tb.c_seg_slot[ch * 32 + (int)__fns(m, 0, j + 1)];
-            };
-            for (int p = warp; p < wl_total; p += nwarp) {
-                const int sg = wl_get(p);
-                const int lo = tb.c_seg_lo[sg], n = tb.c_seg_n[sg], bd = tb.c_seg_band[sg];
-                T rbest = s_band_rho[bd];                        // best true rho of the band so far
-                T best = -INFINITY;
-                const int kdone = s_band_k[bd];
-                for (int base = 0; base < n; base += 32) {
-                    const int i = base + lane;
-                    const T ub = (i < n) ? sm.xi[lo + i] : T(-1);
-                    unsigned bal = __ballot_sync(0xffffffffu, i < n && lo + i != kdone && ub >= rbest * slack);
-                    while (bal) {
-                        const int l = __ffs(bal) - 1;
-                        bal &= bal - 1;
-                        const T ubl = __shfl_sync(0xffffffffu, ub, l);
-                        if (ubl >= rbest * slack) {              // rbest may have risen since the ballot
-                            T smr, rho;
-                            complete(lo + base + l, smr, rho);
-                            best = fmax(best, smr);
-                            rbest = fmax(rbest, rho);
-                        }
-                    }
-                }
-                if (lane == 0) s_seg_smr[sg] = best;
-            }
-            __syncthreads();
             MRC_CLK(8);
             if (tid < nb) {
                 T v = T(0);                              // bands that do not select this spectrum: value never used
-                if ((need >> tid) & 1u) {
-                    v = s_band_smr[tid];
-                    for (int s2 = tb.c_band_seg0[tid]; s2 < tb.c_band_seg0[tid + 1]; ++s2) v = fmax(v, s_seg_smr[s2]);
-                }
+                if ((need >> tid) & 1u) v = s_band_smr[tid];
                 s_smr[c][tid] = v;
             }
         }
