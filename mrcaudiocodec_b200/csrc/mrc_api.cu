@@ -29,11 +29,9 @@ struct TablesDev {
 // blocks of block switching once mrc_set_switch_tables has been called.
 struct GeoDev {
     bool set = false;
-    int a = 0, b = 0, L = 0, nb = 0, nseg = 0;
+    int a = 0, b = 0, L = 0, nb = 0;
     TablesDev td, tf;                 // double and float copies
-    Buf band_lo, band_n, line2band, seg_lo, seg_n, seg_band, band_seg0, seg_slot;
-    int nslot = 0;
-    std::vector<int> h_seg_lo, h_seg_n, h_seg_band, h_seg_slot, h_band_seg0;
+    Buf band_lo, band_n, line2band;
     DevTables<double> tbd;
     DevTables<float> tbf;
     CodecParams cp;
@@ -188,24 +186,12 @@ cudaError_t upload_tables(mrc_ctx* c, GeoDev& g, TablesDev& d, DevTables<T>& tb,
     tb.bark = (const T*)d.bark.p; tb.quiet = (const T*)d.quiet.p;
     tb.band_lo = (const int*)g.band_lo.p; tb.band_n = (const int*)g.band_n.p;
     tb.line2band = (const uint8_t*)g.line2band.p;
-    tb.nseg = g.nseg;
-    tb.seg_lo = (const int*)g.seg_lo.p; tb.seg_n = (const int*)g.seg_n.p;
-    tb.seg_band = (const int*)g.seg_band.p; tb.band_seg0 = (const int*)g.band_seg0.p;
-    tb.nslot = g.nslot; tb.seg_slot = (const int*)g.seg_slot.p;
     memset(tb.c_band_lo, 0, sizeof tb.c_band_lo); memset(tb.c_band_n, 0, sizeof tb.c_band_n);
-    memset(tb.c_seg_lo, 0, sizeof tb.c_seg_lo); memset(tb.c_seg_n, 0, sizeof tb.c_seg_n);
-    memset(tb.c_seg_band, 0, sizeof tb.c_seg_band); memset(tb.c_seg_slot, 0, sizeof tb.c_seg_slot);
-    memset(tb.c_band_seg0, 0, sizeof tb.c_band_seg0);
     for (int b = 0; b < g.nb; ++b) { tb.c_band_lo[b] = (uint16_t)g.h_band_lo[b]; tb.c_band_n[b] = (uint16_t)g.h_band_n[b]; }
-    for (int i = 0; i < g.nseg; ++i) {
-        tb.c_seg_lo[i] = (uint16_t)g.h_seg_lo[i]; tb.c_seg_n[i] = (uint8_t)g.h_seg_n[i];
-        tb.c_seg_band[i] = (uint8_t)g.h_seg_band[i]; tb.c_seg_slot[i] = (uint8_t)g.h_seg_slot[i];
-    }
-    for (int b = 0; b <= g.nb; ++b) tb.c_band_seg0[b] = (uint8_t)g.h_band_seg0[b];
     return cudaSuccess;
 }
 
-// band table of one geometry: lines per band, line -> band, segments of the band-maximum search
+// band table of one geometry: lines per band, line -> band
 int set_geo_bands(mrc_ctx* ctx, GeoDev& g, const int32_t* band_nlines, int n_bands) {
     if (n_bands < 1 || n_bands > MRC_CODED_BANDS)
         return fail(ctx, MRC_E_INVALID, "n_bands out of range (1..25: the reference's tables have 25 or 9 bands)");
@@ -227,35 +213,6 @@ int set_geo_bands(mrc_ctx* ctx, GeoDev& g, const int32_t* band_nlines, int n_ban
     CK(upload(g.band_lo, g.h_band_lo, ctx->stream));
     CK(upload(g.band_n, g.h_band_n, ctx->stream));
     CK(upload(g.line2band, l2b, ctx->stream));
-    // segments of at most MRC_SEG_LINES lines, never straddling a band
-    std::vector<int> slo, sn, sb, b0(n_bands + 1, 0);
-    for (int b = 0; b < n_bands; ++b) {
-        b0[b] = (int)slo.size();
-        const int n = g.h_band_n[b], parts = (n + MRC_SEG_LINES - 1) / MRC_SEG_LINES;
-        for (int q = 0; q < parts; ++q) {
-            const int a0 = (int)((long long)n * q / parts), a1 = (int)((long long)n * (q + 1) / parts);
-            slo.push_back(g.h_band_lo[b] + a0); sn.push_back(a1 - a0); sb.push_back(b);
-        }
-    }
-    b0[n_bands] = (int)slo.size();
-    if ((int)slo.size() > MRC_MAX_SEGS) return fail(ctx, MRC_E_INVALID, "too many band segments");
-    g.nseg = (int)slo.size();
-    CK(upload(g.seg_lo, slo, ctx->stream));
-    CK(upload(g.seg_n, sn, ctx->stream));
-    CK(upload(g.seg_band, sb, ctx->stream));
-    CK(upload(g.band_seg0, b0, ctx->stream));
-    // Work list of the band-maximum search: the segments widest first.  A spectrum only evaluates the segments of the
-    // bands that select it; the kernel compacts this list with the spectrum's band mask and deals it out to its warps.
-    {
-        const int ns = (int)slo.size();
-        std::vector<int> order(ns);
-        for (int i = 0; i < ns; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sn[x] > sn[y]; });
-        g.nslot = ns;
-        CK(upload(g.seg_slot, order, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        g.h_seg_lo = slo; g.h_seg_n = sn; g.h_seg_band = sb; g.h_seg_slot = order; g.h_band_seg0 = b0;
-    }
     CK(cudaStreamSynchronize(ctx->stream));
     return MRC_OK;
 }
@@ -907,7 +864,7 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
                          &d->bark_d, &d->quiet_d, &d->exp_tab};
             for (Buf* b : tb) release(*b);
         }
-        Buf* gb[] = {&g.band_lo, &g.band_n, &g.line2band, &g.seg_lo, &g.seg_n, &g.seg_band, &g.band_seg0, &g.seg_slot};
+        Buf* gb[] = {&g.band_lo, &g.band_n, &g.line2band};
         for (Buf* b : gb) release(*b);
     }
     Buf* all[] = {&ctx->huff, &ctx->header, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,

@@ -23,8 +23,6 @@
 #define MRC_TOK_STRIDE 768      // >= 2*25*15 grant tokens per block
 #define MRC_MAX_LEVELS 15       // grants per band: 0->2, then +1 up to 16 bits
 #define MRC_BSTRIDE 32          // band stride in per-band arrays
-#define MRC_SEG_LINES 96       // 25 critical bands at 48 kHz / 1024 lines -> 30 segments: two per warp of the analysis CTA
-#define MRC_MAX_SEGS 96        // >= nb + L / MRC_SEG_LINES for L <= 2048 ... 4096
 #define MRC_CODED_BANDS 25      // most bands per channel the grant-token machinery holds (25 * 15 <= MRC_GROUP_SLOTS)
 
 // ---- per-block record the cost kernel hands to the chain kernel (one TMA bulk copy per block) ---------------
@@ -92,21 +90,9 @@ struct DevTables {
     const int* band_lo;                          // [nb]
     const int* band_n;                           // [nb]
     const uint8_t* line2band;                    // [L]
-    // bands cut into segments of <= MRC_SEG_LINES lines: the work items of the band-maximum search
-    int nseg;
-    const int* seg_lo;                           // [nseg] first line
-    const int* seg_n;                            // [nseg] lines
-    const int* seg_band;                         // [nseg]
-    const int* band_seg0;                        // [nb+1] first segment of each band
-    // the segments widest first: the work list the kernel compacts per spectrum and deals out to its warps
-    int nslot;                                   // = nseg
-    const int* seg_slot;                         // [nslot]
-    // the same small tables by value (kernel parameters live in the constant bank: a warp-uniform lookup costs a few
-    // cycles instead of a dependent trip to L2) -- used by the analysis kernel's per-band and per-segment loops
+    // the band table by value as well (kernel parameters live in the constant bank: a warp-uniform lookup costs a few
+    // cycles instead of a dependent trip to L2) -- used by the analysis kernel's per-band loops
     uint16_t c_band_lo[MRC_BSTRIDE], c_band_n[MRC_BSTRIDE];
-    uint16_t c_seg_lo[MRC_MAX_SEGS];
-    uint8_t c_seg_n[MRC_MAX_SEGS], c_seg_band[MRC_MAX_SEGS], c_seg_slot[MRC_MAX_SEGS];
-    uint8_t c_band_seg0[MRC_BSTRIDE + 4];
 };
 
 struct HuffDev {
