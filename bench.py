@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 SR = 48000
 TBPS = 128000.0 / 48000.0
 METRIC = "encoded audio-seconds/sec, 48 kHz stereo 128 kb/s/ch"
-NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK = 12616.0      # (23.46 + 47.52) MB / 5626 blocks, profiles/r01z_ncu_full_summary.csv
+NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK = 12489.0      # (23.42 + 46.84) MB / 5626 blocks, profiles/r01zz_ncu_full_summary.csv
 
 
 def parse():
@@ -310,7 +310,7 @@ def main():
                          "bound": "fp64" if is64 else "fp32", "achieved": ach_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
                          # dram__bytes_read + dram__bytes_write of one analysis launch, from the committed ncu capture
-                         # (profiles/r01z_ncu_full_summary.csv: 71.0 MB for 5626 blocks), scaled to this run's launch size
+                         # (profiles/r01zz_ncu_full_summary.csv: 70.3 MB for 5626 blocks), scaled to this run's launch size
                          "traffic": NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK * nblk / max(r_dev["work"]["waves"], 1),
                          "peak_source": "mrc_measure_peaks (FMA chain on this GPU, this run)",
                          "work": "SURVEY 8d reference formulation (40 FLOP per masker-line pair), %d maskers measured; "
