@@ -25,6 +25,11 @@ struct BitReader {
         const unsigned long long x = ((unsigned long long)w[i] << 32) | w[i + 1];
         return (uint32_t)((x << off) >> (64 - n));
     }
+    __device__ __forceinline__ uint32_t peek_at(int at, int n) const {     // n in 1..32 bits starting at bit `at`
+        const int i = at >> 5, off = at & 31;
+        const unsigned long long x = ((unsigned long long)w[i] << 32) | w[i + 1];
+        return (uint32_t)((x << off) >> (64 - n));
+    }
     __device__ __forceinline__ uint32_t read(int n) {
         if (n <= 0) return 0;
         if (pos + n > nbits) { bad = true; pos = nbits; return 0; }
@@ -144,6 +149,7 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
     __shared__ int s_bad, s_joint;
     __shared__ int s_esc[MRC_N_HUFF_TABLES];
     __shared__ int s_boff[2 * MRC_BSTRIDE], s_raw[2];
+    __shared__ uint16_t s_hlut[MRC_N_HUFF_TABLES][1 << MRC_HUFF_PEEK];     // the 9-bit decode tables (4 KB)
 
     const int lp = dm.list ? dm.list[blockIdx.x] : (int)blockIdx.x, p = p0 + lp;
     if (tid == 0) {
@@ -158,6 +164,8 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
         s_bad = 0;
     }
     if (tid < MRC_N_HUFF_TABLES) s_esc[tid] = huff->esc[tid];
+    for (int i = tid; i < (MRC_N_HUFF_TABLES << MRC_HUFF_PEEK) / 2; i += NT)
+        reinterpret_cast<uint32_t*>(&s_hlut[0][0])[i] = reinterpret_cast<const uint32_t*>(&hdec->lut[0][0])[i];
     // stage both chunk payloads as big-endian words
     for (int ch = 0; ch < 2; ++ch) {
         const uint8_t* src = pac + dm.chunk_pos[2 * p + ch];
@@ -176,9 +184,13 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
     __syncthreads();
     const bool joint = s_joint != 0;
 
-    // ---- bit-serial parse, one thread per channel chunk (threads 0 and 32) ------------------------------
-    if ((tid == 0 || tid == 32)) {
-        const int ch = tid >> 5;
+    // ---- parse: warp 0 takes channel 0's chunk, warp 1 channel 1's.  The header fields are read by all lanes alike
+    // (same words, broadcast); Huffman-coded mantissas are decoded 32 bit positions at a time: every lane decodes the
+    // code that WOULD start at its bit, the lanes that really are code starts are found by pointer doubling along
+    // "next start" (five steps), and their symbols land at their rank.  A window yields 32 bits' worth of symbols
+    // (8..16 with the trained books) for the price of a handful of serial ones.
+    if (tid < 64) {
+        const int ch = tid >> 5, lane = tid & 31;
         BitReader br;
         br.w = sm.cw + ch * cwords;
         br.pos = 0;
@@ -190,45 +202,73 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
         if (table != MRC_NO_TABLE && table >= MRC_N_HUFF_TABLES) br.bad = true;
         if (joint) {
             if (ch == 0) {
-                for (int i = 0; i < 4; ++i) s_ovs[i] = (int)br.read(cp.n_scale_bits);
+                for (int i = 0; i < 4; ++i) { const int v = (int)br.read(cp.n_scale_bits); if (lane == 0) s_ovs[i] = v; }
                 unsigned ms = 0;
                 for (int bd = 0; bd < nb; ++bd) ms |= br.read(1) << bd;
-                s_ms = ms;
+                if (lane == 0) s_ms = ms;
             }
         } else {
-            s_ovs[ch] = (int)br.read(cp.n_scale_bits);
+            const int v = (int)br.read(cp.n_scale_bits);
+            if (lane == 0) s_ovs[ch] = v;
         }
         int* mant = sm.mant + ch * L;
         for (int bd = 0; bd < nb && !br.bad; ++bd) {
             int ba = (int)br.read(cp.n_mant_size_bits);
             if (ba) ba += 1;
-            s_alloc[ch * MRC_BSTRIDE + bd] = ba;
-            s_sf[ch * MRC_BSTRIDE + bd] = (int)br.read(cp.n_scale_bits);
+            const int sfv = (int)br.read(cp.n_scale_bits);
+            if (lane == 0) { s_alloc[ch * MRC_BSTRIDE + bd] = ba; s_sf[ch * MRC_BSTRIDE + bd] = sfv; }
             if (!ba) continue;
             const int lo = tb.band_lo[bd], n = tb.band_n[bd];
             if (table == MRC_NO_TABLE) {
                 // raw mantissas: fixed width, so only their position is recorded here; all threads extract them below
-                s_boff[ch * MRC_BSTRIDE + bd] = br.pos;
+                if (lane == 0) s_boff[ch * MRC_BSTRIDE + bd] = br.pos;
                 if (br.pos + n * ba > br.nbits) { br.bad = true; break; }
                 br.pos += n * ba;
             } else {
-                const uint16_t* lut = hdec->lut[table];
+                const uint16_t* lut = s_hlut[table];
                 const int esc = s_esc[table];
-                for (int j = 0; j < n && !br.bad; ++j) {
-                    const int rem = br.nbits - br.pos;
-                    if (rem <= 0) { br.bad = true; break; }
-                    const uint32_t e = lut[br.peek(MRC_HUFF_PEEK)];
-                    const int len = e >> 8, val = e & 0xff;
-                    if (len == 0 || len > rem) { br.bad = true; break; }
-                    br.pos += len;
-                    mant[lo + j] = (val == esc) ? (int)br.read(ba) : val;
+                int done = 0;
+                while (done < n) {
+                    const int pi = br.pos + lane;
+                    int tot = 0, val = 0, len = 0;
+                    bool ok = false;
+                    if (pi < br.nbits) {
+                        const uint32_t e = lut[br.peek_at(pi, MRC_HUFF_PEEK)];
+                        len = e >> 8; val = e & 0xff;
+                        if (len != 0 && pi + len <= br.nbits) {
+                            tot = len;
+                            ok = true;
+                            if (val == esc) {                    // escape code + ba raw bits
+                                if (pi + len + ba <= br.nbits) tot = len + ba; else ok = false;
+                            }
+                        }
+                    }
+                    int J = ok ? min(lane + tot, 32) : 32;       // where the next code starts; 32 = past this window
+                    unsigned R = 1u;                             // lanes that are code starts: the chain from lane 0
+#pragma unroll
+                    for (int st = 0; st < 5; ++st) {
+                        const bool on = (R >> lane) & 1u;
+                        R |= __reduce_or_sync(0xffffffffu, (on && J < 32) ? (1u << J) : 0u);
+                        const int Jn = __shfl_sync(0xffffffffu, J, J & 31);
+                        J = (J < 32) ? Jn : 32;
+                    }
+                    const bool on = (R >> lane) & 1u;
+                    const int rank = __popc(R & ((1u << lane) - 1u));
+                    const int want = n - done, cnt = min(__popc(R), want);
+                    if (__ballot_sync(0xffffffffu, on && rank < want && !ok)) { br.bad = true; break; }
+                    if (on && rank < want) mant[lo + done + rank] = (val == esc) ? (int)br.peek_at(pi + len, ba) : val;
+                    const unsigned lastm = __ballot_sync(0xffffffffu, on && rank == cnt - 1);
+                    br.pos = __shfl_sync(0xffffffffu, pi + tot, __ffs(lastm) - 1);
+                    done += cnt;
                 }
             }
         }
-        s_raw[ch] = (table == MRC_NO_TABLE);
-        if (br.bad) {
-            s_bad = 1;
-            for (int bd = 0; bd < nb; ++bd) s_alloc[ch * MRC_BSTRIDE + bd] = 0;
+        if (lane == 0) {
+            s_raw[ch] = (table == MRC_NO_TABLE);
+            if (br.bad) {
+                s_bad = 1;
+                for (int bd = 0; bd < nb; ++bd) s_alloc[ch * MRC_BSTRIDE + bd] = 0;
+            }
         }
     }
     __syncthreads();
