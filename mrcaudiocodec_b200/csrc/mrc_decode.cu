@@ -98,6 +98,10 @@ __device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecPa
         const int grp = tid / (NT / 2), lt = tid - grp * (NT / 2), gthr = NT / 2;
         const T* X = sm.lines + grp * L;
         cpx<T>* a = sm.buf + grp * Q;
+        // FFT twiddles staged in `v` (written only after the transform): three twiddle loads per butterfly and stage
+        // from shared memory instead of through L1
+        cpx<T>* const tws = reinterpret_cast<cpx<T>*>(sm.v);
+        for (int i = tid; i < (1 << (tb.logLtab - 1)); i += NT) tws[i] = tb.tw_fft[i];
         for (int n = lt; n < Q; n += gthr) {
             const T re = X[2 * n], im = X[L - 1 - 2 * n];
             const cpx<T> w = tb.tw_pre[n];
@@ -106,7 +110,7 @@ __device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecPa
             a[r].y = re * w.y + im * w.x;
         }
         __syncthreads();
-        fft_any<T, Q>(a, lt, gthr, tb.tw_fft, tb.logLtab, tb.tw9, L, tb.w9);
+        fft_any<T, Q>(a, lt, gthr, tws, tb.logLtab, tb.tw9, L, tb.w9);
         T* v = sm.v + grp * L;
         for (int k = lt; k < Q; k += gthr) {
             const cpx<T> w = tb.tw_post[k];
