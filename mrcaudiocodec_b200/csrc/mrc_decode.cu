@@ -222,7 +222,7 @@ decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff,
             const int sfv = (int)br.read(cp.n_scale_bits);
             if (lane == 0) { s_alloc[ch * MRC_BSTRIDE + bd] = ba; s_sf[ch * MRC_BSTRIDE + bd] = sfv; }
             if (!ba) continue;
-            const int lo = tb.band_lo[bd], n = tb.band_n[bd];
+            const int lo = tb.c_band_lo[bd], n = tb.c_band_n[bd];
             if (table == MRC_NO_TABLE) {
                 // raw mantissas: fixed width, so only their position is recorded here; all threads extract them below
                 if (lane == 0) s_boff[ch * MRC_BSTRIDE + bd] = br.pos;
