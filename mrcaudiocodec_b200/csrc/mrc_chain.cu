@@ -301,17 +301,19 @@ table_kernel(CodecParams cp, ClipMap cm, int g0, int /*min_nl*/, ChainIO io, int
             continue;
         }
         const int k0 = grp * MRC_GROUP_CHUNKS;
-        // first chunk the smallest budget cannot fully pay
-        const int b0min = K + r_lo;
-        int klo = nck - 1;
-        for (int k = nck - 1; k >= 0; --k)
-            if (s_mx[k0 + k] > b0min) klo = k;
-        const int j0 = (k0 + klo) * 32, jend = (k0 + nck) * 32;
-        const unsigned sp0 = cpre[j0];
-        const uint4 pc0 = pc[j0];
+        const int jend = (k0 + nck) * 32;
         for (int base = 0; base < ntab; base += TAB_THREADS) {
             const int idx = base + tid;
             const int B0 = K + r_lo + idx;
+            // first chunk the smallest budget of this warp (lane 0's) cannot fully pay: everything before it is granted
+            // for all 32 budgets, and the prefix sums at its start stand for that
+            const int b0min = __shfl_sync(0xffffffffu, B0, 0);
+            int klo = nck - 1;
+            for (int k = nck - 1; k >= 0; --k)
+                if (s_mx[k0 + k] > b0min) klo = k;
+            const int j0 = (k0 + klo) * 32;
+            const unsigned sp0 = cpre[j0];
+            const uint4 pc0 = pc[j0];
             GroupTotals gt;
             gt.spent = sp0; gt.cost = pc0; gt.wbits = make_uint4(0u, 0u, 0u, 0u);
             int rem = B0 - (int)((sp0 & 0xffffu) + (sp0 >> 16));
