@@ -373,7 +373,7 @@ cudaEvent_t pool_event(mrc_ctx* ctx, size_t i) {
 // offset per clip from wave to wave).  Stream `stream2` runs analysis + cost of wave w+1 while `stream` runs the
 // chain walk, the clip-offset scan and quantise+pack of wave w.
 template <typename T>
-int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
+int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     const int L = ctx->L, nc = job.n_clips;
     // taps of a per-block-seam job are sized by that block's geometry
     const int nb = ctx->geo[job.geom].nb, Lt = ctx->geo[job.geom].L;
@@ -439,13 +439,13 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
     // geometries in play, their launch parameters, and (block switching) the per-wave block lists of each
     const int q_lo = job.switching ? 0 : job.geom, q_hi = job.switching ? MRC_N_GEO - 1 : job.geom;
     CodecParams cpq[MRC_N_GEO];
-    int min_nl = 0x7fffffff, max_nl = 0;
+    int max_nl = 0;
     for (int q = q_lo; q <= q_hi; ++q) {
         cpq[q] = ctx->geo[q].cp;
         cpq[q].joint = job.joint;
         cpq[q].flush_nonjoint = job.flush_nonjoint ? 1 : 0;
         cpq[q].no_huff = job.no_huff;
-        for (int v : ctx->geo[q].h_band_n) { min_nl = std::min(min_nl, v); max_nl = std::max(max_nl, v); }
+        for (int v : ctx->geo[q].h_band_n) max_nl = std::max(max_nl, v);
     }
     const CodecParams& cp = cpq[q_lo];     // for the kernels that read only geometry-independent fields
     const int nwaves = (nblk_total + WAVE_BLOCKS - 1) / WAVE_BLOCKS;
@@ -610,7 +610,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         const bool use_tab = job.need_quant && !ctx->no_tables && nblk / (c_hi - c_lo + 1) >= ctx->tab_min_blocks;
         if (use_tab) {
             CK(ensure(ctx->sets[s].tab, W * 2 * (size_t)tabw * 4));
-            launch_table(st2, cp, cm, g0, nblk, min_nl, io[s], r_lo, ntab, tabw, (int*)ctx->sets[s].tab.p);
+            launch_table(st2, cp, cm, g0, nblk, io[s], r_lo, ntab, tabw, (int*)ctx->sets[s].tab.p);
             ++launches;
         }
         CK(cudaEventRecord(ev(w, 2), st2));
@@ -619,17 +619,17 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job, DevTables<T>& tb) {
         CK(cudaEventRecord(ev(w, 3), st));
         if (job.need_quant) {
             if (use_tab)
-                launch_chain_table(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, min_nl, io[s], r_lo, ntab, tabw,
+                launch_chain_table(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, io[s], r_lo, ntab, tabw,
                                    (const int*)ctx->sets[s].tab.p, d_res_in, d_res_out,
                                    (unsigned long long*)ctx->peakctr.p + 4);
             else
-                launch_chain(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, min_nl, io[s], d_res_in, d_res_out,
+                launch_chain(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, io[s], d_res_in, d_res_out,
                              (unsigned long long*)ctx->peakctr.p + 4);
             ++launches;
         }
         CK(cudaEventRecord(ev(w, 4), st));
         if (job.need_quant) {
-            launch_finish(st, cp, cm, g0, nblk, min_nl, io[s]);
+            launch_finish(st, cp, cm, g0, nblk, io[s]);
             launch_offsets(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, io[s]);
             launches += 2;
         }
@@ -761,8 +761,8 @@ int run_encode(mrc_ctx* ctx, const EncodeJob& job) {
         return fail(ctx, MRC_E_STATE, "block switching needs mrc_set_switch_tables");
     if (job.switching && !job.joint)
         return fail(ctx, MRC_E_INVALID, "block switching follows the reference's loop, which is the joint flow: create the context with joint = 1");
-    if (ctx->cfg.precision == MRC_PRECISION_FP32) return run_encode_t<float>(ctx, job, ctx->tbf);
-    return run_encode_t<double>(ctx, job, ctx->tbd);
+    if (ctx->cfg.precision == MRC_PRECISION_FP32) return run_encode_t<float>(ctx, job);
+    return run_encode_t<double>(ctx, job);
 }
 
 int64_t worst_case_bytes(const mrc_ctx* ctx, const int64_t* off, int nc) {

@@ -184,7 +184,7 @@ __device__ __forceinline__ int reservoir_after(const GroupTotals& g, int B0, int
 }
 
 __global__ void __launch_bounds__(32)
-chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int /*min_nl: per block, from the record*/, ChainIO io,
+chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, ChainIO io,
              const int32_t* __restrict__ reservoir_in, int32_t* __restrict__ reservoir_out,
              unsigned long long* __restrict__ iter_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -260,7 +260,7 @@ chain_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int /*mi
 constexpr int TAB_THREADS = 256;
 
 __global__ void __launch_bounds__(TAB_THREADS)
-table_kernel(CodecParams cp, ClipMap cm, int g0, int /*min_nl*/, ChainIO io, int r_lo, int ntab, int tabw, int* __restrict__ tab) {
+table_kernel(CodecParams cp, ClipMap cm, int g0, ChainIO io, int r_lo, int ntab, int tabw, int* __restrict__ tab) {
     __shared__ uint32_t s_tn[MRC_NSLOT];
     __shared__ uint32_t s_dsp[MRC_NSLOT];
     __shared__ uint4 s_dpc[MRC_NSLOT];
@@ -350,7 +350,7 @@ table_kernel(CodecParams cp, ClipMap cm, int g0, int /*min_nl*/, ChainIO io, int
 constexpr int TAB_STAGES = 6;
 
 __global__ void __launch_bounds__(32)
-chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int /*min_nl: per block, from the record*/, ChainIO io, int r_lo,
+chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, ChainIO io, int r_lo,
                    int ntab, int tabw, const int* __restrict__ tab, const int32_t* __restrict__ reservoir_in,
                    int32_t* __restrict__ reservoir_out, unsigned long long* __restrict__ iter_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -421,7 +421,7 @@ chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, in
 constexpr int FIN_WARPS = 8;
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
-finish_kernel(CodecParams cp, ClipMap cm, int g0, int nblk, int /*min_nl*/, ChainIO io) {
+finish_kernel(CodecParams cp, ClipMap cm, int g0, int nblk, ChainIO io) {
     const int lane = threadIdx.x & 31;
     const int lb = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
     if (lb >= nblk) return;
@@ -512,19 +512,18 @@ offsets_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, ChainI
 }  // namespace
 
 void launch_chain(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
-                  int min_nlines, ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out,
+                  ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out,
                   unsigned long long* iter_counter) {
     if (nclips <= 0 || nblk <= 0) return;
     const size_t smem = (size_t)MRC_CHAIN_STAGES * MRC_REC_BYTES;
     cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    chain_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, min_nlines, io, reservoir_in, reservoir_out,
+    chain_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, io, reservoir_in, reservoir_out,
                                            iter_counter);
 }
 
-void launch_finish(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int min_nlines,
-                   ChainIO io) {
+void launch_finish(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, ChainIO io) {
     if (nblk <= 0) return;
-    finish_kernel<<<(nblk + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, st>>>(cp, cm, g0, nblk, min_nlines, io);
+    finish_kernel<<<(nblk + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, st>>>(cp, cm, g0, nblk, io);
 }
 
 void launch_offsets(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
@@ -533,18 +532,18 @@ void launch_offsets(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, i
     offsets_kernel<<<nclips, 32, 0, st>>>(cp, cm, c0, g0, nblk, io);
 }
 
-void launch_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int min_nlines,
+void launch_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk,
                   ChainIO io, int r_lo, int ntab, int tabw, int* tab) {
     if (nblk <= 0) return;
-    table_kernel<<<nblk, TAB_THREADS, 0, st>>>(cp, cm, g0, min_nlines, io, r_lo, ntab, tabw, tab);
+    table_kernel<<<nblk, TAB_THREADS, 0, st>>>(cp, cm, g0, io, r_lo, ntab, tabw, tab);
 }
 
 void launch_chain_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0,
-                        int nblk, int min_nlines, ChainIO io, int r_lo, int ntab, int tabw, const int* tab,
+                        int nblk, ChainIO io, int r_lo, int ntab, int tabw, const int* tab,
                         const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter) {
     if (nclips <= 0 || nblk <= 0) return;
     const size_t smem = (size_t)TAB_STAGES * ((size_t)2 * tabw * 4 + MRC_REC_BYTES);
     cudaFuncSetAttribute(chain_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    chain_table_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, min_nlines, io, r_lo, ntab, tabw, tab,
+    chain_table_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, io, r_lo, ntab, tabw, tab,
                                                  reservoir_in, reservoir_out, iter_counter);
 }

@@ -176,17 +176,17 @@ void launch_cost(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp,
 // serial: one warp per clip c0 .. c0+nclips-1 walks the clip's blocks that lie in [g0, g0+nblk) and records the
 // reservoir each block starts with
 void launch_chain(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
-                  int min_nlines, ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out,
+                  ChainIO io, const int32_t* reservoir_in, int32_t* reservoir_out,
                   unsigned long long* iter_counter);
 // single-stream fast path: tabulate every block's reservoir map for R_in in [r_lo, r_lo+ntab) (parallel), then walk
 // the tables (serial); tab is [nblk][2][tabw] ints, tabw >= ntab + 2 and even
-void launch_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int min_nlines,
+void launch_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk,
                   ChainIO io, int r_lo, int ntab, int tabw, int* tab);
 void launch_chain_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0,
-                        int nblk, int min_nlines, ChainIO io, int r_lo, int ntab, int tabw, const int* tab,
+                        int nblk, ChainIO io, int r_lo, int ntab, int tabw, const int* tab,
                         const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter);
 // parallel: one warp per block replays the block from its recorded reservoir: grant masks, table ids, chunk sizes
-void launch_finish(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int min_nlines,
+void launch_finish(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk,
                    ChainIO io);
 // parallel: one warp per clip turns the chunk sizes into byte offsets inside the clip's .pac
 void launch_offsets(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
