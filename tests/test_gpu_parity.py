@@ -309,3 +309,42 @@ def test_cli_wav_roundtrip(tmp_path):
     od = o.driver.decode_pac(ob, joint=True)
     assert sr == 44100 and dec.shape == od.shape
     assert np.abs(dec.astype(np.int64) - od.astype(np.int64)).max() <= 1
+
+
+def test_buffer_too_small_reports_sizes(codecs):
+    """C ABI error behaviour (include/mrc.h): an output buffer that is too small gives MRC_E_NOSPACE, never a write
+    past the buffer, and the offsets array holds the sizes needed; the retry with that size gives the same bytes.
+    The clips span several waves so that the wave-by-wave copies to the host are exercised with a tiny capacity."""
+    import ctypes as C
+    from mrcaudiocodec_b200 import _lib, synth
+    c = codecs()
+    clips = [synth.synth_clip(60 + i, 40.0, fast=True) for i in range(12)]     # 12 x 1876 blocks: two waves
+    pcm, off = c._concat(clips)
+    ref_out, ref_off = c.encode_batch(pcm, off)
+    total = int(ref_off[-1])
+    for cap in (0, 1000, total // 3, total - 1):
+        guard = np.full(cap + 64, 0xA5, np.uint8)
+        boff = np.zeros(len(clips) + 1, np.int64)
+        rc = c.lib.mrc_encode_batch(c._ctx, pcm.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(clips),
+                                    guard.ctypes.data_as(C.c_void_p), cap, boff.ctypes.data_as(C.c_void_p))
+        assert rc == _lib.MRC_E_NOSPACE
+        assert np.array_equal(boff, ref_off)
+        assert np.all(guard[cap:] == 0xA5), "wrote past the caller's capacity"
+    out = np.empty(total, np.uint8)
+    boff = np.zeros(len(clips) + 1, np.int64)
+    rc = c.lib.mrc_encode_batch(c._ctx, pcm.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(clips),
+                                out.ctypes.data_as(C.c_void_p), total, boff.ctypes.data_as(C.c_void_p))
+    assert rc == 0 and np.array_equal(out, ref_out[:total])
+    # decode side: too few frames
+    foff = np.zeros(len(clips) + 1, np.int64)
+    small = np.full((1000 + 16, 2), 0x5A5A, np.int16)
+    rc = c.lib.mrc_decode_batch(c._ctx, out.ctypes.data_as(C.c_void_p), boff.ctypes.data_as(C.c_void_p), len(clips),
+                                small.ctypes.data_as(C.c_void_p), 1000, foff.ctypes.data_as(C.c_void_p))
+    assert rc == _lib.MRC_E_NOSPACE
+    assert [int(v) for v in np.diff(foff)] == [c.n_blocks(x.shape[0]) * 1024 for x in clips]
+    assert np.all(small == 0x5A5A)
+    dec, foff2 = c.decode_batch(out, boff)
+    assert np.array_equal(foff2, foff)
+    singles = c.decode_clips([out[boff[i]:boff[i + 1]].tobytes() for i in (0, 5, 11)])
+    for k, i in enumerate((0, 5, 11)):
+        assert np.array_equal(dec[foff[i]:foff[i + 1]], singles[k])
