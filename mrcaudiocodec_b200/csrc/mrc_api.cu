@@ -62,7 +62,7 @@ struct mrc_ctx {
 
     // scratch (grow only)
     Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out;
-    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab; } sets[2];
+    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab; } sets[3];
     Buf q_alloc, q_sf, q_mant;
     cudaStream_t stream2 = nullptr, stream3 = nullptr;    // analysis stream, H2D copy stream
     cudaStream_t stream4 = nullptr;                       // D2H copy stream (bitstream of finished waves)
@@ -358,7 +358,9 @@ int plan_switched_blocks(mrc_ctx* ctx, const int16_t* d_pcm, const int64_t* h_cl
 
 constexpr int WAVE_BLOCKS = 1 << 14;   // blocks per wave: ~0.9 GB of hand-off per buffer set in fp64; the serial walk of
                                        // the last wave is the un-overlapped tail of a call, so waves are kept short
-constexpr int NSETS = 2;               // buffer sets: wave w+1 is analysed while wave w is chained and packed
+constexpr int NSETS = 3;               // buffer sets: waves w+1 and w+2 can be analysed while wave w is chained and packed
+                                       // (the serial walk of some waves takes longer than an analysis: with two sets
+                                       // the analysis stream stalled on the set that walk still held)
 
 cudaEvent_t pool_event(mrc_ctx* ctx, size_t i) {
     while (ctx->evpool.size() <= i) {
@@ -448,7 +450,27 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         for (int v : ctx->geo[q].h_band_n) max_nl = std::max(max_nl, v);
     }
     const CodecParams& cp = cpq[q_lo];     // for the kernels that read only geometry-independent fields
-    const int nwaves = (nblk_total + WAVE_BLOCKS - 1) / WAVE_BLOCKS;
+    // Wave boundaries.  Full waves hold WAVE_BLOCKS blocks; the first ones ramp up (the first analysis starts after a
+    // small PCM upload) and the last ones ramp down (what is left un-overlapped at the end of a call is the serial walk
+    // and the packing of the last wave: 1024 blocks instead of up to 16384).  A histogram / taps job of one wave stays
+    // one wave.
+    std::vector<int> wave_g0;              // [nwaves+1]
+    {
+        std::vector<int> sizes, tail;
+        int rem = nblk_total, tailsum = 0;
+        if (nblk_total > 4096 && !job.dev_qtaps) {
+            for (int sz = 1024; sz <= WAVE_BLOCKS / 2 && tailsum + sz <= rem / 2; sz *= 2) { tail.push_back(sz); tailsum += sz; }
+            int body = rem - tailsum;
+            for (int sz = 2048; sz < WAVE_BLOCKS && sz <= body / 4; sz *= 2) { sizes.push_back(sz); body -= sz; }
+            while (body > 0) { const int sz = std::min(body, WAVE_BLOCKS); sizes.push_back(sz); body -= sz; }
+            for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
+        } else if (nblk_total > 0) {
+            sizes.push_back(nblk_total);
+        }
+        wave_g0.push_back(0);
+        for (int sz : sizes) wave_g0.push_back(wave_g0.back() + sz);
+    }
+    const int nwaves = (int)wave_g0.size() - 1;
     std::vector<int32_t> lists;            // [wave][geometry] wave-local indices, back to back
     std::vector<int> list_off((size_t)nwaves * MRC_N_GEO + 1, 0);
     if (job.switching) {
@@ -458,7 +480,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         cm.blk_geom = (const uint8_t*)ctx->blk_geom.p;
         lists.reserve((size_t)nblk_total);
         for (int w = 0; w < nwaves; ++w) {
-            const int g0 = w * WAVE_BLOCKS, nblk = std::min(WAVE_BLOCKS, nblk_total - g0);
+            const int g0 = wave_g0[w], nblk = wave_g0[w + 1] - g0;
             for (int q = 0; q < MRC_N_GEO; ++q) {
                 list_off[(size_t)w * MRC_N_GEO + q] = (int)lists.size();
                 for (int i = 0; i < nblk; ++i)
@@ -480,8 +502,9 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     const bool want_atap = job.t_lines || job.t_smr || job.t_npk;
     const bool want_qtap = job.t_alloc || job.t_sf || job.t_mant || job.dev_qtaps;
     const bool any_tap = want_atap || job.t_alloc || job.t_sf || job.t_mant || job.t_ovs || job.t_ms || job.t_table || job.t_res || job.t_cbytes;
-    const size_t W = (size_t)std::max(std::min(nblk_total, WAVE_BLOCKS), 1);
-    const int nsets = (nblk_total > WAVE_BLOCKS) ? NSETS : 1;
+    size_t W = 1;
+    for (int w = 0; w < nwaves; ++w) W = std::max<size_t>(W, (size_t)(wave_g0[w + 1] - wave_g0[w]));
+    const int nsets = std::max(1, std::min(nwaves, NSETS));
     Handoff<T> ho[NSETS];
     ChainIO io[NSETS];
     for (int s = 0; s < nsets; ++s) {
@@ -542,8 +565,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         ctx->h_prog_cap = 2 * nwaves + 64;
     }
     // Output bytes are final up to the end of the last block of a finished wave (clips are laid out in order, and a
-    // clip's base is known once its predecessors are complete).  After wave v+1 has been queued the host waits for
-    // wave v's pack, reads that position and queues the copy; the kernels of wave v+1 hide it.
+    // clip's base is known once its predecessors are complete).  After wave v+2 has been queued the host waits for
+    // wave v's pack, reads that position and queues the copy; the kernels of the later waves hide it.
     auto drain = [&](int v) -> int {
         CK(cudaEventSynchronize(ev(v, 5)));
         int64_t done = ctx->h_prog[2 * v] + (wave_ended[v] ? 0 : ctx->h_prog[2 * v + 1]);
@@ -561,7 +584,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     if (job.h_pcm) CK(cudaStreamWaitEvent(st3, ctx->ev[0], 0));
     for (int w = 0; w < nwaves; ++w) {
         const int s = w % nsets;
-        const int g0 = w * WAVE_BLOCKS, nblk = std::min(WAVE_BLOCKS, nblk_total - g0);
+        const int g0 = wave_g0[w], nblk = wave_g0[w + 1] - g0;
         while (blk0[c_lo + 1] <= g0) ++c_lo;                       // clip holding block g0
         int c_hi = c_lo;
         while (blk0[c_hi + 1] < g0 + nblk) ++c_hi;                 // clip holding block g0+nblk-1
@@ -654,7 +677,9 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         }
         CK(cudaEventRecord(ev(w, 5), st));
         CK(cudaGetLastError());
-        if (stream_out && w >= 1) { const int rc = drain(w - 1); if (rc != MRC_OK) return rc; }
+        // the host waits for the pack of a wave two behind the one it has just queued: with three buffer sets the
+        // device never runs out of queued work while the host sleeps on that event
+        if (stream_out && w >= 2) { const int rc = drain(w - 2); if (rc != MRC_OK) return rc; }
         if (!any_tap) continue;
         // ---- taps of this wave to the host (parity runs only; synchronous) ----
         auto fetch = [&](const void* dsrc, size_t bytes) -> cudaError_t {
@@ -739,6 +764,14 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         CK(cudaEventElapsedTime(&t, ev(w, 1), ev(w, 2))); t_cost += t;
         CK(cudaEventElapsedTime(&t, ev(w, 3), ev(w, 4))); t_chain += t;
         CK(cudaEventElapsedTime(&t, ev(w, 4), ev(w, 5))); t_pk += t;
+    }
+    if (getenv("MRC_TIMELINE")) {      // development aid: when did each wave's stages start and end (ms since the first)
+        for (int w = 0; w < nwaves; ++w) {
+            float t[6];
+            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], ev(0, 0), ev(w, k));
+            fprintf(stderr, "wave %2d blocks %6d  analysis %7.2f-%7.2f  cost+table -%7.2f | chain %7.2f-%7.2f  pack -%7.2f\n", w,
+                    wave_g0[w + 1] - wave_g0[w], t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
     }
     ctx->ms[0] = t_an; ctx->ms[1] = t_chain; ctx->ms[2] = t_pk; ctx->ms[7] = t_cost;
     if (!job.switching) ctx->ms[3] = 0;
