@@ -491,9 +491,13 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         CK(upload(ctx->blk_list, lists, st));
     }
     // reservoir-map tables of the single-stream fast path: R_in in [r_lo, r_lo + ntab)
-    // [-128, 640): reservoirs below -128 are possible (down to -(largest band + 1)) but rare -- they take the complete
-    // walk like the ones above the table (profiles/r01z_chain_table_range.log)
-    int r_lo = -std::min(128, (max_nl + 1 + 31) / 32 * 32), r_hi = 640;
+    // [-128, 640) for long calls, [-128, 1024) for shorter ones: reservoirs outside the table take the complete walk
+    // (exact either way).  The bench stream's reservoir has its median near 500 and 11 % of the blocks in [640, 1024):
+    // tabulating those costs 2 ms per hour on the analysis stream and takes 12 ms off the serial walk, which pays when
+    // the walk is what a call waits for -- single streams of less than about 45 minutes, where there are too few
+    // waves to hide it (profiles/r01zz_chain_table_range.log: 600 s stream 26.8 k -> 32.8 k audio-s/s, 1 h stream
+    // 43.6 k -> 42.7 k).  Reservoirs below -128 are possible (down to -(largest band + 1)) but rare.
+    int r_lo = -std::min(128, (max_nl + 1 + 31) / 32 * 32), r_hi = (nblk_total >= 8 * WAVE_BLOCKS) ? 640 : 1024;
     if (const char* e = getenv("MRC_CHAIN_TABLE_LO")) r_lo = -std::max(32, (atoi(e) + 31) / 32 * 32);     // tuning knobs: any
     if (const char* e = getenv("MRC_CHAIN_TABLE_HI")) r_hi = std::max(32, (atoi(e) + 31) / 32 * 32);      // range is exact
     const int ntab = -r_lo + r_hi, tabw = (ntab + 2 + 3) / 4 * 4;
