@@ -231,6 +231,19 @@ class Codec(object):
                                                    _ptr(mant), _ptr(ht), _ptr(res), _ptr(cb)))
         return dict(bitAlloc=ba, scaleFactor=sf, mantissa=mant, huffTable=ht, reservoir=res, chunkBytes=cb)
 
+    def stage_reservoir(self, pcm, frame_offsets):
+        """The serial stage's decisions only (no mantissa taps: cheap enough for hour-long streams): per block the
+        Huffman table ids, codingParams.bitReservoir after the block and the two chunk sizes."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        off = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+        nb = sum(self.n_blocks(c) for c in np.diff(off))
+        ht = np.zeros((nb, 2), np.int32)
+        res = np.zeros(nb, np.int32)
+        cb = np.zeros((nb, 2), np.int32)
+        self._check(self.lib.mrc_stage_alloc_quant(self._ctx, _ptr(pcm), _ptr(off), len(off) - 1, None, None, None,
+                                                   _ptr(ht), _ptr(res), _ptr(cb)))
+        return dict(huffTable=ht, reservoir=res, chunkBytes=cb)
+
     # ---- per-block seam ------------------------------------------------------------------------------
     def encode_block(self, data, joint, reservoir, a=None, b=None):
         """data: float64 [2, a+b] (a = b = L by default).  Returns dict + new reservoir."""

@@ -549,8 +549,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     }
 
     // events per wave: 0 analysis start, 1 analysis end, 2 cost end, 3 chain start, 4 chain end, 5 pack end,
-    // 6 PCM of the wave uploaded
-    constexpr int EPW = 7;
+    // 6 PCM of the wave uploaded (7 = that upload queued), 8-9 around the bitstream copy drained after the wave
+    constexpr int EPW = 10;
     for (int i = 0; i < nwaves * EPW; ++i) pool_event(ctx, (size_t)i);
     auto ev = [&](int w, int k) { return ctx->evpool[(size_t)w * EPW + k]; };
     // everything queued on `st` so far (tables of this call, PCM upload) must precede the first analysis
@@ -559,7 +559,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
 
     int launches = 0;
     int64_t copied = 0;                // leading output bytes already queued for the host
-    std::vector<char> wave_ended(nwaves, 0);
+    std::vector<char> wave_ended(nwaves, 0), wave_h2d(nwaves, 0), wave_d2h(nwaves, 0);
     const bool stream_out = job.h_out != nullptr && job.d_out != nullptr && job.need_quant;
     if (stream_out && ctx->h_prog_cap < 2 * nwaves) {
         if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
@@ -576,8 +576,11 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         int64_t done = ctx->h_prog[2 * v] + (wave_ended[v] ? 0 : ctx->h_prog[2 * v + 1]);
         done = std::min(done, std::min(job.h_out_cap, job.out_cap));
         if (done > copied) {
+            CK(cudaEventRecord(ev(v, 8), ctx->stream4));
             CK(cudaMemcpyAsync(job.h_out + copied, job.d_out + copied, (size_t)(done - copied), cudaMemcpyDeviceToHost,
                                ctx->stream4));
+            CK(cudaEventRecord(ev(v, 9), ctx->stream4));
+            wave_d2h[v] = 1;
             copied = done;
         }
         return MRC_OK;
@@ -600,9 +603,11 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
             const int64_t fr_hi = job.h_clip_off[c_hi + 1] - job.h_clip_off[c_hi];
             const int64_t need = job.h_clip_off[c_hi] + std::min<int64_t>(fr_hi, (b_last + 1) * (int64_t)L);
             if (need > uploaded) {
+                CK(cudaEventRecord(ev(w, 7), st3));
                 CK(cudaMemcpyAsync((int16_t*)job.d_pcm + uploaded * 2, job.h_pcm + uploaded * 2,
                                    (size_t)(need - uploaded) * 4, cudaMemcpyHostToDevice, st3));
                 uploaded = need;
+                wave_h2d[w] = 1;
             }
             CK(cudaEventRecord(ev(w, 6), st3));
             CK(cudaStreamWaitEvent(st2, ev(w, 6), 0));
@@ -761,9 +766,12 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(st2));
-    float t_an = 0, t_cost = 0, t_chain = 0, t_pk = 0;
+    if (stream_out) CK(cudaStreamSynchronize(ctx->stream4));
+    float t_an = 0, t_cost = 0, t_chain = 0, t_pk = 0, t_h2d = 0, t_d2h = 0;
     for (int w = 0; w < nwaves; ++w) {
         float t;
+        if (wave_h2d[w]) { CK(cudaEventElapsedTime(&t, ev(w, 7), ev(w, 6))); t_h2d += t; }
+        if (wave_d2h[w]) { CK(cudaEventElapsedTime(&t, ev(w, 8), ev(w, 9))); t_d2h += t; }
         CK(cudaEventElapsedTime(&t, ev(w, 0), ev(w, 1))); t_an += t;
         CK(cudaEventElapsedTime(&t, ev(w, 1), ev(w, 2))); t_cost += t;
         CK(cudaEventElapsedTime(&t, ev(w, 3), ev(w, 4))); t_chain += t;
@@ -778,6 +786,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         }
     }
     ctx->ms[0] = t_an; ctx->ms[1] = t_chain; ctx->ms[2] = t_pk; ctx->ms[7] = t_cost;
+    ctx->ms[4] = t_h2d; ctx->ms[5] = t_d2h;      // copies on the copy streams (they overlap the kernels)
     if (!job.switching) ctx->ms[3] = 0;
     else launches += 2;                // the two transient detector kernels
     ctx->counters[0] = launches;
@@ -798,8 +807,16 @@ int run_encode(mrc_ctx* ctx, const EncodeJob& job) {
         return fail(ctx, MRC_E_STATE, "block switching needs mrc_set_switch_tables");
     if (job.switching && !job.joint)
         return fail(ctx, MRC_E_INVALID, "block switching follows the reference's loop, which is the joint flow: create the context with joint = 1");
-    if (ctx->cfg.precision == MRC_PRECISION_FP32) return run_encode_t<float>(ctx, job);
-    return run_encode_t<double>(ctx, job);
+    const int rc = (ctx->cfg.precision == MRC_PRECISION_FP32) ? run_encode_t<float>(ctx, job) : run_encode_t<double>(ctx, job);
+    if (rc != MRC_OK) {
+        // an early exit may leave work queued that still reads the caller's PCM or writes the caller's output:
+        // nothing of this call may be in flight once it has returned (the error message is already set)
+        cudaStreamSynchronize(ctx->stream3);
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream4);
+    }
+    return rc;
 }
 
 int64_t worst_case_bytes(const mrc_ctx* ctx, const int64_t* off, int nc) {
@@ -954,11 +971,23 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
         const int esc = t->huff_escape[tb];
         if (esc < 0 || esc >= MRC_HUFF_LUT || h.len[tb][esc] == 0)
             return fail(ctx, MRC_E_INVALID, "escape value must be a key of its table");
+        // Everything downstream is sized for the trained books' code lengths: the pack kernel's bit buffer and
+        // worst_case_bytes (escape + 16 raw bits <= 25 bits per line), the cost kernel's 8-bit per-line prices and
+        // 16-bit totals, the decoder's 9-bit look-up.  Reject anything longer here instead of mis-encoding later.
+        for (int v = 0; v < MRC_HUFF_LUT; ++v) {
+            if (h.len[tb][v] > MRC_HUFF_PEEK)
+                return fail(ctx, MRC_E_INVALID, "Huffman code longer than 9 bits (the code books' limit in this library)");
+            if (h.len[tb][v] && (h.code[tb][v] >> h.len[tb][v]) != 0)
+                return fail(ctx, MRC_E_INVALID, "Huffman code has bits above its length");
+        }
+        if ((int64_t)L * (16 + h.len[tb][esc]) >= 65536)
+            return fail(ctx, MRC_E_INVALID, "n_mdct_lines * (16 + escape code length) must stay below 65536");
         h.esc[tb] = esc;
         h.esc_len[tb] = h.len[tb][esc];
         h.esc_code[tb] = h.code[tb][esc];
     }
     CK(ensure(ctx->huff, sizeof(HuffDev)));
+    release(ctx->dec[0]);            // D_HDEC: the decoder's look-up table is rebuilt from the new books on next use
     CK(cudaMemcpyAsync(ctx->huff.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(upload_tables<double>(ctx, g0, g0.td, g0.tbd, t->kbd_window, t->hann_window, t->bark, t->quiet_intensity));
@@ -1009,7 +1038,7 @@ int32_t mrc_encode_batch_device(mrc_ctx* ctx, const int16_t* d_pcm, const int64_
     cudaEventSynchronize(ctx->ev[5]);
     float t = 0;
     cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]);
-    ctx->ms[6] = t; ctx->ms[4] = ctx->ms[5] = 0;
+    ctx->ms[6] = t;
     return rc;
 }
 
@@ -1030,7 +1059,6 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
         copied = 0;
         CK(ensure(ctx->out_dev, (size_t)cap));
         CK(cudaEventRecord(ctx->ev[4], st));
-        CK(cudaEventRecord(ctx->ev[6], st));
         EncodeJob job;
         job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = clip_frame_offsets; job.n_clips = n_clips;
         job.h_pcm = frames > 0 ? pcm : nullptr;             // uploaded wave by wave, overlapped with the kernels
@@ -1056,8 +1084,7 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
     CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
     float t = 0;
-    cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[6]); ctx->ms[4] = t;
-    cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[5]); ctx->ms[5] = t;
+    cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[5]); ctx->ms[5] += t;      // + the tail the waves had not drained
     cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]); ctx->ms[6] = t;
     return MRC_OK;
 }

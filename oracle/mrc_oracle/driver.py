@@ -57,6 +57,33 @@ def encode_pcm(pcm, joint=True, trace=False, **kw):
     return w.getvalue(), blocks
 
 
+def encode_window(pcm_prior, pcm_blocks, reservoir_in, joint=True, **kw):
+    """Blocks k .. k+n-1 out of the middle of a long-block stream: what (Joint)WriteDataBlock (pacfileThem.py:622-790,
+    :793-972) writes for them when the block before left `pcm_prior` in codingParams.priorBlock (:631, :802) and
+    `reservoir_in` in codingParams.bitReservoir (codecThem.py:308, :391) -- the only two things a block inherits.
+    pcm_prior: int16 [nMDCTLines, nCh]; pcm_blocks: int16 [n*nMDCTLines, nCh].
+    Returns (list of n byte strings: both channel chunks of a block with their <L prefixes, list of n reservoirs)."""
+    pcm_blocks = np.asarray(pcm_blocks, dtype=np.int16)
+    nCh = pcm_blocks.shape[1]
+    cp = make_params(numSamples=pcm_blocks.shape[0], nChannels=nCh, **kw)
+    w = PACWriter(cp)
+    L = cp.nMDCTLines
+    assert pcm_blocks.shape[0] % L == 0 and np.asarray(pcm_prior).shape == (L, nCh)
+    cp.priorBlock = [pcm_to_fraction(np.asarray(pcm_prior, dtype=np.int16)[:, c]) for c in range(nCh)]
+    cp.bitReservoir = int(reservoir_in)
+    chunks, res = [], []
+    for b in range(pcm_blocks.shape[0] // L):
+        pos = w.buf.tell()
+        data = [pcm_to_fraction(pcm_blocks[b * L:(b + 1) * L, c]) for c in range(nCh)]
+        if joint:
+            w.JointWriteDataBlock(data, cp)
+        else:
+            w.WriteDataBlock(data, cp)
+        chunks.append(w.buf.getvalue()[pos:])
+        res.append(int(cp.bitReservoir))
+    return chunks, res
+
+
 def encode_pcm_switched(pcm, trace=False, sos=None, **kw):
     """pacfileThem.py:1142-1215 with block switching: every nMDCTLines-frame block goes through TransientDetector;
     block k is written as 8 short blocks (b = 128 each) iff wants_short(detection of k, detection of k+1), else as

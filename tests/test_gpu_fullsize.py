@@ -155,3 +155,31 @@ def test_block_switching_at_scale():
         pos += b
     assert e_sw < e_pl, (e_sw, e_pl)
     c.close()
+
+
+def test_parity_census_bench_stream():
+    """The benchmarked stream (BASELINE configs[1]; MRC_FULLSIZE_MINUTES of it) against the oracle well beyond its
+    prefix: windows at the boundaries of its silent / -70 dBFS seconds (every third 10 s segment) and at random
+    starts, each re-encoded by the oracle from the GPU's reservoir at the window's start; chunk bytes and the
+    reservoir after every block must agree (scripts/parity_census.py; the full census is committed under profiles/)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import parity_census as pc
+    clips = pc.make_material("stream", 60 * MINUTES)
+    r = pc.census(clips, random_windows=int(2 * MINUTES) + 8, window_blocks=16, boundary_blocks=12, boundary_step=3)
+    assert r["chunks_compared"] >= 2 * 16 * (int(2 * MINUTES) + 8) * 0.9, r
+    assert r["chunks_mismatching"] == 0 and r["reservoir_mismatches"] == 0, r
+
+
+def test_parity_census_music_and_batch():
+    """Same census on dense-masker music-like material (one stream) and on a batch of independent clips."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import parity_census as pc
+    minutes = min(MINUTES, 10.0)
+    r = pc.census(pc.make_material("music", 60 * minutes), random_windows=int(3 * minutes) + 4, window_blocks=12,
+                  with_boundaries=False)
+    assert r["chunks_mismatching"] == 0 and r["reservoir_mismatches"] == 0, r
+    r = pc.census(pc.make_material("batch", 60 * minutes), random_windows=int(4 * minutes) + 4, window_blocks=10,
+                  with_boundaries=False)
+    assert r["chunks_mismatching"] == 0 and r["reservoir_mismatches"] == 0, r
