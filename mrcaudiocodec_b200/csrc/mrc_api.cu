@@ -62,7 +62,7 @@ struct mrc_ctx {
 
     // scratch (grow only)
     Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out;
-    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab; } sets[3];
+    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab, comp, rin; } sets[3];
     Buf q_alloc, q_sf, q_mant;
     cudaStream_t stream2 = nullptr, stream3 = nullptr;    // analysis stream, H2D copy stream
     cudaStream_t stream4 = nullptr;                       // D2H copy stream (bitstream of finished waves)
@@ -70,6 +70,7 @@ struct mrc_ctx {
     int h_prog_cap = 0;
     bool no_tables = false;          // MRC_FLAG_NO_CHAIN_TABLES
     int tab_min_blocks = 512;        // blocks per clip in a wave from which the reservoir maps are tabulated
+    int seg_blocks = 32;             // blocks per composed reservoir map (0: walk the per-block maps one by one)
     std::vector<cudaEvent_t> evpool;
     Buf tap_lines, tap_smr, tap_npk;
     Buf pcm_dev, out_dev, xin_dev;
@@ -497,10 +498,11 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     // the walk is what a call waits for -- single streams of less than about 45 minutes, where there are too few
     // waves to hide it (profiles/r01zz_chain_table_range.log: 600 s stream 26.8 k -> 32.8 k audio-s/s, 1 h stream
     // 43.6 k -> 42.7 k).  Reservoirs below -128 are possible (down to -(largest band + 1)) but rare.
-    int r_lo = -std::min(128, (max_nl + 1 + 31) / 32 * 32), r_hi = (nblk_total >= 8 * WAVE_BLOCKS) ? 640 : 1024;
+    int r_lo = -std::min(128, (max_nl + 1 + 31) / 32 * 32), r_hi = 1024;
     if (const char* e = getenv("MRC_CHAIN_TABLE_LO")) r_lo = -std::max(32, (atoi(e) + 31) / 32 * 32);     // tuning knobs: any
     if (const char* e = getenv("MRC_CHAIN_TABLE_HI")) r_hi = std::max(32, (atoi(e) + 31) / 32 * 32);      // range is exact
-    const int ntab = -r_lo + r_hi, tabw = (ntab + 2 + 3) / 4 * 4;
+    const int ntab = -r_lo + r_hi, tabw = (ntab + 2 + 3) / 4 * 4, segw = tabw + 4;
+    const int seg_S = (ntab <= segment_max_ntab()) ? ctx->seg_blocks : 0;
 
     // ---- buffer sets ----
     const bool want_atap = job.t_lines || job.t_smr || job.t_npk;
@@ -644,13 +646,26 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
             CK(ensure(ctx->sets[s].tab, W * 2 * (size_t)tabw * 4));
             launch_table(st2, cp, cm, g0, nblk, io[s], r_lo, ntab, tabw, (int*)ctx->sets[s].tab.p);
             ++launches;
+            if (seg_S > 0) {
+                const size_t nseg = (W + seg_S - 1) / seg_S;
+                CK(ensure(ctx->sets[s].comp, nseg * (size_t)segw * 4));
+                CK(ensure(ctx->sets[s].rin, nseg * 4));
+                launch_segments(st2, cp, cm, g0, nblk, seg_S, io[s], r_lo, ntab, tabw, (const int*)ctx->sets[s].tab.p, segw,
+                                (int*)ctx->sets[s].comp.p, (int*)ctx->sets[s].rin.p);
+                ++launches;
+            }
         }
         CK(cudaEventRecord(ev(w, 2), st2));
         // ---- main stream: chain -> clip offsets -> quantise + pack ----
         CK(cudaStreamWaitEvent(st, ev(w, 2), 0));
         CK(cudaEventRecord(ev(w, 3), st));
         if (job.need_quant) {
-            if (use_tab)
+            if (use_tab && seg_S > 0) {
+                launch_chain_seg(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, seg_S, io[s], r_lo, ntab, tabw,
+                                 (const int*)ctx->sets[s].tab.p, segw, (const int*)ctx->sets[s].comp.p,
+                                 (int*)ctx->sets[s].rin.p, d_res_in, d_res_out, (unsigned long long*)ctx->peakctr.p + 4);
+                ++launches;
+            } else if (use_tab)
                 launch_chain_table(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, io[s], r_lo, ntab, tabw,
                                    (const int*)ctx->sets[s].tab.p, d_res_in, d_res_out,
                                    (unsigned long long*)ctx->peakctr.p + 4);
@@ -929,7 +944,8 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     for (Buf* b : all) release(*b);
     for (auto& b : ctx->dec) release(b);
     for (auto& ws : ctx->sets) {
-        Buf* wb[] = {&ws.lines, &ws.bandmax, &ws.tokens, &ws.ovs, &ws.ms, &ws.rec, &ws.pw, &ws.rsv, &ws.gmask, &ws.cblk, &ws.tab};
+        Buf* wb[] = {&ws.lines, &ws.bandmax, &ws.tokens, &ws.ovs, &ws.ms, &ws.rec, &ws.pw, &ws.rsv, &ws.gmask, &ws.cblk, &ws.tab,
+                     &ws.comp, &ws.rin};
         for (Buf* b : wb) release(*b);
     }
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -998,6 +1014,7 @@ int32_t mrc_set_tables(mrc_ctx* ctx, const mrc_tables* t) {
     const mrc_config& c = ctx->cfg;
     ctx->no_tables = (c.flags & MRC_FLAG_NO_CHAIN_TABLES) != 0;
     if (const char* e = getenv("MRC_CHAIN_TABLE_MIN_BLOCKS")) ctx->tab_min_blocks = std::max(1, atoi(e));   // test knob
+    if (const char* e = getenv("MRC_CHAIN_SEGMENT_BLOCKS")) ctx->seg_blocks = std::max(0, atoi(e));         // test knob
     if (ctx->cp.max_mant_bits != 16) return fail(ctx, MRC_E_INVALID, "only a 16-bit mantissa cap is supported");
     // .pac header template (pacfileThem.py:592-613); numSamples is patched per clip by the pack kernel
     uint8_t* hd = ctx->h_header;

@@ -418,6 +418,225 @@ chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, Ch
     }
 }
 
+// ---- segment-composed reservoir maps ---------------------------------------------------------------------------
+// The per-block maps R_in -> R_out compose.  segment_kernel (parallel: one CTA per segment of `S` consecutive blocks of
+// one clip, one thread per R_in of the tabulated range) chases every R_in through the segment's blocks: a block's
+// table while the running value stays inside the range, the closed form "every token granted" above it, and for the
+// rare value that is neither a complete walk of that block's record, done by the whole warp once per distinct value
+// (the maps contract: after a block or two the thousand trajectories of a segment have merged into a handful).
+// It also composes the closed forms: R_out = R_in + delta for R_in >= theta, when every block of the segment grants
+// everything along the way (digital silence: the reservoir grows by thousands of bits per block, far outside any
+// table).  chain_seg_kernel (serial, one warp per clip) then takes ONE step per segment -- a table entry or the closed
+// form -- and only walks block by block through segments it enters outside both (the few segments in which a silent
+// passage ends, or which straddle two clips).  It records the reservoir at the start of every segment it stepped
+// over; expand_kernel (parallel, one warp per segment) replays those segments block by block for finish_kernel.
+constexpr int SEG_THREADS = 384;
+constexpr int SEG_EPT = 4;                       // table entries per thread: ntab <= 1536
+constexpr int RIN_NONE = (int)0x80000000;
+
+struct BlkStep { int R0, R1, R; };
+
+// One block, every lane with the same R: group by group through table / closed form / complete walk.
+__device__ __forceinline__ BlkStep step_block(const CodecParams& cp, const unsigned char* __restrict__ rec,
+                                              const int* __restrict__ T0, bool joint, int R, int r_lo, int ntab,
+                                              int tabw, int lane, unsigned& n_slow) {
+    const int32_t* mx = reinterpret_cast<const int32_t*>(rec + MRC_REC_MX);
+    const int K = __ldg(mx + MRC_MX_K);
+    BlkStep o;
+    o.R0 = R;
+    o.R1 = R;
+    const int ngroups = joint ? 1 : 2;
+    unsigned dummy = 0;
+    for (int grp = 0; grp < ngroups; ++grp) {
+        const int* T = T0 + grp * tabw;
+        const int B0 = K + R, idx = R - r_lo;
+        if ((unsigned)idx < (unsigned)ntab) R = __ldg(T + idx);
+        else if (B0 >= __ldg(T + ntab + 1)) R = B0 + __ldg(T + ntab);
+        else {
+            const GroupTotals gt = walk_group<false>(
+                reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN), reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP),
+                reinterpret_cast<const uint4*>(rec + MRC_REC_PC), nullptr, mx, grp * MRC_GROUP_CHUNKS,
+                joint ? MRC_NCHUNK : MRC_GROUP_CHUNKS, B0, __ldg(mx + MRC_MX_MINNL), lane, dummy, dummy);
+            R = reservoir_after(gt, B0, __ldg(mx + MRC_MX_FRAC), cp.no_huff, nullptr, nullptr);
+            ++n_slow;
+        }
+        if (grp == 0) o.R1 = R;
+    }
+    o.R = R;
+    return o;
+}
+
+// comp: [nseg][segw] ints: entries 0..ntab-1 the composed map, [ntab] delta, [ntab+1] theta (INT_MAX: no closed form),
+// [ntab+2] 1 if the segment lies inside one clip (else the row is not to be used).  rin[seg] is reset to RIN_NONE.
+__global__ void __launch_bounds__(SEG_THREADS)
+segment_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, ChainIO io, int r_lo, int ntab, int tabw,
+               const int* __restrict__ tab, int segw, int* __restrict__ comp, int* __restrict__ rin) {
+    __shared__ int s_pure, s_flush_lb;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int seg = blockIdx.x;
+    const int lb0 = seg * S, lb1 = min(lb0 + S, nblk_wave);
+    int* row = comp + (size_t)seg * segw;
+    if (tid == 0) {
+        rin[seg] = RIN_NONE;
+        const int ga = g0 + lb0, gb = g0 + lb1 - 1;
+        int lo = 0, hi = cm.n_clips;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cm.clip_blk0[mid] <= ga) lo = mid; else hi = mid;
+        }
+        s_pure = gb < cm.clip_blk0[lo + 1];
+        // wave-local index of the clip's last block (the non-joint Close() flush block) if it falls in this segment
+        s_flush_lb = (cp.flush_nonjoint && gb == cm.clip_blk0[lo + 1] - 1) ? lb1 - 1 : -1;
+    }
+    __syncthreads();
+    if (!s_pure) {
+        if (tid == 0) { row[ntab] = 0; row[ntab + 1] = 0x7fffffff; row[ntab + 2] = 0; }
+        return;
+    }
+    int R[SEG_EPT];
+    bool act[SEG_EPT];
+#pragma unroll
+    for (int e = 0; e < SEG_EPT; ++e) {
+        const int idx = tid + e * SEG_THREADS;
+        act[e] = idx < ntab;
+        R[e] = r_lo + (act[e] ? idx : 0);
+    }
+    long long P = 0, theta = -(1ll << 40);           // thread 0: the composed closed form
+    unsigned dummy = 0;
+    for (int lb = lb0; lb < lb1; ++lb) {
+        const unsigned char* rec = io.rec + (size_t)lb * MRC_REC_BYTES;
+        const int32_t* mx = reinterpret_cast<const int32_t*>(rec + MRC_REC_MX);
+        const int K = __ldg(mx + MRC_MX_K), frac = __ldg(mx + MRC_MX_FRAC), min_nl = __ldg(mx + MRC_MX_MINNL);
+        const bool joint = cp.joint && lb != s_flush_lb;
+        const int ngroups = joint ? 1 : 2, nck = joint ? MRC_NCHUNK : MRC_GROUP_CHUNKS;
+        for (int grp = 0; grp < ngroups; ++grp) {
+            const int* T = tab + (size_t)lb * (2 * tabw) + grp * tabw;
+            const int c_all = __ldg(T + ntab), thr = __ldg(T + ntab + 1);
+            if (tid == 0) {
+                theta = max(theta, (long long)thr - K - P);
+                P += (long long)K + c_all;
+            }
+            bool need[SEG_EPT];
+#pragma unroll
+            for (int e = 0; e < SEG_EPT; ++e) {
+                const int idx = R[e] - r_lo, B0 = K + R[e];
+                need[e] = false;
+                if ((unsigned)idx < (unsigned)ntab) R[e] = __ldg(T + idx);
+                else if (B0 >= thr) R[e] = B0 + c_all;
+                else need[e] = act[e];
+            }
+#pragma unroll
+            for (int e = 0; e < SEG_EPT; ++e) {
+                unsigned m = __ballot_sync(0xffffffffu, need[e]);
+                while (m) {                          // warp-uniform: one complete walk per distinct value
+                    const int l = __ffs(m) - 1;
+                    const int Rl = __shfl_sync(0xffffffffu, R[e], l);
+                    const bool mine = need[e] && R[e] == Rl;
+                    const unsigned same = __ballot_sync(0xffffffffu, mine);
+                    const GroupTotals gt = walk_group<false>(
+                        reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN), reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP),
+                        reinterpret_cast<const uint4*>(rec + MRC_REC_PC), nullptr, mx, grp * MRC_GROUP_CHUNKS, nck, K + Rl,
+                        min_nl, lane, dummy, dummy);
+                    const int Rn = reservoir_after(gt, K + Rl, frac, cp.no_huff, nullptr, nullptr);
+                    if (mine) R[e] = Rn;
+                    m &= ~same;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < SEG_EPT; ++e)
+        if (act[e]) row[tid + e * SEG_THREADS] = R[e];
+    if (tid == 0) {
+        const bool ok = theta < 0x7fffffffll && P > -0x7fffffffll && P < 0x7fffffffll;
+        row[ntab] = ok ? (int)P : 0;
+        row[ntab + 1] = ok ? (int)max(theta, -0x7fffffffll) : 0x7fffffff;
+        row[ntab + 2] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int S, ChainIO io, int r_lo, int ntab,
+                 int tabw, const int* __restrict__ tab, int segw, const int* __restrict__ comp, int* __restrict__ rin,
+                 const int32_t* __restrict__ reservoir_in, int32_t* __restrict__ reservoir_out,
+                 unsigned long long* __restrict__ iter_counter) {
+    const int lane = threadIdx.x;
+    const int clip = c0 + blockIdx.x;
+    const int blk0 = cm.clip_blk0[clip], nblk_clip = cm.clip_blk0[clip + 1] - blk0;
+    const int b_lo = max(blk0, g0) - blk0, b_hi = min(blk0 + nblk_clip, g0 + nblk_wave) - blk0;
+    if (b_hi <= b_lo) return;
+    const int lb_lo = blk0 + b_lo - g0, lb_hi = blk0 + b_hi - g0;      // wave-local
+    const int flush_lb = (cp.flush_nonjoint && b_hi == nblk_clip) ? lb_hi - 1 : -1;
+    int R = (b_lo == 0) ? (reservoir_in ? reservoir_in[clip] : 0) : io.clip_res[clip];
+    unsigned n_slow = 0, n_blk = 0;
+    int lb = lb_lo;
+    while (lb < lb_hi) {
+        if (lb % S == 0) {
+            const int seg = lb / S, seg_end = min(lb + S, nblk_wave);
+            if (seg_end <= lb_hi) {                  // the whole segment belongs to this clip
+                const int* row = comp + (size_t)seg * segw;
+                const int idx = R - r_lo;
+                int Rn = 0;
+                bool took = false;
+                if (row[ntab + 2] != 0) {
+                    if ((unsigned)idx < (unsigned)ntab) { Rn = row[idx]; took = true; }
+                    else if (R >= row[ntab + 1]) { Rn = R + row[ntab]; took = true; }
+                }
+                if (took) {
+                    if (lane == 0) rin[seg] = R;
+                    R = Rn;
+                    lb = seg_end;
+                    continue;
+                }
+            }
+        }
+        const BlkStep o = step_block(cp, io.rec + (size_t)lb * MRC_REC_BYTES, tab + (size_t)lb * (2 * tabw),
+                                     cp.joint && lb != flush_lb, R, r_lo, ntab, tabw, lane, n_slow);
+        if (lane == 0) io.rsv[lb] = make_int4(o.R0, o.R1, o.R, 0);
+        R = o.R;
+        ++lb;
+        ++n_blk;
+    }
+    if (lane == 0) {
+        if (iter_counter) {
+            atomicAdd(iter_counter, (unsigned long long)n_slow);           // complete walks taken by the serial pass
+            atomicAdd(iter_counter + 1, (unsigned long long)n_blk);        // blocks it stepped through one by one
+        }
+        io.clip_res[clip] = R;
+        if (b_hi == nblk_clip && reservoir_out) reservoir_out[clip] = R;
+    }
+}
+
+constexpr int EXP_WARPS = 4;
+
+__global__ void __launch_bounds__(EXP_WARPS * 32)
+expand_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, int nseg, ChainIO io, int r_lo, int ntab,
+              int tabw, const int* __restrict__ tab, const int* __restrict__ rin) {
+    const int lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * EXP_WARPS + (threadIdx.x >> 5);
+    if (seg >= nseg) return;
+    int R = rin[seg];
+    if (R == RIN_NONE) return;                       // the serial pass went through this segment block by block
+    const int lb0 = seg * S, lb1 = min(lb0 + S, nblk_wave);
+    int flush_lb = -1;
+    if (cp.flush_nonjoint) {                         // the segment lies inside one clip: is its last block that clip's last?
+        const int gb = g0 + lb1 - 1;
+        int lo = 0, hi = cm.n_clips;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cm.clip_blk0[mid] <= gb) lo = mid; else hi = mid;
+        }
+        if (gb == cm.clip_blk0[lo + 1] - 1) flush_lb = lb1 - 1;
+    }
+    unsigned n_slow = 0;
+    for (int lb = lb0; lb < lb1; ++lb) {
+        const BlkStep o = step_block(cp, io.rec + (size_t)lb * MRC_REC_BYTES, tab + (size_t)lb * (2 * tabw),
+                                     cp.joint && lb != flush_lb, R, r_lo, ntab, tabw, lane, n_slow);
+        if (lane == 0) io.rsv[lb] = make_int4(o.R0, o.R1, o.R, 0);
+        R = o.R;
+    }
+}
+
 constexpr int FIN_WARPS = 8;
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
@@ -547,3 +766,22 @@ void launch_chain_table(cudaStream_t st, const CodecParams& cp, const ClipMap& c
     chain_table_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, io, r_lo, ntab, tabw, tab,
                                                  reservoir_in, reservoir_out, iter_counter);
 }
+
+void launch_segments(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int S, ChainIO io,
+                     int r_lo, int ntab, int tabw, const int* tab, int segw, int* comp, int* rin) {
+    if (nblk <= 0) return;
+    segment_kernel<<<(nblk + S - 1) / S, SEG_THREADS, 0, st>>>(cp, cm, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, rin);
+}
+
+void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
+                      int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp, int* rin,
+                      const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter) {
+    if (nclips <= 0 || nblk <= 0) return;
+    chain_seg_kernel<<<nclips, 32, 0, st>>>(cp, cm, c0, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, rin,
+                                            reservoir_in, reservoir_out, iter_counter);
+    const int nseg = (nblk + S - 1) / S;
+    expand_kernel<<<(nseg + EXP_WARPS - 1) / EXP_WARPS, EXP_WARPS * 32, 0, st>>>(cp, cm, g0, nblk, S, nseg, io, r_lo, ntab,
+                                                                                 tabw, tab, rin);
+}
+
+int segment_max_ntab() { return SEG_THREADS * SEG_EPT; }

@@ -185,6 +185,15 @@ void launch_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int
 void launch_chain_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0,
                         int nblk, ChainIO io, int r_lo, int ntab, int tabw, const int* tab,
                         const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter);
+// single-stream fast path, second stage: compose the per-block maps over segments of S consecutive blocks (parallel),
+// then one serial step per segment and a parallel replay of the stepped-over segments into io.rsv.
+// comp is [ceil(nblk/S)][segw] ints, segw >= ntab + 3; rin is [ceil(nblk/S)] ints.
+void launch_segments(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int S, ChainIO io,
+                     int r_lo, int ntab, int tabw, const int* tab, int segw, int* comp, int* rin);
+void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
+                      int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp, int* rin,
+                      const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter);
+int segment_max_ntab();
 // parallel: one warp per block replays the block from its recorded reservoir: grant masks, table ids, chunk sizes
 void launch_finish(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk,
                    ChainIO io);

@@ -139,21 +139,30 @@ def test_ragged_batch_and_edge_clips(codecs):
             assert np.abs(d.astype(np.int64) - od.astype(np.int64)).max() <= 1, "clip %d" % i
 
 
-def test_chain_table_fast_path_vs_oracle(monkeypatch):
-    """The single-stream fast path (tabulated reservoir maps, mrc_chain.cu) forced on for short clips: bytes equal
-    the oracle's, for joint and independent channels, including silence (reservoir far outside the table: closed
-    form) and the blocks after it (complete walk)."""
+@pytest.mark.parametrize("seg_blocks", [0, 3, 32])
+def test_chain_table_fast_path_vs_oracle(monkeypatch, seg_blocks):
+    """The single-stream fast path (tabulated reservoir maps, composed over segments of `seg_blocks` blocks; 0 = the
+    per-block maps walked one by one; mrc_chain.cu) forced on for short clips: bytes equal the oracle's, for joint and
+    independent channels, including silence (reservoir far outside the table: closed form) and the blocks after it
+    (complete walk), and for several clips in one wave (segments that straddle two clips are not composed)."""
     import mrc_oracle as o
     from mrcaudiocodec_b200 import Codec, synth
     monkeypatch.setenv("MRC_CHAIN_TABLE_MIN_BLOCKS", "1")
+    monkeypatch.setenv("MRC_CHAIN_SEGMENT_BLOCKS", str(seg_blocks))
     pcm = synth.synth_short(77, 0.8)
+    clips = [pcm, synth.synth_short(78, 0.33), pcm[:5000], synth.synth_short(79, 0.5)]
     for joint in (True, False):
         c = Codec(joint=joint)
         blob = c.encode_clips([pcm])[0]
-        assert c.last_timing()["launches"] >= 8          # table + chain_table were launched
+        assert c.last_timing()["launches"] >= (9 if seg_blocks else 8)     # table (+ segment) + chain were launched
+        blobs = c.encode_clips(clips)
+        st = c.stage_alloc_quant([pcm])
         c.close()
-        ob, _ = o.driver.encode_pcm(pcm, joint=joint)
+        ob, tr = o.driver.encode_pcm(pcm, joint=joint, trace=True)
         assert blob == ob, joint
+        assert st["reservoir"].tolist() == [b["reservoir"] for b in tr]
+        for x, b in zip(clips, blobs):
+            assert b == o.driver.encode_pcm(x, joint=joint)[0], joint
     c = Codec(target_bits_per_sample=64000. / 48000.)
     ob, _ = o.driver.encode_pcm(pcm, joint=True, targetBitsPerSample=64000. / 48000.)
     assert c.encode_clips([pcm])[0] == ob
