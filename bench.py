@@ -11,6 +11,13 @@ and -70 dBFS seconds), joint M/S, 128 kb/s/ch, fp64 code-exact mode.  N>1: every
 `value` is measured with the PCM already in HBM and the bitstream left in HBM; `e2e` goes through the public host
 API (mrc_encode_batch via mrcaudiocodec_b200.Codec.encode_batch) with pinned host buffers, H2D and D2H inside the
 timed region.  The input (691 MB) is larger than L2 (126 MB), so nothing is cache-resident between steps.
+
+roofline: the dominant kernel is analysis_kernel (fused MDCT + psychoacoustic model), an FP64 kernel.  `achieved` =
+the FP64 flops the kernel EXECUTES per block (2 x DFMA + DADD + DMUL thread instructions of one full-wave launch,
+counted by ncu and committed as profiles/analysis_counters.json by scripts/ncu_counters.py) x the blocks of this run
+/ the kernel's launch durations measured live with CUDA events on its stream; `peak` = this GPU's FP64 FMA rate
+measured in the same run (mrc_measure_peaks).  The reference-formulation work (40 flops per masker-line
+pair) is reported beside it as `work_reduction_vs_reference`, not as throughput.
 """
 import argparse
 import json
@@ -28,7 +35,8 @@ sys.path.insert(0, ROOT)
 SR = 48000
 TBPS = 128000.0 / 48000.0
 METRIC = "encoded audio-seconds/sec, 48 kHz stereo 128 kb/s/ch"
-NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK = 12489.0      # (23.42 + 46.84) MB / 5626 blocks, profiles/r01zz_ncu_full_summary.csv
+ALGORITHMIC_BYTES_PER_BLOCK = 4096 + 683 + 8       # PCM in + bitstream + length prefixes
+COUNTERS = os.path.join(ROOT, "profiles", "analysis_counters.json")
 
 
 def parse():
@@ -50,7 +58,10 @@ def parse():
     ap.add_argument("--block-switching", action="store_true",
                     help="encode with the reference's transient detector / look-ahead loop (SURVEY 8 f1): eight "
                          "128-sample short blocks around transients instead of long blocks only")
-    ap.add_argument("--decode", action="store_true", help="also time the decode mirror path on the encoded stream")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decode mirror path (timed by default)")
+    ap.add_argument("--no-music", action="store_true",
+                    help="skip the second encode measurement on dense-masker music-like material (synth_music)")
+    ap.add_argument("--music-seconds", type=float, default=600.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=1.5)
     return ap.parse_args()
@@ -138,7 +149,9 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "1 h synthetic 48 kHz stereo stream, joint M/S, 128 kb/s/ch, fp64 (configs[1]); "
-                                   "each step = %d independent %.1f s samples of it, one per host core" % (cores, sample_s)},
+                                   "each step = %d independent %.1f s samples of it, one per host core; per-HOST figure: "
+                                   "the arm uses all cores of the box whatever --gpus says (%d)" %
+                                   (cores, sample_s, args.gpus)},
             "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": "%d x %.1f s segments per step, %d steps (oracle/mrc_oracle, numpy)" %
                                        (cores, sample_s, args.steps)},
@@ -281,11 +294,38 @@ def main():
             except Exception:
                 pass
         an_ms = r_dev["stage_ms"][0]
-        flops = algorithmic_flops(nblk - n_clips, n_clips, r_dev["maskers"], L)
         is64 = args.precision == "fp64"
         peak_tf = peaks["fp64_tflops"] if is64 else peaks["fp32_tflops"]
-        ach_tf = flops / (an_ms * 1e-3) / 1e12
-        alg_bytes = nblk * (4096 + 2 * L * (8 if is64 else 4) * 1 + 64 * 2 * (8 if is64 else 4) + 1536 + 8)
+        nwaves = max(r_dev["work"]["waves"], 1)
+        # executed work of the dominant kernel: per-block counters from this round's ncu capture of one full-wave launch
+        cnt = None
+        if os.path.exists(COUNTERS):
+            try:
+                cnt = json.load(open(COUNTERS)).get(args.precision)
+            except Exception:
+                cnt = None
+        ref_flops = algorithmic_flops(nblk - n_clips, n_clips, r_dev["maskers"], L)
+        roof = {"kernel": "analysis_kernel (MDCT + psychoacoustics, fused)", "bound": "fp64" if is64 else "fp32",
+                "peak": peak_tf, "unit": "TFLOP/s", "peak_source": "mrc_measure_peaks (FMA chain on this GPU, this run)",
+                "launches_per_step": nwaves, "avg_launch_ms": an_ms / nwaves, "ms_per_step": an_ms}
+        if cnt:
+            flop_key = "fp64_flop_per_block" if is64 else "fp32_flop_per_block"
+            ex_flops = cnt[flop_key] * nblk
+            ach_tf = ex_flops / (an_ms * 1e-3) / 1e12
+            roof.update({
+                "achieved": ach_tf, "frac": ach_tf / peak_tf if peak_tf else None,
+                "traffic": cnt["dram_bytes_per_block"] * nblk / nwaves,
+                "work": "FLOPs the kernel executes: %.0f per block (2 x FMA + ADD + MUL thread instructions of one "
+                        "%d-block launch, ncu, %s) x %d blocks / launch time measured live" %
+                        (cnt[flop_key], cnt["launch_blocks"], cnt.get("source", "profiles/"), nblk),
+                "ncu_pipe_active_pct": cnt.get("pipe_fp64_active_pct" if is64 else "pipe_fma_active_pct"),
+                "ncu_issue_active_pct": cnt.get("issue_active_pct"),
+                "work_reduction_vs_reference": ref_flops / ex_flops,
+                "reference_formulation_flops_per_step": ref_flops})
+        else:
+            roof.update({"achieved": None, "frac": None, "traffic": None,
+                         "work": "profiles/analysis_counters.json missing: no executed-flop count for this build"})
+        alg_bytes = ALGORITHMIC_BYTES_PER_BLOCK * nblk
         line = {
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * r_dev["wall"] / args.steps, "higher_is_better": True,
@@ -301,39 +341,39 @@ def main():
             "device_ms_per_step": 1000.0 * r_dev["dev"] / args.steps,
             "stage_ms_per_step": {"analysis": r_dev["stage_ms"][0], "cost": r_dev["stage_ms"][1],
                                   "chain": r_dev["stage_ms"][2], "pack": r_dev["stage_ms"][3],
-                                  "note": "per-kernel sums; analysis+cost of wave w+1 overlap chain+pack of wave w"},
+                                  "note": "per-kernel sums; analysis+cost(+reservoir maps) of wave w+1 overlap chain+pack of wave w"},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(frames * 4),
                     "d2h_bytes_per_step": int(r_e2e["nbytes"]), "ms_per_step": 1000.0 * r_e2e["wall"] / args.steps},
             "gpu_launches": int(r_dev["launches"]),
             "clocks": r_dev["clocks"],
-            "roofline": {"kernel": "analysis_kernel (MDCT + psychoacoustics, fused)",
-                         "bound": "fp64" if is64 else "fp32", "achieved": ach_tf, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-                         # dram__bytes_read + dram__bytes_write of one analysis launch, from the committed ncu capture
-                         # (profiles/r01zz_ncu_full_summary.csv: 70.3 MB for 5626 blocks), scaled to this run's launch size
-                         "traffic": NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK * nblk / max(r_dev["work"]["waves"], 1),
-                         "peak_source": "mrc_measure_peaks (FMA chain on this GPU, this run)",
-                         "work": "SURVEY 8d reference formulation (40 FLOP per masker-line pair), %d maskers measured; "
-                                 "the %s evaluation executes the work listed under executed_work" %
-                                 (r_dev["maskers"], args.spreading),
-                         "launches_per_step": r_dev["work"]["waves"],
-                         "avg_launch_ms": an_ms / max(r_dev["work"]["waves"], 1), "ms_per_step": an_ms},
-            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (an_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": alg_bytes / (an_ms * 1e-3) / 1e9 / hbm_peak,
+            "roofline": roof,
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (1e-3 * 1000.0 * r_dev["dev"] / args.steps) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes / (1e-3 * 1000.0 * r_dev["dev"] / args.steps) / 1e9 / hbm_peak,
                              "peak_source": hbm_src,
-                             "traffic": NCU_ANALYSIS_DRAM_BYTES_PER_BLOCK * nblk / max(r_dev["work"]["waves"], 1)},
+                             "work": "algorithmic bytes (%d per block: PCM in + bitstream + prefixes) / whole step" %
+                                     ALGORITHMIC_BYTES_PER_BLOCK},
             "pipe_peaks": peaks,
             "executed_work": r_dev["work"],
         }
+        if cnt and cnt.get("wave"):
+            wv = cnt["wave"]
+            line["pipeline_traffic"] = {"dram_bytes_per_block": wv["dram_bytes_per_block"],
+                                        "algorithmic_bytes_per_block": ALGORITHMIC_BYTES_PER_BLOCK,
+                                        "ratio": wv["dram_bytes_per_block"] / ALGORITHMIC_BYTES_PER_BLOCK,
+                                        "gbs_at_this_step_rate": wv["dram_bytes_per_block"] * nblk /
+                                        (1e-3 * 1000.0 * r_dev["dev"] / args.steps) / 1e9,
+                                        "source": "ncu dram__bytes of every kernel of one %d-block wave (%s)" %
+                                                  (wv["blocks"], cnt.get("source", "profiles/"))}
         if args.block_switching:
             line["config"]["workload"] += (", BLOCK SWITCHING on (transient detector + look-ahead, short blocks of 128: "
                                            "%d blocks written for %d blocks of 1024 frames)" %
                                            (r_dev["extra"]["blocks_written"], nblk))
             line["stage_ms_per_step"]["transient_detector"] = r_dev["extra"]["transient_ms"]
-            line["roofline"]["work"] += "; work formula evaluated on the long-block equivalent of the stream"
         if args.spreading == "factorised" and not args.no_sequential_sample and not args.block_switching:
             # the same analysis kernel summing the maskers pair by pair in the reference's order, on a bounded
-            # sample of the same stream: this is the kernel SURVEY 8d's 40-FLOP-per-pair work formula describes
+            # sample of the same stream: the kernel SURVEY 8d's 40-flop-per-pair work formula describes (here the formula
+            # IS roughly what runs, so the reference-formulation flop count is used)
             sample_s = min(seconds, 600.0)
             nfr = int(sample_s * SR)
             cs = Codec(device=local, precision=args.precision, spreading="sequential")
@@ -343,12 +383,13 @@ def main():
             ts = cs.last_timing()
             sflops = algorithmic_flops(cs.n_blocks(nfr) - 1, 1, ts["maskers"], L)
             s_tf = sflops / (ts["analysis_ms"] * 1e-3) / 1e12
-            line["roofline_sequential"] = {"kernel": "analysis_kernel, MRC_FLAG_SPREAD_SEQUENTIAL", "bound": line["roofline"]["bound"],
+            line["roofline_sequential"] = {"kernel": "analysis_kernel, MRC_FLAG_SPREAD_SEQUENTIAL", "bound": roof["bound"],
                                            "achieved": s_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": s_tf / peak_tf,
+                                           "work": "SURVEY 8d formula, 40 flops per (masker, line) pair",
                                            "sample": "first %.0f s of the stream, 1 launch" % sample_s,
                                            "avg_launch_ms": ts["analysis_ms"]}
             cs.close()
-        if args.decode:
+        if not args.no_decode:
             # the mirror path (rows a14-a17): .pac bytes in pinned host memory -> int16 PCM in host memory
             nbytes = int(last_boff[0][-1])
             pac = h_out_np[:nbytes]
@@ -365,7 +406,34 @@ def main():
             td = codec.last_timing()
             line["decode"] = {"e2e_value": seconds / dt, "unit": "audio-s/s", "ms_per_step": 1000.0 * dt,
                               "kernel_ms": td["decode_ms"], "h2d_bytes_per_step": nbytes,
-                              "d2h_bytes_per_step": int(pcm_out.nbytes)}
+                              "d2h_bytes_per_step": int(pcm_out.nbytes),
+                              "note": "decode of this rank's stream through Codec.decode_batch, host buffers, 3 steps"}
+            del h_dec
+        if not args.no_music and args.workload == "stream" and not args.block_switching:
+            # the same encode on dense-masker material (synth_music: chords of harmonic notes, most of the spectrum above
+            # 40 dB SPL): the band-maximum search prunes far less there, so this is the unfriendly end of the input range
+            ms_ = min(args.music_seconds, seconds)
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                parts = list(ex.map(lambda i: synth.synth_music(100 + i, 30.0), range(max(1, int(ms_ // 30)))))
+            mus = np.concatenate(parts, axis=0)
+            moff = np.array([0, mus.shape[0]], dtype=np.int64)
+            d_mus = torch.from_numpy(mus).to(dev)
+            for _ in range(2):
+                codec.encode_batch_device(d_mus.data_ptr(), moff, d_out.data_ptr(), cap)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                codec.encode_batch_device(d_mus.data_ptr(), moff, d_out.data_ptr(), cap)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            tm = codec.last_timing()
+            line["music"] = {"value": (mus.shape[0] / SR) / dt, "unit": "audio-s/s", "seconds": mus.shape[0] / SR,
+                             "ms_per_step": 1000.0 * dt, "analysis_ms": tm["analysis_ms"],
+                             "maskers_per_block": tm["maskers"] / max(tm["blocks"], 1),
+                             "general_pairs_per_block": tm["general_pairs"] / max(tm["blocks"], 1),
+                             "note": "device-resident encode of synth_music material (dense loud maskers), same codec"}
+            del d_mus
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pcm, args.cpu_sample_seconds)
         print(json.dumps(line))

@@ -152,6 +152,24 @@ int32_t mrc_decode_batch_device(mrc_ctx* ctx, const uint8_t* d_pac, const uint8_
                                 const int64_t* clip_byte_offsets, int32_t n_clips, int16_t* d_pcm_out,
                                 int64_t pcm_cap_frames, int64_t* clip_frame_offsets);
 
+/* ---- one stream sharded by block range across GPUs (one context per GPU) ----------------------------------------
+ * The blocks of a stream are independent except for two things a block inherits from the one before it: the previous
+ * n_mdct_lines frames (pacfileThem.py:799-802 -- a halo the shard reads from the PCM itself) and
+ * codingParams.bitReservoir (codecThem.py:391, :503, :274 -- one int).  A shard encodes blocks
+ * [first_block, first_block + n_blocks) of the stream's ceil(total_frames / n_mdct_lines) blocks: transform,
+ * psychoacoustics, bit prices and the composed reservoir maps first (all independent of the reservoir), then it calls
+ * exchange(user, 0, &r) to RECEIVE the reservoir the previous shard ended with (the first shard is given 0), runs the
+ * serial pass, calls exchange(user, 1, &r) to HAND ON its own final reservoir, and only then packs its chunks.  The
+ * shards' outputs concatenated in order are byte-identical to mrc_encode_batch of the whole stream; the first shard
+ * writes the file header (is_first), the last one the Close() flush block (is_last).
+ * pcm : host frames [pcm_frame0, pcm_frame0 + pcm_frames) of the stream; must cover
+ *       [max(first_block - 1, 0) * L, min((first_block + n_blocks) * L, total_frames)).
+ * The callbacks return 0 on success.  Long blocks only (no MRC_FLAG_BLOCK_SWITCHING). */
+typedef int32_t (*mrc_reservoir_exchange)(void* user, int32_t have_result, int32_t* reservoir);
+int32_t mrc_encode_shard(mrc_ctx* ctx, const int16_t* pcm, int64_t pcm_frame0, int64_t pcm_frames, int64_t total_frames,
+                         int64_t first_block, int64_t n_blocks, int32_t is_first, int32_t is_last, uint8_t* out,
+                         int64_t out_cap, int64_t* out_bytes, mrc_reservoir_exchange exchange, void* user);
+
 /* ---- per-block seam (compat layer; explicit bit reservoir in/out) -----------------------------------------
  * mrc_encode_block = codecThem.Encode (joint=0) / JointEncode (joint=1) on one block; joint|2 skips the Huffman
  * stage (EncodeNoHuff, codecThem.py:234-260: table 15, no reservoir credit).

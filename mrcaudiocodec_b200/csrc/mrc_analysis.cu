@@ -224,27 +224,66 @@ __device__ __forceinline__ double spread_line_bound(const Smem<T>& sm, const Dev
     return a + fmax(w, 0.0);
 }
 
-// The same threshold, complete, evaluated by a whole warp: lanes stride over the plateau maskers and the loud
-// maskers, lane 0 adds the threshold in quiet and the two tails, then a butterfly sum.  All lanes return it.
+// masker_range by a whole warp: the count table gives a first guess, then ONE window of 32 consecutive maskers per
+// bound is tested with the reference's own comparison (one masker per lane) -- both predicates hold for a prefix of
+// the ascending maskers, so the number of lanes that pass is the bound.  If a window does not contain its bound
+// (never seen: a 1/32-Bark cell holds a few maskers at most) the scalar search is used.
+template <typename T>
+__device__ __forceinline__ void masker_range_warp(const Smem<T>& sm, double zk, int npk, int lane, int& m_lo, int& m_hi) {
+    if (sm.zlut == nullptr) { masker_range(sm, zk, npk, m_lo, m_hi); return; }
+    int g = (int)((zk - 0.5) * 32.0);
+    const int w0 = (int)sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)] - 8;
+    g = (int)((zk + 0.5) * 32.0) + 1;
+    const int w1 = (int)sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)] - 24;
+    const int i0 = w0 + lane, i1 = w1 + lane;
+    const double z0 = sm.mz[i0 < 0 ? 0 : (i0 < npk ? i0 : 0)], z1 = sm.mz[i1 < 0 ? 0 : (i1 < npk ? i1 : 0)];
+    const bool p0 = i0 < 0 || (i0 < npk && zk - z0 > 0.5);             // maskers more than 0.5 Bark below the line
+    const bool p1 = i1 < 0 || (i1 < npk && !(zk - z1 < -0.5));         // maskers not more than 0.5 Bark above it
+    const int n0 = __popc(__ballot_sync(0xffffffffu, p0)), n1 = __popc(__ballot_sync(0xffffffffu, p1));
+    if (n0 >= 1 && n0 <= 31 && n1 >= 1 && n1 <= 31) {
+        m_lo = w0 + n0;
+        m_hi = w1 + n1;
+        return;
+    }
+    masker_range(sm, zk, npk, m_lo, m_hi);
+}
+
+// The same threshold, complete, evaluated by a whole warp.  Everything that goes through 10**x is one list of items
+// dealt out to the lanes -- item 0 the tail of the maskers more than 0.5 Bark below the line, item 1 the tail of those
+// above, items 2.. the loud maskers below -- so that one pass of the exponential covers a typical line; the plateau
+// maskers are summed lane-strided, lane 2 adds the threshold in quiet, then a butterfly sum.  All lanes return it.
 template <typename T>
 __device__ __forceinline__ double spread_line_warp(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk, int lane,
                                                    unsigned& n_general, unsigned& n_window) {
     MRC_WCLK_BEGIN();
     const double zk = tb.bark_d[k];
+    const double quiet = tb.quiet_d[k];
     int m_lo, m_hi;
-    masker_range(sm, zk, npk, m_lo, m_hi);
+    masker_range_warp(sm, zk, npk, lane, m_lo, m_hi);
     MRC_WCLK(16);
+    const int nl = sm.lcnt[m_lo];
     double a = 0.0;
-    if (lane == 0) a = tb.quiet_d[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
+    for (int base = 0; base < nl + 2; base += 32) {
+        const int item = base + lane, j = item - 2;
+        const bool tail = item < 2;
+        const bool valid = tail ? (item == 0 ? m_lo > 0 : m_hi < npk) : j < nl;
+        int mi = tail ? (item == 0 ? m_lo - 1 : m_hi) : (int)sm.lidx[j < nl ? j : 0];
+        mi = valid ? mi : 0;
+        const double mzv = sm.mz[mi];
+        const double t = __dadd_rn(item == 1 ? __dadd_rn(mzv, -zk) : __dadd_rn(zk, -mzv), -0.5);
+        // loud masker: the reference's exponent, unfused (psychoac.py:70-76); tails: -27 dB per Bark beyond the plateau
+        const double e = __dadd_rn(__dadd_rn(sm.ms15[mi], __dmul_rn(-27.0, t)), __dmul_rn(sm.mg[mi], t));
+        const double y = tail ? -2.7 * t : div10(__dadd_rn(e, -96.0));
+        const double coef = tail ? (item == 0 ? sm.mU[mi] : sm.mS[mi]) : 1.0;
+        const double v = coef * exp10_tab(y, sm.etab);
+        if (valid) a += v;
+    }
     MRC_WSYNC();
     MRC_WCLK(17);
     for (int m = m_lo + lane; m < m_hi; m += 32) a += sm.mc[m];
+    if (lane == 2) a += quiet;
     MRC_WSYNC();
     MRC_WCLK(18);
-    const int nl = sm.lcnt[m_lo];
-    for (int j = lane; j < nl; j += 32) a += loud_term(sm, zk, sm.lidx[j]);
-    MRC_WSYNC();
-    MRC_WCLK(19);
     if (lane == 0) { n_general += (unsigned)nl; n_window += (unsigned)(m_hi - m_lo); }
 #pragma unroll
     for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -303,9 +342,9 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
         for (int i = tid; i < 2 * N; i += NT) sm.sx[i] = T(xin[(size_t)g * 2 * N + i]);
     } else {
         const long long frames = cm.clip_off[s_clip + 1] - cm.clip_off[s_clip];
-        const uint32_t* __restrict__ p32 = reinterpret_cast<const uint32_t*>(pcm) + cm.clip_off[s_clip];
+        const uint32_t* __restrict__ p32 = reinterpret_cast<const uint32_t*>(pcm) + (cm.clip_off[s_clip] - cm.pcm_frame0);
         // the block's a "prior" samples then its b new ones (pacfileThem.py:799-802)
-        const long long s0 = cm.blk_start ? cm.blk_start[g] - tb.a : (long long)(b - 1) * L;
+        const long long s0 = cm.blk_start ? cm.blk_start[g] - tb.a : (long long)(b + cm.blk_base - 1) * L;
         for (int n = tid; n < N; n += NT) {
             const long long s = s0 + n;
             uint32_t w = 0;
@@ -673,7 +712,12 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             auto complete = [&](int k, T& smr, T& rho) {         // whole warp; all lanes get the results
                 const double a = spread_line_warp(sm, tb, k, npk, lane, n_general, n_window);
                 MRC_WCLK_BEGIN();
-                smr = line_spl(k) - thr_of(a);
+                // line_spl(k) - thr_of(a) with the two logarithms side by side (odd lanes the line, even lanes the
+                // threshold): same operations on the same operands, half the latency
+                const T X = sm.lines[c * L + k];
+                const T lg = m_log10((lane & 1) ? (T(2) * (X * X)) / T(0.5) : T(a));
+                const T lg_a = __shfl_sync(0xffffffffu, lg, 0), lg_x = __shfl_sync(0xffffffffu, lg, 1);
+                smr = (fmax(T(96) + T(10) * lg_x, T(-30)) - sc6) - fmax(T(96) + T(10) * lg_a, T(-30));
                 rho = T(x2c(k) / fmax(a, FLOOR));
                 MRC_WCLK(21);
 #ifdef MRC_PHASE_CLOCKS
@@ -796,8 +840,93 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // the partner run (stable: ties in key go to the lower band, then to the run that came first).  Non-joint
     // blocks keep their two channels in separate halves and skip the last round.  All comparisons are on exactly
     // the values the reference's `smr[i] -= 12.0 / 6.0` updates produce.
+    // Fast path: every key is s_b - 6m with m in {0, 2, 3, ..., 15}, so with s_b = 6 q_b + f_b (q_b integer, 0 <= f_b < 6)
+    // a token sits on the integer level v = q_b - m and the order is: level descending, then f_b descending, then band
+    // ascending.  A token's position = tokens on higher levels + bands of its own level that precede its band -- counted
+    // with one 64-bit mask of band ranks per level: no sorting, no searches.  This is the order of the keys in real
+    // arithmetic; the reference's keys carry the rounding of its repeated subtractions (< 1e-12), so the two orders can
+    // only differ where keys of two bands come closer than that.  In fp64 mode the fast path is therefore used only when
+    // all f_b are pairwise at least 1e-9 apart (also across the wrap 0 ~ 6) or belong to bitwise equal SMRs (equal
+    // channels: identical key sequences, ordered by band); otherwise the merge below runs (about once in 10^6 blocks).
+    __shared__ int s_unsafe;
     {
-        __syncthreads();                                 // phase 5 is done reading sm.lines: the merge buffers alias it
+        __syncthreads();                                 // phase 5 is done reading sm.lines: the buffers below alias it
+        MRC_CLK(10);
+        constexpr int NLEV = 128, LEV_OFF = 64;
+        unsigned long long* const lmask = reinterpret_cast<unsigned long long*>(sm.mkey);      // [2][NLEV]
+        int* const lstart = reinterpret_cast<int*>(lmask + 2 * NLEV);                           // [2][NLEV]
+        double* const bf = reinterpret_cast<double*>(lstart + 2 * NLEV);                        // [64] f_b
+        double* const bs = bf + 64;                                                             // [64] s_b
+        int* const bq = reinterpret_cast<int*>(bs + 64);                                        // [64] q_b
+        int* const brank = bq + 64;                                                             // [64]
+        const int ntot = 2 * nb, per_group = nb * MRC_MAX_LEVELS;
+        const double EPS = 1e-9;
+        if (tid == 0) s_unsafe = 0;
+        for (int i = tid; i < 2 * NLEV; i += NT) lmask[i] = 0ull;
+        if (tid < ntot) {
+            const int ch = tid / nb, bd = tid - ch * nb;
+            const bool m = (ms >> bd) & 1u;
+            const double sv = (double)s_smr[(m ? 2 : 0) + ch][bd];
+            double qd = floor(sv * (1.0 / 6.0));
+            double f = fma(-6.0, qd, sv);
+            if (f < 0.0) { qd -= 1.0; f += 6.0; }
+            if (f >= 6.0) { qd += 1.0; f -= 6.0; }
+            bool bad = !(qd > -48.0 && qd < 62.0) || !(f >= 0.0 && f < 6.0);       // also NaN / infinities
+            if (sizeof(T) == 8 && !(f >= EPS && f <= 6.0 - EPS)) bad = true;
+            bf[tid] = f; bs[tid] = sv; bq[tid] = bad ? 0 : (int)qd;
+            if (bad) s_unsafe = 1;
+        }
+        __syncthreads();
+        if (tid < ntot) {
+            const int grp = joint ? 0 : tid / nb;
+            const int b0 = joint ? 0 : grp * nb, b1 = joint ? ntot : b0 + nb;
+            const double f = bf[tid], sv = bs[tid];
+            int r = 0;
+            bool bad = false;
+            for (int j = b0; j < b1; ++j) {
+                const double fj = bf[j];
+                r += (fj > f || (fj == f && j < tid)) ? 1 : 0;
+                if (sizeof(T) == 8 && j != tid && fabs(fj - f) < EPS && !(bs[j] == sv)) bad = true;
+            }
+            brank[tid] = r;
+            if (bad) s_unsafe = 1;
+            const int q = bq[tid];
+            for (int l = 0; l < MRC_MAX_LEVELS; ++l)
+                atomicOr(&lmask[grp * NLEV + (q - (l ? l + 1 : 0) + LEV_OFF)], 1ull << r);
+        }
+        __syncthreads();
+        if (warp < 2) {                                  // tokens on higher levels, per group: suffix sums over the levels
+            int c[4], tot = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { c[i] = __popcll(lmask[warp * NLEV + lane * 4 + i]); tot += c[i]; }
+            int suf = tot;                               // inclusive suffix sum over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += v;
+            }
+            int above = suf - tot;                       // tokens on the levels of higher lanes
+#pragma unroll
+            for (int i = 3; i >= 0; --i) { lstart[warp * NLEV + lane * 4 + i] = above; above += c[i]; }
+        }
+        __syncthreads();
+        uint16_t* ot = ho.tokens + (size_t)lb * MRC_TOK_STRIDE;
+        if (!s_unsafe) {
+            for (int e = tid; e < MRC_TOK_STRIDE; e += NT) {
+                if (e < ntot * MRC_MAX_LEVELS) {
+                    const int bb = e / MRC_MAX_LEVELS, l = e - bb * MRC_MAX_LEVELS;
+                    const int grp = joint ? 0 : bb / nb;
+                    const int li = grp * NLEV + (bq[bb] - (l ? l + 1 : 0) + LEV_OFF);
+                    const int pos = lstart[li] + __popcll(lmask[li] & ((1ull << brank[bb]) - 1ull));
+                    ot[grp * per_group + pos] = (uint16_t)(bb | (l << 8));
+                } else {
+                    ot[e] = 0xffffu;                     // slots past the 2 * nb * 15 tokens
+                }
+            }
+        }
+        __syncthreads();                                 // (the merge buffers alias the arrays above)
+    }
+    if (s_unsafe) {
         MRC_CLK(10);
         T* const key0 = sm.mkey;
         T* const key1 = sm.mkey + 1024;

@@ -62,10 +62,11 @@ struct mrc_ctx {
 
     // scratch (grow only)
     Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out;
-    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab, comp, rin; } sets[3];
+    struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab, comp, segx, rin; } sets[3];
     Buf q_alloc, q_sf, q_mant;
     cudaStream_t stream2 = nullptr, stream3 = nullptr;    // analysis stream, H2D copy stream
     cudaStream_t stream4 = nullptr;                       // D2H copy stream (bitstream of finished waves)
+    cudaStream_t stream5 = nullptr;                       // composition of the reservoir maps (forks off stream2)
     int64_t* h_prog = nullptr;                            // pinned: per wave, how far the output is final
     int h_prog_cap = 0;
     bool no_tables = false;          // MRC_FLAG_NO_CHAIN_TABLES
@@ -287,6 +288,15 @@ struct EncodeJob {
     bool dev_qtaps = false;                // leave alloc / mantissa taps of the (single) wave in q_alloc / q_mant
     int geom = MRC_GEO_LONG;               // d_xin jobs: the geometry of every block (per-block seam with a, b given)
     bool switching = false;                // d_pcm jobs: transient detector + look-ahead decide each block's geometry
+    // one stream sharded by block range (mrc_encode_shard): a single clip whose h_clip_off spans the WHOLE stream, of
+    // which this job encodes shard_blocks blocks starting at block shard_first (+ the flush block when flush_nonjoint);
+    // d_pcm starts at stream frame pcm_frame0.  The reservoir comes from / goes to the neighbouring shards through
+    // `exchange`, called once before the serial pass and once right after it.
+    bool shard = false;
+    int64_t shard_first = 0, shard_blocks = 0, pcm_frame0 = 0;
+    bool shard_header = true;
+    mrc_reservoir_exchange exchange = nullptr;
+    void* exchange_user = nullptr;
 };
 
 // ---- block switching: which nMDCTLines-frame blocks are written as eight short blocks --------------------------
@@ -402,7 +412,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
             const long long fr = job.h_clip_off[c + 1] - job.h_clip_off[c];
             if (fr < 0) return fail(ctx, MRC_E_INVALID, "clip_frame_offsets must be non-decreasing");
             blk0[c] = (int32_t)tot;
-            tot += job.d_xin ? fr / (2 * Lt) : (fr + L - 1) / L + (job.flush_nonjoint ? 1 : 0);
+            if (job.shard) tot += job.shard_blocks + (job.flush_nonjoint ? 1 : 0);
+            else tot += job.d_xin ? fr / (2 * Lt) : (fr + L - 1) / L + (job.flush_nonjoint ? 1 : 0);
             if (tot > 0x7fff0000ll) return fail(ctx, MRC_E_INVALID, "too many blocks in one call");
         }
         blk0[nc] = (int32_t)tot;
@@ -425,6 +436,12 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     CK(cudaMemsetAsync(ctx->peakctr.p, 0, 64, st));
     const int32_t* d_res_in = nullptr;
     int32_t* d_res_out = nullptr;
+    if (job.exchange) {
+        CK(ensure(ctx->res_in, (size_t)nc * 4));
+        CK(ensure(ctx->res_out, (size_t)nc * 4));
+        d_res_in = (const int32_t*)ctx->res_in.p;
+        d_res_out = (int32_t*)ctx->res_out.p;
+    }
     if (job.h_res_in) {
         CK(ensure(ctx->res_in, (size_t)nc * 4));
         CK(cudaMemcpyAsync(ctx->res_in.p, job.h_res_in, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
@@ -439,6 +456,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     cm.clip_blk0 = (const int32_t*)ctx->clip_blk0.p;
     cm.n_clips = nc;
     cm.blk_start = nullptr; cm.blk_geom = nullptr; cm.list = nullptr;
+    cm.pcm_frame0 = job.shard ? job.pcm_frame0 : 0;
+    cm.blk_base = job.shard ? (int)job.shard_first : 0;
     // geometries in play, their launch parameters, and (block switching) the per-wave block lists of each
     const int q_lo = job.switching ? 0 : job.geom, q_hi = job.switching ? MRC_N_GEO - 1 : job.geom;
     CodecParams cpq[MRC_N_GEO];
@@ -448,6 +467,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         cpq[q].joint = job.joint;
         cpq[q].flush_nonjoint = job.flush_nonjoint ? 1 : 0;
         cpq[q].no_huff = job.no_huff;
+        if (job.shard && !job.shard_header) cpq[q].header_bytes = 0;       // the stream's first shard writes the file header
         for (int v : ctx->geo[q].h_band_n) max_nl = std::max(max_nl, v);
     }
     const CodecParams& cp = cpq[q_lo];     // for the kernels that read only geometry-independent fields
@@ -459,7 +479,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     {
         std::vector<int> sizes, tail;
         int rem = nblk_total, tailsum = 0;
-        if (nblk_total > 4096 && !job.dev_qtaps) {
+        if (nblk_total > 4096 && !job.dev_qtaps && !job.shard) {    // a shard is one wave: its tables stay resident while it
+                                                                    // waits for the reservoir of the shard before it
             for (int sz = 1024; sz <= WAVE_BLOCKS / 2 && tailsum + sz <= rem / 2; sz *= 2) { tail.push_back(sz); tailsum += sz; }
             int body = rem - tailsum;
             for (int sz = 2048; sz < WAVE_BLOCKS && sz <= body / 4; sz *= 2) { sizes.push_back(sz); body -= sz; }
@@ -552,7 +573,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
 
     // events per wave: 0 analysis start, 1 analysis end, 2 cost end, 3 chain start, 4 chain end, 5 pack end,
     // 6 PCM of the wave uploaded (7 = that upload queued), 8-9 around the bitstream copy drained after the wave
-    constexpr int EPW = 10;
+    // 10-11 around the composition of the reservoir maps on its own stream
+    constexpr int EPW = 12;
     for (int i = 0; i < nwaves * EPW; ++i) pool_event(ctx, (size_t)i);
     auto ev = [&](int w, int k) { return ctx->evpool[(size_t)w * EPW + k]; };
     // everything queued on `st` so far (tables of this call, PCM upload) must precede the first analysis
@@ -642,6 +664,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
             });
         // long stretches of one clip in the wave: the serial walk is the critical path, tabulate the reservoir maps
         const bool use_tab = job.need_quant && !ctx->no_tables && nblk / (c_hi - c_lo + 1) >= ctx->tab_min_blocks;
+        bool seg_forked = false;
         if (use_tab) {
             CK(ensure(ctx->sets[s].tab, W * 2 * (size_t)tabw * 4));
             launch_table(st2, cp, cm, g0, nblk, io[s], r_lo, ntab, tabw, (int*)ctx->sets[s].tab.p);
@@ -650,21 +673,38 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
                 const size_t nseg = (W + seg_S - 1) / seg_S;
                 CK(ensure(ctx->sets[s].comp, nseg * (size_t)segw * 4));
                 CK(ensure(ctx->sets[s].rin, nseg * 4));
-                launch_segments(st2, cp, cm, g0, nblk, seg_S, io[s], r_lo, ntab, tabw, (const int*)ctx->sets[s].tab.p, segw,
-                                (int*)ctx->sets[s].comp.p, (int*)ctx->sets[s].rin.p);
-                ++launches;
+                CK(ensure(ctx->sets[s].segx, nseg * (size_t)segment_aux_width() * 4));
+                // composing the maps is a short kernel of few CTAs followed by a latency-bound one: on a stream of its
+                // own, so that the next wave's analysis does not queue behind it
+                CK(cudaEventRecord(ev(w, 10), st2));
+                CK(cudaStreamWaitEvent(ctx->stream5, ev(w, 10), 0));
+                launch_segments(ctx->stream5, cp, cm, g0, nblk, seg_S, io[s], r_lo, ntab, tabw, (const int*)ctx->sets[s].tab.p,
+                                segw, (int*)ctx->sets[s].comp.p, (int*)ctx->sets[s].segx.p, (int*)ctx->sets[s].rin.p);
+                CK(cudaEventRecord(ev(w, 11), ctx->stream5));
+                seg_forked = true;
+                launches += 2;
             }
         }
         CK(cudaEventRecord(ev(w, 2), st2));
         // ---- main stream: chain -> clip offsets -> quantise + pack ----
         CK(cudaStreamWaitEvent(st, ev(w, 2), 0));
+        if (seg_forked) CK(cudaStreamWaitEvent(st, ev(w, 11), 0));
+        int32_t shard_res = 0;
+        if (job.exchange) {
+            // everything that does not depend on the reservoir is done (or running); now wait for the shard before us
+            CK(cudaStreamSynchronize(st));
+            if (job.exchange(job.exchange_user, 0, &shard_res) != 0)
+                return fail(ctx, MRC_E_STATE, "reservoir exchange callback failed (receive)");
+            CK(cudaMemcpyAsync(ctx->res_in.p, &shard_res, 4, cudaMemcpyHostToDevice, st));
+        }
         CK(cudaEventRecord(ev(w, 3), st));
         if (job.need_quant) {
             if (use_tab && seg_S > 0) {
                 launch_chain_seg(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, seg_S, io[s], r_lo, ntab, tabw,
                                  (const int*)ctx->sets[s].tab.p, segw, (const int*)ctx->sets[s].comp.p,
-                                 (int*)ctx->sets[s].rin.p, d_res_in, d_res_out, (unsigned long long*)ctx->peakctr.p + 4);
-                ++launches;
+                                 (const int*)ctx->sets[s].segx.p, (int*)ctx->sets[s].rin.p, d_res_in, d_res_out,
+                                 (unsigned long long*)ctx->peakctr.p + 4);
+                launches += 2;
             } else if (use_tab)
                 launch_chain_table(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, io[s], r_lo, ntab, tabw,
                                    (const int*)ctx->sets[s].tab.p, d_res_in, d_res_out,
@@ -675,6 +715,13 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
             ++launches;
         }
         CK(cudaEventRecord(ev(w, 4), st));
+        if (job.exchange) {
+            // hand the reservoir on before anything else: the next shard's serial pass waits for nothing but this
+            CK(cudaMemcpyAsync(&shard_res, ctx->res_out.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (job.exchange(job.exchange_user, 1, &shard_res) != 0)
+                return fail(ctx, MRC_E_STATE, "reservoir exchange callback failed (send)");
+        }
         if (job.need_quant) {
             launch_finish(st, cp, cm, g0, nblk, io[s]);
             launch_offsets(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, io[s]);
@@ -808,7 +855,7 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     ctx->counters[2] = nblk_total;
     ctx->counters[4] = nwaves;
     ctx->counters[1] = (int64_t)pk[0];
-    ctx->counters[3] = (int64_t)pk[4];
+    ctx->counters[3] = (int64_t)pk[4];      // complete walks taken by the serial pass (pk[5]: blocks it stepped one by one)
     ctx->counters[5] = (int64_t)pk[1]; ctx->counters[6] = (int64_t)pk[2]; ctx->counters[7] = (int64_t)pk[3];
     if (job.d_out && nblk_total == 0) for (int c = 0; c <= nc; ++c) job.h_clip_byte_off[c] = 0;
     if (job.h_copied) *job.h_copied = ovf ? 0 : copied;
@@ -828,6 +875,7 @@ int run_encode(mrc_ctx* ctx, const EncodeJob& job) {
         // nothing of this call may be in flight once it has returned (the error message is already set)
         cudaStreamSynchronize(ctx->stream3);
         cudaStreamSynchronize(ctx->stream2);
+        cudaStreamSynchronize(ctx->stream5);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->stream4);
     }
@@ -858,6 +906,32 @@ int64_t nominal_bytes(const mrc_ctx* ctx, const int64_t* off, int nc) {
         if (ctx->cfg.flags & MRC_FLAG_BLOCK_SWITCHING) tot += nblk * 160;
     }
     return tot;
+}
+
+// mrc_encode_shard: the caller's exchange callback behind a relay that remembers what was received and whether the
+// result has been handed on, so that a second attempt of the same shard replays instead of exchanging again
+struct ShardRelay {
+    mrc_reservoir_exchange fn;
+    void* user;
+    int32_t r_in;
+    bool got_in, gave_out;
+};
+
+int32_t shard_relay_fn(void* u, int32_t have_result, int32_t* r) {
+    ShardRelay* q = (ShardRelay*)u;
+    if (!have_result) {
+        if (!q->got_in) {
+            const int32_t rc = q->fn(q->user, 0, &q->r_in);
+            if (rc != 0) return rc;
+            q->got_in = true;
+        }
+        *r = q->r_in;
+        return 0;
+    }
+    if (q->gave_out) return 0;
+    const int32_t rc = q->fn(q->user, 1, r);
+    if (rc == 0) q->gave_out = true;
+    return rc;
 }
 
 }  // namespace
@@ -918,6 +992,14 @@ int32_t mrc_create(const mrc_config* cfg, mrc_ctx** out) {
         delete ctx;
         return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
+    if ((e = cudaStreamCreateWithPriority(&ctx->stream5, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        cudaStreamDestroy(ctx->stream2);
+        cudaStreamDestroy(ctx->stream3);
+        cudaStreamDestroy(ctx->stream4);
+        delete ctx;
+        return fail(nullptr, MRC_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     *out = ctx;
     return MRC_OK;
@@ -945,7 +1027,7 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     for (auto& b : ctx->dec) release(b);
     for (auto& ws : ctx->sets) {
         Buf* wb[] = {&ws.lines, &ws.bandmax, &ws.tokens, &ws.ovs, &ws.ms, &ws.rec, &ws.pw, &ws.rsv, &ws.gmask, &ws.cblk, &ws.tab,
-                     &ws.comp, &ws.rin};
+                     &ws.comp, &ws.segx, &ws.rin};
         for (Buf* b : wb) release(*b);
     }
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -956,6 +1038,8 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     cudaStreamDestroy(ctx->stream3);
     cudaStreamSynchronize(ctx->stream4);
     cudaStreamDestroy(ctx->stream4);
+    cudaStreamSynchronize(ctx->stream5);
+    cudaStreamDestroy(ctx->stream5);
     if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1102,6 +1186,58 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
     CK(cudaStreamSynchronize(st));
     float t = 0;
     cudaEventElapsedTime(&t, ctx->ev[7], ctx->ev[5]); ctx->ms[5] += t;      // + the tail the waves had not drained
+    cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]); ctx->ms[6] = t;
+    return MRC_OK;
+}
+
+int32_t mrc_encode_shard(mrc_ctx* ctx, const int16_t* pcm, int64_t pcm_frame0, int64_t pcm_frames, int64_t total_frames,
+                         int64_t first_block, int64_t n_blocks, int32_t is_first, int32_t is_last, uint8_t* out,
+                         int64_t out_cap, int64_t* out_bytes, mrc_reservoir_exchange exchange, void* user) {
+    if (!ctx) return MRC_E_INVALID;
+    if (!out_bytes || !exchange || pcm_frames < 0 || total_frames < 0 || first_block < 0 || n_blocks < 0 || (!pcm && pcm_frames > 0))
+        return fail(ctx, MRC_E_INVALID, "bad argument");
+    if (ctx->cfg.flags & MRC_FLAG_BLOCK_SWITCHING)
+        return fail(ctx, MRC_E_INVALID, "sharding a stream by block range is built for long blocks only");
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t st = ctx->stream;
+    const int L = ctx->L;
+    const int64_t nblk_stream = (total_frames + L - 1) / L;
+    if (first_block + n_blocks > nblk_stream) return fail(ctx, MRC_E_INVALID, "shard runs past the end of the stream");
+    if (is_last && first_block + n_blocks != nblk_stream) return fail(ctx, MRC_E_INVALID, "the last shard must end with the stream");
+    const int64_t need_lo = std::max<int64_t>(first_block - 1, 0) * L;
+    const int64_t need_hi = std::min<int64_t>((first_block + n_blocks) * L, total_frames);
+    if (n_blocks > 0 && (pcm_frame0 > need_lo || pcm_frame0 + pcm_frames < need_hi))
+        return fail(ctx, MRC_E_INVALID, "pcm does not cover the shard's blocks and their halo");
+    *out_bytes = 0;
+    CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(pcm_frames, 1) * 4));
+    if (pcm_frames > 0)
+        CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)pcm_frames * 4, cudaMemcpyHostToDevice, st));
+    const int64_t off[2] = {0, total_frames};
+    int64_t boff[2] = {0, 0};
+    const int64_t shard_off[2] = {0, (n_blocks + (is_last ? 1 : 0)) * (int64_t)L};      // for the size estimates only
+    int64_t cap = std::min(worst_case_bytes(ctx, shard_off, 1), std::max<int64_t>(2 * nominal_bytes(ctx, shard_off, 1), out_cap));
+    ShardRelay relay = {exchange, user, 0, false, false};     // a retry (staging too small) must not serve the neighbours twice
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(ensure(ctx->out_dev, (size_t)cap));
+        CK(cudaEventRecord(ctx->ev[4], st));
+        EncodeJob job;
+        job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = off; job.n_clips = 1;
+        job.joint = ctx->cfg.joint; job.flush_nonjoint = is_last != 0;
+        job.shard = true; job.shard_first = first_block; job.shard_blocks = n_blocks; job.pcm_frame0 = pcm_frame0;
+        job.shard_header = is_first != 0;
+        job.exchange = shard_relay_fn; job.exchange_user = &relay;
+        job.d_out = (uint8_t*)ctx->out_dev.p; job.out_cap = cap; job.h_clip_byte_off = boff;
+        const int rc = run_encode(ctx, job);
+        if (rc == MRC_E_NOSPACE && attempt == 0) { cap = worst_case_bytes(ctx, shard_off, 1); continue; }
+        if (rc != MRC_OK) return rc;
+        break;
+    }
+    *out_bytes = boff[1];
+    if (boff[1] > out_cap || !out) return fail(ctx, MRC_E_NOSPACE, "output buffer too small (out_bytes holds the size)");
+    if (boff[1] > 0) CK(cudaMemcpyAsync(out, ctx->out_dev.p, (size_t)boff[1], cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    float t = 0;
     cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]); ctx->ms[6] = t;
     return MRC_OK;
 }

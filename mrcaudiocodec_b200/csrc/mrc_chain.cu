@@ -423,16 +423,26 @@ chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, Ch
 // one clip, one thread per R_in of the tabulated range) chases every R_in through the segment's blocks: a block's
 // table while the running value stays inside the range, the closed form "every token granted" above it, and for the
 // rare value that is neither a complete walk of that block's record, done by the whole warp once per distinct value
-// (the maps contract: after a block or two the thousand trajectories of a segment have merged into a handful).
-// It also composes the closed forms: R_out = R_in + delta for R_in >= theta, when every block of the segment grants
-// everything along the way (digital silence: the reservoir grows by thousands of bits per block, far outside any
-// table).  chain_seg_kernel (serial, one warp per clip) then takes ONE step per segment -- a table entry or the closed
-// form -- and only walks block by block through segments it enters outside both (the few segments in which a silent
-// passage ends, or which straddle two clips).  It records the reservoir at the start of every segment it stepped
-// over; expand_kernel (parallel, one warp per segment) replays those segments block by block for finish_kernel.
+// (the maps contract: after a block or two the thousand trajectories of a segment have merged into a handful; where
+// they have not -- digital silence right at the start of a segment shifts every value by the same amount -- the
+// values past the eighth distinct one are given up: entry RIN_NONE).  It also composes the closed forms:
+// R_out = R_in + delta for R_in >= theta, when every block of the segment grants everything along the way (silence:
+// the reservoir grows by thousands of bits per block, far outside any table), and lists up to eight distinct results
+// that lie outside the tabulated range ("exits").
+// extras_kernel (parallel: one warp per exit) follows each exit through the next segments, block by block, until it
+// is back inside the range, and leaves (R_in -> R_out) pairs with the segments it crosses: these are exactly the
+// out-of-range values the real reservoir can enter those segments with.
+// chain_seg_kernel (serial, one warp per clip) then takes ONE step per segment -- table entry, closed form or pair --
+// and walks block by block only through segments it can enter no other way (those that straddle two clips, or follow a
+// wave boundary inside a silent passage).  It records the reservoir at the start of every segment it stepped over;
+// expand_kernel (parallel, one warp per segment) replays those segments block by block for finish_kernel.
 constexpr int SEG_THREADS = 384;
 constexpr int SEG_EPT = 4;                       // table entries per thread: ntab <= 1536
 constexpr int RIN_NONE = (int)0x80000000;
+constexpr int SEG_MAX_WALKS = 8;                 // distinct out-of-table values a warp follows per block and group
+constexpr int SEG_EXITS = 8;                     // distinct out-of-range results kept per segment
+constexpr int SEGX_W = 3 * SEG_EXITS;            // per segment: exits, pair inputs, pair outputs
+constexpr int EXTRA_HOPS = 6;
 
 struct BlkStep { int R0, R1, R; };
 
@@ -466,27 +476,46 @@ __device__ __forceinline__ BlkStep step_block(const CodecParams& cp, const unsig
     return o;
 }
 
-// comp: [nseg][segw] ints: entries 0..ntab-1 the composed map, [ntab] delta, [ntab+1] theta (INT_MAX: no closed form),
-// [ntab+2] 1 if the segment lies inside one clip (else the row is not to be used).  rin[seg] is reset to RIN_NONE.
+// clip that holds global block g
+__device__ __forceinline__ int clip_of_block(const ClipMap& cm, int g) {
+    int lo = 0, hi = cm.n_clips;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cm.clip_blk0[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// insert v into a small set of slots (RIN_NONE = empty); returns the slot or -1 when the set is full
+__device__ __forceinline__ int slot_insert(int* slots, int n, int v) {
+    for (int i = 0; i < n; ++i) {
+        const int old = atomicCAS(slots + i, RIN_NONE, v);
+        if (old == RIN_NONE || old == v) return i;
+    }
+    return -1;
+}
+
+// comp: [nseg][segw] ints: entries 0..ntab-1 the composed map (RIN_NONE: not followed), [ntab] delta, [ntab+1] theta
+// (INT_MAX: no closed form), [ntab+2] 1 if the segment lies inside one clip (else the row is not to be used).
+// segx: [nseg][SEGX_W], reset here; rin[seg] is reset to RIN_NONE.
 __global__ void __launch_bounds__(SEG_THREADS)
 segment_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, ChainIO io, int r_lo, int ntab, int tabw,
-               const int* __restrict__ tab, int segw, int* __restrict__ comp, int* __restrict__ rin) {
+               const int* __restrict__ tab, int segw, int* __restrict__ comp, int* __restrict__ segx,
+               int* __restrict__ rin) {
     __shared__ int s_pure, s_flush_lb;
     const int tid = threadIdx.x, lane = tid & 31;
     const int seg = blockIdx.x;
     const int lb0 = seg * S, lb1 = min(lb0 + S, nblk_wave);
     int* row = comp + (size_t)seg * segw;
+    int* sx = segx + (size_t)seg * SEGX_W;
+    if (tid < SEGX_W) sx[tid] = RIN_NONE;
     if (tid == 0) {
         rin[seg] = RIN_NONE;
         const int ga = g0 + lb0, gb = g0 + lb1 - 1;
-        int lo = 0, hi = cm.n_clips;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (cm.clip_blk0[mid] <= ga) lo = mid; else hi = mid;
-        }
-        s_pure = gb < cm.clip_blk0[lo + 1];
+        const int c = clip_of_block(cm, ga);
+        s_pure = gb < cm.clip_blk0[c + 1];
         // wave-local index of the clip's last block (the non-joint Close() flush block) if it falls in this segment
-        s_flush_lb = (cp.flush_nonjoint && gb == cm.clip_blk0[lo + 1] - 1) ? lb1 - 1 : -1;
+        s_flush_lb = (cp.flush_nonjoint && gb == cm.clip_blk0[c + 1] - 1) ? lb1 - 1 : -1;
     }
     __syncthreads();
     if (!s_pure) {
@@ -521,14 +550,20 @@ segment_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, ChainIO
             for (int e = 0; e < SEG_EPT; ++e) {
                 const int idx = R[e] - r_lo, B0 = K + R[e];
                 need[e] = false;
+                if (R[e] == RIN_NONE) continue;
                 if ((unsigned)idx < (unsigned)ntab) R[e] = __ldg(T + idx);
                 else if (B0 >= thr) R[e] = B0 + c_all;
                 else need[e] = act[e];
             }
+            int walks = 0;
 #pragma unroll
             for (int e = 0; e < SEG_EPT; ++e) {
                 unsigned m = __ballot_sync(0xffffffffu, need[e]);
                 while (m) {                          // warp-uniform: one complete walk per distinct value
+                    if (walks >= SEG_MAX_WALKS) {    // too many distinct values: these trajectories are given up
+                        if (need[e]) R[e] = RIN_NONE;
+                        break;
+                    }
                     const int l = __ffs(m) - 1;
                     const int Rl = __shfl_sync(0xffffffffu, R[e], l);
                     const bool mine = need[e] && R[e] == Rl;
@@ -538,15 +573,21 @@ segment_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, ChainIO
                         reinterpret_cast<const uint4*>(rec + MRC_REC_PC), nullptr, mx, grp * MRC_GROUP_CHUNKS, nck, K + Rl,
                         min_nl, lane, dummy, dummy);
                     const int Rn = reservoir_after(gt, K + Rl, frac, cp.no_huff, nullptr, nullptr);
-                    if (mine) R[e] = Rn;
+                    if (mine) { R[e] = Rn; need[e] = false; }
                     m &= ~same;
+                    ++walks;
                 }
             }
         }
     }
 #pragma unroll
-    for (int e = 0; e < SEG_EPT; ++e)
+    for (int e = 0; e < SEG_EPT; ++e) {
         if (act[e]) row[tid + e * SEG_THREADS] = R[e];
+        // results outside the tabulated range: what the next segment can be entered with (distinct values only)
+        const bool out = act[e] && R[e] != RIN_NONE && (unsigned)(R[e] - r_lo) >= (unsigned)ntab;
+        const unsigned grp_mask = __match_any_sync(0xffffffffu, out ? R[e] : RIN_NONE);
+        if (out && (__ffs(grp_mask) - 1) == lane) slot_insert(sx, SEG_EXITS, R[e]);
+    }
     if (tid == 0) {
         const bool ok = theta < 0x7fffffffll && P > -0x7fffffffll && P < 0x7fffffffll;
         row[ntab] = ok ? (int)P : 0;
@@ -555,9 +596,46 @@ segment_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, ChainIO
     }
 }
 
+// one warp per (segment, exit): follow the exit value through the following segments of the same clip
+__global__ void __launch_bounds__(SEG_EXITS * 32)
+extras_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, int nseg, ChainIO io, int r_lo, int ntab,
+              int tabw, const int* __restrict__ tab, int segw, const int* __restrict__ comp, int* segx) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int seg0 = blockIdx.x;
+    int R = segx[(size_t)seg0 * SEGX_W + w];         // written by segment_kernel (an earlier launch)
+    if (R == RIN_NONE) return;
+    const int clip = clip_of_block(cm, g0 + seg0 * S);
+    const int clip_end = cm.clip_blk0[clip + 1] - g0;                  // wave-local end of the clip
+    unsigned n_slow = 0;
+    for (int hop = 1; hop <= EXTRA_HOPS; ++hop) {
+        const int seg = seg0 + hop;
+        if (seg >= nseg) return;
+        const int lb0 = seg * S, lb1 = min(lb0 + S, nblk_wave);
+        if (lb1 > clip_end) return;                  // the next segment is not wholly inside this clip
+        const int* row = comp + (size_t)seg * segw;
+        int Rn;
+        if (R >= row[ntab + 1]) Rn = R + row[ntab];  // closed form: nothing to leave behind
+        else {
+            const int flush_lb = (cp.flush_nonjoint && lb1 == clip_end) ? lb1 - 1 : -1;
+            Rn = R;
+            for (int lb = lb0; lb < lb1; ++lb)
+                Rn = step_block(cp, io.rec + (size_t)lb * MRC_REC_BYTES, tab + (size_t)lb * (2 * tabw),
+                                cp.joint && lb != flush_lb, Rn, r_lo, ntab, tabw, lane, n_slow).R;
+            if (lane == 0) {
+                int* sx = segx + (size_t)seg * SEGX_W;
+                const int slot = slot_insert(sx + SEG_EXITS, SEG_EXITS, R);
+                if (slot >= 0) sx[2 * SEG_EXITS + slot] = Rn;    // same input -> same output: concurrent writers agree
+            }
+        }
+        R = Rn;
+        if ((unsigned)(R - r_lo) < (unsigned)ntab) return;            // back inside the range: the tables take over
+    }
+}
+
 __global__ void __launch_bounds__(32)
 chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int S, ChainIO io, int r_lo, int ntab,
-                 int tabw, const int* __restrict__ tab, int segw, const int* __restrict__ comp, int* __restrict__ rin,
+                 int tabw, const int* __restrict__ tab, int segw, const int* __restrict__ comp,
+                 const int* __restrict__ segx, int* __restrict__ rin,
                  const int32_t* __restrict__ reservoir_in, int32_t* __restrict__ reservoir_out,
                  unsigned long long* __restrict__ iter_counter) {
     const int lane = threadIdx.x;
@@ -576,13 +654,18 @@ chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int 
             if (seg_end <= lb_hi) {                  // the whole segment belongs to this clip
                 const int* row = comp + (size_t)seg * segw;
                 const int idx = R - r_lo;
-                int Rn = 0;
-                bool took = false;
+                int Rn = RIN_NONE;
                 if (row[ntab + 2] != 0) {
-                    if ((unsigned)idx < (unsigned)ntab) { Rn = row[idx]; took = true; }
-                    else if (R >= row[ntab + 1]) { Rn = R + row[ntab]; took = true; }
+                    if ((unsigned)idx < (unsigned)ntab) Rn = row[idx];
+                    else if (R >= row[ntab + 1]) Rn = R + row[ntab];
+                    else {
+                        const int* sx = segx + (size_t)seg * SEGX_W;
+                        const int v = (lane < SEG_EXITS) ? sx[SEG_EXITS + lane] : RIN_NONE;       // one pair per lane
+                        const unsigned hit = __ballot_sync(0xffffffffu, v == R);
+                        if (hit) Rn = sx[2 * SEG_EXITS + __ffs(hit) - 1];
+                    }
                 }
-                if (took) {
+                if (Rn != RIN_NONE) {
                     if (lane == 0) rin[seg] = R;
                     R = Rn;
                     lb = seg_end;
@@ -621,12 +704,7 @@ expand_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, int nseg
     int flush_lb = -1;
     if (cp.flush_nonjoint) {                         // the segment lies inside one clip: is its last block that clip's last?
         const int gb = g0 + lb1 - 1;
-        int lo = 0, hi = cm.n_clips;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (cm.clip_blk0[mid] <= gb) lo = mid; else hi = mid;
-        }
-        if (gb == cm.clip_blk0[lo + 1] - 1) flush_lb = lb1 - 1;
+        if (gb == cm.clip_blk0[clip_of_block(cm, gb) + 1] - 1) flush_lb = lb1 - 1;
     }
     unsigned n_slow = 0;
     for (int lb = lb0; lb < lb1; ++lb) {
@@ -768,16 +846,19 @@ void launch_chain_table(cudaStream_t st, const CodecParams& cp, const ClipMap& c
 }
 
 void launch_segments(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int S, ChainIO io,
-                     int r_lo, int ntab, int tabw, const int* tab, int segw, int* comp, int* rin) {
+                     int r_lo, int ntab, int tabw, const int* tab, int segw, int* comp, int* segx, int* rin) {
     if (nblk <= 0) return;
-    segment_kernel<<<(nblk + S - 1) / S, SEG_THREADS, 0, st>>>(cp, cm, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, rin);
+    const int nseg = (nblk + S - 1) / S;
+    segment_kernel<<<nseg, SEG_THREADS, 0, st>>>(cp, cm, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, segx, rin);
+    extras_kernel<<<nseg, SEG_EXITS * 32, 0, st>>>(cp, cm, g0, nblk, S, nseg, io, r_lo, ntab, tabw, tab, segw, comp, segx);
 }
 
 void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
-                      int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp, int* rin,
-                      const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter) {
+                      int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp,
+                      const int* segx, int* rin, const int32_t* reservoir_in, int32_t* reservoir_out,
+                      unsigned long long* iter_counter) {
     if (nclips <= 0 || nblk <= 0) return;
-    chain_seg_kernel<<<nclips, 32, 0, st>>>(cp, cm, c0, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, rin,
+    chain_seg_kernel<<<nclips, 32, 0, st>>>(cp, cm, c0, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, segx, rin,
                                             reservoir_in, reservoir_out, iter_counter);
     const int nseg = (nblk + S - 1) / S;
     expand_kernel<<<(nseg + EXP_WARPS - 1) / EXP_WARPS, EXP_WARPS * 32, 0, st>>>(cp, cm, g0, nblk, S, nseg, io, r_lo, ntab,
@@ -785,3 +866,4 @@ void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm,
 }
 
 int segment_max_ntab() { return SEG_THREADS * SEG_EPT; }
+int segment_aux_width() { return SEGX_W; }

@@ -112,6 +112,11 @@ struct ClipMap {
     const uint8_t* blk_geom;     // [nblk_total] MRC_GEO_*
     // the kernels of one geometry run over a list of wave-local block indices (null: all blocks of the wave)
     const int32_t* list;
+    // one stream sharded by block range (single-clip jobs only; both 0 otherwise): the job's first block is block
+    // blk_base of the stream, and the PCM buffer starts at frame pcm_frame0 of the stream (the N/2-sample halo of the
+    // shard's first block included); clip_off still spans the WHOLE stream, so samples past its end read as zero
+    long long pcm_frame0;
+    int blk_base;
 };
 
 template <typename T>
@@ -185,15 +190,18 @@ void launch_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int
 void launch_chain_table(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0,
                         int nblk, ChainIO io, int r_lo, int ntab, int tabw, const int* tab,
                         const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter);
-// single-stream fast path, second stage: compose the per-block maps over segments of S consecutive blocks (parallel),
-// then one serial step per segment and a parallel replay of the stepped-over segments into io.rsv.
-// comp is [ceil(nblk/S)][segw] ints, segw >= ntab + 3; rin is [ceil(nblk/S)] ints.
+// single-stream fast path, second stage: compose the per-block maps over segments of S consecutive blocks and follow
+// the values that leave the tabulated range through the next segments (parallel), then one serial step per segment and
+// a parallel replay of the stepped-over segments into io.rsv.
+// comp is [ceil(nblk/S)][segw] ints, segw >= ntab + 3; segx is [ceil(nblk/S)][segment_aux_width()]; rin [ceil(nblk/S)].
 void launch_segments(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int S, ChainIO io,
-                     int r_lo, int ntab, int tabw, const int* tab, int segw, int* comp, int* rin);
+                     int r_lo, int ntab, int tabw, const int* tab, int segw, int* comp, int* segx, int* rin);
 void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
-                      int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp, int* rin,
-                      const int32_t* reservoir_in, int32_t* reservoir_out, unsigned long long* iter_counter);
+                      int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp,
+                      const int* segx, int* rin, const int32_t* reservoir_in, int32_t* reservoir_out,
+                      unsigned long long* iter_counter);
 int segment_max_ntab();
+int segment_aux_width();
 // parallel: one warp per block replays the block from its recorded reservoir: grant masks, table ids, chunk sizes
 void launch_finish(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk,
                    ChainIO io);

@@ -12,11 +12,16 @@ __device__ __forceinline__ double m_atan(double x) { return atan(x); }
 __device__ __forceinline__ float m_atan(float x) { return atanf(x); }
 
 // pcmfile.py:87-101 with quantize.py:90-111 at 16 bits: x = sign * (2*|c|) / 65535 ; |c| = 32768 -> 0.0 (Q1)
+// The division is done as a multiplication by RN(1/65535) with one correction step (Markstein): y0 = RN(q * rcp),
+// r = q - 65535 * y0 exactly (FMA), y = RN(y0 + r * rcp) -- equal to the correctly rounded quotient for every one of the
+// 32768 magnitudes (checked exhaustively in tests/test_host_logic.py::test_pcm_division_by_reciprocal_is_exact).
 template <typename T>
 __device__ __forceinline__ T pcm_to_fraction(int c) {
     if (c == -32768) return T(0);
     const int mag = c < 0 ? -c : c;
-    const double v = __ddiv_rn(__dmul_rn((double)mag, 2.0), 65535.0);
+    const double q = (double)(2 * mag), rcp = 1.0 / 65535.0;
+    const double y0 = q * rcp;
+    const double v = fma(fma(-65535.0, y0, q), rcp, y0);
     return T(c < 0 ? -v : v);
 }
 

@@ -169,7 +169,8 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     if (tid < 4) dst[tid] = (uint8_t)((uint32_t)nbytes >> (8 * tid));       // <L nBytes
     for (int i = tid; i < nbytes; i += PT) dst[4 + i] = (uint8_t)(bitbuf[i >> 2] >> (24 - 8 * (i & 3)));
 
-    if (s_b == 0 && ch == 0) {                    // first chunk of a clip also writes the file header
+    if (s_b == 0 && ch == 0 && cp.header_bytes > 0) {   // first chunk of a clip also writes the file header (a shard that
+                                                        // does not start the stream has header_bytes = 0)
         uint8_t* h = out + clip_base[s_clip];
         for (int i = tid; i < cp.header_bytes; i += PT) h[i] = header_template[i];
         __syncthreads();

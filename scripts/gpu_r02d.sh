@@ -1,0 +1,11 @@
+#!/bin/bash
+TAG=${1:-r02d}
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "chain or golden or sequential or fresh" > gpurun_out/${TAG}_pytest.log 2>&1
+echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
+timeout 600 python bench.py --steps 3 --warmup 3 --no-sequential-sample --no-cpu-baseline --no-decode --no-music > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/${TAG}_bench.json')); print(d['value'], d['e2e']['value'], d['stage_ms_per_step'], d['executed_work'])"
+MRC_TIMELINE=1 timeout 600 python bench.py --steps 1 --warmup 1 --no-sequential-sample --no-cpu-baseline --no-decode --no-music 2> gpurun_out/${TAG}_timeline.txt > /dev/null
+timeout 300 python scripts/phase_clocks.py 120 > gpurun_out/${TAG}_phase_clocks.log 2>&1
+cat gpurun_out/${TAG}_phase_clocks.log

@@ -96,3 +96,19 @@ def test_synth_is_deterministic():
     assert a.shape == (600000, 2) and np.array_equal(a, b)
     assert a.min() > -32768
     assert not np.any(a[3 * 48000:4 * 48000])            # the exact-silence second
+
+
+def test_pcm_division_by_reciprocal_is_exact():
+    """The kernels convert int16 PCM with x = 2|c| / 65535 (pcmfile.py:87-101, quantize.py:90-111) evaluated as
+    q * rcp with one FMA correction step (mrc_math.cuh pcm_to_fraction).  Exhaustively: for all 32768 magnitudes the
+    result equals the correctly rounded quotient, and the residual FMA is exact."""
+    from fractions import Fraction as F
+    rcp = float(F(1, 65535))
+    assert rcp == 1.0 / 65535.0
+    for c in range(32768):
+        q = 2.0 * c
+        y0 = float(F(q) * F(rcp))
+        r_exact = F(q) - F(65535) * F(y0)
+        r = float(r_exact)
+        assert F(r) == r_exact
+        assert float(F(y0) + F(r) * F(rcp)) == q / 65535.0
