@@ -58,6 +58,10 @@ def parse():
     ap.add_argument("--block-switching", action="store_true",
                     help="encode with the reference's transient detector / look-ahead loop (SURVEY 8 f1): eight "
                          "128-sample short blocks around transients instead of long blocks only")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1 GPUs: weak = every rank encodes its own stream of --seconds (the driver's contract); strong = "
+                         "ONE stream of --seconds sharded by block range across the ranks (N/2-sample halo from the PCM, "
+                         "the reservoir handed rank to rank as one int32; mrcaudiocodec_b200.dist.encode_stream_sharded)")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode mirror path (timed by default)")
     ap.add_argument("--no-music", action="store_true",
                     help="skip the second encode measurement on dense-masker music-like material (synth_music)")
@@ -202,18 +206,31 @@ def main():
 
     seconds = args.seconds
     threads = max(1, min(16, (os.cpu_count() or 8) // max(world, 1)))
-    pcm = synth.synth_clip(rank, seconds, threads=threads, fast=True)            # [frames, 2] int16
-    frames = pcm.shape[0]
+    strong = args.scaling == "strong" and world > 1
+    codec = Codec(device=local, precision=args.precision, spreading=args.spreading,
+                  block_switching=args.block_switching)
+    L = codec.L
+    if strong:
+        # one stream for the whole job: this rank synthesises only the frames of its block range and their halo
+        from mrcaudiocodec_b200 import dist as mdist
+        total_frames = int(round(seconds * SR))
+        nblk_stream = (total_frames + L - 1) // L
+        blk_lo, blk_hi = mdist.shard_range(nblk_stream, rank, world)
+        f_lo, f_hi = codec.shard_pcm_range(total_frames, blk_lo, blk_hi - blk_lo)
+        pcm = synth.synth_range(0, f_lo, f_hi, seconds, threads=threads, fast=True)
+        frames = pcm.shape[0]
+    else:
+        pcm = synth.synth_clip(rank, seconds, threads=threads, fast=True)            # [frames, 2] int16
+        frames = pcm.shape[0]
     if args.workload == "batch":
         cf = int(round(args.clip_seconds * SR))
         off = np.unique(np.append(np.arange(0, frames, cf), frames)).astype(np.int64)
     else:
         off = np.array([0, frames], dtype=np.int64)
     n_clips = len(off) - 1
-    codec = Codec(device=local, precision=args.precision, spreading=args.spreading,
-                  block_switching=args.block_switching)
-    L = codec.L
     nblk = int(sum(codec.n_blocks(f) for f in np.diff(off)))
+    if strong:
+        nblk = blk_hi - blk_lo + (1 if rank == world - 1 else 0)
 
     # device-resident buffers (torch is plumbing: device memory + NCCL)
     d_pcm = torch.from_numpy(pcm).to(dev)
@@ -228,6 +245,10 @@ def main():
     last_boff = [None]
 
     def step_device():
+        if strong:
+            n, _ = mdist.encode_stream_sharded(codec, None, f_lo, total_frames, device=dev,
+                                               device_ptrs=(d_pcm.data_ptr(), frames, d_out.data_ptr(), cap))
+            return int(n)
         boff = codec.encode_batch_device(d_pcm.data_ptr(), off, d_out.data_ptr(), cap)
         if world > 1:                    # the path's only collective: per-shard bitstream lengths -> offsets
             lens[0] = int(boff[-1])
@@ -235,6 +256,9 @@ def main():
         return int(boff[-1])
 
     def step_e2e():
+        if strong:
+            blob, _ = mdist.encode_stream_sharded(codec, h_pcm_np, f_lo, total_frames, device=dev, out=h_out_np)
+            return int(blob.size)
         out, boff = codec.encode_batch(h_pcm_np, off, out=h_out_np)
         last_boff[0] = boff
         if world > 1:
@@ -280,7 +304,7 @@ def main():
     r_dev = timed(step_device)
     r_e2e = timed(step_e2e)
 
-    audio_total = world * seconds * args.steps
+    audio_total = (1 if strong else world) * seconds * args.steps
     value = audio_total / r_dev["wall"]
     e2e_value = audio_total / r_e2e["wall"]
 
@@ -329,9 +353,14 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * r_dev["wall"] / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if is64 else "f32", "data": "synthetic",
-            "config": {"workload": ("%.0f s synthetic 48 kHz stereo 16-bit stream per GPU (BASELINE configs[1] = 1 h), "
-                                    "joint M/S, 128 kb/s/ch, %s mode, long blocks N=2048" % (seconds, args.precision))
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64" if is64 else "f32",
+            "data": "synthetic",
+            "config": {"workload": ("ONE %.0f s synthetic 48 kHz stereo 16-bit stream (BASELINE configs[1] = 1 h) sharded by "
+                                    "block range over %d GPUs: N/2-sample halo read from the PCM, reservoir handed rank to "
+                                    "rank (one int32 per boundary, NCCL send/recv), joint M/S, 128 kb/s/ch, %s mode; "
+                                    "per-rank figures below are rank 0's" % (seconds, world, args.precision)) if strong else
+                       ("%.0f s synthetic 48 kHz stereo 16-bit stream per GPU (BASELINE configs[1] = 1 h), "
+                        "joint M/S, 128 kb/s/ch, %s mode, long blocks N=2048" % (seconds, args.precision))
                        if args.workload == "stream" else
                        ("%d independent clips of %.0f s (%.0f s of synthetic 48 kHz stereo audio per GPU, BASELINE "
                         "configs[3] shape), joint M/S, 128 kb/s/ch, %s mode" % (n_clips, args.clip_seconds, seconds,
@@ -370,7 +399,7 @@ def main():
                                            "%d blocks written for %d blocks of 1024 frames)" %
                                            (r_dev["extra"]["blocks_written"], nblk))
             line["stage_ms_per_step"]["transient_detector"] = r_dev["extra"]["transient_ms"]
-        if args.spreading == "factorised" and not args.no_sequential_sample and not args.block_switching:
+        if args.spreading == "factorised" and not args.no_sequential_sample and not args.block_switching and not strong:
             # the same analysis kernel summing the maskers pair by pair in the reference's order, on a bounded
             # sample of the same stream: the kernel SURVEY 8d's 40-flop-per-pair work formula describes (here the formula
             # IS roughly what runs, so the reference-formulation flop count is used)
@@ -389,7 +418,7 @@ def main():
                                            "sample": "first %.0f s of the stream, 1 launch" % sample_s,
                                            "avg_launch_ms": ts["analysis_ms"]}
             cs.close()
-        if not args.no_decode:
+        if not args.no_decode and not strong:
             # the mirror path (rows a14-a17): .pac bytes in pinned host memory -> int16 PCM in host memory
             nbytes = int(last_boff[0][-1])
             pac = h_out_np[:nbytes]
@@ -409,7 +438,7 @@ def main():
                               "d2h_bytes_per_step": int(pcm_out.nbytes),
                               "note": "decode of this rank's stream through Codec.decode_batch, host buffers, 3 steps"}
             del h_dec
-        if not args.no_music and args.workload == "stream" and not args.block_switching:
+        if not args.no_music and args.workload == "stream" and not args.block_switching and not strong:
             # the same encode on dense-masker material (synth_music: chords of harmonic notes, most of the spectrum above
             # 40 dB SPL): the band-maximum search prunes far less there, so this is the unfriendly end of the input range
             ms_ = min(args.music_seconds, seconds)
@@ -434,7 +463,7 @@ def main():
                              "general_pairs_per_block": tm["general_pairs"] / max(tm["blocks"], 1),
                              "note": "device-resident encode of synth_music material (dense loud maskers), same codec"}
             del d_mus
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not strong:
             line["cpu_baseline"] = cpu_baseline(pcm, args.cpu_sample_seconds)
         print(json.dumps(line))
     codec.close()

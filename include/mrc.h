@@ -169,6 +169,11 @@ typedef int32_t (*mrc_reservoir_exchange)(void* user, int32_t have_result, int32
 int32_t mrc_encode_shard(mrc_ctx* ctx, const int16_t* pcm, int64_t pcm_frame0, int64_t pcm_frames, int64_t total_frames,
                          int64_t first_block, int64_t n_blocks, int32_t is_first, int32_t is_last, uint8_t* out,
                          int64_t out_cap, int64_t* out_bytes, mrc_reservoir_exchange exchange, void* user);
+/* Same with pcm and out in DEVICE memory of ctx's device (kernel-only timing; no retry when out is too small). */
+int32_t mrc_encode_shard_device(mrc_ctx* ctx, const int16_t* d_pcm, int64_t pcm_frame0, int64_t pcm_frames,
+                                int64_t total_frames, int64_t first_block, int64_t n_blocks, int32_t is_first,
+                                int32_t is_last, uint8_t* d_out, int64_t out_cap, int64_t* out_bytes,
+                                mrc_reservoir_exchange exchange, void* user);
 
 /* ---- per-block seam (compat layer; explicit bit reservoir in/out) -----------------------------------------
  * mrc_encode_block = codecThem.Encode (joint=0) / JointEncode (joint=1) on one block; joint|2 skips the Huffman

@@ -49,7 +49,11 @@ EXPORTS = ["mrc_version", "mrc_last_error", "mrc_create", "mrc_destroy", "mrc_se
            "mrc_host_free", "mrc_encode_batch", "mrc_encode_batch_device", "mrc_decode_batch",
            "mrc_decode_batch_device", "mrc_encode_block", "mrc_decode_block", "mrc_stage_analysis",
            "mrc_stage_alloc_quant", "mrc_mantissa_histogram", "mrc_last_timing", "mrc_measure_peaks",
-           "mrc_set_switch_tables", "mrc_encode_block_ab", "mrc_decode_block_ab", "mrc_detect_transients"]
+           "mrc_set_switch_tables", "mrc_encode_block_ab", "mrc_decode_block_ab", "mrc_detect_transients",
+           "mrc_encode_shard", "mrc_encode_shard_device"]
+
+# int32_t (*mrc_reservoir_exchange)(void* user, int32_t have_result, int32_t* reservoir)
+RESERVOIR_EXCHANGE = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32))
 
 _lib = None
 
@@ -84,6 +88,9 @@ def load():
     lib.mrc_encode_block_ab.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mrc_decode_block_ab.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
     lib.mrc_detect_transients.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp]
+    lib.mrc_encode_shard.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                     vp, C.c_int64, vp, RESERVOIR_EXCHANGE, vp]
+    lib.mrc_encode_shard_device.argtypes = lib.mrc_encode_shard.argtypes
     lib.mrc_last_timing.argtypes = [vp, vp, vp]
     lib.mrc_measure_peaks.argtypes = [vp, vp]
     for name in EXPORTS:

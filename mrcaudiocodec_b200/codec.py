@@ -173,6 +173,58 @@ class Codec(object):
                                                      C.c_void_p(d_out_ptr), int(out_cap), _ptr(boff)))
         return boff
 
+    # ---- one stream sharded by block range (SURVEY.md 8e "within one stream") --------------------
+    def shard_pcm_range(self, total_frames, first_block, n_blocks):
+        """frames [lo, hi) of the stream a shard needs: its blocks plus the n_mdct_lines-frame halo before them."""
+        lo = max(int(first_block) - 1, 0) * self.L
+        hi = min((int(first_block) + int(n_blocks)) * self.L, int(total_frames))
+        return lo, max(hi, lo)
+
+    def encode_shard(self, pcm, pcm_frame0, total_frames, first_block, n_blocks, is_first, is_last, recv_reservoir,
+                     send_reservoir, out=None, device_ptrs=None):
+        """Blocks [first_block, first_block + n_blocks) of a stream of total_frames frames.  pcm: int16 [frames, 2]
+        starting at stream frame pcm_frame0 (see shard_pcm_range).  recv_reservoir() -> int is called once everything
+        that does not depend on the reservoir is done and must return the reservoir the previous shard ended with (0
+        for the first shard); send_reservoir(r) is called with this shard's final reservoir right after the serial
+        pass, before the chunks are packed.  Returns the shard's bytes: concatenated in order the shards are the
+        .pac file mrc_encode_batch writes for the whole stream."""
+        if device_ptrs is None:
+            pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, 2)
+        err = []
+
+        def _cb(user, have_result, r):
+            try:
+                if have_result:
+                    send_reservoir(int(r[0]))
+                else:
+                    r[0] = int(recv_reservoir())
+                return 0
+            except Exception as e:         # no exception may cross the C boundary
+                err.append(e)
+                return 1
+        cb = _lib.RESERVOIR_EXCHANGE(_cb)
+        nbytes = C.c_int64(0)
+        if device_ptrs is not None:
+            # (d_pcm pointer, frames it holds, d_out pointer, capacity): kernel-only timing, returns the byte count
+            d_pcm, n_fr, d_out, cap = device_ptrs
+            rc = self.lib.mrc_encode_shard_device(self._ctx, C.c_void_p(d_pcm), int(pcm_frame0), int(n_fr),
+                                                  int(total_frames), int(first_block), int(n_blocks),
+                                                  1 if is_first else 0, 1 if is_last else 0, C.c_void_p(d_out), int(cap),
+                                                  C.byref(nbytes), cb, None)
+            if err:
+                raise err[0]
+            self._check(rc)
+            return int(nbytes.value)
+        if out is None:
+            out = np.empty(256 + (int(n_blocks) + 1) * (int(2 * 1.5 * self.L * 16 // 8 // 4) + 256), dtype=np.uint8)
+        rc = self.lib.mrc_encode_shard(self._ctx, _ptr(pcm), int(pcm_frame0), pcm.shape[0], int(total_frames),
+                                       int(first_block), int(n_blocks), 1 if is_first else 0, 1 if is_last else 0,
+                                       _ptr(out), out.size, C.byref(nbytes), cb, None)
+        if err:
+            raise err[0]
+        self._check(rc)
+        return out[:nbytes.value]
+
     # ---- batch decode ----------------------------------------------------------------------------
     def decode_batch(self, pac, byte_offsets, pcm_out=None):
         pac = np.ascontiguousarray(pac, dtype=np.uint8)

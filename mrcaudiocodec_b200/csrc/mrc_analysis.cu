@@ -861,8 +861,8 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
         int* const brank = bq + 64;                                                             // [64]
         const int ntot = 2 * nb, per_group = nb * MRC_MAX_LEVELS;
         const double EPS = 1e-9;
+        uint16_t* const tokbuf = reinterpret_cast<uint16_t*>(brank + 64);                       // [MRC_TOK_STRIDE]
         if (tid == 0) s_unsafe = 0;
-        for (int i = tid; i < 2 * NLEV; i += NT) lmask[i] = 0ull;
         if (tid < ntot) {
             const int ch = tid / nb, bd = tid - ch * nb;
             const bool m = (ms >> bd) & 1u;
@@ -877,22 +877,36 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             if (bad) s_unsafe = 1;
         }
         __syncthreads();
-        if (tid < ntot) {
-            const int grp = joint ? 0 : tid / nb;
+        // rank of every band among the bands of its group by (f descending, band ascending): one warp per band, the
+        // lanes hold the other bands (two each)
+        for (int bb = warp; bb < ntot; bb += nwarp) {
+            const int grp = joint ? 0 : bb / nb;
             const int b0 = joint ? 0 : grp * nb, b1 = joint ? ntot : b0 + nb;
-            const double f = bf[tid], sv = bs[tid];
+            const double f = bf[bb], sv = bs[bb];
             int r = 0;
             bool bad = false;
-            for (int j = b0; j < b1; ++j) {
-                const double fj = bf[j];
-                r += (fj > f || (fj == f && j < tid)) ? 1 : 0;
-                if (sizeof(T) == 8 && j != tid && fabs(fj - f) < EPS && !(bs[j] == sv)) bad = true;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = b0 + lane + 32 * h;
+                const bool in = j < b1;
+                const double fj = in ? bf[j] : 0.0;
+                r += __popc(__ballot_sync(0xffffffffu, in && (fj > f || (fj == f && j < bb))));
+                if (sizeof(T) == 8 && in && j != bb && fabs(fj - f) < EPS && !(bs[j] == sv)) bad = true;
             }
-            brank[tid] = r;
+            if (lane == 0) brank[bb] = r;
             if (bad) s_unsafe = 1;
-            const int q = bq[tid];
-            for (int l = 0; l < MRC_MAX_LEVELS; ++l)
-                atomicOr(&lmask[grp * NLEV + (q - (l ? l + 1 : 0) + LEV_OFF)], 1ull << r);
+        }
+        __syncthreads();
+        // which bands hold a token on level v: one thread per (group, level) gathers the ranks -- no atomics
+        for (int i = tid; i < 2 * NLEV; i += NT) {
+            const int grp = i / NLEV, v = i - grp * NLEV - LEV_OFF;
+            unsigned long long mk = 0ull;
+            const int b0 = joint ? 0 : grp * nb, b1 = joint ? (grp == 0 ? ntot : 0) : b0 + nb;
+            for (int j = b0; j < b1; ++j) {
+                const int m = bq[j] - v;                 // token of band j on this level: m = 0 or 2 <= m <= 15
+                if (m == 0 || (m >= 2 && m <= MRC_MAX_LEVELS)) mk |= 1ull << brank[j];
+            }
+            lmask[i] = mk;
         }
         __syncthreads();
         if (warp < 2) {                                  // tokens on higher levels, per group: suffix sums over the levels
@@ -909,20 +923,20 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
 #pragma unroll
             for (int i = 3; i >= 0; --i) { lstart[warp * NLEV + lane * 4 + i] = above; above += c[i]; }
         }
+        for (int e = tid; e < MRC_TOK_STRIDE; e += NT) tokbuf[e] = 0xffffu;       // slots past the tokens
         __syncthreads();
         uint16_t* ot = ho.tokens + (size_t)lb * MRC_TOK_STRIDE;
         if (!s_unsafe) {
-            for (int e = tid; e < MRC_TOK_STRIDE; e += NT) {
-                if (e < ntot * MRC_MAX_LEVELS) {
-                    const int bb = e / MRC_MAX_LEVELS, l = e - bb * MRC_MAX_LEVELS;
-                    const int grp = joint ? 0 : bb / nb;
-                    const int li = grp * NLEV + (bq[bb] - (l ? l + 1 : 0) + LEV_OFF);
-                    const int pos = lstart[li] + __popcll(lmask[li] & ((1ull << brank[bb]) - 1ull));
-                    ot[grp * per_group + pos] = (uint16_t)(bb | (l << 8));
-                } else {
-                    ot[e] = 0xffffu;                     // slots past the 2 * nb * 15 tokens
-                }
+            for (int e = tid; e < ntot * MRC_MAX_LEVELS; e += NT) {
+                const int bb = e / MRC_MAX_LEVELS, l = e - bb * MRC_MAX_LEVELS;
+                const int grp = joint ? 0 : bb / nb;
+                const int li = grp * NLEV + (bq[bb] - (l ? l + 1 : 0) + LEV_OFF);
+                const int pos = lstart[li] + __popcll(lmask[li] & ((1ull << brank[bb]) - 1ull));
+                tokbuf[grp * per_group + pos] = (uint16_t)(bb | (l << 8));
             }
+            __syncthreads();
+            for (int e = tid; e < MRC_TOK_STRIDE / 2; e += NT)
+                reinterpret_cast<uint32_t*>(ot)[e] = reinterpret_cast<const uint32_t*>(tokbuf)[e];
         }
         __syncthreads();                                 // (the merge buffers alias the arrays above)
     }

@@ -428,12 +428,12 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     CK(ensure(ctx->clip_run, (size_t)(nc + 1) * 8));
     CK(ensure(ctx->running, 8));
     CK(ensure(ctx->overflow, 4));
-    CK(ensure(ctx->peakctr, 64));
+    CK(ensure(ctx->peakctr, 128));
     CK(cudaMemsetAsync(ctx->clip_bytes.p, 0, (size_t)(nc + 1) * 8, st));
     CK(cudaMemsetAsync(ctx->clip_base.p, 0, (size_t)(nc + 2) * 8, st));
     CK(cudaMemsetAsync(ctx->running.p, 0, 8, st));
     CK(cudaMemsetAsync(ctx->overflow.p, 0, 4, st));
-    CK(cudaMemsetAsync(ctx->peakctr.p, 0, 64, st));
+    CK(cudaMemsetAsync(ctx->peakctr.p, 0, 128, st));
     const int32_t* d_res_in = nullptr;
     int32_t* d_res_out = nullptr;
     if (job.exchange) {
@@ -818,8 +818,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     }
     // the analysis stream has nothing outstanding that the main stream does not already wait for (event 2 of the
     // last wave), so synchronising the main stream ends the call.
-    unsigned long long pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CK(cudaMemcpyAsync(pk, ctx->peakctr.p, 64, cudaMemcpyDeviceToHost, st));
+    unsigned long long pk[16] = {0};
+    CK(cudaMemcpyAsync(pk, ctx->peakctr.p, 128, cudaMemcpyDeviceToHost, st));
     if (job.h_res_out) CK(cudaMemcpyAsync(job.h_res_out, d_res_out, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
     int ovf = 0;
     if (job.d_out) {
@@ -840,6 +840,9 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         CK(cudaEventElapsedTime(&t, ev(w, 4), ev(w, 5))); t_pk += t;
     }
     if (getenv("MRC_TIMELINE")) {      // development aid: when did each wave's stages start and end (ms since the first)
+        fprintf(stderr, "serial pass: %llu complete walks, %llu blocks stepped one by one, %llu segments through pairs, %llu by "
+                "closed form; walked through: %llu not followed, %llu not anticipated, %llu straddling clips\n", pk[4], pk[5], pk[6], pk[7],
+                pk[8], pk[9], pk[10]);
         for (int w = 0; w < nwaves; ++w) {
             float t[6];
             for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], ev(0, 0), ev(w, k));
@@ -1190,9 +1193,10 @@ int32_t mrc_encode_batch(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_f
     return MRC_OK;
 }
 
-int32_t mrc_encode_shard(mrc_ctx* ctx, const int16_t* pcm, int64_t pcm_frame0, int64_t pcm_frames, int64_t total_frames,
-                         int64_t first_block, int64_t n_blocks, int32_t is_first, int32_t is_last, uint8_t* out,
-                         int64_t out_cap, int64_t* out_bytes, mrc_reservoir_exchange exchange, void* user) {
+static int32_t encode_shard_impl(mrc_ctx* ctx, bool on_device, const int16_t* pcm, int64_t pcm_frame0, int64_t pcm_frames,
+                                 int64_t total_frames, int64_t first_block, int64_t n_blocks, int32_t is_first,
+                                 int32_t is_last, uint8_t* out, int64_t out_cap, int64_t* out_bytes,
+                                 mrc_reservoir_exchange exchange, void* user) {
     if (!ctx) return MRC_E_INVALID;
     if (!out_bytes || !exchange || pcm_frames < 0 || total_frames < 0 || first_block < 0 || n_blocks < 0 || (!pcm && pcm_frames > 0))
         return fail(ctx, MRC_E_INVALID, "bad argument");
@@ -1209,37 +1213,74 @@ int32_t mrc_encode_shard(mrc_ctx* ctx, const int16_t* pcm, int64_t pcm_frame0, i
     if (n_blocks > 0 && (pcm_frame0 > need_lo || pcm_frame0 + pcm_frames < need_hi))
         return fail(ctx, MRC_E_INVALID, "pcm does not cover the shard's blocks and their halo");
     *out_bytes = 0;
-    CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(pcm_frames, 1) * 4));
-    if (pcm_frames > 0)
-        CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)pcm_frames * 4, cudaMemcpyHostToDevice, st));
+    if (n_blocks + (is_last ? 1 : 0) == 0) {
+        // nothing to encode: pass the reservoir through; a first shard without blocks still owes the file header
+        int32_t r = 0;
+        if (exchange(user, 0, &r) != 0 || exchange(user, 1, &r) != 0)
+            return fail(ctx, MRC_E_STATE, "reservoir exchange callback failed");
+        if (is_first) {
+            const int hb = ctx->cp.header_bytes;
+            *out_bytes = hb;
+            if (hb > out_cap || !out) return fail(ctx, MRC_E_NOSPACE, "output buffer too small (out_bytes holds the size)");
+            uint8_t hd[sizeof ctx->h_header];
+            memcpy(hd, ctx->h_header, sizeof hd);
+            int64_t ns = total_frames;
+            if (ns % L == 0) ns += L;                // Q9 (pacfileThem.py:595-597)
+            for (int i = 0; i < 4; ++i) hd[10 + i] = (uint8_t)((uint64_t)ns >> (8 * i));
+            if (on_device) CK(cudaMemcpy(out, hd, (size_t)hb, cudaMemcpyHostToDevice));
+            else memcpy(out, hd, (size_t)hb);
+        }
+        return MRC_OK;
+    }
+    if (!on_device) {
+        CK(ensure(ctx->pcm_dev, (size_t)std::max<int64_t>(pcm_frames, 1) * 4));
+        if (pcm_frames > 0)
+            CK(cudaMemcpyAsync(ctx->pcm_dev.p, pcm, (size_t)pcm_frames * 4, cudaMemcpyHostToDevice, st));
+    }
     const int64_t off[2] = {0, total_frames};
     int64_t boff[2] = {0, 0};
     const int64_t shard_off[2] = {0, (n_blocks + (is_last ? 1 : 0)) * (int64_t)L};      // for the size estimates only
     int64_t cap = std::min(worst_case_bytes(ctx, shard_off, 1), std::max<int64_t>(2 * nominal_bytes(ctx, shard_off, 1), out_cap));
     ShardRelay relay = {exchange, user, 0, false, false};     // a retry (staging too small) must not serve the neighbours twice
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        CK(ensure(ctx->out_dev, (size_t)cap));
+    if (on_device) cap = out_cap;                              // the caller's device buffer is the staging
+    for (int attempt = 0; attempt < (on_device ? 1 : 2); ++attempt) {
+        if (!on_device) CK(ensure(ctx->out_dev, (size_t)cap));
         CK(cudaEventRecord(ctx->ev[4], st));
         EncodeJob job;
-        job.d_pcm = (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = off; job.n_clips = 1;
+        job.d_pcm = on_device ? pcm : (const int16_t*)ctx->pcm_dev.p; job.h_clip_off = off; job.n_clips = 1;
         job.joint = ctx->cfg.joint; job.flush_nonjoint = is_last != 0;
         job.shard = true; job.shard_first = first_block; job.shard_blocks = n_blocks; job.pcm_frame0 = pcm_frame0;
         job.shard_header = is_first != 0;
         job.exchange = shard_relay_fn; job.exchange_user = &relay;
-        job.d_out = (uint8_t*)ctx->out_dev.p; job.out_cap = cap; job.h_clip_byte_off = boff;
+        job.d_out = on_device ? out : (uint8_t*)ctx->out_dev.p; job.out_cap = cap; job.h_clip_byte_off = boff;
         const int rc = run_encode(ctx, job);
-        if (rc == MRC_E_NOSPACE && attempt == 0) { cap = worst_case_bytes(ctx, shard_off, 1); continue; }
+        if (rc == MRC_E_NOSPACE && attempt == 0 && !on_device) { cap = worst_case_bytes(ctx, shard_off, 1); continue; }
         if (rc != MRC_OK) return rc;
         break;
     }
     *out_bytes = boff[1];
     if (boff[1] > out_cap || !out) return fail(ctx, MRC_E_NOSPACE, "output buffer too small (out_bytes holds the size)");
-    if (boff[1] > 0) CK(cudaMemcpyAsync(out, ctx->out_dev.p, (size_t)boff[1], cudaMemcpyDeviceToHost, st));
+    if (!on_device && boff[1] > 0) CK(cudaMemcpyAsync(out, ctx->out_dev.p, (size_t)boff[1], cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[5], st));
     CK(cudaStreamSynchronize(st));
     float t = 0;
     cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]); ctx->ms[6] = t;
     return MRC_OK;
+}
+
+int32_t mrc_encode_shard(mrc_ctx* ctx, const int16_t* pcm, int64_t pcm_frame0, int64_t pcm_frames, int64_t total_frames,
+                         int64_t first_block, int64_t n_blocks, int32_t is_first, int32_t is_last, uint8_t* out,
+                         int64_t out_cap, int64_t* out_bytes, mrc_reservoir_exchange exchange, void* user) {
+    return encode_shard_impl(ctx, false, pcm, pcm_frame0, pcm_frames, total_frames, first_block, n_blocks, is_first, is_last,
+                             out, out_cap, out_bytes, exchange, user);
+}
+
+int32_t mrc_encode_shard_device(mrc_ctx* ctx, const int16_t* d_pcm, int64_t pcm_frame0, int64_t pcm_frames,
+                                int64_t total_frames, int64_t first_block, int64_t n_blocks, int32_t is_first,
+                                int32_t is_last, uint8_t* d_out, int64_t out_cap, int64_t* out_bytes,
+                                mrc_reservoir_exchange exchange, void* user) {
+    return encode_shard_impl(ctx, true, d_pcm, pcm_frame0, pcm_frames, total_frames, first_block, n_blocks, is_first, is_last,
+                             d_out, out_cap, out_bytes, exchange, user);
 }
 
 int32_t mrc_stage_analysis(mrc_ctx* ctx, const int16_t* pcm, const int64_t* clip_frame_offsets, int32_t n_clips,

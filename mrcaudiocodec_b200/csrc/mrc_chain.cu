@@ -17,6 +17,8 @@
 // finish_kernel  (parallel, one warp per block): replays the block from the reservoir the chain recorded and
 //                writes what the chain left out: grant masks, table ids, bits written, chunk sizes.
 // offsets_kernel (parallel, one warp per clip): chunk sizes -> byte offsets inside the clip's .pac.
+#include <algorithm>
+#include <cstdio>
 #include "mrc_internal.cuh"
 
 namespace {
@@ -555,28 +557,28 @@ segment_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, ChainIO
                 else if (B0 >= thr) R[e] = B0 + c_all;
                 else need[e] = act[e];
             }
-            int walks = 0;
+            static_assert(SEG_EPT == 4, "the selection below is written out for four entries per thread");
+            for (int walks = 0;; ++walks) {          // warp-uniform: one complete walk per distinct value of the warp
+                const unsigned m0 = __ballot_sync(0xffffffffu, need[0]), m1 = __ballot_sync(0xffffffffu, need[1]);
+                const unsigned m2 = __ballot_sync(0xffffffffu, need[2]), m3 = __ballot_sync(0xffffffffu, need[3]);
+                if (!(m0 | m1 | m2 | m3)) break;
+                if (walks >= SEG_MAX_WALKS) {        // too many distinct values: these trajectories are given up
 #pragma unroll
-            for (int e = 0; e < SEG_EPT; ++e) {
-                unsigned m = __ballot_sync(0xffffffffu, need[e]);
-                while (m) {                          // warp-uniform: one complete walk per distinct value
-                    if (walks >= SEG_MAX_WALKS) {    // too many distinct values: these trajectories are given up
-                        if (need[e]) R[e] = RIN_NONE;
-                        break;
-                    }
-                    const int l = __ffs(m) - 1;
-                    const int Rl = __shfl_sync(0xffffffffu, R[e], l);
-                    const bool mine = need[e] && R[e] == Rl;
-                    const unsigned same = __ballot_sync(0xffffffffu, mine);
-                    const GroupTotals gt = walk_group<false>(
-                        reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN), reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP),
-                        reinterpret_cast<const uint4*>(rec + MRC_REC_PC), nullptr, mx, grp * MRC_GROUP_CHUNKS, nck, K + Rl,
-                        min_nl, lane, dummy, dummy);
-                    const int Rn = reservoir_after(gt, K + Rl, frac, cp.no_huff, nullptr, nullptr);
-                    if (mine) { R[e] = Rn; need[e] = false; }
-                    m &= ~same;
-                    ++walks;
+                    for (int e = 0; e < SEG_EPT; ++e)
+                        if (need[e]) { R[e] = RIN_NONE; need[e] = false; }
+                    break;
                 }
+                const unsigned msel = m0 ? m0 : (m1 ? m1 : (m2 ? m2 : m3));
+                const int Rsel = m0 ? R[0] : (m1 ? R[1] : (m2 ? R[2] : R[3]));
+                const int Rl = __shfl_sync(0xffffffffu, Rsel, __ffs(msel) - 1);
+                const GroupTotals gt = walk_group<false>(
+                    reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN), reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP),
+                    reinterpret_cast<const uint4*>(rec + MRC_REC_PC), nullptr, mx, grp * MRC_GROUP_CHUNKS, nck, K + Rl,
+                    min_nl, lane, dummy, dummy);
+                const int Rn = reservoir_after(gt, K + Rl, frac, cp.no_huff, nullptr, nullptr);
+#pragma unroll
+                for (int e = 0; e < SEG_EPT; ++e)
+                    if (need[e] && R[e] == Rl) { R[e] = Rn; need[e] = false; }
             }
         }
     }
@@ -632,12 +634,22 @@ extras_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, int nseg
     }
 }
 
+// The serial pass.  Everything it reads arrives through TMA bulk copies: the composed rows of the next CS_STAGES
+// segments sit in a ring of shared-memory stages (a step is then a shared-memory look-up, not a trip to L2), and when a
+// segment has to be walked block by block the per-block tables of CS_FB consecutive blocks are fetched with ONE bulk copy
+// (they are contiguous) while the lanes fetch the blocks' budgets in parallel.  Only a complete walk (a value outside a
+// block's table that does not grant everything) reads its record from global memory.
+constexpr int CS_STAGES = 10;
+constexpr int CS_FB = 16;
+
 __global__ void __launch_bounds__(32)
 chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int S, ChainIO io, int r_lo, int ntab,
                  int tabw, const int* __restrict__ tab, int segw, const int* __restrict__ comp,
-                 const int* __restrict__ segx, int* __restrict__ rin,
+                 const int* __restrict__ segx, int* __restrict__ rin, int fb_blocks,
                  const int32_t* __restrict__ reservoir_in, int32_t* __restrict__ reservoir_out,
                  unsigned long long* __restrict__ iter_counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[CS_STAGES + 1];
     const int lane = threadIdx.x;
     const int clip = c0 + blockIdx.x;
     const int blk0 = cm.clip_blk0[clip], nblk_clip = cm.clip_blk0[clip + 1] - blk0;
@@ -645,45 +657,123 @@ chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int 
     if (b_hi <= b_lo) return;
     const int lb_lo = blk0 + b_lo - g0, lb_hi = blk0 + b_hi - g0;      // wave-local
     const int flush_lb = (cp.flush_nonjoint && b_hi == nblk_clip) ? lb_hi - 1 : -1;
+    // segments that lie wholly inside this clip's blocks of the wave: [seg_first, seg_lim)
+    const int seg_first = (lb_lo + S - 1) / S;
+    const int seg_lim = (lb_hi == nblk_wave) ? (nblk_wave + S - 1) / S : lb_hi / S;
+    const unsigned row_bytes = (unsigned)segw * 4u, sx_bytes = (unsigned)SEGX_W * 4u, stage_bytes = row_bytes + sx_bytes;
+    const unsigned tb_bytes = (unsigned)(2 * tabw) * 4u;               // both groups' tables of one block
+    unsigned char* const fb = smem_raw + (size_t)CS_STAGES * stage_bytes;
+    if (lane == 0) {
+        for (int i = 0; i <= CS_STAGES; ++i) mbar_init(&s_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int seg) {               // lane 0 only
+        const int st = (seg - seg_first) % CS_STAGES;
+        unsigned char* dst = smem_raw + (size_t)st * stage_bytes;
+        mbar_expect_tx(&s_bar[st], stage_bytes);
+        bulk_g2s(dst, comp + (size_t)seg * segw, row_bytes, &s_bar[st]);
+        bulk_g2s(dst + row_bytes, segx + (size_t)seg * SEGX_W, sx_bytes, &s_bar[st]);
+    };
+    if (lane == 0)
+        for (int i = 0; i < CS_STAGES && seg_first + i < seg_lim; ++i) issue(seg_first + i);
     int R = (b_lo == 0) ? (reservoir_in ? reservoir_in[clip] : 0) : io.clip_res[clip];
-    unsigned n_slow = 0, n_blk = 0;
+    unsigned n_slow = 0, n_blk = 0, n_pair = 0, n_closed = 0, n_esc = 0, n_nopair = 0, n_impure = 0, fb_parity = 0, dummy = 0;
     int lb = lb_lo;
     while (lb < lb_hi) {
-        if (lb % S == 0) {
-            const int seg = lb / S, seg_end = min(lb + S, nblk_wave);
-            if (seg_end <= lb_hi) {                  // the whole segment belongs to this clip
-                const int* row = comp + (size_t)seg * segw;
-                const int idx = R - r_lo;
-                int Rn = RIN_NONE;
-                if (row[ntab + 2] != 0) {
-                    if ((unsigned)idx < (unsigned)ntab) Rn = row[idx];
-                    else if (R >= row[ntab + 1]) Rn = R + row[ntab];
-                    else {
-                        const int* sx = segx + (size_t)seg * SEGX_W;
-                        const int v = (lane < SEG_EXITS) ? sx[SEG_EXITS + lane] : RIN_NONE;       // one pair per lane
-                        const unsigned hit = __ballot_sync(0xffffffffu, v == R);
-                        if (hit) Rn = sx[2 * SEG_EXITS + __ffs(hit) - 1];
-                    }
-                }
-                if (Rn != RIN_NONE) {
-                    if (lane == 0) rin[seg] = R;
-                    R = Rn;
-                    lb = seg_end;
-                    continue;
+        int end;
+        const int seg = lb / S;
+        if (lb % S == 0 && seg >= seg_first && seg < seg_lim) {
+            const int k = seg - seg_first, st = k % CS_STAGES;
+            mbar_wait(&s_bar[st], (unsigned)((k / CS_STAGES) & 1));
+            const int* row = reinterpret_cast<const int*>(smem_raw + (size_t)st * stage_bytes);
+            const int* sx = row + segw;
+            const int seg_end = min(lb + S, nblk_wave);
+            const int idx = R - r_lo;
+            int Rn = RIN_NONE;
+            const bool pure = row[ntab + 2] != 0;
+            if (pure) {
+                if ((unsigned)idx < (unsigned)ntab) Rn = row[idx];
+                else if (R >= row[ntab + 1]) { Rn = R + row[ntab]; ++n_closed; }
+                else {
+                    const int v = (lane < SEG_EXITS) ? sx[SEG_EXITS + lane] : RIN_NONE;       // one pair per lane
+                    const unsigned hit = __ballot_sync(0xffffffffu, v == R);
+                    if (hit) { Rn = sx[2 * SEG_EXITS + __ffs(hit) - 1]; ++n_pair; }
                 }
             }
+            __syncwarp();                            // every lane is done with the stage before it is refilled
+            if (lane == 0 && seg + CS_STAGES < seg_lim) issue(seg + CS_STAGES);
+            if (Rn != RIN_NONE) {
+                if (lane == 0) rin[seg] = R;
+                R = Rn;
+                lb = seg_end;
+                continue;
+            }
+            if (!pure) ++n_impure;
+            else if ((unsigned)idx < (unsigned)ntab) ++n_esc;
+            else ++n_nopair;
+#ifdef MRC_DEBUG_CHAIN
+            if (lane == 0) printf("walk-through: block %d (%.2f s) R=%d %s\n", g0 + lb, (g0 + lb) / 46.875, R,
+                                  (unsigned)idx < (unsigned)ntab ? "not followed" : "not anticipated");
+#endif
+            end = seg_end;
+        } else {
+            end = min((seg + 1) * S, lb_hi);         // a piece of a segment shared with another clip or wave edge
         }
-        const BlkStep o = step_block(cp, io.rec + (size_t)lb * MRC_REC_BYTES, tab + (size_t)lb * (2 * tabw),
-                                     cp.joint && lb != flush_lb, R, r_lo, ntab, tabw, lane, n_slow);
-        if (lane == 0) io.rsv[lb] = make_int4(o.R0, o.R1, o.R, 0);
-        R = o.R;
-        ++lb;
-        ++n_blk;
+        // block by block through [lb, end), fb_blocks at a time
+        for (int q0 = lb; q0 < end; q0 += fb_blocks) {
+            const int nq = min(fb_blocks, end - q0);
+            if (lane == 0) {
+                mbar_expect_tx(&s_bar[CS_STAGES], (unsigned)nq * tb_bytes);
+                bulk_g2s(fb, tab + (size_t)q0 * (2 * tabw), (unsigned)nq * tb_bytes, &s_bar[CS_STAGES]);
+            }
+            int hK = 0, hF = 0, hM = 0;              // lane i: budget, fraction flag, narrowest band of block q0 + i
+            if (lane < nq) {
+                const int32_t* mx = reinterpret_cast<const int32_t*>(io.rec + (size_t)(q0 + lane) * MRC_REC_BYTES + MRC_REC_MX);
+                hK = __ldg(mx + MRC_MX_K); hF = __ldg(mx + MRC_MX_FRAC); hM = __ldg(mx + MRC_MX_MINNL);
+            }
+            mbar_wait(&s_bar[CS_STAGES], fb_parity);
+            fb_parity ^= 1u;
+            for (int i = 0; i < nq; ++i) {
+                const int q = q0 + i;
+                const int K = __shfl_sync(0xffffffffu, hK, i);
+                const bool joint = cp.joint && q != flush_lb;
+                const int* T0 = reinterpret_cast<const int*>(fb + (size_t)i * tb_bytes);
+                const int R0 = R;
+                int R1 = R;
+                for (int grp = 0; grp < (joint ? 1 : 2); ++grp) {
+                    const int* T = T0 + grp * tabw;
+                    const int B0 = K + R, idx = R - r_lo;
+                    if ((unsigned)idx < (unsigned)ntab) R = T[idx];
+                    else if (B0 >= T[ntab + 1]) R = B0 + T[ntab];
+                    else {
+                        const unsigned char* rec = io.rec + (size_t)q * MRC_REC_BYTES;
+                        const GroupTotals gt = walk_group<false>(
+                            reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN), reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP),
+                            reinterpret_cast<const uint4*>(rec + MRC_REC_PC), nullptr, reinterpret_cast<const int32_t*>(rec + MRC_REC_MX),
+                            grp * MRC_GROUP_CHUNKS, joint ? MRC_NCHUNK : MRC_GROUP_CHUNKS, B0, __shfl_sync(0xffffffffu, hM, i),
+                            lane, dummy, dummy);
+                        R = reservoir_after(gt, B0, __shfl_sync(0xffffffffu, hF, i), cp.no_huff, nullptr, nullptr);
+                        ++n_slow;
+                    }
+                    if (grp == 0) R1 = R;
+                }
+                if (lane == 0) io.rsv[q] = make_int4(R0, R1, R, 0);
+            }
+            n_blk += (unsigned)nq;
+            __syncwarp();                            // before the next batch overwrites the tables
+        }
+        lb = end;
     }
     if (lane == 0) {
         if (iter_counter) {
             atomicAdd(iter_counter, (unsigned long long)n_slow);           // complete walks taken by the serial pass
             atomicAdd(iter_counter + 1, (unsigned long long)n_blk);        // blocks it stepped through one by one
+            atomicAdd(iter_counter + 2, (unsigned long long)n_pair);       // segments entered through an (exit -> result) pair
+            atomicAdd(iter_counter + 3, (unsigned long long)n_closed);     // segments stepped by the closed form
+            atomicAdd(iter_counter + 4, (unsigned long long)n_esc);        // entered inside the range, trajectory not followed
+            atomicAdd(iter_counter + 5, (unsigned long long)n_nopair);     // entered outside the range, value not anticipated
+            atomicAdd(iter_counter + 6, (unsigned long long)n_impure);
         }
         io.clip_res[clip] = R;
         if (b_hi == nblk_clip && reservoir_out) reservoir_out[clip] = R;
@@ -858,8 +948,14 @@ void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm,
                       const int* segx, int* rin, const int32_t* reservoir_in, int32_t* reservoir_out,
                       unsigned long long* iter_counter) {
     if (nclips <= 0 || nblk <= 0) return;
-    chain_seg_kernel<<<nclips, 32, 0, st>>>(cp, cm, c0, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, segx, rin,
-                                            reservoir_in, reservoir_out, iter_counter);
+    // shared memory: the ring of composed rows + as many per-block tables as fit (at most CS_FB, at least one)
+    const size_t ring = (size_t)CS_STAGES * ((size_t)segw * 4 + SEGX_W * 4), tb = (size_t)2 * tabw * 4;
+    int fbn = (int)std::min<size_t>(CS_FB, (200 * 1024 - ring) / tb);
+    if (fbn < 1) fbn = 1;
+    const size_t smem = ring + (size_t)fbn * tb;
+    cudaFuncSetAttribute(chain_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    chain_seg_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, segx, rin, fbn,
+                                               reservoir_in, reservoir_out, iter_counter);
     const int nseg = (nblk + S - 1) / S;
     expand_kernel<<<(nseg + EXP_WARPS - 1) / EXP_WARPS, EXP_WARPS * 32, 0, st>>>(cp, cm, g0, nblk, S, nseg, io, r_lo, ntab,
                                                                                  tabw, tab, rin);

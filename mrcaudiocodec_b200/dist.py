@@ -8,11 +8,15 @@ Nothing here touches the bitstream: the bytes of a clip do not depend on which r
 (tests/test_dist_gloo.py checks the bookkeeping with world_size 2 on the gloo backend; tests/test_gpu_parity.py checks
 that a sharded batch equals the single-context batch on the GPU).
 
-A single long stream does not shard this way in exact mode: block-to-block the reference carries bitReservoir
-(codecThem.py:224,274,332,503), so a shard would need the reservoir of the block before its first one.  Transform and
-psychoacoustics of a block range only need an N/2-sample halo of PCM, and libmrc already pipelines them against the
-serial reservoir walk inside one GPU (DESIGN.md "Waves"); across GPUs the walk stays serial, so long single streams
-are kept on one GPU and batches are what scales."""
+A single long stream shards by BLOCK RANGE (encode_stream_sharded): rank r encodes a contiguous range of the stream's
+blocks.  A block inherits two things from the block before it -- the previous n_mdct_lines frames (pacfileThem.py
+:799-802), which the shard reads as an N/2-sample halo from the PCM itself, and codingParams.bitReservoir
+(codecThem.py:224,274,332,391,503), one int.  Everything that does not depend on the reservoir (transform,
+psychoacoustics, bit prices, the composed reservoir maps) runs on all ranks at once; then the reservoir travels down the
+ranks, one point-to-point message of one int32 per boundary (the serial pass over a shard's composed maps takes well
+under a millisecond), and every rank packs its chunks as soon as it has handed the reservoir on.  The concatenated
+shards are byte-identical to the single-GPU file.  Still no collective on the data path: the all-gather of the shards'
+byte counts gives the offsets for the concatenation."""
 import numpy as np
 
 
@@ -76,3 +80,37 @@ def write_concatenated(path, blobs, offsets, rank, world):
         for i, b in zip(range(lo, hi), blobs):
             fh.seek(int(offsets[i]))
             fh.write(b)
+
+
+def encode_stream_sharded(codec, pcm_shard, pcm_frame0, total_frames, group=None, device=None, out=None,
+                          device_ptrs=None):
+    """One stream of total_frames frames encoded by all ranks, rank r taking the block range
+    shard_range(ceil(total_frames / L), r, world).  pcm_shard: int16 [frames, 2] starting at stream frame pcm_frame0 and
+    covering codec.shard_pcm_range(total_frames, first_block, n_blocks) (each rank only needs its own range: generate or
+    read per rank).  Returns (this rank's bytes, shard byte offsets int64 [world + 1]): rank r's bytes belong at
+    offsets[r] of the .pac file."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    nblk = (int(total_frames) + codec.L - 1) // codec.L
+    lo, hi = shard_range(nblk, rank, world)
+    box = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def recv():
+        if rank == 0:
+            return 0
+        dist.recv(box, src=rank - 1, group=group)
+        return int(box.item())
+
+    def send(r):
+        if rank + 1 < world:
+            box.fill_(int(r))
+            dist.send(box, dst=rank + 1, group=group)
+
+    blob = codec.encode_shard(pcm_shard, pcm_frame0, total_frames, lo, hi - lo, rank == 0, rank == world - 1, recv, send,
+                              out=out, device_ptrs=device_ptrs)
+    n = blob if device_ptrs is not None else len(blob)      # device-resident runs return the byte count only
+    _, offsets = gather_clip_offsets([n], world, group, device) if world > 1 else \
+        (None, np.array([0, n], dtype=np.int64))
+    return blob, offsets

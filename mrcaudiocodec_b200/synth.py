@@ -66,6 +66,27 @@ def synth_clip(seed, seconds, sample_rate=48000, quiet=True, threads=1, fast=Fal
     return np.concatenate(parts, axis=0) if parts else np.zeros((0, 2), np.int16)
 
 
+def synth_range(seed, frame_lo, frame_hi, total_seconds, sample_rate=48000, quiet=True, threads=1, fast=False):
+    """frames [frame_lo, frame_hi) of synth_clip(seed, total_seconds): only the 10 s segments that overlap the range are
+    synthesised (what one rank of a stream sharded by block range needs)."""
+    n = int(round(total_seconds * sample_rate))
+    frame_hi = min(int(frame_hi), n)
+    frame_lo = max(0, min(int(frame_lo), frame_hi))
+    seg_n = SEG_SECONDS * sample_rate
+    dtype = np.float32 if fast else np.float64
+    s0, s1 = frame_lo // seg_n, (frame_hi + seg_n - 1) // seg_n
+    jobs = [(seed, s, sample_rate, min(seg_n, n - s * seg_n), quiet, dtype) for s in range(s0, s1)]
+    if threads > 1 and len(jobs) > 1:
+        with ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(lambda a: _segment(*a), jobs))
+    else:
+        parts = [_segment(*a) for a in jobs]
+    if not parts:
+        return np.zeros((0, 2), np.int16)
+    x = np.concatenate(parts, axis=0)
+    return np.ascontiguousarray(x[frame_lo - s0 * seg_n:frame_hi - s0 * seg_n])
+
+
 def synth_short(seed, seconds, sample_rate=48000):
     """A short test clip that still contains every regime: tones+noise, a transient, 0.2 s of exact silence,
     0.2 s at -70 dBFS.  Used for fixtures the CPU oracle / reference must finish in seconds."""

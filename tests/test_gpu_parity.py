@@ -357,3 +357,34 @@ def test_buffer_too_small_reports_sizes(codecs):
     singles = c.decode_clips([out[boff[i]:boff[i + 1]].tobytes() for i in (0, 5, 11)])
     for k, i in enumerate((0, 5, 11)):
         assert np.array_equal(dec[foff[i]:foff[i + 1]], singles[k])
+
+
+@pytest.mark.parametrize("joint", [True, False])
+def test_stream_sharded_by_block_range_equals_whole(joint, monkeypatch):
+    """One stream cut into block ranges (mrc_encode_shard: halo of n_mdct_lines frames from the PCM, the reservoir handed
+    from shard to shard as one int): the shards, encoded one after the other on this GPU, concatenate to the bytes of
+    the whole-stream encode and of the oracle -- with the cuts inside silence (reservoir far outside the tabulated
+    range), at a ragged tail, and with an empty shard."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import Codec, synth
+    monkeypatch.setenv("MRC_CHAIN_TABLE_MIN_BLOCKS", "1")
+    pcm = synth.synth_short(31, 1.1)[:-333]                 # ragged: the last block is zero padded
+    L = 1024
+    total = pcm.shape[0]
+    nblk = (total + L - 1) // L
+    c = Codec(joint=joint)
+    whole = c.encode_clips([pcm])[0]
+    assert whole == o.driver.encode_pcm(pcm, joint=joint)[0]
+    sil = int(0.35 * total) // L + 3                        # a block inside the clip's silent stretch
+    for cuts in ([0, nblk], [0, 7, nblk], [0, sil, sil + 2, nblk], [0, 1, 1, nblk - 1, nblk]):
+        parts, r = [], [0]
+        for i in range(len(cuts) - 1):
+            b0, n = cuts[i], cuts[i + 1] - cuts[i]
+            lo, hi = c.shard_pcm_range(total, b0, n)
+            got = []
+            parts.append(c.encode_shard(pcm[lo:hi], lo, total, b0, n, i == 0, i == len(cuts) - 2, lambda: r[0],
+                                        got.append).tobytes())
+            assert len(got) == 1
+            r[0] = got[0]
+        assert b"".join(parts) == whole, cuts
+    c.close()
