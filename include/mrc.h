@@ -177,7 +177,10 @@ int32_t mrc_encode_shard_device(mrc_ctx* ctx, const int16_t* d_pcm, int64_t pcm_
 
 /* ---- per-block seam (compat layer; explicit bit reservoir in/out) -----------------------------------------
  * mrc_encode_block = codecThem.Encode (joint=0) / JointEncode (joint=1) on one block; joint|2 skips the Huffman
- * stage (EncodeNoHuff, codecThem.py:234-260: table 15, no reservoir credit).
+ * stage (EncodeNoHuff, codecThem.py:234-260: table 15, no reservoir credit); joint|4 (with joint bit 0 clear) is
+ * codecThem.Encode with codingParams.nChannels = 1 (:216 loops over the channels): data is ONE channel [a+b], every
+ * output holds one channel's worth ([n_bands], [n_mdct_lines], [1]), ms_switch is not written, and the reservoir
+ * returned is the one after that channel.
  * data             : [2][2*n_mdct_lines] float64 signed fractions (prior block, current block) per channel
  * reservoir        : in/out codingParams.bitReservoir
  * scale_factor,bit_alloc : [2][n_bands]; mantissa: [2][n_mdct_lines] aligned to MDCT lines (0 where the band has

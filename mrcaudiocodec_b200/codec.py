@@ -19,12 +19,15 @@ class Codec(object):
     def __init__(self, sample_rate=48000, n_mdct_lines=1024, n_scale_bits=4, n_mant_size_bits=4,
                  target_bits_per_sample=128000. / 48000., joint=True, precision="fp64", device=0,
                  band_limits=None, spreading="factorised", chain_tables=True, block_switching=False,
-                 switch_tables=None, transient_sos_sections=None):
+                 switch_tables=None, transient_sos_sections=None, window="kbd"):
         """block_switching=True: encode_batch follows the reference's `__main__` loop (transient detector, one
         block of look-ahead, eight 128-sample short blocks around transients; pacfileThem.py:1142-1215).
         switch_tables=True (implied by block_switching) only loads the extra block geometries, which is what
         decoding a switched stream and the per-block seam with a != b need.  transient_sos_sections overrides the
-        detector's filter (default: designed with scipy exactly like the reference)."""
+        detector's filter (default: designed with scipy exactly like the reference).
+        window: "kbd" (the reference codec's KBD alpha=4 window) or "sine" (window.py:10-25, SineWindow) for both the
+        MDCT analysis and the IMDCT synthesis; a stream must be decoded with the window it was encoded with (the .pac
+        header does not record it)."""
         self.lib = _lib.load()
         self.L = int(n_mdct_lines)
         self.sample_rate = int(sample_rate)
@@ -49,7 +52,9 @@ class Codec(object):
         rc = self.lib.mrc_create(C.byref(cfg), C.byref(self._ctx))
         if rc != 0:
             raise _lib.MrcError(rc, self.lib.mrc_last_error(None).decode())
-        self.tables = Tables(self.L, self.sample_rate, band_limits)
+        if window != "kbd" and (block_switching or switch_tables):
+            raise ValueError("block switching uses the reference's KBD transition windows (window.py:104-121)")
+        self.tables = Tables(self.L, self.sample_rate, band_limits, window)
         t = _lib.MrcTables()
         T = self.tables
         t.n_bands = T.n_bands
@@ -302,7 +307,10 @@ class Codec(object):
         a = self.L if a is None else int(a)
         b = self.L if b is None else int(b)
         nl, nbands, _, _ = self.geometry(a, b)
-        data = np.ascontiguousarray(data, dtype=np.float64).reshape(2, a + b)
+        if int(joint) & 4:                      # one channel (nChannels = 1): outputs hold channel 0 only
+            data = np.ascontiguousarray(data, dtype=np.float64).reshape(1, a + b)
+        else:
+            data = np.ascontiguousarray(data, dtype=np.float64).reshape(2, a + b)
         res = np.array([int(reservoir)], dtype=np.int32)
         sf = np.zeros((2, nbands), np.int32)
         ba = np.zeros((2, nbands), np.int32)

@@ -15,7 +15,8 @@ so a reference-style PACFile can be pointed at the GPU with `pacfileThem.codec =
 mantissa[ch] is the compacted int32 array (table 15) or the list of "code" / "esccode/mantissa" strings
 (tables 0..3), exactly what calculateHuffmanGain returns (codecThem.py:178-203).
 
-Two channels only.  Block switching: codingParams.a / codingParams.b may each be nMDCTLines or
+One or two channels (nChannels = 1: Encode / EncodeNoHuff / Decode, the reference's loops over
+codingParams.nChannels, codecThem.py:216; the whole-file batch API is stereo).  Block switching: codingParams.a / codingParams.b may each be nMDCTLines or
 128, as the reference's `__main__` loop sets them (pacfileThem.py:1193-1210); the band table follows a + b like
 pacfileThem.py:808-816 (25 bands for two long halves, else the 9-band short table), nMDCTLines must be 1024 then.
 Every call is one round trip to the GPU: this layer is for parity and integration, the batch API in codec.py is
@@ -45,8 +46,8 @@ def _codec_for(cp, precision=None):
     for v in (cp.a, cp.b):
         if v != cp.nMDCTLines and v != 128:
             raise NotImplementedError("codec_gpu serves window halves of nMDCTLines or 128 samples")
-    if getattr(cp, "nChannels", 2) != 2:
-        raise NotImplementedError("codec_gpu serves two-channel streams")
+    if getattr(cp, "nChannels", 2) not in (1, 2):
+        raise NotImplementedError("codec_gpu serves one- and two-channel streams")
     precision = precision or getattr(cp, "precision", "fp64")
     switched = not (cp.a == cp.b == cp.nMDCTLines)
     key = (int(cp.sampleRate), int(cp.nMDCTLines), int(cp.nScaleBits), int(cp.nMantSizeBits),
@@ -82,25 +83,31 @@ def _compact(c, r, ch, a, b, as_codes=True):
 
 def _encode(data, codingParams, joint, no_huff=False):
     c = _codec_for(codingParams)
-    x = np.stack([np.asarray(data[0], dtype=np.float64), np.asarray(data[1], dtype=np.float64)])
-    r, res = c.encode_block(x, (1 if joint else 0) | (2 if no_huff else 0), int(codingParams.bitReservoir),
-                            a=codingParams.a, b=codingParams.b)
+    nch = int(getattr(codingParams, "nChannels", 2))
+    if nch == 1:
+        if joint:
+            raise ValueError("JointEncode needs two channels (codecThem.py:363-364)")
+        x = np.asarray(data[0], dtype=np.float64)[None, :]
+    else:
+        x = np.stack([np.asarray(data[0], dtype=np.float64), np.asarray(data[1], dtype=np.float64)])
+    r, res = c.encode_block(x, (1 if joint else 0) | (2 if no_huff else 0) | (4 if nch == 1 else 0),
+                            int(codingParams.bitReservoir), a=codingParams.a, b=codingParams.b)
     codingParams.bitReservoir = res
-    S = [r["scaleFactor"][ch].astype(np.int32) for ch in range(2)]
-    A = [r["bitAlloc"][ch].astype(int) for ch in range(2)]
-    M = [_compact(c, r, ch, codingParams.a, codingParams.b) for ch in range(2)]
-    H = [int(r["huffTable"][ch]) for ch in range(2)]
+    S = [r["scaleFactor"][ch].astype(np.int32) for ch in range(nch)]
+    A = [r["bitAlloc"][ch].astype(int) for ch in range(nch)]
+    M = [_compact(c, r, ch, codingParams.a, codingParams.b) for ch in range(nch)]
+    H = [int(r["huffTable"][ch]) for ch in range(nch)]
     return c, r, S, A, M, H
 
 
 def Encode(data, codingParams):
     c, r, S, A, M, H = _encode(data, codingParams, joint=False)
-    return (S, A, M, [int(r["overallScale"][0]), int(r["overallScale"][1])], H)
+    return (S, A, M, [int(r["overallScale"][ch]) for ch in range(len(S))], H)
 
 
 def EncodeNoHuff(data, codingParams):
     c, r, S, A, M, H = _encode(data, codingParams, joint=False, no_huff=True)
-    return (S, A, M, [int(r["overallScale"][0]), int(r["overallScale"][1])], H)
+    return (S, A, M, [int(r["overallScale"][ch]) for ch in range(len(S))], H)
 
 
 def JointEncode(data, codingParams):

@@ -284,6 +284,7 @@ struct EncodeJob {
     int32_t* t_npk = nullptr;
     int32_t* t_alloc = nullptr; int32_t* t_sf = nullptr; int32_t* t_mant = nullptr; int32_t* t_table = nullptr;
     int32_t* t_res = nullptr; int32_t* t_cbytes = nullptr;
+    int32_t* t_res_mid = nullptr;          // reservoir between the two channels of a non-joint block (after channel 0)
     bool need_quant = true;
     bool dev_qtaps = false;                // leave alloc / mantissa taps of the (single) wave in q_alloc / q_mant
     int geom = MRC_GEO_LONG;               // d_xin jobs: the geometry of every block (per-block seam with a, b given)
@@ -528,7 +529,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
     // ---- buffer sets ----
     const bool want_atap = job.t_lines || job.t_smr || job.t_npk;
     const bool want_qtap = job.t_alloc || job.t_sf || job.t_mant || job.dev_qtaps;
-    const bool any_tap = want_atap || job.t_alloc || job.t_sf || job.t_mant || job.t_ovs || job.t_ms || job.t_table || job.t_res || job.t_cbytes;
+    const bool any_tap = want_atap || job.t_alloc || job.t_sf || job.t_mant || job.t_ovs || job.t_ms || job.t_table || job.t_res ||
+                         job.t_cbytes || job.t_res_mid;
     size_t W = 1;
     for (int w = 0; w < nwaves; ++w) W = std::max<size_t>(W, (size_t)(wave_g0[w + 1] - wave_g0[w]));
     const int nsets = std::max(1, std::min(nwaves, NSETS));
@@ -805,6 +807,11 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
             int32_t* d = job.t_mant + (size_t)g0 * 2 * Lt;
             for (size_t r = 0; r < (size_t)nblk * 2; ++r)
                 for (int i = 0; i < Lt; ++i) d[r * Lt + i] = src[r * L + i];
+        }
+        if (job.t_res_mid) {
+            CK(fetch(io[s].rsv, (size_t)nblk * sizeof(int4)));
+            const int4* src = (const int4*)hb.data();
+            for (int b = 0; b < nblk; ++b) job.t_res_mid[g0 + b] = src[b].y;
         }
         if (job.t_table || job.t_res || job.t_cbytes) {
             CK(fetch(io[s].cblk, (size_t)nblk * sizeof(ChainBlk)));
@@ -1324,10 +1331,37 @@ int32_t mrc_encode_block_ab(mrc_ctx* ctx, const double* data, int32_t a, int32_t
         return fail(ctx, MRC_E_INVALID, "window halves a and b must each be n_mdct_lines or 128");
     const int q = (a != Lc ? 2 : 0) | (b != Lc ? 1 : 0);
     const int N = a + b;
+    const bool mono = (joint & 4) != 0;       // one channel (codingParams.nChannels = 1): run it as both channels of an
+    if (mono && (joint & 1))                  // independent-channel block and keep channel 0 and the reservoir after it
+        return fail(ctx, MRC_E_INVALID, "a single channel has no joint (M/S) flow");
     CK(ensure(ctx->xin_dev, (size_t)2 * N * 8));
-    CK(cudaMemcpyAsync(ctx->xin_dev.p, data, (size_t)2 * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->xin_dev.p, data, (size_t)(mono ? 1 : 2) * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (mono)
+        CK(cudaMemcpyAsync((double*)ctx->xin_dev.p + N, data, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
     const int64_t off[2] = {0, N};
     int32_t res_in = *reservoir, res_out = 0;
+    if (mono) {
+        const int nbq = ctx->geo[q].nb, Lq = ctx->geo[q].L;
+        std::vector<int32_t> sf2(2 * nbq), ba2(2 * nbq), mant2(2 * (size_t)Lq);
+        int32_t ovs4[4], ht2[2], cb2[2], mid = 0;
+        EncodeJob mj;
+        mj.d_xin = (const double*)ctx->xin_dev.p; mj.h_clip_off = off; mj.n_clips = 1;
+        mj.geom = q;
+        mj.joint = 0; mj.no_huff = (joint & 2) ? 1 : 0; mj.flush_nonjoint = false;
+        mj.h_res_in = &res_in; mj.h_res_out = &res_out;
+        mj.t_alloc = ba2.data(); mj.t_sf = sf2.data(); mj.t_mant = mant2.data(); mj.t_table = ht2;
+        mj.t_cbytes = cb2; mj.t_ovs = ovs4; mj.t_res_mid = &mid;
+        const int rc = run_encode(ctx, mj);
+        if (rc != MRC_OK) return rc;
+        if (scale_factor) memcpy(scale_factor, sf2.data(), (size_t)nbq * 4);
+        if (bit_alloc) memcpy(bit_alloc, ba2.data(), (size_t)nbq * 4);
+        if (mantissa) memcpy(mantissa, mant2.data(), (size_t)Lq * 4);
+        if (overall_scale) overall_scale[0] = ovs4[0];
+        if (huff_table) huff_table[0] = ht2[0];
+        if (chunk_bytes) chunk_bytes[0] = cb2[0];
+        *reservoir = mid;
+        return MRC_OK;
+    }
     EncodeJob job;
     job.d_xin = (const double*)ctx->xin_dev.p; job.h_clip_off = off; job.n_clips = 1;
     job.geom = q;

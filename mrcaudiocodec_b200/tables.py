@@ -101,10 +101,16 @@ def load_huffman():
 class Tables(object):
     """Everything mrc_set_tables needs, as contiguous numpy arrays kept alive by this object."""
 
-    def __init__(self, n_mdct_lines, sample_rate, band_limits=None):
+    def __init__(self, n_mdct_lines, sample_rate, band_limits=None, window="kbd"):
         L = int(n_mdct_lines)
         self.band_nlines = np.ascontiguousarray(band_lines(L, sample_rate, band_limits), dtype=np.int32)
-        self.kbd = np.ascontiguousarray(kbd_window(2 * L), dtype=np.float64)
+        # the analysis/synthesis window is a table to the kernels: KBD(alpha=4) is what the reference codec uses
+        # (codecThem.py:316, :406-431 through TransitionWindow); the sine window (window.py:10-25) is the module's other
+        # Princen-Bradley window, selectable here
+        if window not in ("kbd", "sine"):
+            raise ValueError("window must be 'kbd' or 'sine'")
+        self.window_name = window
+        self.kbd = np.ascontiguousarray(kbd_window(2 * L) if window == "kbd" else sine_window(2 * L), dtype=np.float64)
         self.hann = np.ascontiguousarray(hann_window(2 * L), dtype=np.float64)
         f = mdct_freqs(L, sample_rate)
         self.bark = np.ascontiguousarray(bark(f), dtype=np.float64)

@@ -388,3 +388,61 @@ def test_stream_sharded_by_block_range_equals_whole(joint, monkeypatch):
             r[0] = got[0]
         assert b"".join(parts) == whole, cuts
     c.close()
+
+
+def test_sine_window_selector():
+    """window="sine" (window.py:10-25): MDCT lines equal the oracle's MDCT of the sine-windowed block, and encode ->
+    decode with the same window reconstructs (Princen-Bradley: TDAC cancels), unlike decoding with the other window."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import Codec, synth
+    from mrcaudiocodec_b200.tables import sine_window
+    assert np.array_equal(sine_window(2048), o.window.sine_coeffs(2048))
+    pcm = synth.synth_short(5, 0.4)
+    c = Codec(window="sine")
+    a = c.stage_analysis([pcm])
+    L = 1024
+    x = np.concatenate((np.zeros((L, 2), np.int16), pcm, np.zeros((2 * L, 2), np.int16)))
+    for b in (0, 3, 11):
+        for ch in range(2):
+            blk = o.pcm.pcm_to_fraction(x[b * L:(b + 2) * L, ch])
+            ref = o.mdct.MDCT(o.window.SineWindow(blk), L, L)
+            assert np.abs(a["mdct"][b, ch] - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-30)
+    blob = c.encode_clips([pcm])[0]
+    dec = c.decode_clips([blob])[0][:pcm.shape[0]].astype(np.float64)
+    ck = Codec()
+    dec_wrong = ck.decode_clips([blob])[0][:pcm.shape[0]].astype(np.float64)
+    ref = pcm.astype(np.float64)
+    loud = np.abs(ref).max(axis=1) > 64
+    snr = 10 * np.log10(np.sum(ref[loud] ** 2) / np.sum((dec[loud] - ref[loud]) ** 2))
+    snr_wrong = 10 * np.log10(np.sum(ref[loud] ** 2) / np.sum((dec_wrong[loud] - ref[loud]) ** 2))
+    assert snr > 10.0 and snr > snr_wrong + 3.0, (snr, snr_wrong)
+    c.close()
+    ck.close()
+
+
+def test_reference_seam_mono(golden):
+    """nChannels = 1 through the non-joint seam (codecThem.py:216 loops over codingParams.nChannels): the oracle's
+    PACFile loop over a mono stream with its codec swapped for codec_gpu writes the oracle's own bytes -- Encode,
+    EncodeNoHuff and Decode -- including the Huffman books (quiet passage) and the reservoir carried block to block."""
+    import mrc_oracle as o
+    from mrcaudiocodec_b200 import codec_gpu
+    g = golden("indep48k_64")
+    mono = np.ascontiguousarray(g["pcm"][:14 * 1024, :1])
+    kw = dict(joint=False, sampleRate=int(g["sampleRate"]), targetBitsPerSample=float(g["tbps"]))
+    ref, _ = o.driver.encode_pcm(mono, **kw)
+    saved = o.pacfile.codec
+    o.pacfile.codec = codec_gpu
+    try:
+        blob, _ = o.driver.encode_pcm(mono, **kw)
+        dec = o.driver.decode_pac(blob, joint=False)
+    finally:
+        o.pacfile.codec = saved
+    assert blob == ref
+    assert pacfile_nchannels(blob) == 1
+    od = o.driver.decode_pac(ref, joint=False)
+    assert dec.shape == od.shape and np.abs(dec.astype(np.int64) - od.astype(np.int64)).max() <= 1
+
+
+def pacfile_nchannels(blob):
+    from mrcaudiocodec_b200 import pacfile
+    return pacfile.parse_header(blob)["nChannels"]
