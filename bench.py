@@ -434,7 +434,8 @@ def main():
             dt = (time.perf_counter() - t0) / 3
             td = codec.last_timing()
             line["decode"] = {"e2e_value": seconds / dt, "unit": "audio-s/s", "ms_per_step": 1000.0 * dt,
-                              "kernel_ms": td["decode_ms"], "h2d_bytes_per_step": nbytes,
+                              "kernel_ms": td["decode_ms"], "host_chain_walk_ms": td["chain_ms"],
+                              "h2d_bytes_per_step": nbytes,
                               "d2h_bytes_per_step": int(pcm_out.nbytes),
                               "note": "decode of this rank's stream through Codec.decode_batch, host buffers, 3 steps"}
             del h_dec

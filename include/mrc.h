@@ -243,7 +243,7 @@ int32_t mrc_mantissa_histogram(mrc_ctx* ctx, const int16_t* pcm, const int64_t* 
 
 /* ---- instrumentation ------------------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the stream each kernel is launched on, summed over waves) of the stages of the
- * last encode/decode call: [0] analysis kernels, [1] chain (serial reservoir walk) kernels, [2] clip-offset scan +
+ * last encode/decode call: [0] analysis kernels, [1] chain (serial reservoir walk) kernels (after a decode: host milliseconds of the header checks and the <L nBytes> chain walk), [2] clip-offset scan +
  * quantise/pack kernels, [3] decode kernels (after an encode with block switching: the transient detector kernels),
  * [4] H2D, [5] D2H (encode: sums of the wave-by-wave copies on the copy streams, which overlap the kernels; decode: 0, not timed apart), [6] whole call on the main stream, [7] cost kernels.
  * Analysis+cost of wave w+1 overlap chain+pack of wave w, so [0]+[7]+[1]+[2] can exceed [6].

@@ -71,14 +71,14 @@ struct Smem {
     cpx<T>* buf;    // [L]      FFT work buffer
     T* lines;       // [4][L]   MDCT lines L,R,M,S
     T* xi;          // [L]      FFT intensity, later SMR-per-line scratch
-    // masker tables of the current spectrum, always double (Q = L/2 >= number of maskers)
-    double* mz;     // [Q]      Bark position
-    double* ms15;   // [Q]      SPL - 15
-    double* mg;     // [Q]      0.37*max(SPL-40,0)
-    double* mc;     // [Q]      10^((SPL-15-96)/10): intensity inside +-0.5 Bark
-    double* mU;     // [Q]      quiet maskers at or below i, decayed to z_i (upper slope, -27 dB/Bark)
-    double* mS;     // [Q]      maskers at or above i, decayed to z_i (lower slope, -27 dB/Bark); [npk] = 0
-    double* mP;     // [Q]      sum of mc below i ([npk] = total); only for the pass-1 bound (npk < Q always)
+    // masker tables of the current spectrum, in the mode's own precision (Q = L/2 >= number of maskers)
+    T* mz;          // [Q]      Bark position
+    T* ms15;        // [Q]      SPL - 15
+    T* mg;          // [Q]      0.37*max(SPL-40,0)
+    T* mc;          // [Q]      10^((SPL-15-96)/10): intensity inside +-0.5 Bark
+    T* mU;          // [Q]      quiet maskers at or below i, decayed to z_i (upper slope, -27 dB/Bark)
+    T* mS;          // [Q]      maskers at or above i, decayed to z_i (lower slope, -27 dB/Bark); [npk] = 0
+    T* mP;          // [Q]      sum of mc below i ([npk] = total); only for the pass-1 bound (npk < Q always)
     int* pbin;      // [Q]      peak bins; once the masker tables are built the same words hold zlut
     uint16_t* zlut; // [MRC_ZLUT+1] number of maskers with z < g/32 Bark (only when Q ints can hold it)
     int* lcnt;      // [Q+1]    number of loud maskers (g > 0) below index i
@@ -97,21 +97,18 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     s.buf = reinterpret_cast<cpx<T>*>(p); p += 2 * L;
     s.lines = p;         p += 4 * L;
     s.xi = p;            p += L;
-    double* d = reinterpret_cast<double*>(p);
-    s.mz = d;            d += Q;
-    s.ms15 = d;          d += Q;
-    s.mg = d;            d += Q;
-    s.etab = d;          d += 64;
-    // mc, mU, mS, mP (4Q doubles) live in the FFT work buffer when it is large enough (it is idle while maskers
-    // are spread), else in a region of their own.
-    const size_t need = (size_t)(4 * Q) * 8;
-    double* r;
-    if ((size_t)(2 * L) * sizeof(T) >= need) r = reinterpret_cast<double*>(s.buf);
-    else { r = d; d += need / 8; }
+    s.mz = p;            p += Q;
+    s.ms15 = p;          p += Q;
+    s.mg = p;            p += Q;
+    // mc, mU, mS, mP (4Q values = the FFT work buffer's 2L) live in the FFT work buffer: it is idle while maskers are
+    // spread
+    T* r = reinterpret_cast<T*>(s.buf);
     s.mc = r;
     s.mU = r + Q;
     s.mS = r + 2 * Q;
     s.mP = r + 3 * Q;
+    double* d = reinterpret_cast<double*>((reinterpret_cast<size_t>(p) + 7) & ~(size_t)7);
+    s.etab = d;          d += 64;
     int* ip = reinterpret_cast<int*>(d);
     s.pbin = ip;         ip += Q;
     s.zlut = (Q * 4 >= (MRC_ZLUT + 2) * 2) ? reinterpret_cast<uint16_t*>(s.pbin) : nullptr;
@@ -151,51 +148,51 @@ __device__ __forceinline__ T tsample(const T* sx, int N, int c, int n) {
 // position of line k among the maskers: m_lo = number of maskers with dz > 0.5 (a prefix: z_m ascends),
 // m_hi = first masker with dz < -0.5, dz = z_k - z_m as the reference computes it
 template <typename T>
-__device__ __forceinline__ void masker_range(const Smem<T>& sm, double zk, int npk, int& m_lo, int& m_hi) {
+__device__ __forceinline__ void masker_range(const Smem<T>& sm, T zk, int npk, int& m_lo, int& m_hi) {
     if (sm.zlut != nullptr) {
         // start from the count table (maskers per 1/32 Bark cell, prefix-summed), then settle with the exact
         // comparisons: a cell holds two or three maskers at most
-        int g = (int)((zk - 0.5) * 32.0);
+        int g = (int)((zk - T(0.5)) * T(32.0));
         int m = sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)];
-        while (m > 0 && !(zk - sm.mz[m - 1] > 0.5)) --m;
-        while (m < npk && zk - sm.mz[m] > 0.5) ++m;
+        while (m > 0 && !(zk - sm.mz[m - 1] > T(0.5))) --m;
+        while (m < npk && zk - sm.mz[m] > T(0.5)) ++m;
         m_lo = m;
-        g = (int)((zk + 0.5) * 32.0) + 1;
+        g = (int)((zk + T(0.5)) * T(32.0)) + 1;
         m = sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)];
         if (m < m_lo) m = m_lo;
-        while (m > m_lo && zk - sm.mz[m - 1] < -0.5) --m;
-        while (m < npk && !(zk - sm.mz[m] < -0.5)) ++m;
+        while (m > m_lo && zk - sm.mz[m - 1] < T(-0.5)) --m;
+        while (m < npk && !(zk - sm.mz[m] < T(-0.5))) ++m;
         m_hi = m;
         return;
     }
     int lo = 0, hi = npk;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (zk - sm.mz[mid] > 0.5) lo = mid + 1; else hi = mid;
+        if (zk - sm.mz[mid] > T(0.5)) lo = mid + 1; else hi = mid;
     }
     m_lo = lo;
     hi = npk;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (zk - sm.mz[mid] < -0.5) hi = mid; else lo = mid + 1;
+        if (zk - sm.mz[mid] < T(-0.5)) hi = mid; else lo = mid + 1;
     }
     m_hi = lo;
 }
 
 // one loud masker (index m) onto a line more than 0.5 Bark above it: the reference's exponent, unfused
 template <typename T>
-__device__ __forceinline__ double loud_term(const Smem<T>& sm, double zk, int m) {
-    const double t = __dadd_rn(__dadd_rn(zk, -sm.mz[m]), -0.5);
-    const double e = __dadd_rn(__dadd_rn(sm.ms15[m], __dmul_rn(-27.0, t)), __dmul_rn(sm.mg[m], t));
-    return exp10_tab(div10(__dadd_rn(e, -96.0)), sm.etab);
+__device__ __forceinline__ T loud_term(const Smem<T>& sm, T zk, int m) {
+    const T t = rn_add(rn_add(zk, -sm.mz[m]), T(-0.5));
+    const T e = rn_add(rn_add(sm.ms15[m], rn_mul(T(-27.0), t)), rn_mul(sm.mg[m], t));
+    return sp_exp10(sp_div10(rn_add(e, T(-96.0))), sm.etab);
 }
 
 // the two geometric tails at line k
 template <typename T>
-__device__ __forceinline__ double tail_terms(const Smem<T>& sm, double zk, int npk, int m_lo, int m_hi) {
-    double a = 0.0;
-    if (m_lo > 0) a += sm.mU[m_lo - 1] * exp10_tab(-2.7 * ((zk - sm.mz[m_lo - 1]) - 0.5), sm.etab);
-    if (m_hi < npk) a += sm.mS[m_hi] * exp10_tab(-2.7 * ((sm.mz[m_hi] - zk) - 0.5), sm.etab);
+__device__ __forceinline__ T tail_terms(const Smem<T>& sm, T zk, int npk, int m_lo, int m_hi) {
+    T a = T(0.0);
+    if (m_lo > 0) a += sm.mU[m_lo - 1] * sp_exp10(T(-2.7) * ((zk - sm.mz[m_lo - 1]) - T(0.5)), sm.etab);
+    if (m_hi < npk) a += sm.mS[m_hi] * sp_exp10(T(-2.7) * ((sm.mz[m_hi] - zk) - T(0.5)), sm.etab);
     return a;
 }
 
@@ -210,18 +207,19 @@ __device__ __forceinline__ double tail_terms(const Smem<T>& sm, double zk, int n
 // spread_line_bound: a LOWER bound of that threshold, cheap enough for every line: only the MRC_NEAR_LOUD nearest
 // loud maskers, and the plateau sum as a difference of prefix sums minus its worst-case rounding error.
 template <typename T>
-__device__ __forceinline__ double spread_line_bound(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk,
+__device__ __forceinline__ T spread_line_bound(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk,
                                                     unsigned& n_general) {
-    const double zk = tb.bark_d[k];
+    const T zk = tb.bark[k];
     int m_lo, m_hi;
     masker_range(sm, zk, npk, m_lo, m_hi);
-    double a = tb.quiet_d[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
+    T a = tb.quiet[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
     const int nl = sm.lcnt[m_lo];
     const int j0 = nl > MRC_NEAR_LOUD ? nl - MRC_NEAR_LOUD : 0;
     for (int j = nl - 1; j >= j0; --j) a += loud_term(sm, zk, sm.lidx[j]);
     n_general += (unsigned)(nl - j0);
-    const double w = (sm.mP[m_hi] - sm.mP[m_lo]) - 1.4210854715202004e-14 * sm.mP[npk];     // 2^-46 of the total
-    return a + fmax(w, 0.0);
+    // worst-case rounding of the two prefix sums: 2^-46 of the total in fp64, 4e-5 in fp32
+    const T w = (sm.mP[m_hi] - sm.mP[m_lo]) - (sizeof(T) == 8 ? T(1.4210854715202004e-14) : T(4e-5)) * sm.mP[npk];
+    return a + fmax(w, T(0.0));
 }
 
 // masker_range by a whole warp: the count table gives a first guess, then ONE window of 32 consecutive maskers per
@@ -229,16 +227,16 @@ __device__ __forceinline__ double spread_line_bound(const Smem<T>& sm, const Dev
 // the ascending maskers, so the number of lanes that pass is the bound.  If a window does not contain its bound
 // (never seen: a 1/32-Bark cell holds a few maskers at most) the scalar search is used.
 template <typename T>
-__device__ __forceinline__ void masker_range_warp(const Smem<T>& sm, double zk, int npk, int lane, int& m_lo, int& m_hi) {
+__device__ __forceinline__ void masker_range_warp(const Smem<T>& sm, T zk, int npk, int lane, int& m_lo, int& m_hi) {
     if (sm.zlut == nullptr) { masker_range(sm, zk, npk, m_lo, m_hi); return; }
-    int g = (int)((zk - 0.5) * 32.0);
+    int g = (int)((zk - T(0.5)) * T(32.0));
     const int w0 = (int)sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)] - 8;
-    g = (int)((zk + 0.5) * 32.0) + 1;
+    g = (int)((zk + T(0.5)) * T(32.0)) + 1;
     const int w1 = (int)sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)] - 24;
     const int i0 = w0 + lane, i1 = w1 + lane;
-    const double z0 = sm.mz[i0 < 0 ? 0 : (i0 < npk ? i0 : 0)], z1 = sm.mz[i1 < 0 ? 0 : (i1 < npk ? i1 : 0)];
-    const bool p0 = i0 < 0 || (i0 < npk && zk - z0 > 0.5);             // maskers more than 0.5 Bark below the line
-    const bool p1 = i1 < 0 || (i1 < npk && !(zk - z1 < -0.5));         // maskers not more than 0.5 Bark above it
+    const T z0 = sm.mz[i0 < 0 ? 0 : (i0 < npk ? i0 : 0)], z1 = sm.mz[i1 < 0 ? 0 : (i1 < npk ? i1 : 0)];
+    const bool p0 = i0 < 0 || (i0 < npk && zk - z0 > T(0.5));             // maskers more than 0.5 Bark below the line
+    const bool p1 = i1 < 0 || (i1 < npk && !(zk - z1 < T(-0.5)));         // maskers not more than 0.5 Bark above it
     const int n0 = __popc(__ballot_sync(0xffffffffu, p0)), n1 = __popc(__ballot_sync(0xffffffffu, p1));
     if (n0 >= 1 && n0 <= 31 && n1 >= 1 && n1 <= 31) {
         m_lo = w0 + n0;
@@ -253,29 +251,29 @@ __device__ __forceinline__ void masker_range_warp(const Smem<T>& sm, double zk, 
 // above, items 2.. the loud maskers below -- so that one pass of the exponential covers a typical line; the plateau
 // maskers are summed lane-strided, lane 2 adds the threshold in quiet, then a butterfly sum.  All lanes return it.
 template <typename T>
-__device__ __forceinline__ double spread_line_warp(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk, int lane,
+__device__ __forceinline__ T spread_line_warp(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk, int lane,
                                                    unsigned& n_general, unsigned& n_window) {
     MRC_WCLK_BEGIN();
-    const double zk = tb.bark_d[k];
-    const double quiet = tb.quiet_d[k];
+    const T zk = tb.bark[k];
+    const T quiet = tb.quiet[k];
     int m_lo, m_hi;
     masker_range_warp(sm, zk, npk, lane, m_lo, m_hi);
     MRC_WCLK(16);
     const int nl = sm.lcnt[m_lo];
-    double a = 0.0;
+    T a = T(0.0);
     for (int base = 0; base < nl + 2; base += 32) {
         const int item = base + lane, j = item - 2;
         const bool tail = item < 2;
         const bool valid = tail ? (item == 0 ? m_lo > 0 : m_hi < npk) : j < nl;
         int mi = tail ? (item == 0 ? m_lo - 1 : m_hi) : (int)sm.lidx[j < nl ? j : 0];
         mi = valid ? mi : 0;
-        const double mzv = sm.mz[mi];
-        const double t = __dadd_rn(item == 1 ? __dadd_rn(mzv, -zk) : __dadd_rn(zk, -mzv), -0.5);
+        const T mzv = sm.mz[mi];
+        const T t = rn_add(item == 1 ? rn_add(mzv, -zk) : rn_add(zk, -mzv), T(-0.5));
         // loud masker: the reference's exponent, unfused (psychoac.py:70-76); tails: -27 dB per Bark beyond the plateau
-        const double e = __dadd_rn(__dadd_rn(sm.ms15[mi], __dmul_rn(-27.0, t)), __dmul_rn(sm.mg[mi], t));
-        const double y = tail ? -2.7 * t : div10(__dadd_rn(e, -96.0));
-        const double coef = tail ? (item == 0 ? sm.mU[mi] : sm.mS[mi]) : 1.0;
-        const double v = coef * exp10_tab(y, sm.etab);
+        const T e = rn_add(rn_add(sm.ms15[mi], rn_mul(T(-27.0), t)), rn_mul(sm.mg[mi], t));
+        const T y = tail ? T(-2.7) * t : sp_div10(rn_add(e, T(-96.0)));
+        const T coef = tail ? (item == 0 ? sm.mU[mi] : sm.mS[mi]) : T(1.0);
+        const T v = coef * sp_exp10(y, sm.etab);
         if (valid) a += v;
     }
     MRC_WSYNC();
@@ -292,7 +290,7 @@ __device__ __forceinline__ double spread_line_warp(const Smem<T>& sm, const DevT
 }
 
 template <typename T, int L_>
-__global__ void __launch_bounds__(L_ / 2, (L_ <= 1024) ? 2 : 1)
+__global__ void __launch_bounds__(L_ / 2, (L_ <= 1024) ? (sizeof(T) == 4 ? 3 : 2) : 1)
 analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __restrict__ pcm,
                 const double* __restrict__ xin, int g0, Handoff<T> ho, AnalysisTaps<T> taps,
                 unsigned long long* peak_counter) {
@@ -309,7 +307,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ int s_scale[4];
     __shared__ unsigned int s_ms;
     __shared__ int s_wcnt[33];
-    __shared__ double s_scan[5][32];
+    __shared__ T s_scan[5][32];
     __shared__ T s_band_smr[MRC_BSTRIDE];
     __shared__ int s_npk;
 #ifdef MRC_PHASE_CLOCKS
@@ -530,27 +528,27 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
         // d. masker parameters (psychoac.py:163-165, :37-49), in double in both modes
         {
             const int i = tid;                       // npk <= Q == NT: one masker per thread
-            double z = 0, s15 = 0, g = 0, cmid = 0;
+            T z = 0, s15 = 0, g = 0, cmid = 0;
             bool loud = false;
             if (i < npk) {
                 // products and sums kept unfused (__dmul_rn/__dadd_rn), in the reference's order
                 const int p = sm.pbin[i];
-                const double x0 = (double)sm.xi[p - 1], x1 = (double)sm.xi[p], x2 = (double)sm.xi[p + 1];
-                const double sum = __dadd_rn(__dadd_rn(x0, x1), x2);
-                const double spl = fmax(__dadd_rn(96.0, __dmul_rn(10.0, log10(sum))), -30.0);
-                const double num = __dadd_rn(__dadd_rn(__dmul_rn((double)(p - 1), x0), __dmul_rn((double)p, x1)),
-                                             __dmul_rn((double)(p + 1), x2));
-                const double f = __ddiv_rn(__dmul_rn((double)tb.fstep, num), sum);
-                const double fq = __ddiv_rn(f, 7500.0);
-                z = __dadd_rn(__dmul_rn(13.0, atan(__ddiv_rn(__dmul_rn(0.76, f), 1000.0))),
-                              __dmul_rn(3.5, atan(__dmul_rn(fq, fq))));
-                s15 = __dadd_rn(spl, -15.0);
-                g = __dmul_rn(0.37, fmax(__dadd_rn(spl, -40.0), 0.0));
-                loud = g > 0.0;
+                const T x0 = sm.xi[p - 1], x1 = sm.xi[p], x2 = sm.xi[p + 1];
+                const T sum = rn_add(rn_add(x0, x1), x2);
+                const T spl = fmax(rn_add(T(96.0), rn_mul(T(10.0), m_log10(sum))), T(-30.0));
+                const T num = rn_add(rn_add(rn_mul(T(p - 1), x0), rn_mul(T(p), x1)),
+                                             rn_mul(T(p + 1), x2));
+                const T f = rn_div(rn_mul(T(tb.fstep), num), sum);
+                const T fq = rn_div(f, T(7500.0));
+                z = rn_add(rn_mul(T(13.0), m_atan(rn_div(rn_mul(T(0.76), f), T(1000.0)))),
+                              rn_mul(T(3.5), m_atan(rn_mul(fq, fq))));
+                s15 = rn_add(spl, T(-15.0));
+                g = rn_mul(T(0.37), fmax(rn_add(spl, T(-40.0)), T(0.0)));
+                loud = g > T(0.0);
                 n_loud += loud ? 1u : 0u;
                 sm.mz[i] = z; sm.ms15[i] = s15; sm.mg[i] = g;
                 if (!cp.spread_seq) {
-                    cmid = exp10_tab(div10(__dadd_rn(s15, -96.0)), sm.etab);
+                    cmid = sp_exp10(sp_div10(rn_add(s15, T(-96.0))), sm.etab);
                     sm.mc[i] = cmid;
                 }
             }
@@ -570,10 +568,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                     s_wcnt[lane] = incl - v;
                 }
                 // decay between neighbouring maskers: rho(d) = 10^(-2.7 d), the -27 dB/Bark slope of both sides
-                double rU = 0.0, rS = 0.0;           // rU = rho(z_i - z_{i-1}); rS = rho(z_{i+1} - z_i)
+                T rU = T(0.0), rS = T(0.0);           // rU = rho(z_i - z_{i-1}); rS = rho(z_{i+1} - z_i)
                 if (i < npk) {
-                    if (i > 0) rU = exp10_tab(-2.7 * (z - sm.mz[i - 1]), sm.etab);
-                    if (i + 1 < npk) rS = exp10_tab(-2.7 * (sm.mz[i + 1] - z), sm.etab);
+                    if (i > 0) rU = sp_exp10(T(-2.7) * (z - sm.mz[i - 1]), sm.etab);
+                    if (i + 1 < npk) rS = sp_exp10(T(-2.7) * (sm.mz[i + 1] - z), sm.etab);
                 }
                 __syncthreads();
                 const int lpos = s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u));
@@ -582,11 +580,11 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 // two affine recurrences by warp scans:  U_i = cq_i + rU_i * U_{i-1}  (ascending, quiet maskers only)
                 //                                        S_i = c_i  + rS_i * S_{i+1}  (descending, all maskers)
                 // The descending one runs on the mirrored index j = npk-1-i, held by thread j.
-                double aU = rU, bU = (i < npk && !loud) ? cmid : 0.0;
-                double pP = (i < npk) ? cmid : 0.0;          // plain running sum of the plateau intensities
+                T aU = rU, bU = (i < npk && !loud) ? cmid : T(0.0);
+                T pP = (i < npk) ? cmid : T(0.0);          // plain running sum of the plateau intensities
                 // mirrored element for S: thread tid holds masker im = npk-1-tid
                 const int im = npk - 1 - tid;
-                double aS = 0.0, bS = 0.0;
+                T aS = T(0.0), bS = T(0.0);
                 // exchange through shared memory: stash (rS, c) of masker i, read those of masker im
                 sm.mU[i < npk ? i : npk] = rS;       // temporary use of mU/mS as exchange buffers
                 __syncthreads();
@@ -594,9 +592,9 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 __syncthreads();
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const double alU = __shfl_up_sync(0xffffffffu, aU, o), blU = __shfl_up_sync(0xffffffffu, bU, o);
-                    const double alS = __shfl_up_sync(0xffffffffu, aS, o), blS = __shfl_up_sync(0xffffffffu, bS, o);
-                    const double plP = __shfl_up_sync(0xffffffffu, pP, o);
+                    const T alU = __shfl_up_sync(0xffffffffu, aU, o), blU = __shfl_up_sync(0xffffffffu, bU, o);
+                    const T alS = __shfl_up_sync(0xffffffffu, aS, o), blS = __shfl_up_sync(0xffffffffu, bS, o);
+                    const T plP = __shfl_up_sync(0xffffffffu, pP, o);
                     if (lane >= o) {
                         bU = fma(aU, blU, bU); aU = aU * alU;
                         bS = fma(aS, blS, bS); aS = aS * alS;
@@ -609,14 +607,14 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 }
                 __syncthreads();
                 if (warp == 0) {
-                    double a1 = (lane < nwarp) ? s_scan[0][lane] : 1.0, b1 = (lane < nwarp) ? s_scan[1][lane] : 0.0;
-                    double a2 = (lane < nwarp) ? s_scan[2][lane] : 1.0, b2 = (lane < nwarp) ? s_scan[3][lane] : 0.0;
-                    double p3 = (lane < nwarp) ? s_scan[4][lane] : 0.0;
+                    T a1 = (lane < nwarp) ? s_scan[0][lane] : T(1.0), b1 = (lane < nwarp) ? s_scan[1][lane] : T(0.0);
+                    T a2 = (lane < nwarp) ? s_scan[2][lane] : T(1.0), b2 = (lane < nwarp) ? s_scan[3][lane] : T(0.0);
+                    T p3 = (lane < nwarp) ? s_scan[4][lane] : T(0.0);
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        const double al1 = __shfl_up_sync(0xffffffffu, a1, o), bl1 = __shfl_up_sync(0xffffffffu, b1, o);
-                        const double al2 = __shfl_up_sync(0xffffffffu, a2, o), bl2 = __shfl_up_sync(0xffffffffu, b2, o);
-                        const double pl3 = __shfl_up_sync(0xffffffffu, p3, o);
+                        const T al1 = __shfl_up_sync(0xffffffffu, a1, o), bl1 = __shfl_up_sync(0xffffffffu, b1, o);
+                        const T al2 = __shfl_up_sync(0xffffffffu, a2, o), bl2 = __shfl_up_sync(0xffffffffu, b2, o);
+                        const T pl3 = __shfl_up_sync(0xffffffffu, p3, o);
                         if (lane >= o) {
                             b1 = fma(a1, bl1, b1); a1 = a1 * al1;
                             b2 = fma(a2, bl2, b2); a2 = a2 * al2;
@@ -633,7 +631,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 }
                 if (i < npk) sm.mU[i] = bU;
                 if (im >= 0) sm.mS[im] = bS;
-                if (tid == 0) { sm.mS[npk] = 0.0; sm.mP[0] = 0.0; }
+                if (tid == 0) { sm.mS[npk] = T(0.0); sm.mP[0] = T(0.0); }
                 if (i < npk) sm.mP[i + 1] = pP;          // inclusive sum up to i = sum below i+1
             }
         }
@@ -644,7 +642,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             // stretch, no counting and no prefix sum.
             __syncthreads();
             auto cell_of = [&](int i) {
-                int cell = (int)(sm.mz[i] * 32.0) + 1;               // counted from cell+1 on: z < g/32 for g > z*32
+                int cell = (int)(sm.mz[i] * T(32.0)) + 1;               // counted from cell+1 on: z < g/32 for g > z*32
                 return cell < 1 ? 1 : (cell > MRC_ZLUT ? MRC_ZLUT : cell);
             };
             if (tid < npk) {
@@ -660,16 +658,16 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
         const T sc6 = T(6) * T(s_scale[c]);
         auto line_spl = [&](int k) -> T {           // SPL of the (scaled) MDCT line, scale undone
             const T X = sm.lines[c * L + k];
-            return fmax(T(96) + T(10) * m_log10((T(2) * (X * X)) / T(0.5)), T(-30)) - sc6;
+            return fmax(T(96) + T(10) * m_log10((T(2) * (X * X)) / T(T(0.5))), T(-30)) - sc6;
         };
-        auto thr_of = [&](double a) -> T { return fmax(T(96) + T(10) * m_log10(T(a)), T(-30)); };
+        auto thr_of = [&](T a) -> T { return fmax(T(96) + T(10) * m_log10(T(a)), T(-30)); };
         if (cp.spread_seq) {
             // reference order (psychoac.py:68-78, :168): every masker onto every line, one 10**x per pair
             const int k0 = tid, k1 = tid + Q;
-            const double z0 = tb.bark_d[k0], z1 = tb.bark_d[k1];
-            double a0 = tb.quiet_d[k0], a1 = tb.quiet_d[k1];
+            const T z0 = tb.bark[k0], z1 = tb.bark[k1];
+            T a0 = tb.quiet[k0], a1 = tb.quiet[k1];
             for (int m = 0; m < npk; ++m) {
-                const double zm = sm.mz[m], s15 = sm.ms15[m], gg = sm.mg[m];
+                const T zm = sm.mz[m], s15 = sm.ms15[m], gg = sm.mg[m];
                 a0 += masker_intensity(z0 - zm, s15, gg);
                 a1 += masker_intensity(z1 - zm, s15, gg);
             }
@@ -693,10 +691,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             //           true rho seen so far (less 1e-9) gets its complete threshold too; lines whose bound stays
             //           below cannot be the maximum.
             // The band SMR is the maximum of the completely evaluated lines' SMRs: exact.
-            const double FLOOR = 2.5118864315095823e-13;        // 10^((-30-96)/10): where SPL() clamps
-            auto x2c = [&](int k) -> double {
-                const double X = (double)sm.lines[c * L + k];
-                return fmax((2.0 * (X * X)) / 0.5, FLOOR);
+            const T FLOOR = T(2.5118864315095823e-13);        // 10^((-30-96)/10): where SPL() clamps
+            auto x2c = [&](int k) -> T {
+                const T X = sm.lines[c * L + k];
+                return fmax((T(2.0) * (X * X)) / T(0.5), FLOOR);
             };
             {
                 const int k0 = tid, k1 = tid + Q;
@@ -708,14 +706,14 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             }
             __syncthreads();
             MRC_CLK(6);
-            const T slack = sizeof(T) == 8 ? T(1.0 - 1e-9) : T(1.0 - 1e-4);   // bound vs true value: rounding only
+            const T slack = sizeof(T) == 8 ? T(T(1.0) - 1e-9) : T(T(1.0) - 1e-4);   // bound vs true value: rounding only
             auto complete = [&](int k, T& smr, T& rho) {         // whole warp; all lanes get the results
-                const double a = spread_line_warp(sm, tb, k, npk, lane, n_general, n_window);
+                const T a = spread_line_warp(sm, tb, k, npk, lane, n_general, n_window);
                 MRC_WCLK_BEGIN();
                 // line_spl(k) - thr_of(a) with the two logarithms side by side (odd lanes the line, even lanes the
                 // threshold): same operations on the same operands, half the latency
                 const T X = sm.lines[c * L + k];
-                const T lg = m_log10((lane & 1) ? (T(2) * (X * X)) / T(0.5) : T(a));
+                const T lg = m_log10((lane & 1) ? (T(2) * (X * X)) / T(T(0.5)) : T(a));
                 const T lg_a = __shfl_sync(0xffffffffu, lg, 0), lg_x = __shfl_sync(0xffffffffu, lg, 1);
                 smr = (fmax(T(96) + T(10) * lg_x, T(-30)) - sc6) - fmax(T(96) + T(10) * lg_a, T(-30));
                 rho = T(x2c(k) / fmax(a, FLOOR));
@@ -1046,11 +1044,9 @@ extern "C" int mrc_debug_phase_clocks(unsigned long long* out32, int reset) {
 
 size_t analysis_smem_bytes(int L, int elem) {
     const size_t Q = L / 2;
-    size_t spread = (size_t)(4 * Q) * 8;                               // mc, mU, mS, mP
-    if ((size_t)(2 * L) * elem >= spread) spread = 0;                  // ... living in the FFT work buffer
     size_t merge = (size_t)2048 * elem + 2048 * 2;                     // merge buffers of the grant order
     if ((size_t)(4 * L) * elem >= merge) merge = 0;                    // ... living in `lines`
-    return (size_t)(11 * L) * elem + (3 * Q + 64) * 8 + spread + (2 * Q + 1) * 4 + Q * 2 + 32 + merge;
+    return (size_t)(11 * L) * elem + 3 * Q * elem + 8 + 64 * 8 + (2 * Q + 1) * 4 + Q * 2 + 32 + merge;
 }
 
 template <typename T>

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -668,24 +669,25 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         const bool use_tab = job.need_quant && !ctx->no_tables && nblk / (c_hi - c_lo + 1) >= ctx->tab_min_blocks;
         bool seg_forked = false;
         if (use_tab) {
+            // The reservoir maps (per block, then composed over segments) only feed the serial pass: they run on a stream of
+            // their own that forks off after the cost kernel, so that the next wave's analysis does not queue behind them
+            // (the composition is a short kernel of few CTAs followed by a latency-bound one).
             CK(ensure(ctx->sets[s].tab, W * 2 * (size_t)tabw * 4));
-            launch_table(st2, cp, cm, g0, nblk, io[s], r_lo, ntab, tabw, (int*)ctx->sets[s].tab.p);
+            CK(cudaEventRecord(ev(w, 10), st2));
+            CK(cudaStreamWaitEvent(ctx->stream5, ev(w, 10), 0));
+            launch_table(ctx->stream5, cp, cm, g0, nblk, io[s], r_lo, ntab, tabw, (int*)ctx->sets[s].tab.p);
             ++launches;
             if (seg_S > 0) {
                 const size_t nseg = (W + seg_S - 1) / seg_S;
                 CK(ensure(ctx->sets[s].comp, nseg * (size_t)segw * 4));
                 CK(ensure(ctx->sets[s].rin, nseg * 4));
                 CK(ensure(ctx->sets[s].segx, nseg * (size_t)segment_aux_width() * 4));
-                // composing the maps is a short kernel of few CTAs followed by a latency-bound one: on a stream of its
-                // own, so that the next wave's analysis does not queue behind it
-                CK(cudaEventRecord(ev(w, 10), st2));
-                CK(cudaStreamWaitEvent(ctx->stream5, ev(w, 10), 0));
                 launch_segments(ctx->stream5, cp, cm, g0, nblk, seg_S, io[s], r_lo, ntab, tabw, (const int*)ctx->sets[s].tab.p,
                                 segw, (int*)ctx->sets[s].comp.p, (int*)ctx->sets[s].segx.p, (int*)ctx->sets[s].rin.p);
-                CK(cudaEventRecord(ev(w, 11), ctx->stream5));
-                seg_forked = true;
                 launches += 2;
             }
+            CK(cudaEventRecord(ev(w, 11), ctx->stream5));
+            seg_forked = true;
         }
         CK(cudaEventRecord(ev(w, 2), st2));
         // ---- main stream: chain -> clip offsets -> quantise + pack ----

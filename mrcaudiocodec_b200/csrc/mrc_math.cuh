@@ -5,7 +5,7 @@
 #include <stdint.h>
 
 __device__ __forceinline__ double m_log10(double x) { return log10(x); }
-__device__ __forceinline__ float m_log10(float x) { return __log2f(x) * 0.30102999566398120f; }
+__device__ __forceinline__ float m_log10(float x) { return __log2f(x) * 0.30102999566398120f; }      // MUFU.LG2
 __device__ __forceinline__ double m_exp10(double x) { return exp10(x); }
 __device__ __forceinline__ float m_exp10(float x) { return exp2f(x * 3.3219280948873623f); }
 __device__ __forceinline__ double m_atan(double x) { return atan(x); }
@@ -19,6 +19,10 @@ template <typename T>
 __device__ __forceinline__ T pcm_to_fraction(int c) {
     if (c == -32768) return T(0);
     const int mag = c < 0 ? -c : c;
+    if (sizeof(T) == 4) {                       // fast mode: one float multiply (relative error 6e-8)
+        const float v = (float)(2 * mag) * (1.0f / 65535.0f);
+        return T(c < 0 ? -v : v);
+    }
     const double q = (double)(2 * mag), rcp = 1.0 / 65535.0;
     const double y0 = q * rcp;
     const double v = fma(fma(-65535.0, y0, q), rcp, y0);
@@ -114,4 +118,21 @@ __device__ __forceinline__ double exp10_tab(double y, const double* __restrict__
     const double t = tab[n & 63];
     const double v = fma(t, p, t);
     return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
+
+// ---- the same helpers in the precision of the mode (fp64: the code-exact arithmetic above; fp32: the fast mode's
+// float arithmetic with the hardware's approximate exponential / logarithm -- MUFU.EX2 / MUFU.LG2) ---------------
+__device__ __forceinline__ double rn_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double rn_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double rn_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float rn_add(float a, float b) { return a + b; }
+__device__ __forceinline__ float rn_mul(float a, float b) { return a * b; }
+__device__ __forceinline__ float rn_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double sp_div10(double q) { return div10(q); }
+__device__ __forceinline__ float sp_div10(float q) { return q * 0.1f; }
+__device__ __forceinline__ double sp_exp10(double y, const double* __restrict__ tab) { return exp10_tab(y, tab); }
+__device__ __forceinline__ float sp_exp10(float y, const double* __restrict__) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y * 3.3219280948873623f));
+    return r;
 }

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--kernel", default="analysis_kernel<double")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--precision", default="fp64", help="key of --out the counters are stored under (fp64 | fp32)")
     a = ap.parse_args()
     hdr, units, rows = raw_rows(a.full, a.kernel.split("<")[0])
     idx = {h: i for i, h in enumerate(hdr)}
@@ -53,7 +54,9 @@ def main():
     cyc = g("sm__cycles_elapsed.max")
     per_cycle = lambda op: g("smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op)
     dfma, dadd, dmul = per_cycle("dfma") * cyc, per_cycle("dadd") * cyc, per_cycle("dmul") * cyc
+    ffma, fadd, fmul = per_cycle("ffma") * cyc, per_cycle("fadd") * cyc, per_cycle("fmul") * cyc
     flops = 2.0 * dfma + dadd + dmul
+    flops32 = 2.0 * ffma + fadd + fmul
     dram = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
         to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
     out = {
@@ -61,6 +64,10 @@ def main():
         "launch_blocks": blocks, "launch_ms_under_ncu": g("gpu__time_duration.sum"),
         "fp64_thread_inst_per_block": {"dfma": dfma / blocks, "dadd": dadd / blocks, "dmul": dmul / blocks},
         "fp64_flop_per_block": flops / blocks,
+        "fp32_thread_inst_per_block": {"ffma": ffma / blocks, "fadd": fadd / blocks, "fmul": fmul / blocks},
+        "fp32_flop_per_block": flops32 / blocks,
+        "pipe_fma_active_pct": g("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")
+        if "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active" in idx else None,
         "warp_inst_per_block": g("smsp__inst_executed.sum") / blocks,
         "pipe_fp64_active_pct": g("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
         "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
@@ -89,13 +96,25 @@ def main():
             b = m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
             t = m.get("gpu__time_duration.sum", 0.0)
             short = name.split("::")[-1].split("<")[0]
+            if short not in ("analysis_kernel", "cost_kernel", "table_kernel", "segment_kernel", "extras_kernel",
+                             "chain_seg_kernel", "chain_kernel", "expand_kernel", "finish_kernel", "offsets_kernel",
+                             "clip_scan_kernel", "pack_kernel"):
+                continue                      # e.g. the pipe micro-benchmarks of mrc_measure_peaks
             if short not in best or grid > best[short]["grid"]:
-                best[short] = {"grid": grid, "dram_bytes": b, "time": t}
+                best[short] = {"grid": grid, "dram_bytes": b, "time_ns": t}
         wave_blocks = best.get("analysis_kernel", {}).get("grid", blocks)
         out["wave"] = {"blocks": wave_blocks, "kernels": best,
                        "dram_bytes_per_block": sum(v["dram_bytes"] for v in best.values()) / wave_blocks}
+    import os
+    allp = {}
+    if os.path.exists(a.out):
+        try:
+            allp = json.load(open(a.out))
+        except Exception:
+            allp = {}
+    allp[a.precision] = out
     with open(a.out, "w") as fh:
-        json.dump(out, fh, indent=1)
+        json.dump(allp, fh, indent=1)
     print(json.dumps(out, indent=1)[:1500])
 
 
