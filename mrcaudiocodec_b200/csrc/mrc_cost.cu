@@ -52,6 +52,9 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     // is actually written (.y), one byte per book (<= 9 + 16 + 16) -- the inner loop below is one 8-byte load, four
     // byte permutes and four adds per line
     __shared__ uint2 s_lv[MRC_MAX_LEVELS][MRC_HUFF_LUT + 1];
+    __shared__ unsigned char s_sf[MRC_NSLOT];              // scale factor of every (band, level) pair
+    __shared__ int4 s_piece[2 * MRC_BSTRIDE + 2 * 64];     // (band of the 2nb list, first line in s_lines, lines, -)
+    __shared__ int s_npiece;
 
     const size_t lb = cm.list ? (size_t)cm.list[blockIdx.x] : (size_t)blockIdx.x;
     const int g = g0 + (int)lb;
@@ -104,16 +107,40 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     __syncthreads();
 
     // ---- phase 1: price every (band, level) ---------------------------------------------------------------
+    // Work items are (piece of a band, level): bands wider than CP lines are cut into pieces of at most CP lines (the widest
+    // band holds a sixth of all lines: one thread per (band, level) made everybody wait for its 363 iterations); adjacent
+    // threads share a piece (broadcast reads of the lines) and the pieces of a band add up in its accumulator.
+    constexpr int CP = 32;
+    unsigned* const acc = reinterpret_cast<unsigned*>(s_c4);            // [npair][2] cost; s_w4 likewise: bits written
+    unsigned* const accw = reinterpret_cast<unsigned*>(s_w4);
     for (int p = tid; p < npair; p += CT) {
         const int bb = p / MRC_MAX_LEVELS, lvl = p - bb * MRC_MAX_LEVELS;
         const int ch = bb >= nb, bd = bb - ch * nb;
-        const int Rb = lvl + 2;
-        const int sf = scale_factor_of(s_bmax[ch * MRC_BSTRIDE + bd], cp.n_scale_bits, Rb);
-        const double* x = s_lines + ch * L + s_blo[bd];
-        const int n = s_bn[bd];
+        s_sf[p] = (unsigned char)scale_factor_of(s_bmax[ch * MRC_BSTRIDE + bd], cp.n_scale_bits, lvl + 2);
+        acc[2 * p] = acc[2 * p + 1] = 0u;
+        accw[2 * p] = accw[2 * p + 1] = 0u;
+    }
+    if (tid == 0) {
+        int np_ = 0;
+        for (int bb = 0; bb < nb2; ++bb) {
+            const int ch = bb >= nb, bd = bb - ch * nb;
+            for (int o = 0; o < s_bn[bd]; o += CP) {
+                s_piece[np_++] = make_int4(bb, ch * L + s_blo[bd] + o, min(CP, s_bn[bd] - o), 0);
+            }
+        }
+        s_npiece = np_;
+    }
+    __syncthreads();
+    const int nitem = s_npiece * MRC_MAX_LEVELS;
+    for (int it = tid; it < nitem; it += CT) {
+        const int pc = it / MRC_MAX_LEVELS, lvl = it - pc * MRC_MAX_LEVELS;
+        const int4 pi = s_piece[pc];
+        const int p = pi.x * MRC_MAX_LEVELS + lvl, Rb = lvl + 2;
+        const int sf = s_sf[p];
+        const double* x = s_lines + pi.y;
         const uint2* __restrict__ tabl = s_lv[lvl];
         unsigned c01 = 0, c23 = 0, w01 = 0, w23 = 0;        // books 0|1 and 2|3 in 16-bit fields: sums < 363 * 41
-        for (int i = 0; i < n; ++i) {
+        for (int i = 0; i < pi.z; ++i) {
             const int m = mantissa_of(x[i], sf, cp.n_scale_bits, Rb);
             const uint2 e = tabl[m < MRC_HUFF_LUT ? m : MRC_HUFF_LUT];
             c01 += __byte_perm(e.x, 0u, 0x4140);
@@ -121,8 +148,10 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
             w01 += __byte_perm(e.y, 0u, 0x4140);
             w23 += __byte_perm(e.y, 0u, 0x4342);
         }
-        s_c4[p] = (unsigned long long)c01 | ((unsigned long long)c23 << 32);
-        s_w4[p] = (unsigned long long)w01 | ((unsigned long long)w23 << 32);
+        atomicAdd(&acc[2 * p], c01);
+        atomicAdd(&acc[2 * p + 1], c23);
+        atomicAdd(&accw[2 * p], w01);
+        atomicAdd(&accw[2 * p + 1], w23);
     }
     __syncthreads();
 

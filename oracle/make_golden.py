@@ -33,7 +33,24 @@ CASES = {
     "indep48k_128": (3, 0.5, 48000, False, 128),
     "joint44k_default": (4, 0.5, 44100, True, None),
     "indep48k_64": (5, 0.5, 48000, False, 64),
+    # real material: cuts from the reference's own training WAVs (44.1 kHz stereo), the reference's default rate
+    "wav_harps44k": (("wav", "tonal/harps.wav", 3.0), 0.6, 44100, True, None),
+    "wav_speech44k": (("wav", "speech/spfg53_1.wav", 1.5), 0.6, 44100, True, None),
 }
+
+
+def read_wav_cut(rel, start_s, seconds):
+    """int16 [n, 2] cut of one of /root/reference/training_data/*/*.wav (stdlib wave: plain RIFF parsing)."""
+    import wave
+    w = wave.open(os.path.join("/root/reference/training_data", rel), "rb")
+    sr, nch = w.getframerate(), w.getnchannels()
+    assert w.getsampwidth() == 2
+    w.setpos(int(start_s * sr))
+    x = np.frombuffer(w.readframes(int(seconds * sr)), dtype="<i2").reshape(-1, nch)
+    w.close()
+    if nch == 1:
+        x = np.repeat(x, 2, axis=1)
+    return np.ascontiguousarray(x[:, :2]), sr
 
 
 def line_aligned(mant, bitAlloc, nLines, table, codes_escape=None):
@@ -56,7 +73,11 @@ def line_aligned(mant, bitAlloc, nLines, table, codes_escape=None):
 
 def run_case(name):
     seed, seconds, sr, joint, kbps = CASES[name]
-    pcm = synth.synth_short(seed, seconds, sr)
+    if isinstance(seed, tuple):
+        pcm, wsr = read_wav_cut(seed[1], seed[2], seconds)
+        assert wsr == sr, (wsr, sr)
+    else:
+        pcm = synth.synth_short(seed, seconds, sr)
     tbps = 2.86 if kbps is None else kbps * 1000.0 / sr
     m = ref_shim.load()
     codec = m["codecThem"]

@@ -25,5 +25,6 @@ def golden():
     return load
 
 
-GOLDEN_CASES = ["joint48k_128", "joint48k_64", "indep48k_128", "joint44k_default", "indep48k_64"]
+GOLDEN_CASES = ["joint48k_128", "joint48k_64", "indep48k_128", "joint44k_default", "indep48k_64", "wav_harps44k",
+                "wav_speech44k"]      # the last two: cuts from the reference's own training WAVs (oracle/make_golden.py)
 SWITCHED_CASES = ["switched48k_128", "switched44k_default"]
