@@ -121,6 +121,16 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
         s.mkey = reinterpret_cast<T*>(a);
     }
     s.mid = reinterpret_cast<uint16_t*>(s.mkey + 2048);
+#ifdef MRC_DEBUG_ASSERTS
+    {   // everything carved must lie inside the dynamic shared memory the launch asked for
+        unsigned dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        const unsigned char* end1 = reinterpret_cast<const unsigned char*>(s.lidx + Q);
+        const unsigned char* end2 = reinterpret_cast<const unsigned char*>(s.mid + 2048);
+        MRC_ASSERT(end1 <= raw + dyn && end2 <= raw + dyn);
+        MRC_ASSERT(reinterpret_cast<const unsigned char*>(s.etab + 64) <= reinterpret_cast<const unsigned char*>(s.pbin));
+    }
+#endif
     return s;
 }
 
@@ -520,6 +530,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (lane == 31) s_npk = incl;
             }
             __syncthreads();
+            MRC_ASSERT(s_npk <= Q);
             if (found >= 0) sm.pbin[s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u))] = found;
             __syncthreads();
             MRC_CLK(4);
@@ -930,6 +941,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 const int grp = joint ? 0 : bb / nb;
                 const int li = grp * NLEV + (bq[bb] - (l ? l + 1 : 0) + LEV_OFF);
                 const int pos = lstart[li] + __popcll(lmask[li] & ((1ull << brank[bb]) - 1ull));
+                MRC_ASSERT(li >= 0 && li < 2 * NLEV && pos >= 0 && pos < per_group * (joint ? 2 : 1));
                 tokbuf[grp * per_group + pos] = (uint16_t)(bb | (l << 8));
             }
             __syncthreads();

@@ -96,6 +96,7 @@ __device__ __forceinline__ GroupTotals walk_group(const uint32_t* tn, const uint
         f = 31;                                      // so its prefix is the group total
     }
     const int jstar = (k0 + k) * 32 + f;
+    MRC_ASSERT(k >= 0 && f >= 0 && jstar < MRC_NSLOT);
     g.spent = cpre[jstar];
     g.cost = pc[jstar];
     if (FULL) {
@@ -113,6 +114,7 @@ __device__ __forceinline__ GroupTotals walk_group(const uint32_t* tn, const uint
     while (k < nck && rem >= min_nl) {
         ++n_iter;
         const int slot = (k0 + k) * 32 + lane;
+        MRC_ASSERT(slot < MRC_NSLOT);
         const uint32_t t = tn[slot];
         const int n = (int)(t >> 16);
         const bool cand = t != INVALID_TOKEN && ((active >> lane) & 1u) && n <= rem;
@@ -582,6 +584,7 @@ segment_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, ChainIO
             }
         }
     }
+    MRC_ASSERT(ntab + 3 <= segw && ntab <= SEG_EPT * SEG_THREADS);
 #pragma unroll
     for (int e = 0; e < SEG_EPT; ++e) {
         if (act[e]) row[tid + e * SEG_THREADS] = R[e];
@@ -712,10 +715,6 @@ chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int 
             if (!pure) ++n_impure;
             else if ((unsigned)idx < (unsigned)ntab) ++n_esc;
             else ++n_nopair;
-#ifdef MRC_DEBUG_CHAIN
-            if (lane == 0) printf("walk-through: block %d (%.2f s) R=%d %s\n", g0 + lb, (g0 + lb) / 46.875, R,
-                                  (unsigned)idx < (unsigned)ntab ? "not followed" : "not anticipated");
-#endif
             end = seg_end;
         } else {
             end = min((seg + 1) * S, lb_hi);         // a piece of a segment shared with another clip or wave edge

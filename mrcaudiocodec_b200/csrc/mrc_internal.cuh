@@ -20,6 +20,24 @@
 #include <stdint.h>
 #include "../../include/mrc.h"
 
+// -DMRC_DEBUG_ASSERTS (make debug -> libmrc_debug.so, run by scripts/debug_asserts.py): index checks at the places
+// where a wrong size would write outside a buffer -- the carving of the analysis kernel's shared memory, the token
+// slots of the serial walk, the pack kernel's bit buffer, the reservoir-map rows.  compute-sanitizer is closed on the
+// GPU pool this was developed on, so this build is the memory-safety net; it is never the shipped library.
+#ifdef MRC_DEBUG_ASSERTS
+#include <cstdio>
+#define MRC_ASSERT(cond)                                                                                            \
+    do {                                                                                                            \
+        if (!(cond)) {                                                                                              \
+            printf("MRC_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                               \
+            __trap();                                                                                               \
+        }                                                                                                           \
+    } while (0)
+#else
+#define MRC_ASSERT(cond)
+#endif
+
 #define MRC_TOK_STRIDE 768      // >= 2*25*15 grant tokens per block
 #define MRC_MAX_LEVELS 15       // grants per band: 0->2, then +1 up to 16 bits
 #define MRC_BSTRIDE 32          // band stride in per-band arrays

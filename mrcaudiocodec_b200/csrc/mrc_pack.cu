@@ -85,6 +85,7 @@ pack_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
     auto put = [&](int pos, uint32_t v, int n) {       // n <= 32 bits of v at bit position pos, MSB first
         if (n <= 0) return;
         const int w = pos >> 5, off = pos & 31;
+        MRC_ASSERT(pos >= 0 && n <= 32 && w + 1 < nwords);
         const unsigned long long x = (unsigned long long)v << (64 - off - n);
         const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
         if (hi) atomicOr(&bitbuf[w], hi);
