@@ -232,23 +232,37 @@ __device__ __forceinline__ T spread_line_bound(const Smem<T>& sm, const DevTable
     return a + fmax(w, T(0.0));
 }
 
-// masker_range by a whole warp: the count table gives a first guess, then ONE window of 32 consecutive maskers per
-// bound is tested with the reference's own comparison (one masker per lane) -- both predicates hold for a prefix of
-// the ascending maskers, so the number of lanes that pass is the bound.  If a window does not contain its bound
-// (never seen: a 1/32-Bark cell holds a few maskers at most) the scalar search is used.
+// Complete thresholds are evaluated by GROUPS of GW lanes.  GW = 32 (a warp per line) measured best: with two groups of
+// 16 to a warp every band of a spectrum fits in one round and two lines share every instruction issued, but the 16-wide
+// window of masker_range_grp misses its bound more often (scalar search) and the phase is bound by its slowest band either
+// way (profiles/r02_phase_clocks.log: a warp waits 12 k cycles per spectrum for the slowest group after 7.5 k of its own).
+constexpr int GW = 32;
+struct Grp {
+    unsigned mask;      // the group's lanes inside its warp
+    int gl;             // this thread's lane inside the group
+    int shift;          // the group's first lane
+};
+__device__ __forceinline__ unsigned grp_ballot(const Grp& g, bool p) {
+    return (__ballot_sync(g.mask, p) >> g.shift) & ((GW == 32) ? 0xffffffffu : ((1u << (GW & 31)) - 1u));
+}
+
+// masker_range by a group: the count table gives a first guess, then ONE window of GW consecutive maskers per bound
+// is tested with the reference's own comparison (one masker per lane) -- both predicates hold for a prefix of the
+// ascending maskers, so the number of lanes that pass is the bound.  If a window does not contain its bound (a
+// 1/32-Bark cell holds a few maskers at most) the scalar search is used.
 template <typename T>
-__device__ __forceinline__ void masker_range_warp(const Smem<T>& sm, T zk, int npk, int lane, int& m_lo, int& m_hi) {
+__device__ __forceinline__ void masker_range_grp(const Smem<T>& sm, T zk, int npk, const Grp& g, int& m_lo, int& m_hi) {
     if (sm.zlut == nullptr) { masker_range(sm, zk, npk, m_lo, m_hi); return; }
-    int g = (int)((zk - T(0.5)) * T(32.0));
-    const int w0 = (int)sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)] - 8;
-    g = (int)((zk + T(0.5)) * T(32.0)) + 1;
-    const int w1 = (int)sm.zlut[g < 0 ? 0 : (g > MRC_ZLUT ? MRC_ZLUT : g)] - 24;
-    const int i0 = w0 + lane, i1 = w1 + lane;
+    int c = (int)((zk - T(0.5)) * T(32.0));
+    const int w0 = (int)sm.zlut[c < 0 ? 0 : (c > MRC_ZLUT ? MRC_ZLUT : c)] - GW / 4;
+    c = (int)((zk + T(0.5)) * T(32.0)) + 1;
+    const int w1 = (int)sm.zlut[c < 0 ? 0 : (c > MRC_ZLUT ? MRC_ZLUT : c)] - 3 * GW / 4;
+    const int i0 = w0 + g.gl, i1 = w1 + g.gl;
     const T z0 = sm.mz[i0 < 0 ? 0 : (i0 < npk ? i0 : 0)], z1 = sm.mz[i1 < 0 ? 0 : (i1 < npk ? i1 : 0)];
     const bool p0 = i0 < 0 || (i0 < npk && zk - z0 > T(0.5));             // maskers more than 0.5 Bark below the line
     const bool p1 = i1 < 0 || (i1 < npk && !(zk - z1 < T(-0.5)));         // maskers not more than 0.5 Bark above it
-    const int n0 = __popc(__ballot_sync(0xffffffffu, p0)), n1 = __popc(__ballot_sync(0xffffffffu, p1));
-    if (n0 >= 1 && n0 <= 31 && n1 >= 1 && n1 <= 31) {
+    const int n0 = __popc(grp_ballot(g, p0)), n1 = __popc(grp_ballot(g, p1));
+    if (n0 >= 1 && n0 < GW && n1 >= 1 && n1 < GW) {
         m_lo = w0 + n0;
         m_hi = w1 + n1;
         return;
@@ -256,23 +270,24 @@ __device__ __forceinline__ void masker_range_warp(const Smem<T>& sm, T zk, int n
     masker_range(sm, zk, npk, m_lo, m_hi);
 }
 
-// The same threshold, complete, evaluated by a whole warp.  Everything that goes through 10**x is one list of items
-// dealt out to the lanes -- item 0 the tail of the maskers more than 0.5 Bark below the line, item 1 the tail of those
-// above, items 2.. the loud maskers below -- so that one pass of the exponential covers a typical line; the plateau
-// maskers are summed lane-strided, lane 2 adds the threshold in quiet, then a butterfly sum.  All lanes return it.
+// The same threshold, complete, evaluated by a group of lanes.  Everything that goes through 10**x is one list of
+// items dealt out to the lanes -- item 0 the tail of the maskers more than 0.5 Bark below the line, item 1 the tail of
+// those above, items 2.. the loud maskers below -- so that one pass of the exponential covers a typical line; the
+// plateau maskers are summed lane-strided, lane 2 adds the threshold in quiet, then a butterfly sum.  All lanes of the
+// group return it.
 template <typename T>
-__device__ __forceinline__ T spread_line_warp(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk, int lane,
-                                                   unsigned& n_general, unsigned& n_window) {
+__device__ __forceinline__ T spread_line_grp(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk, const Grp& g,
+                                             unsigned& n_general, unsigned& n_window) {
     MRC_WCLK_BEGIN();
     const T zk = tb.bark[k];
     const T quiet = tb.quiet[k];
     int m_lo, m_hi;
-    masker_range_warp(sm, zk, npk, lane, m_lo, m_hi);
+    masker_range_grp(sm, zk, npk, g, m_lo, m_hi);
     MRC_WCLK(16);
     const int nl = sm.lcnt[m_lo];
     T a = T(0.0);
-    for (int base = 0; base < nl + 2; base += 32) {
-        const int item = base + lane, j = item - 2;
+    for (int base = 0; base < nl + 2; base += GW) {
+        const int item = base + g.gl, j = item - 2;
         const bool tail = item < 2;
         const bool valid = tail ? (item == 0 ? m_lo > 0 : m_hi < npk) : j < nl;
         int mi = tail ? (item == 0 ? m_lo - 1 : m_hi) : (int)sm.lidx[j < nl ? j : 0];
@@ -286,15 +301,13 @@ __device__ __forceinline__ T spread_line_warp(const Smem<T>& sm, const DevTables
         const T v = coef * sp_exp10(y, sm.etab);
         if (valid) a += v;
     }
-    MRC_WSYNC();
     MRC_WCLK(17);
-    for (int m = m_lo + lane; m < m_hi; m += 32) a += sm.mc[m];
-    if (lane == 2) a += quiet;
-    MRC_WSYNC();
+    for (int m = m_lo + g.gl; m < m_hi; m += GW) a += sm.mc[m];
+    if (g.gl == 2) a += quiet;
     MRC_WCLK(18);
-    if (lane == 0) { n_general += (unsigned)nl; n_window += (unsigned)(m_hi - m_lo); }
+    if (g.gl == 0) { n_general += (unsigned)nl; n_window += (unsigned)(m_hi - m_lo); }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    for (int o = GW / 2; o; o >>= 1) a += __shfl_xor_sync(g.mask, a, o, GW);
     MRC_WCLK(20);
     return a;
 }
@@ -718,14 +731,18 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             __syncthreads();
             MRC_CLK(6);
             const T slack = sizeof(T) == 8 ? T(T(1.0) - 1e-9) : T(T(1.0) - 1e-4);   // bound vs true value: rounding only
-            auto complete = [&](int k, T& smr, T& rho) {         // whole warp; all lanes get the results
-                const T a = spread_line_warp(sm, tb, k, npk, lane, n_general, n_window);
+            Grp grp;
+            grp.shift = lane & ~(GW - 1);
+            grp.gl = lane - grp.shift;
+            grp.mask = ((GW == 32) ? 0xffffffffu : ((1u << (GW & 31)) - 1u)) << grp.shift;
+            auto complete = [&](int k, T& smr, T& rho) {         // whole group; all its lanes get the results
+                const T a = spread_line_grp(sm, tb, k, npk, grp, n_general, n_window);
                 MRC_WCLK_BEGIN();
                 // line_spl(k) - thr_of(a) with the two logarithms side by side (odd lanes the line, even lanes the
                 // threshold): same operations on the same operands, half the latency
                 const T X = sm.lines[c * L + k];
                 const T lg = m_log10((lane & 1) ? (T(2) * (X * X)) / T(T(0.5)) : T(a));
-                const T lg_a = __shfl_sync(0xffffffffu, lg, 0), lg_x = __shfl_sync(0xffffffffu, lg, 1);
+                const T lg_a = __shfl_sync(grp.mask, lg, 0, GW), lg_x = __shfl_sync(grp.mask, lg, 1, GW);
                 smr = (fmax(T(96) + T(10) * lg_x, T(-30)) - sc6) - fmax(T(96) + T(10) * lg_a, T(-30));
                 rho = T(x2c(k) / fmax(a, FLOOR));
                 MRC_WCLK(21);
@@ -733,39 +750,44 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 if (lane == 0) atomicAdd(&g_phase_clk[22], 1ull);
 #endif
             };
-            // pass 2, one warp per BAND that selects this spectrum (about half of them do, so one round of the CTA's
-            // warps usually covers them; bands are dealt out from the top: their lines see the most loud maskers and
-            // take longest): the band's line with the highest bound gets its complete threshold; its true rho is the
-            // bar every other line of the band has to reach with its bound to be evaluated as well (rare: the bounds
-            // are tight, about one extra line per block).
+            // pass 2, one GROUP of lanes per BAND that selects this spectrum (32 groups: one round of the CTA covers
+            // every band; bands are dealt out from the top: their lines see the most loud maskers and take longest):
+            // the band's line with the highest bound gets its complete threshold; its true rho is the bar every other
+            // line of the band has to reach with its bound to be evaluated as well (rare: the bounds are tight, about
+            // one extra line per block).  The two groups of a warp run their bands in lock step where they can and
+            // diverge where they must (all their synchronising operations name only the group's lanes).
             {
                 const unsigned bl = need & band_mask;
                 const int nbl = __popc(bl);
-                for (int p = warp; p < nbl; p += nwarp) {
+                constexpr int GPW = 32 / GW;                 // groups per warp
+                for (int p = warp * GPW + (lane / GW); p < nbl; p += nwarp * GPW) {
+                    MRC_WCLK_BEGIN();
                     const int bd = 31 - (int)__fns(__brev(bl), 0, p + 1);     // p-th needed band from the top
                     const int lo = tb.c_band_lo[bd], n = tb.c_band_n[bd];
                     T ubest = T(-1);
                     int kbest = lo;
-                    for (int i = lane; i < n; i += 32) {
+                    for (int i = grp.gl; i < n; i += GW) {
                         const T v = sm.xi[lo + i];
                         if (v > ubest) { ubest = v; kbest = lo + i; }
                     }
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        const T ov = __shfl_xor_sync(0xffffffffu, ubest, o);
-                        const int ok = __shfl_xor_sync(0xffffffffu, kbest, o);
+                    for (int o = GW / 2; o; o >>= 1) {
+                        const T ov = __shfl_xor_sync(grp.mask, ubest, o, GW);
+                        const int ok = __shfl_xor_sync(grp.mask, kbest, o, GW);
                         if (ov > ubest || (ov == ubest && ok < kbest)) { ubest = ov; kbest = ok; }
                     }
                     T best, rbest;
+                    MRC_WCLK(24);
                     complete(kbest, best, rbest);
-                    for (int base = 0; base < n; base += 32) {
-                        const int i = base + lane;
+                    MRC_WCLK(25);
+                    for (int base = 0; base < n; base += GW) {
+                        const int i = base + grp.gl;
                         const T ub = (i < n) ? sm.xi[lo + i] : T(-1);
-                        unsigned bal = __ballot_sync(0xffffffffu, i < n && lo + i != kbest && ub >= rbest * slack);
+                        unsigned bal = grp_ballot(grp, i < n && lo + i != kbest && ub >= rbest * slack);
                         while (bal) {
                             const int l = __ffs(bal) - 1;
                             bal &= bal - 1;
-                            const T ubl = __shfl_sync(0xffffffffu, ub, l);
+                            const T ubl = __shfl_sync(grp.mask, ub, l, GW);
                             if (ubl >= rbest * slack) {          // rbest may have risen since the ballot
                                 T smr, rho;
                                 complete(lo + base + l, smr, rho);
@@ -774,9 +796,17 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                             }
                         }
                     }
-                    if (lane == 0) s_band_smr[bd] = best;
+                    if (grp.gl == 0) s_band_smr[bd] = best;
+                    MRC_WCLK(26);
                 }
             }
+#ifdef MRC_PHASE_CLOCKS
+            {
+                MRC_WCLK_BEGIN();
+                __syncthreads();
+                MRC_WCLK(27);                        // warp 0's wait for the slowest group
+            }
+#endif
             __syncthreads();
             MRC_CLK(7);
             MRC_CLK(8);

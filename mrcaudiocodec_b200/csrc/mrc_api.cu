@@ -718,7 +718,6 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
                              (unsigned long long*)ctx->peakctr.p + 4);
             ++launches;
         }
-        CK(cudaEventRecord(ev(w, 4), st));
         if (job.exchange) {
             // hand the reservoir on before anything else: the next shard's serial pass waits for nothing but this
             CK(cudaMemcpyAsync(&shard_res, ctx->res_out.p, 4, cudaMemcpyDeviceToHost, st));
@@ -726,6 +725,11 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
             if (job.exchange(job.exchange_user, 1, &shard_res) != 0)
                 return fail(ctx, MRC_E_STATE, "reservoir exchange callback failed (send)");
         }
+        if (job.need_quant && use_tab && seg_S > 0) {
+            launch_expand(st, cp, cm, g0, nblk, seg_S, io[s], r_lo, ntab, tabw, (const int*)ctx->sets[s].tab.p,
+                          (const int*)ctx->sets[s].rin.p);
+        }
+        CK(cudaEventRecord(ev(w, 4), st));
         if (job.need_quant) {
             launch_finish(st, cp, cm, g0, nblk, io[s]);
             launch_offsets(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, io[s]);

@@ -429,9 +429,9 @@ chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, Ch
 // rare value that is neither a complete walk of that block's record, done by the whole warp once per distinct value
 // (the maps contract: after a block or two the thousand trajectories of a segment have merged into a handful; where
 // they have not -- digital silence right at the start of a segment shifts every value by the same amount -- the
-// values past the eighth distinct one are given up: entry RIN_NONE).  It also composes the closed forms:
+// values past the sixteenth distinct one are given up: entry RIN_NONE).  It also composes the closed forms:
 // R_out = R_in + delta for R_in >= theta, when every block of the segment grants everything along the way (silence:
-// the reservoir grows by thousands of bits per block, far outside any table), and lists up to eight distinct results
+// the reservoir grows by thousands of bits per block, far outside any table), and lists up to sixteen distinct results
 // that lie outside the tabulated range ("exits").
 // extras_kernel (parallel: one warp per exit) follows each exit through the next segments, block by block, until it
 // is back inside the range, and leaves (R_in -> R_out) pairs with the segments it crosses: these are exactly the
@@ -441,10 +441,10 @@ chain_table_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, Ch
 // wave boundary inside a silent passage).  It records the reservoir at the start of every segment it stepped over;
 // expand_kernel (parallel, one warp per segment) replays those segments block by block for finish_kernel.
 constexpr int SEG_THREADS = 384;
-constexpr int SEG_EPT = 4;                       // table entries per thread: ntab <= 1536
+constexpr int SEG_EPT = 6;                       // table entries per thread: ntab <= 2304
 constexpr int RIN_NONE = (int)0x80000000;
-constexpr int SEG_MAX_WALKS = 8;                 // distinct out-of-table values a warp follows per block and group
-constexpr int SEG_EXITS = 8;                     // distinct out-of-range results kept per segment
+constexpr int SEG_MAX_WALKS = 16;                 // distinct out-of-table values a warp follows per block and group
+constexpr int SEG_EXITS = 16;                    // distinct out-of-range results kept per segment
 constexpr int SEGX_W = 3 * SEG_EXITS;            // per segment: exits, pair inputs, pair outputs
 constexpr int EXTRA_HOPS = 6;
 
@@ -559,19 +559,21 @@ segment_kernel(CodecParams cp, ClipMap cm, int g0, int nblk_wave, int S, ChainIO
                 else if (B0 >= thr) R[e] = B0 + c_all;
                 else need[e] = act[e];
             }
-            static_assert(SEG_EPT == 4, "the selection below is written out for four entries per thread");
             for (int walks = 0;; ++walks) {          // warp-uniform: one complete walk per distinct value of the warp
-                const unsigned m0 = __ballot_sync(0xffffffffu, need[0]), m1 = __ballot_sync(0xffffffffu, need[1]);
-                const unsigned m2 = __ballot_sync(0xffffffffu, need[2]), m3 = __ballot_sync(0xffffffffu, need[3]);
-                if (!(m0 | m1 | m2 | m3)) break;
+                unsigned msel = 0u;                  // lanes of the first entry that still needs a walk, and its value
+                int Rsel = 0;
+#pragma unroll
+                for (int e = SEG_EPT - 1; e >= 0; --e) {
+                    const unsigned me = __ballot_sync(0xffffffffu, need[e]);
+                    if (me) { msel = me; Rsel = R[e]; }
+                }
+                if (!msel) break;
                 if (walks >= SEG_MAX_WALKS) {        // too many distinct values: these trajectories are given up
 #pragma unroll
                     for (int e = 0; e < SEG_EPT; ++e)
                         if (need[e]) { R[e] = RIN_NONE; need[e] = false; }
                     break;
                 }
-                const unsigned msel = m0 ? m0 : (m1 ? m1 : (m2 ? m2 : m3));
-                const int Rsel = m0 ? R[0] : (m1 ? R[1] : (m2 ? R[2] : R[3]));
                 const int Rl = __shfl_sync(0xffffffffu, Rsel, __ffs(msel) - 1);
                 const GroupTotals gt = walk_group<false>(
                     reinterpret_cast<const uint32_t*>(rec + MRC_REC_TN), reinterpret_cast<const uint32_t*>(rec + MRC_REC_CP),
@@ -955,6 +957,11 @@ void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm,
     cudaFuncSetAttribute(chain_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     chain_seg_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, segx, rin, fbn,
                                                reservoir_in, reservoir_out, iter_counter);
+}
+
+void launch_expand(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int S, ChainIO io, int r_lo,
+                   int ntab, int tabw, const int* tab, const int* rin) {
+    if (nblk <= 0) return;
     const int nseg = (nblk + S - 1) / S;
     expand_kernel<<<(nseg + EXP_WARPS - 1) / EXP_WARPS, EXP_WARPS * 32, 0, st>>>(cp, cm, g0, nblk, S, nseg, io, r_lo, ntab,
                                                                                  tabw, tab, rin);

@@ -218,6 +218,9 @@ void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm,
                       int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp,
                       const int* segx, int* rin, const int32_t* reservoir_in, int32_t* reservoir_out,
                       unsigned long long* iter_counter);
+// the parallel replay of the stepped-over segments (after launch_chain_seg; nothing the next shard waits for)
+void launch_expand(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int S, ChainIO io, int r_lo,
+                   int ntab, int tabw, const int* tab, const int* rin);
 int segment_max_ntab();
 int segment_aux_width();
 // parallel: one warp per block replays the block from its recorded reservoir: grant masks, table ids, chunk sizes

@@ -28,7 +28,7 @@ buf = np.zeros(32, np.uint64)
 lib.mrc_debug_phase_clocks(None, 1)
 c.encode_clips([pcm])
 lib.mrc_debug_phase_clocks(buf.ctypes.data_as(C.c_void_p), 0)
-tot = float(buf[:16].sum() + buf[23])
+tot = float(buf[:16].sum() + buf[23])      # 16..22, 24..27 are sub-step clocks of warp 0's lane 0
 nblk = c.n_blocks(pcm.shape[0])
 print("blocks %d, cycles per CTA %.0f" % (nblk, tot / nblk))
 for i, n in enumerate(NAMES):
@@ -36,10 +36,14 @@ for i, n in enumerate(NAMES):
 for i, n in ((13, "  1a MDCT: window + pre-twiddle"), (14, "  1b MDCT: FFT (then 1 = post-twiddle)"), (15, "  3a scale / Hann window placement"),
              (23, "  3b Hann FFT (then 3 = intensities)")):
     print("%-44s %6.2f%%  %8.0f cycles/CTA" % (n, 100.0 * buf[i] / tot, buf[i] / nblk))
-sub = ["16 masker_range", "17 quiet + two tails (lane 0)", "18 plateau sum", "19 loud maskers", "20 butterfly sum",
-       "21 two log10 + division"]
+sub = ["16 masker_range", "17 tails + loud maskers (one pass of 10**x)", "18 plateau sum + quiet", "19 -", "20 butterfly sum",
+       "21 two log10 + division", "22 (count)", "23 -", "24 pass 2: band's best bound (warp 0's group, per band)",
+       "25 pass 2: first complete threshold", "26 pass 2: scan for further candidates (+ their thresholds)",
+       "27 pass 2: warp 0 waiting at the barrier (per spectrum)"]
 ncomp = float(buf[22])
 print("complete(): %.1f evaluations per block, cycles each (lane 0's clock):" % (ncomp / nblk))
 for i, n in enumerate(sub):
-    print("  %-34s %8.0f" % (n, buf[16 + i] / max(ncomp, 1.0)))
+    if i in (6, 7):
+        continue
+    print("  %-60s %8.0f" % (n, buf[16 + i] / max(ncomp, 1.0)))
 c.close()
