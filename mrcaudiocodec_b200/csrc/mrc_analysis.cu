@@ -33,6 +33,7 @@
 // scripts/phase_clocks.py through mrc_debug_phase_clocks); never defined in the shipped library.
 #ifdef MRC_PHASE_CLOCKS
 __device__ unsigned long long g_phase_clk[32];
+__device__ unsigned long long g_band_clk[3][32];      // pass 2 per band: cycles, tasks, complete thresholds
 #define MRC_CLK(i)                                                                                                  \
     do {                                                                                                            \
         if (threadIdx.x == 0) {                                                                                     \
@@ -762,6 +763,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 constexpr int GPW = 32 / GW;                 // groups per warp
                 for (int p = warp * GPW + (lane / GW); p < nbl; p += nwarp * GPW) {
                     MRC_WCLK_BEGIN();
+#ifdef MRC_PHASE_CLOCKS
+                    const long long tb0_ = clock64();
+                    unsigned ncomp_ = 0;
+#endif
                     const int bd = 31 - (int)__fns(__brev(bl), 0, p + 1);     // p-th needed band from the top
                     const int lo = tb.c_band_lo[bd], n = tb.c_band_n[bd];
                     T ubest = T(-1);
@@ -798,6 +803,12 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                     }
                     if (grp.gl == 0) s_band_smr[bd] = best;
                     MRC_WCLK(26);
+#ifdef MRC_PHASE_CLOCKS
+                    if (lane == 0) {
+                        atomicAdd(&g_band_clk[0][bd], (unsigned long long)(clock64() - tb0_));
+                        atomicAdd(&g_band_clk[1][bd], 1ull);
+                    }
+#endif
                 }
             }
 #ifdef MRC_PHASE_CLOCKS
@@ -1073,6 +1084,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
 }  // namespace
 
 #ifdef MRC_PHASE_CLOCKS
+extern "C" int mrc_debug_band_clocks(unsigned long long* out96) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out96, g_band_clk, sizeof g_band_clk) == cudaSuccess ? 0 : -1;
+}
 extern "C" int mrc_debug_phase_clocks(unsigned long long* out32, int reset) {
     cudaDeviceSynchronize();
     if (out32 && cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof g_phase_clk) != cudaSuccess) return -1;

@@ -46,4 +46,11 @@ for i, n in enumerate(sub):
     if i in (6, 7):
         continue
     print("  %-60s %8.0f" % (n, buf[16 + i] / max(ncomp, 1.0)))
+bc = np.zeros((3, 32), np.uint64)
+lib.mrc_debug_band_clocks.argtypes = [C.c_void_p]
+lib.mrc_debug_band_clocks(bc.ctypes.data_as(C.c_void_p))
+print('pass 2 per band (both encodes): tasks per block, cycles per task')
+for b in range(25):
+    if bc[1][b]:
+        print('  band %2d  %5.2f  %7.0f' % (b, bc[1][b] / (2.0 * nblk), bc[0][b] / float(bc[1][b])))
 c.close()
