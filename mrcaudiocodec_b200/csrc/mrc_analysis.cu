@@ -66,12 +66,22 @@ constexpr int MRC_ZLUT = 832;         // cells of 1/32 Bark: Bark(24 kHz) = 24.6
 #endif
 constexpr int MRC_NEAR_LOUD = MRC_NEAR_LOUD_N;     // loud maskers included in the pass-1 bound of a line's threshold
 
+// What pass 1 leaves per line for pass 2: an UPPER bound of the line's rho (rounded up to float: it only selects
+// candidates) and the line's position among the maskers (m_lo | m_hi << 16), so that the warp that completes a line's
+// threshold does not search for it again.
+struct LineInfo {
+    float ub;
+    uint32_t rng;
+};
+
 template <typename T>
 struct Smem {
-    T* sx;          // [2][2L]  time samples L, R
+    T* sx;          // [2][2L]  time samples L, R -- only when the block arrives as doubles (per-block seam, XIN)
+    uint32_t* px;   // [2L]     the block's PCM frames as they lie in the clip: left | right << 16 (otherwise)
     cpx<T>* buf;    // [L]      FFT work buffer
     T* lines;       // [4][L]   MDCT lines L,R,M,S
     T* xi;          // [L]      FFT intensity, later SMR-per-line scratch
+    struct LineInfo* li;   // [L] pass 1 -> pass 2: bound and masker range of every line (aliases xi in fp64)
     // masker tables of the current spectrum, in the mode's own precision (Q = L/2 >= number of maskers)
     T* mz;          // [Q]      Bark position
     T* ms15;        // [Q]      SPL - 15
@@ -80,6 +90,8 @@ struct Smem {
     T* mU;          // [Q]      quiet maskers at or below i, decayed to z_i (upper slope, -27 dB/Bark)
     T* mS;          // [Q]      maskers at or above i, decayed to z_i (lower slope, -27 dB/Bark); [npk] = 0
     T* mP;          // [Q]      sum of mc below i ([npk] = total); only for the pass-1 bound (npk < Q always)
+    const cpx<T>* stL;  // stage tables of the L-point transform (Hann spectra) and of the L/2-point one (MDCT), power-of-two
+    const cpx<T>* stQ;  // L only (mrc_fft.cuh: fft_sw)
     int* pbin;      // [Q]      peak bins; once the masker tables are built the same words hold zlut
     uint16_t* zlut; // [MRC_ZLUT+1] number of maskers with z < g/32 Bark (only when Q ints can hold it)
     int* lcnt;      // [Q+1]    number of loud maskers (g > 0) below index i
@@ -89,18 +101,36 @@ struct Smem {
     double* etab;   // [64]     2^(j/64)
 };
 
-template <typename T>
+// stage-table entries (complex) a block of L lines keeps in shared memory
+__host__ __device__ constexpr int stage_entries_of(int L) {
+    if (L & (L - 1)) return 0;
+    int lg = 0;
+    while ((1 << lg) < L) ++lg;
+    return fft_stage_entries(lg) + fft_stage_entries(lg - 1);
+}
+
+template <typename T, bool XIN>
 __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     Smem<T> s;
     const int Q = L / 2;
     T* p = reinterpret_cast<T*>(raw);
-    s.sx = p;            p += 4 * L;
+    if constexpr (XIN) { s.sx = p; s.px = nullptr; p += 4 * L; }
+    else { s.sx = nullptr; s.px = reinterpret_cast<uint32_t*>(p); p += (2 * L * 4) / (int)sizeof(T); }
     s.buf = reinterpret_cast<cpx<T>*>(p); p += 2 * L;
     s.lines = p;         p += 4 * L;
     s.xi = p;            p += L;
     s.mz = p;            p += Q;
     s.ms15 = p;          p += Q;
     s.mg = p;            p += Q;
+    {
+        int lg = 0;
+        while ((1 << lg) < L) ++lg;
+        s.stL = reinterpret_cast<const cpx<T>*>(p);
+        s.stQ = s.stL + ((L & (L - 1)) ? 0 : fft_stage_entries(lg));
+        p += 2 * stage_entries_of(L);
+    }
+    if (sizeof(T) == 8) s.li = reinterpret_cast<LineInfo*>(s.xi);
+    else { s.li = reinterpret_cast<LineInfo*>(p); p += (L * (int)sizeof(LineInfo)) / (int)sizeof(T); }
     // mc, mU, mS, mP (4Q values = the FFT work buffer's 2L) live in the FFT work buffer: it is idle while maskers are
     // spread
     T* r = reinterpret_cast<T*>(s.buf);
@@ -146,14 +176,43 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
-// time sample of spectrum c (0 L, 1 R, 2 M, 3 S) -- codecThem.py:363-364
+// time sample n of spectrum c (0 L, 1 R, 2 M, 3 S) -- codecThem.py:363-364 -- from the block's PCM frames (converted here:
+// the frames stay packed in shared memory, 8 KB instead of 32 KB of doubles and one 4-byte read per frame) or, on the
+// per-block seam, from the doubles the caller handed in
+template <typename T, bool XIN>
+__device__ __forceinline__ void frame_lr(const Smem<T>& sm, int N, int n, T& l, T& r) {
+    if constexpr (XIN) { l = sm.sx[n]; r = sm.sx[N + n]; }
+    else {
+        const uint32_t w = sm.px[n];
+        l = pcm_to_fraction<T>((int)(short)(w & 0xffffu));
+        r = pcm_to_fraction<T>((int)(short)(w >> 16));
+    }
+}
 template <typename T>
-__device__ __forceinline__ T tsample(const T* sx, int N, int c, int n) {
-    const T l = sx[n], r = sx[N + n];
+__device__ __forceinline__ T spec_of(int c, T l, T r) {
     if (c == 0) return l;
     if (c == 1) return r;
     if (c == 2) return (l + r) / T(2);
     return (l - r) / T(2);
+}
+template <typename T, bool XIN>
+__device__ __forceinline__ T tsample(const Smem<T>& sm, int N, int c, int n) {
+    if constexpr (XIN) return spec_of<T>(c, sm.sx[n], sm.sx[N + n]);
+    else {
+        const uint32_t w = sm.px[n];
+        if (c == 0) return pcm_to_fraction<T>((int)(short)(w & 0xffffu));
+        if (c == 1) return pcm_to_fraction<T>((int)(short)(w >> 16));
+        return spec_of<T>(c, pcm_to_fraction<T>((int)(short)(w & 0xffffu)), pcm_to_fraction<T>((int)(short)(w >> 16)));
+    }
+}
+// two neighbouring table values with one load (i even)
+__device__ __forceinline__ void ld2(const double* p, int i, double& a, double& b) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p + i));
+    a = v.x; b = v.y;
+}
+__device__ __forceinline__ void ld2(const float* p, int i, float& a, float& b) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p + i));
+    a = v.x; b = v.y;
 }
 
 // position of line k among the maskers: m_lo = number of maskers with dz > 0.5 (a prefix: z_m ascends),
@@ -219,9 +278,8 @@ __device__ __forceinline__ T tail_terms(const Smem<T>& sm, T zk, int npk, int m_
 // loud maskers, and the plateau sum as a difference of prefix sums minus its worst-case rounding error.
 template <typename T>
 __device__ __forceinline__ T spread_line_bound(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk,
-                                                    unsigned& n_general) {
+                                                    unsigned& n_general, int& m_lo, int& m_hi) {
     const T zk = tb.bark[k];
-    int m_lo, m_hi;
     masker_range(sm, zk, npk, m_lo, m_hi);
     T a = tb.quiet[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
     const int nl = sm.lcnt[m_lo];
@@ -247,30 +305,6 @@ __device__ __forceinline__ unsigned grp_ballot(const Grp& g, bool p) {
     return (__ballot_sync(g.mask, p) >> g.shift) & ((GW == 32) ? 0xffffffffu : ((1u << (GW & 31)) - 1u));
 }
 
-// masker_range by a group: the count table gives a first guess, then ONE window of GW consecutive maskers per bound
-// is tested with the reference's own comparison (one masker per lane) -- both predicates hold for a prefix of the
-// ascending maskers, so the number of lanes that pass is the bound.  If a window does not contain its bound (a
-// 1/32-Bark cell holds a few maskers at most) the scalar search is used.
-template <typename T>
-__device__ __forceinline__ void masker_range_grp(const Smem<T>& sm, T zk, int npk, const Grp& g, int& m_lo, int& m_hi) {
-    if (sm.zlut == nullptr) { masker_range(sm, zk, npk, m_lo, m_hi); return; }
-    int c = (int)((zk - T(0.5)) * T(32.0));
-    const int w0 = (int)sm.zlut[c < 0 ? 0 : (c > MRC_ZLUT ? MRC_ZLUT : c)] - GW / 4;
-    c = (int)((zk + T(0.5)) * T(32.0)) + 1;
-    const int w1 = (int)sm.zlut[c < 0 ? 0 : (c > MRC_ZLUT ? MRC_ZLUT : c)] - 3 * GW / 4;
-    const int i0 = w0 + g.gl, i1 = w1 + g.gl;
-    const T z0 = sm.mz[i0 < 0 ? 0 : (i0 < npk ? i0 : 0)], z1 = sm.mz[i1 < 0 ? 0 : (i1 < npk ? i1 : 0)];
-    const bool p0 = i0 < 0 || (i0 < npk && zk - z0 > T(0.5));             // maskers more than 0.5 Bark below the line
-    const bool p1 = i1 < 0 || (i1 < npk && !(zk - z1 < T(-0.5)));         // maskers not more than 0.5 Bark above it
-    const int n0 = __popc(grp_ballot(g, p0)), n1 = __popc(grp_ballot(g, p1));
-    if (n0 >= 1 && n0 < GW && n1 >= 1 && n1 < GW) {
-        m_lo = w0 + n0;
-        m_hi = w1 + n1;
-        return;
-    }
-    masker_range(sm, zk, npk, m_lo, m_hi);
-}
-
 // The same threshold, complete, evaluated by a group of lanes.  Everything that goes through 10**x is one list of
 // items dealt out to the lanes -- item 0 the tail of the maskers more than 0.5 Bark below the line, item 1 the tail of
 // those above, items 2.. the loud maskers below -- so that one pass of the exponential covers a typical line; the
@@ -282,8 +316,8 @@ __device__ __forceinline__ T spread_line_grp(const Smem<T>& sm, const DevTables<
     MRC_WCLK_BEGIN();
     const T zk = tb.bark[k];
     const T quiet = tb.quiet[k];
-    int m_lo, m_hi;
-    masker_range_grp(sm, zk, npk, g, m_lo, m_hi);
+    const uint32_t rng = sm.li[k].rng;           // the line's masker range, found in pass 1
+    const int m_lo = (int)(rng & 0xffffu), m_hi = (int)(rng >> 16);
     MRC_WCLK(16);
     const int nl = sm.lcnt[m_lo];
     T a = T(0.0);
@@ -313,7 +347,7 @@ __device__ __forceinline__ T spread_line_grp(const Smem<T>& sm, const DevTables<
     return a;
 }
 
-template <typename T, int L_>
+template <typename T, int L_, bool XIN>
 __global__ void __launch_bounds__(L_ / 2, (L_ <= 1024) ? (sizeof(T) == 4 ? 3 : 2) : 1)
 analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __restrict__ pcm,
                 const double* __restrict__ xin, int g0, Handoff<T> ho, AnalysisTaps<T> taps,
@@ -323,7 +357,9 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     static_assert(NT % 32 == 0, "whole warps");
     const int nb = tb.nb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    Smem<T> sm = carve<T>(smem_raw, L);
+    Smem<T> sm = carve<T, XIN>(smem_raw, L);
+    constexpr bool POW2 = FftShape<L>::pow2;
+    constexpr int LOGL = FftShape<L>::logP;          // log2 L (power-of-two L only)
 
     __shared__ int s_clip, s_b, s_nblk_clip;
     __shared__ T s_red[4][32];
@@ -333,6 +369,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     __shared__ int s_wcnt[33];
     __shared__ T s_scan[5][32];
     __shared__ T s_band_smr[MRC_BSTRIDE];
+    __shared__ unsigned s_best[MRC_BSTRIDE];     // per band: highest pass-1 bound (float bits, low 11 bits = 2047 - line)
     __shared__ int s_npk;
 #ifdef MRC_PHASE_CLOCKS
     __shared__ long long s_clk_last;
@@ -340,6 +377,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
 #endif
 
     if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
+    if constexpr (POW2) {            // stage tables of both transforms: staged once, published by the barriers below
+        cpx<T>* dst = const_cast<cpx<T>*>(sm.stL);
+        for (int i = tid; i < stage_entries_of(L); i += NT) dst[i] = tb.tw_stage[i];
+    }
     const int lb = cm.list ? cm.list[blockIdx.x] : (int)blockIdx.x;   // index inside this wave's hand-off buffers
     const int g = g0 + lb;                    // global block index
     if (tid == 0) {
@@ -360,7 +401,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     const int nspec = joint ? 4 : 2;
 
     // ---- phase 0: frame [ (b-1)L, (b+1)L ) of the clip, zero outside ------------------------------------
-    if (xin != nullptr) {
+    if constexpr (XIN) {
         for (int i = tid; i < 2 * N; i += NT) sm.sx[i] = T(xin[(size_t)g * 2 * N + i]);
     } else {
         const long long frames = cm.clip_off[s_clip + 1] - cm.clip_off[s_clip];
@@ -371,60 +412,87 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             const long long s = s0 + n;
             uint32_t w = 0;
             if (s >= 0 && s < frames) w = __ldg(p32 + s);
-            const int cl = (int)(short)(w & 0xffffu), cr = (int)(short)(w >> 16);
-            sm.sx[n] = pcm_to_fraction<T>(cl);
-            sm.sx[N + n] = pcm_to_fraction<T>(cr);
+            sm.px[n] = w;
         }
     }
     __syncthreads();
     MRC_CLK(0);
 
     // ---- phase 1: KBD window + MDCT, two spectra at a time (each an L/2-point complex FFT) --------------
-    // The FFT twiddles are staged in `xi` (idle until the first intensities are written): three twiddle loads per
-    // butterfly and stage from shared memory instead of through the L1 the other tables compete for.
+    // Power-of-two L: swizzled work buffers and per-stage twiddle tables (mrc_fft.cuh, fft_sw).  9 * 2^p lines (the
+    // transition blocks of block switching): the root table staged in `xi` (idle until the first intensities are written).
     cpx<T>* const tws = reinterpret_cast<cpx<T>*>(sm.xi);
     const int ntw = 1 << (tb.logLtab - 1);
-    for (int i = tid; i < ntw; i += NT) tws[i] = tb.tw_fft[i];       // published by the barrier before the first FFT
+    if constexpr (!POW2)
+        for (int i = tid; i < ntw; i += NT) tws[i] = tb.tw_fft[i];   // published by the barrier before the first FFT
     {
         const int grp = tid / (NT / 2), lt = tid - grp * (NT / 2), gthr = NT / 2;
         const T two_over_n = T(2) / T(N);
         for (int pair = 0; pair < nspec / 2; ++pair) {
             const int c = pair * 2 + grp;
             cpx<T>* a = sm.buf + grp * Q;
-            for (int n = lt; n < Q; n += gthr) {
-                T re, im;
-                // n0 = (b+1)/2 (mdct.py:66) is the standard phase N/4 + 1/2 shifted by rot = (a-b)/4 samples: the
-                // transform of the sequence rotated by rot, wrapped samples negated (the kernel is antiperiodic)
-                auto y = [&](int i) {
-                    if constexpr (FftShape<L>::pow2) return tb.kbd[i] * tsample(sm.sx, N, c, i);     // a == b
-                    else {
+            if constexpr (POW2) {
+                // one input index per thread (NT == Q) for BOTH spectra of the pair: the four frames and window values it
+                // needs are read once.  With y(i) = window[i] * x[i] extended antiperiodically (y(i +- N) = -y(i)):
+                //   re = -y(3Q-1-2n) - y(3Q+2n),  im = y(Q-1-2n) - y(Q+2n)      (mdct.py:64-70 reduced to N/4 points)
+                const int n = fft_place_index<LOGL - 1>(tid);
+                int iA = 3 * Q + 2 * n, iB = Q - 1 - 2 * n;
+                T sA = T(-1), sB = T(1);
+                if (iA >= N) { iA -= N; sA = T(1); }
+                if (iB < 0) { iB += N; sB = T(-1); }
+                const int i1 = 3 * Q - 1 - 2 * n, i4 = Q + 2 * n;
+                T l1, r1, lA, rA, lB, rB, l4, r4;
+                frame_lr<T, XIN>(sm, N, i1, l1, r1);
+                frame_lr<T, XIN>(sm, N, iA, lA, rA);
+                frame_lr<T, XIN>(sm, N, iB, lB, rB);
+                frame_lr<T, XIN>(sm, N, i4, l4, r4);
+                const T k1 = tb.kbd[i1], kA = tb.kbd[iA], kB = tb.kbd[iB], k4 = tb.kbd[i4];
+                const cpx<T> w = tb.tw_pre[n];
+                const int r = fft_swz<T>(fft_r4_pos(n, LOGL - 1));
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int cc = pair * 2 + h;
+                    const T re = fma(sA, kA * spec_of<T>(cc, lA, rA), -(k1 * spec_of<T>(cc, l1, r1)));
+                    const T im = fma(sB, kB * spec_of<T>(cc, lB, rB), -(k4 * spec_of<T>(cc, l4, r4)));
+                    cpx<T> v;
+                    v.x = re * w.x - im * w.y;
+                    v.y = re * w.y + im * w.x;
+                    sm.buf[h * Q + r] = v;
+                }
+            } else {
+                for (int n = lt; n < Q; n += gthr) {
+                    T re, im;
+                    // n0 = (b+1)/2 (mdct.py:66) is the standard phase N/4 + 1/2 shifted by rot = (a-b)/4 samples: the
+                    // transform of the sequence rotated by rot, wrapped samples negated (the kernel is antiperiodic)
+                    auto y = [&](int i) {
                         int j = i + tb.rot;
                         T sg = T(1);
                         if (j >= N) { j -= N; sg = T(-1); }
                         else if (j < 0) { j += N; sg = T(-1); }
-                        return sg * (tb.kbd[j] * tsample(sm.sx, N, c, j));
+                        return sg * (tb.kbd[j] * tsample<T, XIN>(sm, N, c, j));
+                    };
+                    if (n < Q / 2) {
+                        re = -y(3 * Q - 1 - 2 * n) - y(3 * Q + 2 * n);
+                        im = y(Q - 1 - 2 * n) - y(Q + 2 * n);
+                    } else {
+                        re = y(2 * n - Q) - y(3 * Q - 1 - 2 * n);
+                        im = -y(Q + 2 * n) - y(5 * Q - 1 - 2 * n);
                     }
-                };
-                if (n < Q / 2) {
-                    re = -y(3 * Q - 1 - 2 * n) - y(3 * Q + 2 * n);
-                    im = y(Q - 1 - 2 * n) - y(Q + 2 * n);
-                } else {
-                    re = y(2 * n - Q) - y(3 * Q - 1 - 2 * n);
-                    im = -y(Q + 2 * n) - y(5 * Q - 1 - 2 * n);
+                    const cpx<T> w = tb.tw_pre[n];
+                    const int r = fft_pos<Q>(n);
+                    a[r].x = re * w.x - im * w.y;
+                    a[r].y = re * w.y + im * w.x;
                 }
-                const cpx<T> w = tb.tw_pre[n];
-                const int r = fft_pos<Q>(n);
-                a[r].x = re * w.x - im * w.y;
-                a[r].y = re * w.y + im * w.x;
             }
             __syncthreads();
             MRC_CLK(13);
-            fft_any<T, Q>(a, lt, gthr, tws, tb.logLtab, tb.tw9, L, tb.w9);
+            if constexpr (POW2) fft_sw<T, LOGL - 1>(a, lt, gthr, sm.stQ);
+            else fft_any<T, Q>(a, lt, gthr, tws, tb.logLtab, tb.tw9, L, tb.w9);
             MRC_CLK(14);
             T* X = sm.lines + c * L;
             for (int k = lt; k < Q; k += gthr) {
                 const cpx<T> w = tb.tw_post[k];
-                const cpx<T> t = a[k];
+                const cpx<T> t = a[POW2 ? fft_swz<T>(k) : k];
                 X[2 * k] = two_over_n * (t.x * w.x - t.y * w.y);
                 X[L - 1 - 2 * k] = -two_over_n * (t.x * w.y + t.y * w.x);
             }
@@ -500,19 +568,46 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             continue;                                    // uniform: s_ms is shared
         }
         // a. Hann window, real 2L-point FFT through an L-point complex FFT
-        for (int i = tid; i < ntw; i += NT) tws[i] = tb.tw_fft[i];   // xi held the previous spectrum's per-line scratch
-        for (int n = tid; n < L; n += NT) {
-            const int r = fft_pos<L>(n);
-            sm.buf[r].x = tb.hann[2 * n] * tsample(sm.sx, N, c, 2 * n);
-            sm.buf[r].y = tb.hann[2 * n + 1] * tsample(sm.sx, N, c, 2 * n + 1);
+        if constexpr (POW2) {
+            for (int it = 0; it < L / NT; ++it) {
+                const int n = fft_place_index<LOGL>(tid + it * NT);
+                T h0, h1, x0, x1;
+                ld2(tb.hann, 2 * n, h0, h1);
+                if constexpr (XIN) {
+                    x0 = tsample<T, XIN>(sm, N, c, 2 * n);
+                    x1 = tsample<T, XIN>(sm, N, c, 2 * n + 1);
+                } else {
+                    const uint2 w = *reinterpret_cast<const uint2*>(sm.px + 2 * n);
+                    const int la = (int)(short)(w.x & 0xffffu), ra = (int)(short)(w.x >> 16);
+                    const int lb2 = (int)(short)(w.y & 0xffffu), rb = (int)(short)(w.y >> 16);
+                    if (c == 0) { x0 = pcm_to_fraction<T>(la); x1 = pcm_to_fraction<T>(lb2); }
+                    else if (c == 1) { x0 = pcm_to_fraction<T>(ra); x1 = pcm_to_fraction<T>(rb); }
+                    else {
+                        x0 = spec_of<T>(c, pcm_to_fraction<T>(la), pcm_to_fraction<T>(ra));
+                        x1 = spec_of<T>(c, pcm_to_fraction<T>(lb2), pcm_to_fraction<T>(rb));
+                    }
+                }
+                cpx<T> v;
+                v.x = h0 * x0;
+                v.y = h1 * x1;
+                sm.buf[fft_swz<T>(fft_r4_pos(n, LOGL))] = v;
+            }
+        } else {
+            for (int i = tid; i < ntw; i += NT) tws[i] = tb.tw_fft[i];   // xi held the previous spectrum's per-line scratch
+            for (int n = tid; n < L; n += NT) {
+                const int r = fft_pos<L>(n);
+                sm.buf[r].x = tb.hann[2 * n] * tsample<T, XIN>(sm, N, c, 2 * n);
+                sm.buf[r].y = tb.hann[2 * n + 1] * tsample<T, XIN>(sm, N, c, 2 * n + 1);
+            }
         }
         __syncthreads();
         MRC_CLK(15);
-        fft_any<T, L>(sm.buf, tid, NT, tws, tb.logLtab, tb.tw9, L, tb.w9);
+        if constexpr (POW2) fft_sw<T, LOGL>(sm.buf, tid, NT, sm.stL);
+        else fft_any<T, L>(sm.buf, tid, NT, tws, tb.logLtab, tb.tw9, L, tb.w9);
         MRC_CLK(23);
         // b. X[k] = E[k] + W^k O[k];  XI = 4|X|^2 / (N^2 * 3/8)   (psychoac.py:151)
         for (int k = tid; k < L; k += NT) {
-            const cpx<T> zk = sm.buf[k], zc = sm.buf[k ? L - k : 0];
+            const cpx<T> zk = sm.buf[POW2 ? fft_swz<T>(k) : k], zc = sm.buf[POW2 ? fft_swz<T>(k ? L - k : 0) : (k ? L - k : 0)];
             const T ex = (zk.x + zc.x) * T(0.5), ey = (zk.y - zc.y) * T(0.5);
             const T dx = zk.x - zc.x, dy = zk.y + zc.y;           // D = Zk - conj(Zc)
             const T ox = dy * T(0.5), oy = -dx * T(0.5);          // O = D / (2j)
@@ -581,102 +676,86 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             if (!cp.spread_seq) {
                 // ordered list of the loud maskers (g > 0: their upper slope depends on their level)
                 const unsigned bal = __ballot_sync(0xffffffffu, loud);
-                if (lane == 0) s_wcnt[warp] = __popc(bal);
-                __syncthreads();                     // also publishes mz for the neighbour reads below
-                if (warp == 0) {
-                    int v = (lane < nwarp) ? s_wcnt[lane] : 0;
-                    int incl = v;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    s_wcnt[lane] = incl - v;
-                }
+                __syncthreads();                     // publishes mz for the neighbour reads below
                 // decay between neighbouring maskers: rho(d) = 10^(-2.7 d), the -27 dB/Bark slope of both sides
                 T rU = T(0.0), rS = T(0.0);           // rU = rho(z_i - z_{i-1}); rS = rho(z_{i+1} - z_i)
                 if (i < npk) {
                     if (i > 0) rU = sp_exp10(T(-2.7) * (z - sm.mz[i - 1]), sm.etab);
                     if (i + 1 < npk) rS = sp_exp10(T(-2.7) * (sm.mz[i + 1] - z), sm.etab);
                 }
-                __syncthreads();
-                const int lpos = s_wcnt[warp] + __popc(bal & ((1u << lane) - 1u));
-                if (i <= npk) sm.lcnt[i] = lpos;     // entry npk = total (threads >= npk are not loud)
-                if (loud) sm.lidx[lpos] = (uint16_t)i;
-                // two affine recurrences by warp scans:  U_i = cq_i + rU_i * U_{i-1}  (ascending, quiet maskers only)
-                //                                        S_i = c_i  + rS_i * S_{i+1}  (descending, all maskers)
-                // The descending one runs on the mirrored index j = npk-1-i, held by thread j.
+                // two affine recurrences and a plain sum by warp scans:
+                //   U_i = cq_i + rU_i * U_{i-1}   ascending, quiet maskers only     (maps composed with shfl_up)
+                //   S_i = c_i  + rS_i * S_{i+1}   descending, all maskers          (maps composed with shfl_down)
+                //   P_i = c_i  + P_{i-1}
                 T aU = rU, bU = (i < npk && !loud) ? cmid : T(0.0);
-                T pP = (i < npk) ? cmid : T(0.0);          // plain running sum of the plateau intensities
-                // mirrored element for S: thread tid holds masker im = npk-1-tid
-                const int im = npk - 1 - tid;
-                T aS = T(0.0), bS = T(0.0);
-                // exchange through shared memory: stash (rS, c) of masker i, read those of masker im
-                sm.mU[i < npk ? i : npk] = rS;       // temporary use of mU/mS as exchange buffers
-                __syncthreads();
-                if (im >= 0) { aS = sm.mU[im]; bS = sm.mc[im]; }
-                __syncthreads();
+                T aS = rS, bS = (i < npk) ? cmid : T(0.0);
+                T pP = (i < npk) ? cmid : T(0.0);
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const T alU = __shfl_up_sync(0xffffffffu, aU, o), blU = __shfl_up_sync(0xffffffffu, bU, o);
-                    const T alS = __shfl_up_sync(0xffffffffu, aS, o), blS = __shfl_up_sync(0xffffffffu, bS, o);
+                    const T alS = __shfl_down_sync(0xffffffffu, aS, o), blS = __shfl_down_sync(0xffffffffu, bS, o);
                     const T plP = __shfl_up_sync(0xffffffffu, pP, o);
                     if (lane >= o) {
                         bU = fma(aU, blU, bU); aU = aU * alU;
-                        bS = fma(aS, blS, bS); aS = aS * alS;
                         pP += plP;
                     }
+                    if (lane + o < 32) { bS = fma(aS, blS, bS); aS = aS * alS; }
                 }
-                if (lane == 31) {
-                    s_scan[0][warp] = aU; s_scan[1][warp] = bU; s_scan[2][warp] = aS; s_scan[3][warp] = bS;
-                    s_scan[4][warp] = pP;
-                }
+                if (lane == 31) { s_scan[0][warp] = aU; s_scan[1][warp] = bU; s_scan[4][warp] = pP; }
+                if (lane == 0) { s_scan[2][warp] = aS; s_scan[3][warp] = bS; s_wcnt[warp] = __popc(bal); }
                 __syncthreads();
-                if (warp == 0) {
-                    T a1 = (lane < nwarp) ? s_scan[0][lane] : T(1.0), b1 = (lane < nwarp) ? s_scan[1][lane] : T(0.0);
-                    T a2 = (lane < nwarp) ? s_scan[2][lane] : T(1.0), b2 = (lane < nwarp) ? s_scan[3][lane] : T(0.0);
-                    T p3 = (lane < nwarp) ? s_scan[4][lane] : T(0.0);
+                // every warp combines the per-warp totals itself (lane w holds warp w's): no second barrier, nobody idles
+                {
+                    const bool in = lane < nwarp;
+                    T a1 = in ? s_scan[0][lane] : T(1.0), b1 = in ? s_scan[1][lane] : T(0.0);
+                    T a2 = in ? s_scan[2][lane] : T(1.0), b2 = in ? s_scan[3][lane] : T(0.0);
+                    T p3 = in ? s_scan[4][lane] : T(0.0);
+                    int lc = in ? s_wcnt[lane] : 0;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const T al1 = __shfl_up_sync(0xffffffffu, a1, o), bl1 = __shfl_up_sync(0xffffffffu, b1, o);
-                        const T al2 = __shfl_up_sync(0xffffffffu, a2, o), bl2 = __shfl_up_sync(0xffffffffu, b2, o);
+                        const T al2 = __shfl_down_sync(0xffffffffu, a2, o), bl2 = __shfl_down_sync(0xffffffffu, b2, o);
                         const T pl3 = __shfl_up_sync(0xffffffffu, p3, o);
+                        const int lcl = __shfl_up_sync(0xffffffffu, lc, o);
                         if (lane >= o) {
                             b1 = fma(a1, bl1, b1); a1 = a1 * al1;
-                            b2 = fma(a2, bl2, b2); a2 = a2 * al2;
                             p3 += pl3;
+                            lc += lcl;
                         }
+                        if (lane + o < 32) { b2 = fma(a2, bl2, b2); a2 = a2 * al2; }
                     }
-                    if (lane < nwarp) { s_scan[1][lane] = b1; s_scan[3][lane] = b2; s_scan[4][lane] = p3; }
+                    // carried in: U, P and the loud count from the warps before, S from the warps after
+                    const int wb = warp > 0 ? warp - 1 : 0, wa = warp + 1 < 32 ? warp + 1 : 31;
+                    const T cU = __shfl_sync(0xffffffffu, b1, wb), cP = __shfl_sync(0xffffffffu, p3, wb);
+                    const int cL = __shfl_sync(0xffffffffu, lc, wb);
+                    const T cS = __shfl_sync(0xffffffffu, b2, wa);
+                    if (warp > 0) { bU = fma(aU, cU, bU); pP += cP; }
+                    if (warp + 1 < nwarp) bS = fma(aS, cS, bS);
+                    const int lpos = (warp > 0 ? cL : 0) + __popc(bal & ((1u << lane) - 1u));
+                    if (i <= npk) sm.lcnt[i] = lpos;     // entry npk = total (threads >= npk are not loud)
+                    if (loud) sm.lidx[lpos] = (uint16_t)i;
                 }
-                __syncthreads();
-                if (warp > 0) {                      // value carried in from the warps before
-                    bU = fma(aU, s_scan[1][warp - 1], bU);
-                    bS = fma(aS, s_scan[3][warp - 1], bS);
-                    pP += s_scan[4][warp - 1];
-                }
-                if (i < npk) sm.mU[i] = bU;
-                if (im >= 0) sm.mS[im] = bS;
+                if (i < npk) { sm.mU[i] = bU; sm.mS[i] = bS; sm.mP[i + 1] = pP; }   // P: inclusive sum up to i = sum below i+1
                 if (tid == 0) { sm.mS[npk] = T(0.0); sm.mP[0] = T(0.0); }
-                if (i < npk) sm.mP[i + 1] = pP;          // inclusive sum up to i = sum below i+1
+                if (sm.zlut != nullptr) {
+                    // count table over Bark cells for masker_range (the peak bins in these words were last read before
+                    // the first barrier above): zlut[g] = number of maskers with z < g/32 Bark.  The maskers ascend in z, so
+                    // the count is a step function of the cell: masker i raises it to i+1 from its own cell up to the next
+                    // masker's -- every thread fills its stretch, no counting and no prefix sum.
+                    auto cell_of = [&](T zz) {
+                        int cell = (int)(zz * T(32.0)) + 1;               // counted from cell+1 on: z < g/32 for g > z*32
+                        return cell < 1 ? 1 : (cell > MRC_ZLUT ? MRC_ZLUT : cell);
+                    };
+                    if (tid < npk) {
+                        const int c0 = cell_of(z), c1 = (tid + 1 < npk) ? cell_of(sm.mz[tid + 1]) : MRC_ZLUT + 1;
+                        for (int g = c0; g < c1; ++g) sm.zlut[g] = (uint16_t)(tid + 1);
+                        if (tid == 0) for (int g = 0; g < c0; ++g) sm.zlut[g] = 0;
+                    }
+                    if (npk == 0) for (int g = tid; g <= MRC_ZLUT; g += NT) sm.zlut[g] = 0;
+                }
             }
         }
-        if (!cp.spread_seq && sm.zlut != nullptr) {
-            // count table over Bark cells for masker_range (the peak bins in these words are no longer needed):
-            // zlut[g] = number of maskers with z < g/32 Bark.  The maskers ascend in z, so the count is a step function
-            // of the cell: masker i raises it to i+1 from its own cell up to the next masker's -- every thread fills its
-            // stretch, no counting and no prefix sum.
-            __syncthreads();
-            auto cell_of = [&](int i) {
-                int cell = (int)(sm.mz[i] * T(32.0)) + 1;               // counted from cell+1 on: z < g/32 for g > z*32
-                return cell < 1 ? 1 : (cell > MRC_ZLUT ? MRC_ZLUT : cell);
-            };
-            if (tid < npk) {
-                const int c0 = cell_of(tid), c1 = (tid + 1 < npk) ? cell_of(tid + 1) : MRC_ZLUT + 1;
-                for (int g = c0; g < c1; ++g) sm.zlut[g] = (uint16_t)(tid + 1);
-                if (tid == 0) for (int g = 0; g < c0; ++g) sm.zlut[g] = 0;
-            }
-            if (npk == 0) for (int g = tid; g <= MRC_ZLUT; g += NT) sm.zlut[g] = 0;
-        }
+        if (tid < MRC_BSTRIDE) s_best[tid] = 0u;
         __syncthreads();
         MRC_CLK(5);
         // e. masked threshold at the MDCT lines, f. SMR per line (psychoac.py:212-214), band maxima (:215-219)
@@ -722,12 +801,32 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                 return fmax((T(2.0) * (X * X)) / T(0.5), FLOOR);
             };
             {
-                const int k0 = tid, k1 = tid + Q;
-                T r0 = T(-1), r1 = T(-1);                // lines of bands that do not select this spectrum: never candidates
-                if ((need >> tb.line2band[k0]) & 1u) r0 = T(x2c(k0) / fmax(spread_line_bound(sm, tb, k0, npk, n_general), FLOOR));
-                if ((need >> tb.line2band[k1]) & 1u) r1 = T(x2c(k1) / fmax(spread_line_bound(sm, tb, k1, npk, n_general), FLOOR));
-                sm.xi[k0] = r0;
-                sm.xi[k1] = r1;
+                // lines of bands that do not select this spectrum are never candidates (ub = -1)
+                auto bound_of = [&](int k) {
+                    const int bd = tb.line2band[k];
+                    float ub = -1.0f;
+                    uint32_t rng = 0;
+                    if ((need >> bd) & 1u) {
+                        int m_lo, m_hi;
+                        const T r = T(x2c(k) / fmax(spread_line_bound(sm, tb, k, npk, n_general, m_lo, m_hi), FLOOR));
+                        if constexpr (sizeof(T) == 8) ub = __double2float_ru(r); else ub = r;
+                        rng = (uint32_t)m_lo | ((uint32_t)m_hi << 16);
+                    }
+                    // the band's first candidate: (about) the highest bound, by one shared atomic per band and warp.  ANY
+                    // line may go first -- pass 2 evaluates every line whose bound reaches the best true value -- so the
+                    // low mantissa bits make room for the line index.
+                    const unsigned key = ub > 0.0f ? ((__float_as_uint(ub) & ~2047u) | (unsigned)(2047 - k)) : 0u;
+                    const unsigned same = __match_any_sync(0xffffffffu, bd);
+                    const unsigned top = __reduce_max_sync(same, key);
+                    if (lane == __ffs(same) - 1 && top) atomicMax(&s_best[bd], top);
+                    LineInfo v;
+                    v.ub = ub;
+                    v.rng = rng;
+                    sm.li[k] = v;
+                };
+                static_assert(L <= 2048, "line index in 11 bits");
+                bound_of(tid);
+                bound_of(tid + Q);
             }
             __syncthreads();
             MRC_CLK(6);
@@ -769,25 +868,15 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
 #endif
                     const int bd = 31 - (int)__fns(__brev(bl), 0, p + 1);     // p-th needed band from the top
                     const int lo = tb.c_band_lo[bd], n = tb.c_band_n[bd];
-                    T ubest = T(-1);
-                    int kbest = lo;
-                    for (int i = grp.gl; i < n; i += GW) {
-                        const T v = sm.xi[lo + i];
-                        if (v > ubest) { ubest = v; kbest = lo + i; }
-                    }
-#pragma unroll
-                    for (int o = GW / 2; o; o >>= 1) {
-                        const T ov = __shfl_xor_sync(grp.mask, ubest, o, GW);
-                        const int ok = __shfl_xor_sync(grp.mask, kbest, o, GW);
-                        if (ov > ubest || (ov == ubest && ok < kbest)) { ubest = ov; kbest = ok; }
-                    }
+                    const unsigned key = s_best[bd];
+                    const int kbest = key ? 2047 - (int)(key & 2047u) : lo;
                     T best, rbest;
                     MRC_WCLK(24);
                     complete(kbest, best, rbest);
                     MRC_WCLK(25);
                     for (int base = 0; base < n; base += GW) {
                         const int i = base + grp.gl;
-                        const T ub = (i < n) ? sm.xi[lo + i] : T(-1);
+                        const T ub = (i < n) ? T(sm.li[lo + i].ub) : T(-1);
                         unsigned bal = grp_ballot(grp, i < n && lo + i != kbest && ub >= rbest * slack);
                         while (bal) {
                             const int l = __ffs(bal) - 1;
@@ -1099,11 +1188,13 @@ extern "C" int mrc_debug_phase_clocks(unsigned long long* out32, int reset) {
 }
 #endif
 
-size_t analysis_smem_bytes(int L, int elem) {
+size_t analysis_smem_bytes(int L, int elem, bool xin) {
     const size_t Q = L / 2;
     size_t merge = (size_t)2048 * elem + 2048 * 2;                     // merge buffers of the grant order
     if ((size_t)(4 * L) * elem >= merge) merge = 0;                    // ... living in `lines`
-    return (size_t)(11 * L) * elem + 3 * Q * elem + 8 + 64 * 8 + (2 * Q + 1) * 4 + Q * 2 + 32 + merge;
+    const size_t samples = xin ? (size_t)(4 * L) * elem : (size_t)8 * L;       // doubles of the seam, or packed PCM frames
+    const size_t stage = (size_t)stage_entries_of(L) * 2 * elem + (elem == 8 ? 0 : (size_t)L * sizeof(LineInfo));
+    return samples + (size_t)(7 * L) * elem + 3 * Q * elem + stage + 8 + 64 * 8 + (2 * Q + 1) * 4 + Q * 2 + 32 + merge;
 }
 
 template <typename T>
@@ -1111,11 +1202,16 @@ void launch_analysis(cudaStream_t st, const DevTables<T>& tb, const CodecParams&
                      const int16_t* pcm, const double* xin, int g0, int nblk, Handoff<T> ho, AnalysisTaps<T> taps,
                      unsigned long long* peak_counter) {
     if (nblk <= 0) return;
-    const size_t smem = analysis_smem_bytes(tb.L, sizeof(T));
+    const bool x = xin != nullptr;
+    const size_t smem = analysis_smem_bytes(tb.L, sizeof(T), x);
+#define MRC_LAUNCH_ANALYSIS_X(LL, XX)                                                                            \
+    {                                                                                                            \
+        cudaFuncSetAttribute(analysis_kernel<T, LL, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        analysis_kernel<T, LL, XX><<<nblk, LL / 2, smem, st>>>(tb, cp, cm, pcm, xin, g0, ho, taps, peak_counter); \
+    }
 #define MRC_LAUNCH_ANALYSIS(LL)                                                                                  \
     case LL:                                                                                                     \
-        cudaFuncSetAttribute(analysis_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        analysis_kernel<T, LL><<<nblk, LL / 2, smem, st>>>(tb, cp, cm, pcm, xin, g0, ho, taps, peak_counter);     \
+        if (x) MRC_LAUNCH_ANALYSIS_X(LL, true) else MRC_LAUNCH_ANALYSIS_X(LL, false)                             \
         break;
     switch (tb.L) {
         MRC_LAUNCH_ANALYSIS(128)       // short blocks (128 + 128)
@@ -1127,6 +1223,7 @@ void launch_analysis(cudaStream_t st, const DevTables<T>& tb, const CodecParams&
         default: break;
     }
 #undef MRC_LAUNCH_ANALYSIS
+#undef MRC_LAUNCH_ANALYSIS_X
 }
 
 template void launch_analysis<double>(cudaStream_t, const DevTables<double>&, const CodecParams&, const ClipMap&,

@@ -23,7 +23,7 @@ struct Buf {
 };
 
 struct TablesDev {
-    Buf kbd, hann, tw_pre, tw_post, tw_fft, tw_rfft, tw9, bark, quiet, bark_d, quiet_d, exp_tab;
+    Buf kbd, hann, tw_pre, tw_post, tw_fft, tw_rfft, tw9, tw_stage, bark, quiet, bark_d, quiet_d, exp_tab;
 };
 
 // Everything that depends on the block geometry (window halves a, b): long blocks always; the transition and short
@@ -167,6 +167,21 @@ cudaError_t upload_tables(mrc_ctx* c, GeoDev& g, TablesDev& d, DevTables<T>& tb,
     if ((e = upload(d.tw_pre, pre, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.tw_post, post, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.tw_fft, fft, c->stream)) != cudaSuccess) return e;
+    // per-stage twiddles of the L-point (Hann spectra) and L/2-point (MDCT) transforms, power-of-two L: stage h holds
+    // W1[j] = exp(-2 pi i j / 4h) and W2[j] = exp(-2 pi i 2j / 4h), j < h (mrc_fft.cuh: fft_stage_entries, fft_sw)
+    std::vector<cpx<T>> stage;
+    if (pow2) {
+        for (int lg = logLtab; lg >= logLtab - 1; --lg)
+            for (int h = (lg & 1) ? 2 : 4; 4 * h <= (1 << lg); h <<= 2)
+                for (int w = 1; w <= 2; ++w)
+                    for (int j = 0; j < h; ++j) {
+                        const double f = -2.0 * pi * (double)(w * j) / (double)(4 * h);
+                        cpx<T> v; v.x = (T)cos(f); v.y = (T)sin(f);
+                        stage.push_back(v);
+                    }
+    }
+    if (stage.empty()) stage.resize(1);
+    if ((e = upload(d.tw_stage, stage, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.tw_rfft, rfft, c->stream)) != cudaSuccess) return e;
     if ((e = upload(d.tw9, tw9, c->stream)) != cudaSuccess) return e;
     std::vector<double> bark_d(bark_t, bark_t + L), quiet_d(quiet_t, quiet_t + L), etab(64);
@@ -186,6 +201,7 @@ cudaError_t upload_tables(mrc_ctx* c, GeoDev& g, TablesDev& d, DevTables<T>& tb,
     tb.kbd = (const T*)d.kbd.p; tb.hann = (const T*)d.hann.p;
     tb.tw_pre = (const cpx<T>*)d.tw_pre.p; tb.tw_post = (const cpx<T>*)d.tw_post.p;
     tb.tw_fft = (const cpx<T>*)d.tw_fft.p; tb.tw_rfft = (const cpx<T>*)d.tw_rfft.p;
+    tb.tw_stage = (const cpx<T>*)d.tw_stage.p;
     tb.bark = (const T*)d.bark.p; tb.quiet = (const T*)d.quiet.p;
     tb.band_lo = (const int*)g.band_lo.p; tb.band_n = (const int*)g.band_n.p;
     tb.line2band = (const uint8_t*)g.line2band.p;
@@ -1027,7 +1043,7 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (GeoDev& g : ctx->geo) {
         for (TablesDev* d : {&g.td, &g.tf}) {
-            Buf* tb[] = {&d->kbd, &d->hann, &d->tw_pre, &d->tw_post, &d->tw_fft, &d->tw_rfft, &d->tw9, &d->bark, &d->quiet,
+            Buf* tb[] = {&d->kbd, &d->hann, &d->tw_pre, &d->tw_post, &d->tw_fft, &d->tw_rfft, &d->tw9, &d->tw_stage, &d->bark, &d->quiet,
                          &d->bark_d, &d->quiet_d, &d->exp_tab};
             for (Buf* b : tb) release(*b);
         }

@@ -79,6 +79,113 @@ __device__ __forceinline__ void fft_r4(cpx<T>* a, int logn, int lt, int nthr, co
     }
 }
 
+// ---- conflict-free variant for the analysis kernel (power-of-two sizes) ----------------------------------------
+// The L1/shared data pipe is what bounds the analysis kernel (profiles/r02p_ncu_full_analysis.csv: 64 % busy, half of
+// its wavefronts bank-conflict replays, four fifths of those in the transforms), so the work buffer is SWIZZLED and
+// the twiddles come from per-stage tables:
+//   * element e lives at fft_swz(e): the low index bits XORed with two higher ones, chosen so that the 8 lanes of a
+//     quarter warp (16-byte elements; 16 lanes and 8-byte elements in fp32) hit 8 different bank slots in EVERY access
+//     pattern of the transform -- radix-2 stage (lanes vary e1..e3), radix-4 stages with h = 1 (e2..e4), h = 2
+//     (e0, e3, e4), h = 4 (e0, e1, e4), h >= 8 (e0..e2) -- and in the consumers that read consecutive elements;
+//   * stage h reads W1[j] = W_4h^j and W2[j] = W_4h^2j from two contiguous runs of h entries (consecutive lanes,
+//     consecutive entries) and forms W3 = W1 * W2 in registers: the strided reads of one shared root table cost up to 8
+//     wavefronts per load, and the FP64 pipe has room for the four extra operations.
+template <typename T> __device__ __forceinline__ int fft_swz(int e);
+template <> __device__ __forceinline__ int fft_swz<double>(int e) { return e ^ (((e >> 3) & 1) * 3) ^ (((e >> 4) & 1) * 6); }
+template <> __device__ __forceinline__ int fft_swz<float>(int e) { return e ^ (((e >> 4) & 1) * 5) ^ (((e >> 5) & 1) * 10); }
+
+// entries (complex) of the stage tables of a 2^logn-point transform: 2h per stage h = h0, 4 h0, ... (4h <= n), where
+// h0 = 4 for even logn (the h = 1 stage has unit twiddles) and 2 for odd logn (after the radix-2 stage)
+__host__ __device__ constexpr int fft_stage_entries(int logn) {
+    int tot = 0;
+    for (int h = (logn & 1) ? 2 : 4; 4 * h <= (1 << logn); h <<= 2) tot += 2 * h;
+    return tot;
+}
+
+// Which input goes where, lane by lane.  Thread index idx (0 .. n-1 over the threads and their trips) handles input
+// element place_index(idx); it is stored at fft_swz(fft_r4_pos(.)).  For n >= 512 the map is chosen so that a warp
+// reads 32 consecutive inputs while the 8 lanes of every quarter warp write 8 different bank slots: the three input
+// bits that the digit reversal sends to the lowest three output bits are the lane's low bits XORed with three bits of
+// the warp index (a bijection of 0 .. n-1).
+template <int LOGN>
+__device__ __forceinline__ int fft_place_index(int idx) {
+    if constexpr (LOGN < 9) return idx;
+    else {
+        const int lane = idx & 31, hi = idx >> 5, y = (lane ^ hi) & 7, rest = hi >> 3;
+        if constexpr (LOGN == 9) return lane | ((rest & 1) << 5) | (y << 6);                    // output bits 0..2 <- input bits 8, 6, 7
+        else if constexpr (LOGN == 10)                                                            //              <- input bits 8, 9, 6
+            return lane | ((rest & 1) << 5) | ((y & 1) << 6) | (((rest >> 1) & 1) << 7) | ((y >> 1) << 8);
+        else return lane | ((rest & 7) << 5) | (y << 8) | ((rest >> 3) << 11);                    // LOGN >= 11: <- input bits 10, 8, 9
+    }
+}
+
+// In-place DIT transform of size 2^LOGN on swizzled data placed by fft_r4_pos; `st` = the stage tables (shared
+// memory).  Warp-local early stages as in fft_r4<.., WL = true> (lt warp-aligned, n >= 128: the swizzle stays inside
+// aligned runs of 16 elements).  Ends with a block barrier.
+template <typename T, int LOGN>
+__device__ __forceinline__ void fft_sw(cpx<T>* a, int lt, int nthr, const cpx<T>* __restrict__ st) {
+    constexpr int n = 1 << LOGN;
+    constexpr bool WL = n >= 128;
+    int h = 1;
+    if constexpr (LOGN & 1) {
+        for (int bi = lt; bi < (n >> 2); bi += nthr) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int q = WL ? ((bi >> 5) << 6) + (bi & 31) + 32 * t : bi + (n >> 2) * t;
+                const int p0 = fft_swz<T>(2 * q), p1 = fft_swz<T>(2 * q + 1);
+                const cpx<T> u = a[p0], v = a[p1];
+                a[p0].x = u.x + v.x;  a[p0].y = u.y + v.y;
+                a[p1].x = u.x - v.x;  a[p1].y = u.y - v.y;
+            }
+        }
+        if (WL) __syncwarp(); else __syncthreads();
+        h = 2;
+    } else {
+        // h = 1: unit twiddles
+        for (int bi = lt; bi < (n >> 2); bi += nthr) {
+            const int b0 = 4 * bi;
+            const int p0 = fft_swz<T>(b0), p1 = fft_swz<T>(b0 + 1), p2 = fft_swz<T>(b0 + 2), p3 = fft_swz<T>(b0 + 3);
+            const cpx<T> x0 = a[p0], x1 = a[p1], x2 = a[p2], x3 = a[p3];
+            const T s02x = x0.x + x2.x, s02y = x0.y + x2.y, d02x = x0.x - x2.x, d02y = x0.y - x2.y;
+            const T s13x = x1.x + x3.x, s13y = x1.y + x3.y, d13x = x1.x - x3.x, d13y = x1.y - x3.y;
+            a[p0].x = s02x + s13x;  a[p0].y = s02y + s13y;
+            a[p1].x = d02x + d13y;  a[p1].y = d02y - d13x;
+            a[p2].x = s02x - s13x;  a[p2].y = s02y - s13y;
+            a[p3].x = d02x - d13y;  a[p3].y = d02y + d13x;
+        }
+        if (WL && 16 <= n) __syncwarp(); else __syncthreads();
+        h = 4;
+    }
+    for (; 4 * h <= n; h <<= 2) {
+        const int logh = 31 - __clz(h);
+        for (int bi = lt; bi < (n >> 2); bi += nthr) {
+            const int j = bi & (h - 1);
+            const int base = ((bi >> logh) << (logh + 2)) + j;
+            const cpx<T> w1 = st[j], w2 = st[h + j];
+            int p0, p1, p2, p3;
+            if (h >= (sizeof(T) == 8 ? 32 : 64)) {        // the legs differ above the swizzle's control bits
+                p0 = fft_swz<T>(base); p1 = p0 + h; p2 = p0 + 2 * h; p3 = p0 + 3 * h;
+            } else {
+                p0 = fft_swz<T>(base); p1 = fft_swz<T>(base + h); p2 = fft_swz<T>(base + 2 * h); p3 = fft_swz<T>(base + 3 * h);
+            }
+            const cpx<T> x0 = a[p0], x1 = a[p1], x2 = a[p2], x3 = a[p3];
+            const T w3x = w1.x * w2.x - w1.y * w2.y, w3y = w1.x * w2.y + w1.y * w2.x;
+            const T t1x = x1.x * w1.x - x1.y * w1.y, t1y = x1.x * w1.y + x1.y * w1.x;
+            const T t2x = x2.x * w2.x - x2.y * w2.y, t2y = x2.x * w2.y + x2.y * w2.x;
+            const T t3x = x3.x * w3x - x3.y * w3y, t3y = x3.x * w3y + x3.y * w3x;
+            const T s02x = x0.x + t2x, s02y = x0.y + t2y, d02x = x0.x - t2x, d02y = x0.y - t2y;
+            const T s13x = t1x + t3x, s13y = t1y + t3y, d13x = t1x - t3x, d13y = t1y - t3y;
+            a[p0].x = s02x + s13x;  a[p0].y = s02y + s13y;
+            a[p1].x = d02x + d13y;  a[p1].y = d02y - d13x;          // d02 - j d13
+            a[p2].x = s02x - s13x;  a[p2].y = s02y - s13y;
+            a[p3].x = d02x - d13y;  a[p3].y = d02y + d13x;          // d02 + j d13
+        }
+        st += 2 * h;
+        if (WL && 16 * h <= 128 && 16 * h <= n) __syncwarp();
+        else __syncthreads();
+    }
+}
+
 // ---- transform sizes 2^p and 9 * 2^p (block switching: a + b = 1152 gives 288- and 576-point transforms) -------
 // n = 9 P, P = 2^p: input index i = 9 i1 + i2 goes to sub-array i2 (a P-point transform over i1), then one radix-9
 // pass:  X[k1 + P k2] = sum_{i2} ( W_n^(i2 k1) * Sub_i2[k1] ) * W_9^(i2 k2)   -- in place: column k1 in, column k1 out.

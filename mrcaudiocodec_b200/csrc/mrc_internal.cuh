@@ -99,6 +99,7 @@ struct DevTables {
     const cpx<T>* tw_pre;                        // [L/2]  exp(-j*pi*(4n+1)/(4L))
     const cpx<T>* tw_post;                       // [L/2]  exp(-j*pi*k/L)
     const cpx<T>* tw_fft;                        // [L/2]  exp(-2*pi*j*k/L)
+    const cpx<T>* tw_stage;                      // per-stage twiddles of the L- and L/2-point transforms (mrc_fft.cuh, power-of-two L)
     const cpx<T>* tw_rfft;                       // [L]    exp(-2*pi*j*k/(2L))
     const T* bark;                               // [L]
     const T* quiet;                              // [L]
@@ -240,7 +241,7 @@ void launch_pack(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp,
 void launch_clip_scan(cudaStream_t st, const int64_t* clip_bytes, int64_t* clip_base, int c0, int n,
                       int64_t* running);
 
-size_t analysis_smem_bytes(int L, int elem);
+size_t analysis_smem_bytes(int L, int elem, bool xin);
 
 // mrc_transient.cu -- block switching: per nMDCTLines-frame block, flags bit 0 = transient in the first 128 samples,
 // bit 1 = transient later in the block (pacfileThem.py:1021-1056)
