@@ -90,6 +90,7 @@ struct Smem {
     T* mU;          // [Q]      quiet maskers at or below i, decayed to z_i (upper slope, -27 dB/Bark)
     T* mS;          // [Q]      maskers at or above i, decayed to z_i (lower slope, -27 dB/Bark); [npk] = 0
     T* mP;          // [Q]      sum of mc below i ([npk] = total); only for the pass-1 bound (npk < Q always)
+    T* zb;          // [L]      Bark position of every MDCT line (tb.bark staged: pass 2 reads it at the head of a dependent chain)
     const cpx<T>* stL;  // stage tables of the L-point transform (Hann spectra) and of the L/2-point one (MDCT), power-of-two
     const cpx<T>* stQ;  // L only (mrc_fft.cuh: fft_sw)
     int* pbin;      // [Q]      peak bins; once the masker tables are built the same words hold zlut
@@ -129,6 +130,7 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
         s.stQ = s.stL + ((L & (L - 1)) ? 0 : fft_stage_entries(lg));
         p += 2 * stage_entries_of(L);
     }
+    s.zb = p;            p += L;
     if (sizeof(T) == 8) s.li = reinterpret_cast<LineInfo*>(s.xi);
     else { s.li = reinterpret_cast<LineInfo*>(p); p += (L * (int)sizeof(LineInfo)) / (int)sizeof(T); }
     // mc, mU, mS, mP (4Q values = the FFT work buffer's 2L) live in the FFT work buffer: it is idle while maskers are
@@ -279,7 +281,7 @@ __device__ __forceinline__ T tail_terms(const Smem<T>& sm, T zk, int npk, int m_
 template <typename T>
 __device__ __forceinline__ T spread_line_bound(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk,
                                                     unsigned& n_general, int& m_lo, int& m_hi) {
-    const T zk = tb.bark[k];
+    const T zk = sm.zb[k];
     masker_range(sm, zk, npk, m_lo, m_hi);
     T a = tb.quiet[k] + tail_terms(sm, zk, npk, m_lo, m_hi);
     const int nl = sm.lcnt[m_lo];
@@ -314,7 +316,7 @@ template <typename T>
 __device__ __forceinline__ T spread_line_grp(const Smem<T>& sm, const DevTables<T>& tb, int k, int npk, const Grp& g,
                                              unsigned& n_general, unsigned& n_window) {
     MRC_WCLK_BEGIN();
-    const T zk = tb.bark[k];
+    const T zk = sm.zb[k];
     const T quiet = tb.quiet[k];
     const uint32_t rng = sm.li[k].rng;           // the line's masker range, found in pass 1
     const int m_lo = (int)(rng & 0xffffu), m_hi = (int)(rng >> 16);
@@ -377,6 +379,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
 #endif
 
     if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
+    for (int i = tid; i < L; i += NT) sm.zb[i] = tb.bark[i];
     if constexpr (POW2) {            // stage tables of both transforms: staged once, published by the barriers below
         cpx<T>* dst = const_cast<cpx<T>*>(sm.stL);
         for (int i = tid; i < stage_entries_of(L); i += NT) dst[i] = tb.tw_stage[i];
@@ -816,9 +819,12 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                     // line may go first -- pass 2 evaluates every line whose bound reaches the best true value -- so the
                     // low mantissa bits make room for the line index.
                     const unsigned key = ub > 0.0f ? ((__float_as_uint(ub) & ~2047u) | (unsigned)(2047 - k)) : 0u;
-                    const unsigned same = __match_any_sync(0xffffffffu, bd);
-                    const unsigned top = __reduce_max_sync(same, key);
-                    if (lane == __ffs(same) - 1 && top) atomicMax(&s_best[bd], top);
+                    // a warp's 32 consecutive lines mostly lie in one band: one reduction and one atomic; otherwise (the
+                    // narrow bands at the bottom, a warp across a band edge) every lane posts its own
+                    if (__all_sync(0xffffffffu, bd == __shfl_sync(0xffffffffu, bd, 0))) {
+                        const unsigned top = __reduce_max_sync(0xffffffffu, key);
+                        if (lane == 0 && top) atomicMax(&s_best[bd], top);
+                    } else if (key) atomicMax(&s_best[bd], key);
                     LineInfo v;
                     v.ub = ub;
                     v.rng = rng;
@@ -1194,7 +1200,7 @@ size_t analysis_smem_bytes(int L, int elem, bool xin) {
     if ((size_t)(4 * L) * elem >= merge) merge = 0;                    // ... living in `lines`
     const size_t samples = xin ? (size_t)(4 * L) * elem : (size_t)8 * L;       // doubles of the seam, or packed PCM frames
     const size_t stage = (size_t)stage_entries_of(L) * 2 * elem + (elem == 8 ? 0 : (size_t)L * sizeof(LineInfo));
-    return samples + (size_t)(7 * L) * elem + 3 * Q * elem + stage + 8 + 64 * 8 + (2 * Q + 1) * 4 + Q * 2 + 32 + merge;
+    return samples + (size_t)(8 * L) * elem + 3 * Q * elem + stage + 8 + 64 * 8 + (2 * Q + 1) * 4 + Q * 2 + 32 + merge;
 }
 
 template <typename T>

@@ -132,7 +132,7 @@ __device__ __forceinline__ void fft_sw(cpx<T>* a, int lt, int nthr, const cpx<T>
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 const int q = WL ? ((bi >> 5) << 6) + (bi & 31) + 32 * t : bi + (n >> 2) * t;
-                const int p0 = fft_swz<T>(2 * q), p1 = fft_swz<T>(2 * q + 1);
+                const int p0 = fft_swz<T>(2 * q), p1 = p0 ^ 1;       // the swizzle is linear over GF(2)
                 const cpx<T> u = a[p0], v = a[p1];
                 a[p0].x = u.x + v.x;  a[p0].y = u.y + v.y;
                 a[p1].x = u.x - v.x;  a[p1].y = u.y - v.y;
@@ -144,7 +144,7 @@ __device__ __forceinline__ void fft_sw(cpx<T>* a, int lt, int nthr, const cpx<T>
         // h = 1: unit twiddles
         for (int bi = lt; bi < (n >> 2); bi += nthr) {
             const int b0 = 4 * bi;
-            const int p0 = fft_swz<T>(b0), p1 = fft_swz<T>(b0 + 1), p2 = fft_swz<T>(b0 + 2), p3 = fft_swz<T>(b0 + 3);
+            const int p0 = fft_swz<T>(b0), p1 = p0 ^ 1, p2 = p0 ^ 2, p3 = p0 ^ 3;
             const cpx<T> x0 = a[p0], x1 = a[p1], x2 = a[p2], x3 = a[p3];
             const T s02x = x0.x + x2.x, s02y = x0.y + x2.y, d02x = x0.x - x2.x, d02y = x0.y - x2.y;
             const T s13x = x1.x + x3.x, s13y = x1.y + x3.y, d13x = x1.x - x3.x, d13y = x1.y - x3.y;
@@ -158,16 +158,13 @@ __device__ __forceinline__ void fft_sw(cpx<T>* a, int lt, int nthr, const cpx<T>
     }
     for (; 4 * h <= n; h <<= 2) {
         const int logh = 31 - __clz(h);
+        const int k1 = fft_swz<T>(h), k2 = fft_swz<T>(2 * h), k3 = fft_swz<T>(3 * h);
         for (int bi = lt; bi < (n >> 2); bi += nthr) {
             const int j = bi & (h - 1);
             const int base = ((bi >> logh) << (logh + 2)) + j;
             const cpx<T> w1 = st[j], w2 = st[h + j];
-            int p0, p1, p2, p3;
-            if (h >= (sizeof(T) == 8 ? 32 : 64)) {        // the legs differ above the swizzle's control bits
-                p0 = fft_swz<T>(base); p1 = p0 + h; p2 = p0 + 2 * h; p3 = p0 + 3 * h;
-            } else {
-                p0 = fft_swz<T>(base); p1 = fft_swz<T>(base + h); p2 = fft_swz<T>(base + 2 * h); p3 = fft_swz<T>(base + 3 * h);
-            }
+            // leg i sits at base + i h = base ^ (i h) (disjoint bits), and the swizzle is linear over GF(2)
+            const int p0 = fft_swz<T>(base), p1 = p0 ^ k1, p2 = p0 ^ k2, p3 = p0 ^ k3;
             const cpx<T> x0 = a[p0], x1 = a[p1], x2 = a[p2], x3 = a[p3];
             const T w3x = w1.x * w2.x - w1.y * w2.y, w3y = w1.x * w2.y + w1.y * w2.x;
             const T t1x = x1.x * w1.x - x1.y * w1.y, t1y = x1.x * w1.y + x1.y * w1.x;

@@ -17,16 +17,12 @@ __device__ __forceinline__ float m_atan(float x) { return atanf(x); }
 // 32768 magnitudes (checked exhaustively in tests/test_host_logic.py::test_pcm_division_by_reciprocal_is_exact).
 template <typename T>
 __device__ __forceinline__ T pcm_to_fraction(int c) {
-    if (c == -32768) return T(0);
-    const int mag = c < 0 ? -c : c;
-    if (sizeof(T) == 4) {                       // fast mode: one float multiply (relative error 6e-8)
-        const float v = (float)(2 * mag) * (1.0f / 65535.0f);
-        return T(c < 0 ? -v : v);
-    }
-    const double q = (double)(2 * mag), rcp = 1.0 / 65535.0;
+    // every step below is odd in q (round-to-nearest is symmetric), so the sign needs no separate handling
+    const int q2 = (c == -32768) ? 0 : 2 * c;
+    if (sizeof(T) == 4) return T((float)q2 * (1.0f / 65535.0f));        // fast mode: one float multiply (relative error 6e-8)
+    const double q = (double)q2, rcp = 1.0 / 65535.0;
     const double y0 = q * rcp;
-    const double v = fma(fma(-65535.0, y0, q), rcp, y0);
-    return T(c < 0 ? -v : v);
+    return T(fma(fma(-65535.0, y0, q), rcp, y0));
 }
 
 // quantize.py:12-38 magnitude code of |x| with nBits (sign handled by the caller).
