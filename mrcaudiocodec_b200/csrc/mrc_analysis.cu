@@ -81,7 +81,11 @@ struct Smem {
     cpx<T>* buf;    // [L]      FFT work buffer
     T* lines;       // [4][L]   MDCT lines L,R,M,S
     T* xi;          // [L]      FFT intensity, later SMR-per-line scratch
-    struct LineInfo* li;   // [L] pass 1 -> pass 2: bound and masker range of every line (aliases xi in fp64)
+    struct LineInfo* li;   // [L] pass 1 -> pass 2: bound and masker range of every line (fp64: aliases xi)
+    uint32_t* rng;  // [L]      fp32: the ranges on their own (the bounds are floats already: they stay in xi)
+    T* xi4;         // [4][L]   fast mode (fp32, power-of-two L): the intensities of all four spectra, from the spectra of L
+                    //          and R by linearity; lies over the block's samples, which are no longer needed by then
+    cpx<T>* buf2;   // [L]      fast mode: second FFT work buffer (R next to L), over xi .. ms15
     // masker tables of the current spectrum, in the mode's own precision (Q = L/2 >= number of maskers)
     T* mz;          // [Q]      Bark position
     T* ms15;        // [Q]      SPL - 15
@@ -115,11 +119,14 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     Smem<T> s;
     const int Q = L / 2;
     T* p = reinterpret_cast<T*>(raw);
+    const bool lin = sizeof(T) == 4 && !(L & (L - 1));
+    s.xi4 = lin ? p : nullptr;
     if constexpr (XIN) { s.sx = p; s.px = nullptr; p += 4 * L; }
-    else { s.sx = nullptr; s.px = reinterpret_cast<uint32_t*>(p); p += (2 * L * 4) / (int)sizeof(T); }
+    else { s.sx = nullptr; s.px = reinterpret_cast<uint32_t*>(p); p += lin ? 4 * L : (2 * L * 4) / (int)sizeof(T); }
     s.buf = reinterpret_cast<cpx<T>*>(p); p += 2 * L;
     s.lines = p;         p += 4 * L;
     s.xi = p;            p += L;
+    s.buf2 = reinterpret_cast<cpx<T>*>(s.xi);     // L + 2Q = 2L values: xi, mz, ms15
     s.mz = p;            p += Q;
     s.ms15 = p;          p += Q;
     s.mg = p;            p += Q;
@@ -131,8 +138,9 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
         p += 2 * stage_entries_of(L);
     }
     s.zb = p;            p += L;
-    if (sizeof(T) == 8) s.li = reinterpret_cast<LineInfo*>(s.xi);
-    else { s.li = reinterpret_cast<LineInfo*>(p); p += (L * (int)sizeof(LineInfo)) / (int)sizeof(T); }
+    s.li = reinterpret_cast<LineInfo*>(s.xi);
+    s.rng = nullptr;
+    if (sizeof(T) == 4) { s.rng = reinterpret_cast<uint32_t*>(p); p += L; }
     // mc, mU, mS, mP (4Q values = the FFT work buffer's 2L) live in the FFT work buffer: it is idle while maskers are
     // spread
     T* r = reinterpret_cast<T*>(s.buf);
@@ -165,6 +173,20 @@ __device__ __forceinline__ Smem<T> carve(unsigned char* raw, int L) {
     }
 #endif
     return s;
+}
+
+template <typename T>
+__device__ __forceinline__ void li_store(const Smem<T>& sm, int k, float ub, uint32_t rng) {
+    if constexpr (sizeof(T) == 8) { LineInfo v; v.ub = ub; v.rng = rng; sm.li[k] = v; }
+    else { sm.xi[k] = ub; sm.rng[k] = rng; }
+}
+template <typename T>
+__device__ __forceinline__ float li_ub(const Smem<T>& sm, int k) {
+    if constexpr (sizeof(T) == 8) return sm.li[k].ub; else return sm.xi[k];
+}
+template <typename T>
+__device__ __forceinline__ uint32_t li_rng(const Smem<T>& sm, int k) {
+    if constexpr (sizeof(T) == 8) return sm.li[k].rng; else return sm.rng[k];
 }
 
 template <typename T>
@@ -318,7 +340,7 @@ __device__ __forceinline__ T spread_line_grp(const Smem<T>& sm, const DevTables<
     MRC_WCLK_BEGIN();
     const T zk = sm.zb[k];
     const T quiet = tb.quiet[k];
-    const uint32_t rng = sm.li[k].rng;           // the line's masker range, found in pass 1
+    const uint32_t rng = li_rng<T>(sm, k);       // the line's masker range, found in pass 1
     const int m_lo = (int)(rng & 0xffffu), m_hi = (int)(rng >> 16);
     MRC_WCLK(16);
     const int nl = sm.lcnt[m_lo];
@@ -362,6 +384,10 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     Smem<T> sm = carve<T, XIN>(smem_raw, L);
     constexpr bool POW2 = FftShape<L>::pow2;
     constexpr int LOGL = FftShape<L>::logP;          // log2 L (power-of-two L only)
+    // Fast mode (fp32, power-of-two L): the transforms are linear, so the MDCT lines and the Hann spectra of M and S come
+    // from those of L and R -- two MDCTs and two FFTs per joint block instead of four and four.  The rounding of the S
+    // spectrum is then relative to L and R instead of to S itself, which is what separates this mode from the exact one.
+    constexpr bool LIN = POW2 && sizeof(T) == 4;
 
     __shared__ int s_clip, s_b, s_nblk_clip;
     __shared__ T s_red[4][32];
@@ -431,7 +457,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     {
         const int grp = tid / (NT / 2), lt = tid - grp * (NT / 2), gthr = NT / 2;
         const T two_over_n = T(2) / T(N);
-        for (int pair = 0; pair < nspec / 2; ++pair) {
+        for (int pair = 0; pair < (LIN ? 1 : nspec / 2); ++pair) {
             const int c = pair * 2 + grp;
             cpx<T>* a = sm.buf + grp * Q;
             if constexpr (POW2) {
@@ -502,6 +528,16 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             __syncthreads();
             MRC_CLK(1);
         }
+        if constexpr (LIN) {
+            if (nspec == 4) {
+                for (int k = tid; k < L; k += NT) {
+                    const T l = sm.lines[k], r = sm.lines[L + k];
+                    sm.lines[2 * L + k] = (l + r) / T(2);
+                    sm.lines[3 * L + k] = (l - r) / T(2);
+                }
+                __syncthreads();
+            }
+        }
     }
 
     if (taps.lines4 != nullptr) {
@@ -564,69 +600,121 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // reference-order mode evaluate everything.
     const bool all_bands = !joint || cp.spread_seq || taps.smr4 != nullptr || taps.npeaks != nullptr;
     const unsigned band_mask = (nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u);
+    if constexpr (LIN) {
+        // Hann spectra of L and R side by side (half the threads each), then the intensities of all the spectra at once
+        for (int it = 0; it < L / NT; ++it) {
+            const int n = fft_place_index<LOGL>(tid + it * NT);
+            T h0, h1, l0, r0, l1, r1;
+            ld2(tb.hann, 2 * n, h0, h1);
+            frame_lr<T, XIN>(sm, N, 2 * n, l0, r0);
+            frame_lr<T, XIN>(sm, N, 2 * n + 1, l1, r1);
+            const int r = fft_swz<T>(fft_r4_pos(n, LOGL));
+            cpx<T> v;
+            v.x = h0 * l0; v.y = h1 * l1;
+            sm.buf[r] = v;
+            v.x = h0 * r0; v.y = h1 * r1;
+            sm.buf2[r] = v;
+        }
+        __syncthreads();
+        MRC_CLK(15);
+        {
+            const int grp = tid / (NT / 2), lt = tid - grp * (NT / 2);
+            fft_sw<T, LOGL>(grp ? sm.buf2 : sm.buf, lt, NT / 2, sm.stL);
+        }
+        MRC_CLK(23);
+        // X[k] = E[k] + W^k O[k] for L and R; M = (L + R)/2, S = (L - R)/2;  XI = 4|X|^2 / (N^2 * 3/8)   (psychoac.py:151)
+        for (int k = tid; k < L; k += NT) {
+            const int pk = fft_swz<T>(k), pc = fft_swz<T>(k ? L - k : 0);
+            const cpx<T> w = tb.tw_rfft[k];
+            T xr[2], xim[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const cpx<T>* z = h ? sm.buf2 : sm.buf;
+                const cpx<T> zk = z[pk], zc = z[pc];
+                const T ex = (zk.x + zc.x) * T(0.5), ey = (zk.y - zc.y) * T(0.5);
+                const T dx = zk.x - zc.x, dy = zk.y + zc.y;           // D = Zk - conj(Zc)
+                const T ox = dy * T(0.5), oy = -dx * T(0.5);          // O = D / (2j)
+                xr[h] = ex + (ox * w.x - oy * w.y);
+                xim[h] = ey + (ox * w.y + oy * w.x);
+            }
+            sm.xi4[k] = T(4) * (xr[0] * xr[0] + xim[0] * xim[0]) / xi_den;
+            sm.xi4[L + k] = T(4) * (xr[1] * xr[1] + xim[1] * xim[1]) / xi_den;
+            if (nspec == 4) {
+                const T mr = (xr[0] + xr[1]) * T(0.5), mi = (xim[0] + xim[1]) * T(0.5);
+                const T sr = (xr[0] - xr[1]) * T(0.5), si = (xim[0] - xim[1]) * T(0.5);
+                sm.xi4[2 * L + k] = T(4) * (mr * mr + mi * mi) / xi_den;
+                sm.xi4[3 * L + k] = T(4) * (sr * sr + si * si) / xi_den;
+            }
+        }
+        __syncthreads();
+        MRC_CLK(3);
+    }
     for (int c = 0; c < nspec; ++c) {
         const unsigned need = all_bands ? band_mask : ((c < 2 ? ~s_ms : s_ms) & band_mask);
         if (need == 0u) {
             if (tid < nb) s_smr[c][tid] = T(0);
             continue;                                    // uniform: s_ms is shared
         }
-        // a. Hann window, real 2L-point FFT through an L-point complex FFT
-        if constexpr (POW2) {
-            for (int it = 0; it < L / NT; ++it) {
-                const int n = fft_place_index<LOGL>(tid + it * NT);
-                T h0, h1, x0, x1;
-                ld2(tb.hann, 2 * n, h0, h1);
-                if constexpr (XIN) {
-                    x0 = tsample<T, XIN>(sm, N, c, 2 * n);
-                    x1 = tsample<T, XIN>(sm, N, c, 2 * n + 1);
-                } else {
-                    const uint2 w = *reinterpret_cast<const uint2*>(sm.px + 2 * n);
-                    const int la = (int)(short)(w.x & 0xffffu), ra = (int)(short)(w.x >> 16);
-                    const int lb2 = (int)(short)(w.y & 0xffffu), rb = (int)(short)(w.y >> 16);
-                    if (c == 0) { x0 = pcm_to_fraction<T>(la); x1 = pcm_to_fraction<T>(lb2); }
-                    else if (c == 1) { x0 = pcm_to_fraction<T>(ra); x1 = pcm_to_fraction<T>(rb); }
-                    else {
-                        x0 = spec_of<T>(c, pcm_to_fraction<T>(la), pcm_to_fraction<T>(ra));
-                        x1 = spec_of<T>(c, pcm_to_fraction<T>(lb2), pcm_to_fraction<T>(rb));
+        if constexpr (!LIN) {
+            // a. Hann window, real 2L-point FFT through an L-point complex FFT
+            if constexpr (POW2) {
+                for (int it = 0; it < L / NT; ++it) {
+                    const int n = fft_place_index<LOGL>(tid + it * NT);
+                    T h0, h1, x0, x1;
+                    ld2(tb.hann, 2 * n, h0, h1);
+                    if constexpr (XIN) {
+                        x0 = tsample<T, XIN>(sm, N, c, 2 * n);
+                        x1 = tsample<T, XIN>(sm, N, c, 2 * n + 1);
+                    } else {
+                        const uint2 w = *reinterpret_cast<const uint2*>(sm.px + 2 * n);
+                        const int la = (int)(short)(w.x & 0xffffu), ra = (int)(short)(w.x >> 16);
+                        const int lb2 = (int)(short)(w.y & 0xffffu), rb = (int)(short)(w.y >> 16);
+                        if (c == 0) { x0 = pcm_to_fraction<T>(la); x1 = pcm_to_fraction<T>(lb2); }
+                        else if (c == 1) { x0 = pcm_to_fraction<T>(ra); x1 = pcm_to_fraction<T>(rb); }
+                        else {
+                            x0 = spec_of<T>(c, pcm_to_fraction<T>(la), pcm_to_fraction<T>(ra));
+                            x1 = spec_of<T>(c, pcm_to_fraction<T>(lb2), pcm_to_fraction<T>(rb));
+                        }
                     }
+                    cpx<T> v;
+                    v.x = h0 * x0;
+                    v.y = h1 * x1;
+                    sm.buf[fft_swz<T>(fft_r4_pos(n, LOGL))] = v;
                 }
-                cpx<T> v;
-                v.x = h0 * x0;
-                v.y = h1 * x1;
-                sm.buf[fft_swz<T>(fft_r4_pos(n, LOGL))] = v;
+            } else {
+                for (int i = tid; i < ntw; i += NT) tws[i] = tb.tw_fft[i];   // xi held the previous spectrum's per-line scratch
+                for (int n = tid; n < L; n += NT) {
+                    const int r = fft_pos<L>(n);
+                    sm.buf[r].x = tb.hann[2 * n] * tsample<T, XIN>(sm, N, c, 2 * n);
+                    sm.buf[r].y = tb.hann[2 * n + 1] * tsample<T, XIN>(sm, N, c, 2 * n + 1);
+                }
             }
-        } else {
-            for (int i = tid; i < ntw; i += NT) tws[i] = tb.tw_fft[i];   // xi held the previous spectrum's per-line scratch
-            for (int n = tid; n < L; n += NT) {
-                const int r = fft_pos<L>(n);
-                sm.buf[r].x = tb.hann[2 * n] * tsample<T, XIN>(sm, N, c, 2 * n);
-                sm.buf[r].y = tb.hann[2 * n + 1] * tsample<T, XIN>(sm, N, c, 2 * n + 1);
+            __syncthreads();
+            MRC_CLK(15);
+            if constexpr (POW2) fft_sw<T, LOGL>(sm.buf, tid, NT, sm.stL);
+            else fft_any<T, L>(sm.buf, tid, NT, tws, tb.logLtab, tb.tw9, L, tb.w9);
+            MRC_CLK(23);
+            // b. X[k] = E[k] + W^k O[k];  XI = 4|X|^2 / (N^2 * 3/8)   (psychoac.py:151)
+            for (int k = tid; k < L; k += NT) {
+                const cpx<T> zk = sm.buf[POW2 ? fft_swz<T>(k) : k], zc = sm.buf[POW2 ? fft_swz<T>(k ? L - k : 0) : (k ? L - k : 0)];
+                const T ex = (zk.x + zc.x) * T(0.5), ey = (zk.y - zc.y) * T(0.5);
+                const T dx = zk.x - zc.x, dy = zk.y + zc.y;           // D = Zk - conj(Zc)
+                const T ox = dy * T(0.5), oy = -dx * T(0.5);          // O = D / (2j)
+                const cpx<T> w = tb.tw_rfft[k];
+                const T xr = ex + (ox * w.x - oy * w.y), xim = ey + (ox * w.y + oy * w.x);
+                sm.xi[k] = T(4) * (xr * xr + xim * xim) / xi_den;
             }
+            __syncthreads();
+            MRC_CLK(3);
         }
-        __syncthreads();
-        MRC_CLK(15);
-        if constexpr (POW2) fft_sw<T, LOGL>(sm.buf, tid, NT, sm.stL);
-        else fft_any<T, L>(sm.buf, tid, NT, tws, tb.logLtab, tb.tw9, L, tb.w9);
-        MRC_CLK(23);
-        // b. X[k] = E[k] + W^k O[k];  XI = 4|X|^2 / (N^2 * 3/8)   (psychoac.py:151)
-        for (int k = tid; k < L; k += NT) {
-            const cpx<T> zk = sm.buf[POW2 ? fft_swz<T>(k) : k], zc = sm.buf[POW2 ? fft_swz<T>(k ? L - k : 0) : (k ? L - k : 0)];
-            const T ex = (zk.x + zc.x) * T(0.5), ey = (zk.y - zc.y) * T(0.5);
-            const T dx = zk.x - zc.x, dy = zk.y + zc.y;           // D = Zk - conj(Zc)
-            const T ox = dy * T(0.5), oy = -dx * T(0.5);          // O = D / (2j)
-            const cpx<T> w = tb.tw_rfft[k];
-            const T xr = ex + (ox * w.x - oy * w.y), xim = ey + (ox * w.y + oy * w.x);
-            sm.xi[k] = T(4) * (xr * xr + xim * xim) / xi_den;
-        }
-        __syncthreads();
-        MRC_CLK(3);
+        const T* const xic = LIN ? sm.xi4 + c * L : sm.xi;       // this spectrum's intensities
         // c. strict local maxima at bins 1 .. L-102, ascending order (psychoac.py:158-170)
         {
             int found = -1;
             for (int t = tid; t < Q; t += NT) {       // NT == Q: one trip
                 const int p0 = 2 * t, p1 = p0 + 1;
-                if (p0 >= 1 && p0 <= L - 102 && sm.xi[p0] > sm.xi[p0 - 1] && sm.xi[p0] > sm.xi[p0 + 1]) found = p0;
-                if (p1 <= L - 102 && sm.xi[p1] > sm.xi[p1 - 1] && sm.xi[p1] > sm.xi[p1 + 1]) found = p1;
+                if (p0 >= 1 && p0 <= L - 102 && xic[p0] > xic[p0 - 1] && xic[p0] > xic[p0 + 1]) found = p0;
+                if (p1 <= L - 102 && xic[p1] > xic[p1 - 1] && xic[p1] > xic[p1 + 1]) found = p1;
             }
             const unsigned bal = __ballot_sync(0xffffffffu, found >= 0);
             if (lane == 0) s_wcnt[warp] = __popc(bal);
@@ -656,7 +744,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
             if (i < npk) {
                 // products and sums kept unfused (__dmul_rn/__dadd_rn), in the reference's order
                 const int p = sm.pbin[i];
-                const T x0 = sm.xi[p - 1], x1 = sm.xi[p], x2 = sm.xi[p + 1];
+                const T x0 = xic[p - 1], x1 = xic[p], x2 = xic[p + 1];
                 const T sum = rn_add(rn_add(x0, x1), x2);
                 const T spl = fmax(rn_add(T(96.0), rn_mul(T(10.0), m_log10(sum))), T(-30.0));
                 const T num = rn_add(rn_add(rn_mul(T(p - 1), x0), rn_mul(T(p), x1)),
@@ -825,10 +913,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                         const unsigned top = __reduce_max_sync(0xffffffffu, key);
                         if (lane == 0 && top) atomicMax(&s_best[bd], top);
                     } else if (key) atomicMax(&s_best[bd], key);
-                    LineInfo v;
-                    v.ub = ub;
-                    v.rng = rng;
-                    sm.li[k] = v;
+                    li_store<T>(sm, k, ub, rng);
                 };
                 static_assert(L <= 2048, "line index in 11 bits");
                 bound_of(tid);
@@ -882,7 +967,7 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
                     MRC_WCLK(25);
                     for (int base = 0; base < n; base += GW) {
                         const int i = base + grp.gl;
-                        const T ub = (i < n) ? T(sm.li[lo + i].ub) : T(-1);
+                        const T ub = (i < n) ? T(li_ub<T>(sm, lo + i)) : T(-1);
                         unsigned bal = grp_ballot(grp, i < n && lo + i != kbest && ub >= rbest * slack);
                         while (bal) {
                             const int l = __ffs(bal) - 1;
@@ -1198,8 +1283,9 @@ size_t analysis_smem_bytes(int L, int elem, bool xin) {
     const size_t Q = L / 2;
     size_t merge = (size_t)2048 * elem + 2048 * 2;                     // merge buffers of the grant order
     if ((size_t)(4 * L) * elem >= merge) merge = 0;                    // ... living in `lines`
-    const size_t samples = xin ? (size_t)(4 * L) * elem : (size_t)8 * L;       // doubles of the seam, or packed PCM frames
-    const size_t stage = (size_t)stage_entries_of(L) * 2 * elem + (elem == 8 ? 0 : (size_t)L * sizeof(LineInfo));
+    const bool lin = elem == 4 && !(L & (L - 1));                      // fast mode: four intensity arrays over the samples
+    const size_t samples = (xin || lin) ? (size_t)(4 * L) * elem : (size_t)8 * L;   // values of the seam, or packed PCM frames
+    const size_t stage = (size_t)stage_entries_of(L) * 2 * elem + (elem == 8 ? 0 : (size_t)L * 4);
     return samples + (size_t)(8 * L) * elem + 3 * Q * elem + stage + 8 + 64 * 8 + (2 * Q + 1) * 4 + Q * 2 + 32 + merge;
 }
 
