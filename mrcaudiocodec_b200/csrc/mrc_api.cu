@@ -76,7 +76,7 @@ struct mrc_ctx {
     std::vector<cudaEvent_t> evpool;
     Buf tap_lines, tap_smr, tap_npk;
     Buf pcm_dev, out_dev, xin_dev;
-    Buf dec[16];
+    Buf dec[20];
 
     double ms[8] = {0};
     int64_t counters[8] = {0};

@@ -140,163 +140,184 @@ __device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecPa
     }
 }
 
-template <typename T, int L_>
-__global__ void __launch_bounds__(L_ / 2)
-decode_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, const HuffDecDev* __restrict__ hdec,
-              DecodeMap dm, const uint8_t* __restrict__ pac, int p0, T* __restrict__ y, int* error_flag, int cwords) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int L = L_, NT = L / 2;
-    const int tid = threadIdx.x, nb = tb.nb;
-    DSmem<T> sm = dcarve<T>(smem_raw, L, cwords);
-    __shared__ int s_alloc[2 * MRC_BSTRIDE], s_sf[2 * MRC_BSTRIDE], s_ovs[4];
-    __shared__ unsigned s_ms;
-    __shared__ int s_bad, s_joint;
-    __shared__ int s_esc[MRC_N_HUFF_TABLES];
-    __shared__ int s_boff[2 * MRC_BSTRIDE], s_raw[2];
-    __shared__ uint16_t s_hlut[MRC_N_HUFF_TABLES][1 << MRC_HUFF_PEEK];     // the 9-bit decode tables (4 KB)
+// ---- parse: ONE WARP PER CHUNK ---------------------------------------------------------------------------------
+// The chunk grammar is serial (every field's position depends on the fields before it), so a chunk is one warp's work
+// whatever is done; what can be chosen is how many chunks are in flight.  Parsing inside the synthesis CTA (one CTA of
+// L/2 threads per pair, two of its sixteen warps parsing while fourteen wait) kept six chunks in flight per SM and the
+// whole kernel waited on that latency (profiles/r02t: 69 % of all stall samples at the barrier after the parse).  Here a
+// CTA is eight independent warps, each with its chunk staged in its own slice of shared memory: ~56 chunks in flight per
+// SM.  Output per pair: mantissa codes (u16), bit allocation and scale factor per band, overall scales, ms_switch and
+// flags -- 4.2 KB that the synthesis kernel reads back coalesced.
+constexpr int PARSE_WARPS = 8;
 
-    const int lp = dm.list ? dm.list[blockIdx.x] : (int)blockIdx.x, p = p0 + lp;
-    if (tid == 0) {
+struct ParseGeo {
+    int nb, geom, L, Lmax, n_scale_bits, n_mant_size_bits, joint, flush_nonjoint;
+    uint16_t band_lo[MRC_BSTRIDE], band_n[MRC_BSTRIDE];
+};
+
+__global__ void __launch_bounds__(PARSE_WARPS * 32)
+parse_kernel(ParseGeo pg, const HuffDev* __restrict__ huff, const HuffDecDev* __restrict__ hdec, DecodeMap dm,
+             const uint8_t* __restrict__ pac, int p0, int npairs, ParseOut po, int* error_flag, int cwords) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint16_t s_hlut[MRC_N_HUFF_TABLES][1 << MRC_HUFF_PEEK];     // the 9-bit decode tables (4 KB)
+    __shared__ int s_esc[MRC_N_HUFF_TABLES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nb = pg.nb;
+    if (tid < MRC_N_HUFF_TABLES) s_esc[tid] = huff->esc[tid];
+    for (int i = tid; i < (MRC_N_HUFF_TABLES << MRC_HUFF_PEEK) / 2; i += PARSE_WARPS * 32)
+        reinterpret_cast<uint32_t*>(&s_hlut[0][0])[i] = reinterpret_cast<const uint32_t*>(&hdec->lut[0][0])[i];
+    __syncthreads();
+    const int ci = blockIdx.x * PARSE_WARPS + warp;            // chunk of this warp: (list entry, channel)
+    if (ci >= 2 * npairs) return;
+    const int li = ci >> 1, ch = ci & 1;
+    const int lp = dm.list ? dm.list[li] : li, p = p0 + lp;
+    bool joint;
+    {
         int lo = 0, hi = dm.n_clips;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (dm.clip_pair0[mid] <= p) lo = mid; else hi = mid;
         }
         const int last = dm.clip_pair0[lo + 1] - 1;
-        s_joint = cp.joint && !(cp.flush_nonjoint && p == last);
-        s_ms = 0u;
-        s_bad = 0;
+        joint = pg.joint && !(pg.flush_nonjoint && p == last);
     }
-    if (tid < MRC_N_HUFF_TABLES) s_esc[tid] = huff->esc[tid];
-    for (int i = tid; i < (MRC_N_HUFF_TABLES << MRC_HUFF_PEEK) / 2; i += NT)
-        reinterpret_cast<uint32_t*>(&s_hlut[0][0])[i] = reinterpret_cast<const uint32_t*>(&hdec->lut[0][0])[i];
-    // stage both chunk payloads as big-endian words
-    for (int ch = 0; ch < 2; ++ch) {
+    // stage the chunk payload as big-endian words: aligned 32-bit loads, realigned by the payload's byte offset
+    uint32_t* cw = reinterpret_cast<uint32_t*>(smem_raw) + warp * cwords;
+    const int nbytes = min((int)dm.chunk_len[2 * p + ch], (cwords - 2) * 4);
+    {
         const uint8_t* src = pac + dm.chunk_pos[2 * p + ch];
-        const int nbytes = min((int)dm.chunk_len[2 * p + ch], (cwords - 2) * 4);
-        uint32_t* dst = sm.cw + ch * cwords;
-        for (int wi = tid; wi < cwords; wi += NT) {
+        const int mis = (int)(reinterpret_cast<size_t>(src) & 3);
+        const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src - mis);
+        for (int wi = lane; wi < cwords; wi += 32) {
+            const int valid = nbytes - 4 * wi;                 // payload bytes from this word on
             uint32_t w = 0;
-            const int b0 = wi * 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (b0 + j < nbytes) w |= (uint32_t)__ldg(src + b0 + j) << (24 - 8 * j);
-            dst[wi] = w;
+            if (valid > 0) {
+                const uint32_t lo = __ldg(src32 + wi);
+                const uint32_t hi = (mis && valid + mis > 4) ? __ldg(src32 + wi + 1) : 0u;
+                w = __byte_perm(__funnelshift_r(lo, hi, 8 * mis), 0u, 0x0123);
+                if (valid < 4) w &= 0xffffffffu << (8 * (4 - valid));
+            }
+            cw[wi] = w;
         }
     }
-    for (int i = tid; i < 2 * L; i += NT) sm.mant[i] = 0;
-    __syncthreads();
-    const bool joint = s_joint != 0;
-
-    // ---- parse: warp 0 takes channel 0's chunk, warp 1 channel 1's.  The header fields are read by all lanes alike
-    // (same words, broadcast); Huffman-coded mantissas are decoded 32 bit positions at a time: every lane decodes the
-    // code that WOULD start at its bit, the lanes that really are code starts are found by pointer doubling along
-    // "next start" (five steps), and their symbols land at their rank.  A window yields 32 bits' worth of symbols
-    // (8..16 with the trained books) for the price of a handful of serial ones.
-    if (tid < 64) {
-        const int ch = tid >> 5, lane = tid & 31;
-        BitReader br;
-        br.w = sm.cw + ch * cwords;
-        br.pos = 0;
-        br.nbits = 8 * min((int)dm.chunk_len[2 * p + ch], (cwords - 2) * 4);
-        br.bad = false;
-        const int table = (int)br.read(4);
-        const int swA = (int)br.read(1), swB = (int)br.read(1);
-        if (((swA << 1) | swB) != tb.geom) br.bad = true;          // both chunks of a pair carry the pair's geometry
-        if (table != MRC_NO_TABLE && table >= MRC_N_HUFF_TABLES) br.bad = true;
-        if (joint) {
-            if (ch == 0) {
-                for (int i = 0; i < 4; ++i) { const int v = (int)br.read(cp.n_scale_bits); if (lane == 0) s_ovs[i] = v; }
-                unsigned ms = 0;
-                for (int bd = 0; bd < nb; ++bd) ms |= br.read(1) << bd;
-                if (lane == 0) s_ms = ms;
-            }
-        } else {
-            const int v = (int)br.read(cp.n_scale_bits);
-            if (lane == 0) s_ovs[ch] = v;
+    __syncwarp();
+    BitReader br;
+    br.w = cw;
+    br.pos = 0;
+    br.nbits = 8 * nbytes;
+    br.bad = false;
+    const int table = (int)br.read(4);
+    const int swA = (int)br.read(1), swB = (int)br.read(1);
+    if (((swA << 1) | swB) != pg.geom) br.bad = true;          // both chunks of a pair carry the pair's geometry
+    if (table != MRC_NO_TABLE && table >= MRC_N_HUFF_TABLES) br.bad = true;
+    uint8_t* o_ovs = po.ovs + (size_t)lp * 4;
+    if (joint) {
+        if (ch == 0) {
+            for (int i = 0; i < 4; ++i) { const int v = (int)br.read(pg.n_scale_bits); if (lane == 0) o_ovs[i] = (uint8_t)v; }
+            unsigned ms = 0;
+            for (int bd = 0; bd < nb; ++bd) ms |= br.read(1) << bd;
+            if (lane == 0) po.ms[lp] = ms;
         }
-        int* mant = sm.mant + ch * L;
-        for (int bd = 0; bd < nb && !br.bad; ++bd) {
-            int ba = (int)br.read(cp.n_mant_size_bits);
-            if (ba) ba += 1;
-            const int sfv = (int)br.read(cp.n_scale_bits);
-            if (lane == 0) { s_alloc[ch * MRC_BSTRIDE + bd] = ba; s_sf[ch * MRC_BSTRIDE + bd] = sfv; }
-            if (!ba) continue;
-            const int lo = tb.c_band_lo[bd], n = tb.c_band_n[bd];
-            if (table == MRC_NO_TABLE) {
-                // raw mantissas: fixed width, so only their position is recorded here; all threads extract them below
-                if (lane == 0) s_boff[ch * MRC_BSTRIDE + bd] = br.pos;
-                if (br.pos + n * ba > br.nbits) { br.bad = true; break; }
-                br.pos += n * ba;
-            } else {
-                const uint16_t* lut = s_hlut[table];
-                const int esc = s_esc[table];
-                int done = 0;
-                while (done < n) {
-                    const int pi = br.pos + lane;
-                    int tot = 0, val = 0, len = 0;
-                    bool ok = false;
-                    if (pi < br.nbits) {
-                        const uint32_t e = lut[br.peek_at(pi, MRC_HUFF_PEEK)];
-                        len = e >> 8; val = e & 0xff;
-                        if (len != 0 && pi + len <= br.nbits) {
-                            tot = len;
-                            ok = true;
-                            if (val == esc) {                    // escape code + ba raw bits
-                                if (pi + len + ba <= br.nbits) tot = len + ba; else ok = false;
-                            }
+    } else {
+        const int v = (int)br.read(pg.n_scale_bits);
+        if (lane == 0) { o_ovs[ch] = (uint8_t)v; if (ch == 0) po.ms[lp] = 0u; }
+    }
+    uint16_t* mant = po.mant + ((size_t)lp * 2 + ch) * pg.Lmax;
+    uint8_t* o_alloc = po.alloc + ((size_t)lp * 2 + ch) * MRC_BSTRIDE;
+    uint8_t* o_sf = po.sf + ((size_t)lp * 2 + ch) * MRC_BSTRIDE;
+    int bd = 0;
+    for (; bd < nb && !br.bad; ++bd) {
+        int ba = (int)br.read(pg.n_mant_size_bits);
+        if (ba) ba += 1;
+        const int sfv = (int)br.read(pg.n_scale_bits);
+        if (lane == 0) { o_alloc[bd] = (uint8_t)ba; o_sf[bd] = (uint8_t)sfv; }
+        if (!ba) continue;
+        const int lo = pg.band_lo[bd], n = pg.band_n[bd];
+        if (table == MRC_NO_TABLE) {
+            // raw mantissas: fixed width, one per lane and trip
+            if (br.pos + n * ba > br.nbits) { br.bad = true; break; }
+            for (int i = lane; i < n; i += 32) mant[lo + i] = (uint16_t)br.peek_at(br.pos + i * ba, ba);
+            br.pos += n * ba;
+        } else {
+            // Huffman-coded mantissas, 32 bit positions at a time: every lane decodes the code that WOULD start at its
+            // bit, the lanes that really are code starts are found by pointer doubling along "next start" (five steps),
+            // and their symbols land at their rank
+            const uint16_t* lut = s_hlut[table];
+            const int esc = s_esc[table];
+            int done = 0;
+            while (done < n) {
+                const int pi = br.pos + lane;
+                int tot = 0, val = 0, len = 0;
+                bool ok = false;
+                if (pi < br.nbits) {
+                    const uint32_t e = lut[br.peek_at(pi, MRC_HUFF_PEEK)];
+                    len = e >> 8; val = e & 0xff;
+                    if (len != 0 && pi + len <= br.nbits) {
+                        tot = len;
+                        ok = true;
+                        if (val == esc) {                    // escape code + ba raw bits
+                            if (pi + len + ba <= br.nbits) tot = len + ba; else ok = false;
                         }
                     }
-                    int J = ok ? min(lane + tot, 32) : 32;       // where the next code starts; 32 = past this window
-                    unsigned R = 1u;                             // lanes that are code starts: the chain from lane 0
-#pragma unroll
-                    for (int st = 0; st < 5; ++st) {
-                        const bool on = (R >> lane) & 1u;
-                        R |= __reduce_or_sync(0xffffffffu, (on && J < 32) ? (1u << J) : 0u);
-                        const int Jn = __shfl_sync(0xffffffffu, J, J & 31);
-                        J = (J < 32) ? Jn : 32;
-                    }
-                    const bool on = (R >> lane) & 1u;
-                    const int rank = __popc(R & ((1u << lane) - 1u));
-                    const int want = n - done, cnt = min(__popc(R), want);
-                    if (__ballot_sync(0xffffffffu, on && rank < want && !ok)) { br.bad = true; break; }
-                    if (on && rank < want) mant[lo + done + rank] = (val == esc) ? (int)br.peek_at(pi + len, ba) : val;
-                    const unsigned lastm = __ballot_sync(0xffffffffu, on && rank == cnt - 1);
-                    br.pos = __shfl_sync(0xffffffffu, pi + tot, __ffs(lastm) - 1);
-                    done += cnt;
                 }
+                int J = ok ? min(lane + tot, 32) : 32;       // where the next code starts; 32 = past this window
+                unsigned R = 1u;                             // lanes that are code starts: the chain from lane 0
+#pragma unroll
+                for (int st = 0; st < 5; ++st) {
+                    const bool on = (R >> lane) & 1u;
+                    R |= __reduce_or_sync(0xffffffffu, (on && J < 32) ? (1u << J) : 0u);
+                    const int Jn = __shfl_sync(0xffffffffu, J, J & 31);
+                    J = (J < 32) ? Jn : 32;
+                }
+                const bool on = (R >> lane) & 1u;
+                const int rank = __popc(R & ((1u << lane) - 1u));
+                const int want = n - done, cnt = min(__popc(R), want);
+                if (__ballot_sync(0xffffffffu, on && rank < want && !ok)) { br.bad = true; break; }
+                if (on && rank < want)
+                    mant[lo + done + rank] = (uint16_t)((val == esc) ? (int)br.peek_at(pi + len, ba) : val);
+                const unsigned lastm = __ballot_sync(0xffffffffu, on && rank == cnt - 1);
+                br.pos = __shfl_sync(0xffffffffu, pi + tot, __ffs(lastm) - 1);
+                done += cnt;
             }
         }
-        if (lane == 0) {
-            s_raw[ch] = (table == MRC_NO_TABLE);
-            if (br.bad) {
-                s_bad = 1;
-                for (int bd = 0; bd < nb; ++bd) s_alloc[ch * MRC_BSTRIDE + bd] = 0;
-            }
+    }
+    if (lane == 0) {
+        for (; bd < nb; ++bd) o_alloc[bd] = 0;               // fields a malformed chunk never reached
+        po.flags[(size_t)lp * 2 + ch] = (uint8_t)((br.bad ? 1 : 0) | (joint ? 2 : 0));
+        if (br.bad) atomicExch(error_flag, 1);
+    }
+}
+
+// ---- synthesis of the parsed pairs: one CTA per pair ----------------------------------------------------------
+template <typename T, int L_>
+__global__ void __launch_bounds__(L_ / 2)
+decode_kernel(DevTables<T> tb, CodecParams cp, DecodeMap dm, ParseOut po, T* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int L = L_, NT = L / 2;
+    const int tid = threadIdx.x, nb = tb.nb;
+    DSmem<T> sm = dcarve<T>(smem_raw, L, 0);
+    __shared__ int s_alloc[2 * MRC_BSTRIDE], s_sf[2 * MRC_BSTRIDE], s_ovs[4];
+    const int lp = dm.list ? dm.list[blockIdx.x] : (int)blockIdx.x;
+    const unsigned f0 = po.flags[(size_t)lp * 2], f1 = po.flags[(size_t)lp * 2 + 1];
+    const bool bad = ((f0 | f1) & 1u) != 0, joint = (f0 & 2u) != 0;
+    // a malformed chunk decodes its pair as silence (the error flag is already raised)
+    if (tid < 2 * nb) {
+        const int ch = tid / nb, bd = tid - ch * nb;
+        s_alloc[ch * MRC_BSTRIDE + bd] = bad ? 0 : (int)po.alloc[((size_t)lp * 2 + ch) * MRC_BSTRIDE + bd];
+        s_sf[ch * MRC_BSTRIDE + bd] = (int)po.sf[((size_t)lp * 2 + ch) * MRC_BSTRIDE + bd];
+    }
+    if (tid < 4) s_ovs[tid] = bad ? 0 : (int)po.ovs[(size_t)lp * 4 + tid];
+    const unsigned ms = (bad || !joint) ? 0u : po.ms[lp];
+    {
+        const uint32_t* m32 = reinterpret_cast<const uint32_t*>(po.mant + (size_t)lp * 2 * cp.Lmax);
+        for (int i = tid; i < L; i += NT) {                  // two codes per load; channel stride Lmax
+            const int ch = i / (L / 2), k2 = i - ch * (L / 2);
+            const uint32_t w = m32[ch * (cp.Lmax / 2) + k2];
+            sm.mant[ch * L + 2 * k2] = (int)(w & 0xffffu);
+            sm.mant[ch * L + 2 * k2 + 1] = (int)(w >> 16);
         }
     }
     __syncthreads();
-    if (!s_bad) {
-        for (int i = tid; i < 2 * L; i += NT) {
-            const int ch = i / L, k = i - ch * L;
-            if (!s_raw[ch]) continue;
-            const int bd = tb.line2band[k];
-            const int ba = s_alloc[ch * MRC_BSTRIDE + bd];
-            if (!ba) continue;
-            BitReader br;
-            br.w = sm.cw + ch * cwords;
-            br.pos = s_boff[ch * MRC_BSTRIDE + bd] + (k - tb.band_lo[bd]) * ba;
-            sm.mant[i] = (int)br.peek(ba);
-        }
-        __syncthreads();
-    }
-    if (s_bad) {
-        if (tid == 0) atomicExch(error_flag, 1);
-        if (tid < 2 * nb) s_alloc[(tid / nb) * MRC_BSTRIDE + tid % nb] = 0;
-        if (tid < 4) s_ovs[tid] = 0;
-        __syncthreads();
-    }
-    synthesize<T, L>(tb, cp, sm, joint, s_alloc, s_sf, s_ovs, s_ms, y + (size_t)lp * 4 * cp.Lmax);
+    synthesize<T, L>(tb, cp, sm, joint, s_alloc, s_sf, s_ovs, ms, y + (size_t)lp * 4 * cp.Lmax);
 }
 
 template <typename T, int L_>
@@ -385,17 +406,45 @@ int chunk_words(const CodecParams& cp) {
 
 }  // namespace
 
+// layout of the parse output of one wave inside one allocation (every array 256-byte aligned)
+static size_t po_align(size_t x) { return (x + 255) & ~(size_t)255; }
+size_t parse_out_bytes(int npairs, int Lmax) {
+    const size_t n = (size_t)npairs;
+    return po_align(n * 2 * Lmax * 2) + 2 * po_align(n * 2 * MRC_BSTRIDE) + po_align(n * 4) + po_align(n * 4) + po_align(n * 2);
+}
+ParseOut parse_out_carve(void* base, int npairs, int Lmax) {
+    const size_t n = (size_t)npairs;
+    unsigned char* p = static_cast<unsigned char*>(base);
+    ParseOut po;
+    po.mant = reinterpret_cast<uint16_t*>(p);  p += po_align(n * 2 * Lmax * 2);
+    po.alloc = p;                              p += po_align(n * 2 * MRC_BSTRIDE);
+    po.sf = p;                                 p += po_align(n * 2 * MRC_BSTRIDE);
+    po.ovs = p;                                p += po_align(n * 4);
+    po.ms = reinterpret_cast<uint32_t*>(p);    p += po_align(n * 4);
+    po.flags = p;
+    return po;
+}
+
 template <typename T>
 void launch_decode(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
                    const HuffDecDev* hdec, const DecodeMap& dm, const uint8_t* pac, int p0, int npairs, T* y,
-                   int* error_flag) {
+                   int* error_flag, const ParseOut& po) {
     if (npairs <= 0) return;
     const int cw = chunk_words(cp);
-    const size_t smem = decode_smem_bytes(tb.L, sizeof(T), cw);
+    ParseGeo pg;
+    pg.nb = tb.nb; pg.geom = tb.geom; pg.L = tb.L; pg.Lmax = cp.Lmax;
+    pg.n_scale_bits = cp.n_scale_bits; pg.n_mant_size_bits = cp.n_mant_size_bits;
+    pg.joint = cp.joint; pg.flush_nonjoint = cp.flush_nonjoint;
+    for (int b = 0; b < MRC_BSTRIDE; ++b) { pg.band_lo[b] = tb.c_band_lo[b]; pg.band_n[b] = tb.c_band_n[b]; }
+    const size_t psmem = (size_t)PARSE_WARPS * cw * 4;
+    cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    parse_kernel<<<(2 * npairs + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, psmem, st>>>(
+        pg, huff, hdec, dm, pac, p0, npairs, po, error_flag, cw);
+    const size_t smem = decode_smem_bytes(tb.L, sizeof(T), 0);
 #define MRC_LAUNCH_DEC(LL)                                                                                     \
     case LL:                                                                                                   \
         cudaFuncSetAttribute(decode_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        decode_kernel<T, LL><<<npairs, LL / 2, smem, st>>>(tb, cp, huff, hdec, dm, pac, p0, y, error_flag, cw);  \
+        decode_kernel<T, LL><<<npairs, LL / 2, smem, st>>>(tb, cp, dm, po, y);                                  \
         break;
     switch (tb.L) {
         MRC_LAUNCH_DEC(128)
@@ -441,7 +490,8 @@ void launch_ola(cudaStream_t st, const CodecParams& cp, const DecodeMap& dm, int
 
 #define MRC_INST(T)                                                                                            \
     template void launch_decode<T>(cudaStream_t, const DevTables<T>&, const CodecParams&, const HuffDev*,       \
-                                   const HuffDecDev*, const DecodeMap&, const uint8_t*, int, int, T*, int*);    \
+                                   const HuffDecDev*, const DecodeMap&, const uint8_t*, int, int, T*, int*,     \
+                                   const ParseOut&);                                                            \
     template void launch_decode_ints<T>(cudaStream_t, const DevTables<T>&, const CodecParams&, int,             \
                                         const int32_t*, const int32_t*, const int32_t*, const int32_t*,         \
                                         const int32_t*, int, T*);                                               \

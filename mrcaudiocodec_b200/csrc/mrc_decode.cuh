@@ -19,11 +19,24 @@ struct DecodeMap {
     const int32_t* list;         // wave-local pairs of the geometry being launched (null: all)
 };
 
-// parse + dequantise + M/S + IMDCT + window for pairs [p0, p0+npairs): writes y [npairs][2][2L] (head, tail)
+// what the parse kernel (one warp per chunk) hands to the synthesis kernel (one CTA per pair), wave-local pair index
+struct ParseOut {
+    uint16_t* mant;              // [npairs][2][Lmax]  mantissa codes
+    uint8_t* alloc;              // [npairs][2][32]    bits per mantissa, per band (0 = band not coded)
+    uint8_t* sf;                 // [npairs][2][32]    scale factor per band
+    uint8_t* ovs;                // [npairs][4]        overall scale factors
+    uint32_t* ms;                // [npairs]           ms_switch mask
+    uint8_t* flags;              // [npairs][2]        bit 0: malformed chunk, bit 1: joint pair
+};
+size_t parse_out_bytes(int npairs, int Lmax);
+ParseOut parse_out_carve(void* base, int npairs, int Lmax);
+
+// parse (one warp per chunk), then dequantise + M/S + IMDCT + window (one CTA per pair) for pairs [p0, p0+npairs):
+// writes y [npairs][2][2L] (head, tail)
 template <typename T>
 void launch_decode(cudaStream_t st, const DevTables<T>& tb, const CodecParams& cp, const HuffDev* huff,
                    const HuffDecDev* hdec, const DecodeMap& dm, const uint8_t* pac, int p0, int npairs, T* y,
-                   int* error_flag);
+                   int* error_flag, const ParseOut& po);
 
 // same synthesis from explicit integers (per-block seam): ints are [npairs][2][..] like mrc_decode_block
 template <typename T>
