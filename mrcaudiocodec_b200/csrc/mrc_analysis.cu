@@ -24,10 +24,12 @@
 // One CTA = one block, NT = L/2 threads; thread t owns MDCT lines t and t+L/2.  L = (a+b)/2 is a template parameter:
 // nMDCTLines for long blocks, 576 for the transition blocks of block switching (a+b = 1024+128), 128 for short ones.
 #include <algorithm>
+#include <cstdlib>
 
 #include "mrc_internal.cuh"
 #include "mrc_math.cuh"
 #include "mrc_fft.cuh"
+#include "mrc_tma.cuh"
 
 // -DMRC_PHASE_CLOCKS: development build that accumulates, per CTA, the cycles between phase boundaries (read by
 // scripts/phase_clocks.py through mrc_debug_phase_clocks); never defined in the shipped library.
@@ -371,17 +373,27 @@ __device__ __forceinline__ T spread_line_grp(const Smem<T>& sm, const DevTables<
     return a;
 }
 
+// what the last warp leaves for the CTA's NEXT block while the current one is finished: the block's place in its clip
+// and, when its 2L frames lie inside the clip at a 16-byte aligned address, the frames themselves (one bulk copy into
+// `px`, which the current block no longer reads by then)
+struct NextBlock {
+    int state;               // 0 nothing, 1 place + frames on their way (mbarrier), 2 place only
+    int clip, b, nblk_clip;
+};
+
+// One block: `it` = its index in this launch (wave-local, or into the geometry's list), it_next = the CTA's next one (-1:
+// none).
 template <typename T, int L_, bool XIN>
-__global__ void __launch_bounds__(L_ / 2, (L_ <= 1024) ? (sizeof(T) == 4 ? 3 : 2) : 1)
-analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __restrict__ pcm,
-                const double* __restrict__ xin, int g0, Handoff<T> ho, AnalysisTaps<T> taps,
-                unsigned long long* peak_counter) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void analysis_block(const Smem<T>& sm, const DevTables<T>& tb, const CodecParams& cp,
+                                               const ClipMap& cm, const int16_t* __restrict__ pcm,
+                                               const double* __restrict__ xin, int g0, int it, int it_next,
+                                               const Handoff<T>& ho, const AnalysisTaps<T>& taps,
+                                               unsigned long long* peak_counter, unsigned long long* mbar,
+                                               NextBlock* nxt, unsigned& mbar_parity) {
     constexpr int L = L_, N = 2 * L, Q = L / 2, NT = Q, nwarp = NT >> 5;
     static_assert(NT % 32 == 0, "whole warps");
     const int nb = tb.nb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    Smem<T> sm = carve<T, XIN>(smem_raw, L);
     constexpr bool POW2 = FftShape<L>::pow2;
     constexpr int LOGL = FftShape<L>::logP;          // log2 L (power-of-two L only)
     // Fast mode (fp32, power-of-two L): the transforms are linear, so the MDCT lines and the Hann spectra of M and S come
@@ -404,23 +416,21 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     if (threadIdx.x == 0) s_clk_last = clock64();
 #endif
 
-    if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
-    for (int i = tid; i < L; i += NT) sm.zb[i] = tb.bark[i];
-    if constexpr (POW2) {            // stage tables of both transforms: staged once, published by the barriers below
-        cpx<T>* dst = const_cast<cpx<T>*>(sm.stL);
-        for (int i = tid; i < stage_entries_of(L); i += NT) dst[i] = tb.tw_stage[i];
-    }
-    const int lb = cm.list ? cm.list[blockIdx.x] : (int)blockIdx.x;   // index inside this wave's hand-off buffers
+    const int lb = cm.list ? cm.list[it] : it;   // index inside this wave's hand-off buffers
     const int g = g0 + lb;                    // global block index
+    const int pre = nxt->state;               // left by this CTA's previous block (published by the barrier that closed it)
     if (tid == 0) {
-        int lo = 0, hi = cm.n_clips;          // last clip whose first block <= g
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (cm.clip_blk0[mid] <= g) lo = mid; else hi = mid;
+        if (pre) { s_clip = nxt->clip; s_b = nxt->b; s_nblk_clip = nxt->nblk_clip; }
+        else {
+            int lo = 0, hi = cm.n_clips;      // last clip whose first block <= g
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (cm.clip_blk0[mid] <= g) lo = mid; else hi = mid;
+            }
+            s_clip = lo;
+            s_b = g - cm.clip_blk0[lo];
+            s_nblk_clip = cm.clip_blk0[lo + 1] - cm.clip_blk0[lo];
         }
-        s_clip = lo;
-        s_b = g - cm.clip_blk0[lo];
-        s_nblk_clip = cm.clip_blk0[lo + 1] - cm.clip_blk0[lo];
         s_ms = 0u;
     }
     __syncthreads();
@@ -432,6 +442,9 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     // ---- phase 0: frame [ (b-1)L, (b+1)L ) of the clip, zero outside ------------------------------------
     if constexpr (XIN) {
         for (int i = tid; i < 2 * N; i += NT) sm.sx[i] = T(xin[(size_t)g * 2 * N + i]);
+    } else if (pre == 1) {
+        mbar_wait(mbar, mbar_parity);         // the frames were fetched while the previous block was finished
+        mbar_parity ^= 1u;
     } else {
         const long long frames = cm.clip_off[s_clip + 1] - cm.clip_off[s_clip];
         const uint32_t* __restrict__ p32 = reinterpret_cast<const uint32_t*>(pcm) + (cm.clip_off[s_clip] - cm.pcm_frame0);
@@ -1011,6 +1024,32 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
         MRC_CLK(9);
         if (taps.npeaks != nullptr && tid == 0) taps.npeaks[lb * 4 + c] = npk;
     }
+    // The block's samples are no longer needed (every barrier of the loop above lies behind): the last warp's first lane
+    // places the CTA's next block and asks the copy engine for its frames.
+    if (tid == NT - 32) {
+        int st = 0;
+        if (!XIN && it_next >= 0) {
+            const int gn = g0 + (cm.list ? cm.list[it_next] : it_next);
+            int lo = 0, hi = cm.n_clips;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (cm.clip_blk0[mid] <= gn) lo = mid; else hi = mid;
+            }
+            const int bn = gn - cm.clip_blk0[lo];
+            nxt->clip = lo; nxt->b = bn; nxt->nblk_clip = cm.clip_blk0[lo + 1] - cm.clip_blk0[lo];
+            const long long frames = cm.clip_off[lo + 1] - cm.clip_off[lo];
+            const long long s0 = cm.blk_start ? cm.blk_start[gn] - tb.a : (long long)(bn + cm.blk_base - 1) * L;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(pcm) + (cm.clip_off[lo] - cm.pcm_frame0) + s0;
+            st = 2;
+            if (s0 >= 0 && s0 + N <= frames && (reinterpret_cast<size_t>(src) & 15) == 0) {
+                fence_proxy_async();          // the CTA's reads and writes of this buffer come first
+                mbar_expect_tx(mbar, (unsigned)(N * 4));
+                bulk_g2s(sm.px, src, (unsigned)(N * 4), mbar);
+                st = 1;
+            }
+        }
+        nxt->state = st;
+    }
     if (tid == 0) {
         if (peak_counter) atomicAdd(peak_counter, (unsigned long long)my_peaks);
     }
@@ -1261,6 +1300,50 @@ analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __re
     MRC_CLK(12);
 }
 
+// A CTA takes MRC_BLOCKS_PER_CTA blocks (blockIdx.x, blockIdx.x + gridDim.x, ...: consecutive blocks go to different CTAs,
+// so the cheap blocks of a silent passage are spread evenly): the tables that do not depend on the block -- 2^(j/64), the
+// Bark positions of the lines, the FFT stage twiddles -- are staged once per CTA, and every block but the first finds its
+// frames already in shared memory (one cp.async.bulk issued while the block before is finished).  Measured on the 1 h
+// stream (scripts/gpu_bpc.sh, audio-s/s fp64 / fp32): 1 block per CTA 56.4k / 87.0k, 2: 56.6k / 86.9k, 4: 56.2k / 85.9k,
+// 16: 54.0k, a grid of fully persistent CTAs 53.6k / 82.5k -- the staging it saves is small, and the kernels of the
+// neighbouring waves (cost, pack, reservoir maps, on streams of their own) get their SMs when analysis CTAs retire: long-
+// lived CTAs hold them back (pack 6.3 -> 13.1 ms per hour with persistent CTAs).  So: two.  The per-block seam (XIN)
+// launches one CTA per block.
+#ifndef MRC_BLOCKS_PER_CTA
+#define MRC_BLOCKS_PER_CTA 2
+#endif
+template <typename T, int L_, bool XIN>
+__global__ void __launch_bounds__(L_ / 2, (L_ <= 1024) ? (sizeof(T) == 4 ? 3 : 2) : 1)
+analysis_kernel(DevTables<T> tb, CodecParams cp, ClipMap cm, const int16_t* __restrict__ pcm,
+                const double* __restrict__ xin, int g0, int nblk, Handoff<T> ho, AnalysisTaps<T> taps,
+                unsigned long long* peak_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int L = L_, NT = L / 2;
+    const int tid = threadIdx.x;
+    Smem<T> sm = carve<T, XIN>(smem_raw, L);
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ NextBlock s_next;
+    if (tid < 64) sm.etab[tid] = tb.exp_tab[tid];
+    for (int i = tid; i < L; i += NT) sm.zb[i] = tb.bark[i];
+    if constexpr (FftShape<L>::pow2) {
+        cpx<T>* dst = const_cast<cpx<T>*>(sm.stL);
+        for (int i = tid; i < stage_entries_of(L); i += NT) dst[i] = tb.tw_stage[i];
+    }
+    if (tid == 0) {
+        s_next.state = 0;
+        mbar_init(&s_mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    unsigned parity = 0;
+    for (int it = blockIdx.x; it < nblk; it += gridDim.x) {
+        const int nx = it + (int)gridDim.x;
+        analysis_block<T, L_, XIN>(sm, tb, cp, cm, pcm, xin, g0, it, nx < nblk ? nx : -1, ho, taps, peak_counter, &s_mbar,
+                                   &s_next, parity);
+        __syncthreads();                     // the next block rewrites what this one's last phase still reads
+    }
+}
+
 }  // namespace
 
 #ifdef MRC_PHASE_CLOCKS
@@ -1278,6 +1361,16 @@ extern "C" int mrc_debug_phase_clocks(unsigned long long* out32, int reset) {
     return 0;
 }
 #endif
+
+static int blocks_per_cta() {          // MRC_BLOCKS_PER_CTA in the environment overrides the built-in value (tuning)
+    static int n = 0;
+    if (n == 0) {
+        const char* e = getenv("MRC_BLOCKS_PER_CTA");
+        n = e ? atoi(e) : MRC_BLOCKS_PER_CTA;
+        if (n < 1) n = 1;
+    }
+    return n;
+}
 
 size_t analysis_smem_bytes(int L, int elem, bool xin) {
     const size_t Q = L / 2;
@@ -1299,7 +1392,9 @@ void launch_analysis(cudaStream_t st, const DevTables<T>& tb, const CodecParams&
 #define MRC_LAUNCH_ANALYSIS_X(LL, XX)                                                                            \
     {                                                                                                            \
         cudaFuncSetAttribute(analysis_kernel<T, LL, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        analysis_kernel<T, LL, XX><<<nblk, LL / 2, smem, st>>>(tb, cp, cm, pcm, xin, g0, ho, taps, peak_counter); \
+        const int grid = XX ? nblk : (nblk + blocks_per_cta() - 1) / blocks_per_cta();                            \
+        analysis_kernel<T, LL, XX><<<grid, LL / 2, smem, st>>>(tb, cp, cm, pcm, xin, g0, nblk, ho, taps,         \
+                                                               peak_counter);                                    \
     }
 #define MRC_LAUNCH_ANALYSIS(LL)                                                                                  \
     case LL:                                                                                                     \
