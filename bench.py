@@ -334,16 +334,22 @@ def main():
                 "launches_per_step": nwaves, "avg_launch_ms": an_ms / nwaves, "ms_per_step": an_ms}
         if cnt:
             flop_key = "fp64_flop_per_block" if is64 else "fp32_flop_per_block"
+            inst = cnt["fp64_thread_inst_per_block" if is64 else "fp32_thread_inst_per_block"]
+            slots = sum(inst.values())                     # an ADD or a MUL takes the pipe slot an FMA would
             ex_flops = cnt[flop_key] * nblk
             ach_tf = ex_flops / (an_ms * 1e-3) / 1e12
             roof.update({
                 "achieved": ach_tf, "frac": ach_tf / peak_tf if peak_tf else None,
+                "frac_pipe_slots": (slots * nblk / (an_ms * 1e-3)) / (peak_tf * 1e12 / 2.0) if peak_tf else None,
                 "traffic": cnt["dram_bytes_per_block"] * nblk / nwaves,
                 "work": "FLOPs the kernel executes: %.0f per block (2 x FMA + ADD + MUL thread instructions of one "
-                        "%d-block launch, ncu, %s) x %d blocks / launch time measured live" %
+                        "%d-block launch, ncu, %s) x %d blocks / the kernel's launch durations measured live inside the step "
+                        "(where it shares the SMs with the cost / reservoir-map / pack kernels of the neighbouring waves); "
+                        "frac_pipe_slots counts FMA, ADD and MUL as one pipe slot each" %
                         (cnt[flop_key], cnt["launch_blocks"], cnt.get("source", "profiles/"), nblk),
                 "ncu_pipe_active_pct": cnt.get("pipe_fp64_active_pct" if is64 else "pipe_fma_active_pct"),
                 "ncu_issue_active_pct": cnt.get("issue_active_pct"),
+                "ncu_launch_ms_alone": cnt.get("launch_ms_under_ncu"),
                 "work_reduction_vs_reference": ref_flops / ex_flops,
                 "reference_formulation_flops_per_step": ref_flops})
         else:

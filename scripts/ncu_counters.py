@@ -44,13 +44,15 @@ def main():
     ap.add_argument("--kernel", default="analysis_kernel<double")
     ap.add_argument("--tag", default="")
     ap.add_argument("--precision", default="fp64", help="key of --out the counters are stored under (fp64 | fp32)")
+    ap.add_argument("--blocks-per-cta", type=int, default=2,
+                    help="blocks one analysis CTA takes (MRC_BLOCKS_PER_CTA of the build): blocks of a launch = grid x this")
     a = ap.parse_args()
     hdr, units, rows = raw_rows(a.full, a.kernel.split("<")[0])
     idx = {h: i for i, h in enumerate(hdr)}
     rows = [x for x in rows if a.kernel in x[idx["Kernel Name"]]]
     r = max(rows, key=lambda x: grid_blocks(x[idx["Grid Size"]]))       # the largest launch captured
     g = lambda name: float(r[idx[name]])
-    blocks = grid_blocks(r[idx["Grid Size"]])
+    blocks = grid_blocks(r[idx["Grid Size"]]) * a.blocks_per_cta
     cyc = g("sm__cycles_elapsed.max")
     per_cycle = lambda op: g("smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op)
     dfma, dadd, dmul = per_cycle("dfma") * cyc, per_cycle("dadd") * cyc, per_cycle("dmul") * cyc
@@ -61,7 +63,7 @@ def main():
         to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
     out = {
         "kernel": r[idx["Kernel Name"]][:80], "source": a.full.replace("gpurun_out/", "profiles/ (summary of) "), "tag": a.tag,
-        "launch_blocks": blocks, "launch_ms_under_ncu": g("gpu__time_duration.sum"),
+        "launch_blocks": blocks, "blocks_per_cta": a.blocks_per_cta, "launch_ms_under_ncu": g("gpu__time_duration.sum"),
         "fp64_thread_inst_per_block": {"dfma": dfma / blocks, "dadd": dadd / blocks, "dmul": dmul / blocks},
         "fp64_flop_per_block": flops / blocks,
         "fp32_thread_inst_per_block": {"ffma": ffma / blocks, "fadd": fadd / blocks, "fmul": fmul / blocks},
@@ -102,7 +104,7 @@ def main():
                 continue                      # e.g. the pipe micro-benchmarks of mrc_measure_peaks
             if short not in best or grid > best[short]["grid"]:
                 best[short] = {"grid": grid, "dram_bytes": b, "time_ns": t}
-        wave_blocks = best.get("analysis_kernel", {}).get("grid", blocks)
+        wave_blocks = best["analysis_kernel"]["grid"] * a.blocks_per_cta if "analysis_kernel" in best else blocks
         out["wave"] = {"blocks": wave_blocks, "kernels": best,
                        "dram_bytes_per_block": sum(v["dram_bytes"] for v in best.values()) / wave_blocks}
     import os

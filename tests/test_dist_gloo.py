@@ -90,7 +90,8 @@ class _FakeShardCodec(object):
         lo = max(first_block - 1, 0) * self.L
         return lo, max(min((first_block + n_blocks) * self.L, total_frames), lo)
 
-    def encode_shard(self, pcm, pcm_frame0, total_frames, first_block, n_blocks, is_first, is_last, recv, send):
+    def encode_shard(self, pcm, pcm_frame0, total_frames, first_block, n_blocks, is_first, is_last, recv, send,
+                     out=None, device_ptrs=None):
         lo, hi = self.shard_pcm_range(total_frames, first_block, n_blocks)
         assert pcm_frame0 <= lo and pcm_frame0 + pcm.shape[0] >= hi
         r = recv()
