@@ -120,15 +120,52 @@ cost_kernel(DevTables<T> tb, CodecParams cp, const HuffDev* __restrict__ huff, C
         acc[2 * p] = acc[2 * p + 1] = 0u;
         accw[2 * p] = accw[2 * p + 1] = 0u;
     }
-    if (tid == 0) {
-        int np_ = 0;
-        for (int bb = 0; bb < nb2; ++bb) {
-            const int ch = bb >= nb, bd = bb - ch * nb;
-            for (int o = 0; o < s_bn[bd]; o += CP) {
-                s_piece[np_++] = make_int4(bb, ch * L + s_blo[bd] + o, min(CP, s_bn[bd] - o), 0);
-            }
+    // Piece list, by one warp: first every full piece (CP lines), then the partial ones from the widest band down -- sizes
+    // descend, so the lanes of a warp (two or three neighbouring pieces at 15 levels each) run the same number of lines and
+    // every round of the item loop below gives all threads about the same work (in band order a warp mixed 4-line and
+    // 32-line pieces, and 30 % of the kernel's stall samples were threads waiting for the longest item).
+    if (warp == 0) {
+        int nfull[2], part[2], tot_full = 0, tot_part = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int bb = lane + 32 * h;
+            const int n = bb < nb2 ? s_bn[bb >= nb ? bb - nb : bb] : 0;
+            nfull[h] = n / CP;
+            part[h] = (n % CP) ? 1 : 0;
         }
-        s_npiece = np_;
+        // exclusive prefix of the full pieces in band order; of the partial ones in reverse band order
+        int fo[2], po[2];
+        {
+            int a = nfull[0], b = nfull[1];
+            int ia = a, ib = b;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb2 = __shfl_up_sync(0xffffffffu, ib, o);
+                if (lane >= o) { ia += ta; ib += tb2; }
+            }
+            const int suma = __shfl_sync(0xffffffffu, ia, 31), sumb = __shfl_sync(0xffffffffu, ib, 31);
+            fo[0] = ia - a; fo[1] = suma + ib - b;
+            tot_full = suma + sumb;
+            int pa = part[0], pb = part[1];
+            int ja = pa, jb = pb;                      // inclusive suffix sums (bands above, then this one)
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ta = __shfl_down_sync(0xffffffffu, ja, o), tb2 = __shfl_down_sync(0xffffffffu, jb, o);
+                if (lane + o < 32) { ja += ta; jb += tb2; }
+            }
+            const int allb = __shfl_sync(0xffffffffu, jb, 0);
+            const int alla = __shfl_sync(0xffffffffu, ja, 0);
+            po[1] = jb - pb;                           // partial pieces of higher bands (all in the second half)
+            po[0] = allb + ja - pa;
+            tot_part = alla + allb;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int bb = lane + 32 * h;
+            if (bb >= nb2) continue;
+            const int ch = bb >= nb, bd = bb - ch * nb, first = ch * L + s_blo[bd];
+            for (int q = 0; q < nfull[h]; ++q) s_piece[fo[h] + q] = make_int4(bb, first + q * CP, CP, 0);
+            if (part[h]) s_piece[tot_full + po[h]] = make_int4(bb, first + nfull[h] * CP, s_bn[bd] % CP, 0);
+        }
+        if (lane == 0) s_npiece = tot_full + tot_part;
     }
     __syncthreads();
     const int nitem = s_npiece * MRC_MAX_LEVELS;
