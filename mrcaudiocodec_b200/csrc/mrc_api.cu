@@ -6,7 +6,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <memory>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -69,6 +72,9 @@ struct mrc_ctx {
     cudaStream_t stream4 = nullptr;                       // D2H copy stream (bitstream of finished waves)
     cudaStream_t stream5 = nullptr;                       // composition of the reservoir maps (forks off stream2)
     int64_t* h_prog = nullptr;                            // pinned: per wave, how far the output is final
+    unsigned char* h_idx = nullptr;                       // pinned: decode's chunk index of the wave being issued (3 slots)
+    size_t h_idx_slot = 0;                                // bytes per slot
+    cudaEvent_t h_idx_ev[3] = {nullptr, nullptr, nullptr};
     int h_prog_cap = 0;
     bool no_tables = false;          // MRC_FLAG_NO_CHAIN_TABLES
     int tab_min_blocks = 512;        // blocks per clip in a wave from which the reservoir maps are tabulated
@@ -1073,6 +1079,9 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream5);
     cudaStreamDestroy(ctx->stream5);
     if (ctx->h_prog) cudaFreeHost(ctx->h_prog);
+    if (ctx->h_idx) cudaFreeHost(ctx->h_idx);
+    for (auto& e : ctx->h_idx_ev)
+        if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MRC_OK;
