@@ -210,12 +210,15 @@ def main():
     codec = Codec(device=local, precision=args.precision, spreading=args.spreading,
                   block_switching=args.block_switching)
     L = codec.L
+    relay = None
     if strong:
         # one stream for the whole job: this rank synthesises only the frames of its block range and their halo
         from mrcaudiocodec_b200 import dist as mdist
+        if os.environ.get("MRC_SHARD_RELAY", "gloo") == "gloo":
+            relay = dist.new_group(backend="gloo")     # the reservoir hand-off (one int, host to host) as a CPU message
         total_frames = int(round(seconds * SR))
         nblk_stream = (total_frames + L - 1) // L
-        blk_lo, blk_hi = mdist.shard_range(nblk_stream, rank, world)
+        blk_lo, blk_hi = mdist.stream_shard_range(nblk_stream, rank, world)
         f_lo, f_hi = codec.shard_pcm_range(total_frames, blk_lo, blk_hi - blk_lo)
         pcm = synth.synth_range(0, f_lo, f_hi, seconds, threads=threads, fast=True)
         frames = pcm.shape[0]
@@ -246,7 +249,7 @@ def main():
 
     def step_device():
         if strong:
-            n, _ = mdist.encode_stream_sharded(codec, None, f_lo, total_frames, device=dev,
+            n, _ = mdist.encode_stream_sharded(codec, None, f_lo, total_frames, device=dev, relay_group=relay,
                                                device_ptrs=(d_pcm.data_ptr(), frames, d_out.data_ptr(), cap))
             return int(n)
         boff = codec.encode_batch_device(d_pcm.data_ptr(), off, d_out.data_ptr(), cap)
@@ -257,7 +260,8 @@ def main():
 
     def step_e2e():
         if strong:
-            blob, _ = mdist.encode_stream_sharded(codec, h_pcm_np, f_lo, total_frames, device=dev, out=h_out_np)
+            blob, _ = mdist.encode_stream_sharded(codec, h_pcm_np, f_lo, total_frames, device=dev, out=h_out_np,
+                                                  relay_group=relay)
             return int(blob.size)
         out, boff = codec.encode_batch(h_pcm_np, off, out=h_out_np)
         last_boff[0] = boff

@@ -65,7 +65,7 @@ struct mrc_ctx {
     uint8_t h_header[4 + 18 + 4 + 2 * MRC_MAX_BANDS];
 
     // scratch (grow only)
-    Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out;
+    Buf clip_off, clip_blk0, clip_bytes, clip_base, clip_res, clip_run, running, overflow, peakctr, res_in, res_out, bound;
     struct WaveSet { Buf lines, bandmax, tokens, ovs, ms, rec, pw, rsv, gmask, cblk, tab, comp, segx, rin; } sets[3];
     Buf q_alloc, q_sf, q_mant;
     cudaStream_t stream2 = nullptr, stream3 = nullptr;    // analysis stream, H2D copy stream
@@ -677,6 +677,9 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
                 if (n > 0) { fn(q, cmq, n); ++launches; }
             }
         };
+        // long stretches of one clip in the wave: the serial walk is the critical path, tabulate the reservoir maps
+        const bool use_tab = job.need_quant && !ctx->no_tables && nblk / (c_hi - c_lo + 1) >= ctx->tab_min_blocks;
+        bool seg_forked = false;
         for_geos([&](int q, const ClipMap& cmq, int n) {
             launch_analysis<T>(st2, tb_of<T>(ctx, q), cpq[q], cmq, job.d_pcm, job.d_xin, g0, n, ho[s], taps,
                                (unsigned long long*)ctx->peakctr.p);
@@ -687,9 +690,6 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
                 launch_cost<T>(st2, tb_of<T>(ctx, q), cpq[q], (const HuffDev*)ctx->huff.p, cmq, g0, n, ho[s],
                                (unsigned char*)ctx->sets[s].rec.p, (unsigned char*)ctx->sets[s].pw.p);
             });
-        // long stretches of one clip in the wave: the serial walk is the critical path, tabulate the reservoir maps
-        const bool use_tab = job.need_quant && !ctx->no_tables && nblk / (c_hi - c_lo + 1) >= ctx->tab_min_blocks;
-        bool seg_forked = false;
         if (use_tab) {
             // The reservoir maps (per block, then composed over segments) only feed the serial pass: they run on a stream of
             // their own that forks off after the cost kernel, so that the next wave's analysis does not queue behind them
@@ -716,6 +716,26 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         CK(cudaStreamWaitEvent(st, ev(w, 2), 0));
         if (seg_forked) CK(cudaStreamWaitEvent(st, ev(w, 11), 0));
         int32_t shard_res = 0;
+        // A shard that is not the stream's first walks AHEAD of its reservoir: the serial pass runs from a guessed value
+        // while the shards before it are still at work, leaving the reservoir at every segment boundary; when the true value
+        // arrives, a second pass walks from it only until it meets that trajectory (the maps contract: a segment or two),
+        // and the reservoir for the next shard is known without another pass over the whole shard.  Exact: from a common
+        // value on, the two walks are the same walk.
+        const bool ahead = job.exchange && job.shard && !job.shard_header && job.need_quant && use_tab && seg_S > 0 && nc == 1 &&
+                           nwaves == 1 && !getenv("MRC_SHARD_NO_SPECULATION");
+        int* d_bound = nullptr;
+        if (ahead) {
+            const size_t nseg = ((size_t)nblk + seg_S - 1) / seg_S;
+            CK(ensure(ctx->bound, (nseg + 1) * 4));
+            d_bound = (int*)ctx->bound.p;
+            const int32_t guess = 512;
+            CK(cudaMemcpyAsync(ctx->res_in.p, &guess, 4, cudaMemcpyHostToDevice, st));
+            launch_chain_seg(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, seg_S, io[s], r_lo, ntab, tabw,
+                             (const int*)ctx->sets[s].tab.p, segw, (const int*)ctx->sets[s].comp.p,
+                             (const int*)ctx->sets[s].segx.p, (int*)ctx->sets[s].rin.p, d_res_in, d_res_out,
+                             (unsigned long long*)ctx->peakctr.p + 4, d_bound, nullptr);
+            ++launches;
+        }
         if (job.exchange) {
             // everything that does not depend on the reservoir is done (or running); now wait for the shard before us
             CK(cudaStreamSynchronize(st));
@@ -725,7 +745,15 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         }
         CK(cudaEventRecord(ev(w, 3), st));
         if (job.need_quant) {
-            if (use_tab && seg_S > 0) {
+            if (ahead) {
+                if (shard_res != 512) {
+                    launch_chain_seg(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, seg_S, io[s], r_lo, ntab, tabw,
+                                     (const int*)ctx->sets[s].tab.p, segw, (const int*)ctx->sets[s].comp.p,
+                                     (const int*)ctx->sets[s].segx.p, (int*)ctx->sets[s].rin.p, d_res_in, d_res_out,
+                                     (unsigned long long*)ctx->peakctr.p + 4, nullptr, d_bound);
+                    ++launches;
+                }
+            } else if (use_tab && seg_S > 0) {
                 launch_chain_seg(st, cp, cm, c_lo, c_hi - c_lo + 1, g0, nblk, seg_S, io[s], r_lo, ntab, tabw,
                                  (const int*)ctx->sets[s].tab.p, segw, (const int*)ctx->sets[s].comp.p,
                                  (const int*)ctx->sets[s].segx.p, (int*)ctx->sets[s].rin.p, d_res_in, d_res_out,
@@ -878,6 +906,8 @@ int run_encode_t(mrc_ctx* ctx, const EncodeJob& job) {
         fprintf(stderr, "serial pass: %llu complete walks, %llu blocks stepped one by one, %llu segments through pairs, %llu by "
                 "closed form; walked through: %llu not followed, %llu not anticipated, %llu straddling clips\n", pk[4], pk[5], pk[6], pk[7],
                 pk[8], pk[9], pk[10]);
+        if (job.shard) fprintf(stderr, "shard walked ahead of its reservoir: met the guessed trajectory after %llu segment(s) "
+                               "(0: not met, or not walked ahead)\n", pk[11]);
         for (int w = 0; w < nwaves; ++w) {
             float t[6];
             for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], ev(0, 0), ev(w, k));
@@ -1057,7 +1087,7 @@ int32_t mrc_destroy(mrc_ctx* ctx) {
         for (Buf* b : gb) release(*b);
     }
     Buf* all[] = {&ctx->huff, &ctx->header, &ctx->clip_off, &ctx->clip_blk0, &ctx->clip_bytes,
-                  &ctx->clip_base, &ctx->running, &ctx->overflow, &ctx->peakctr, &ctx->res_in, &ctx->res_out,
+                  &ctx->clip_base, &ctx->running, &ctx->overflow, &ctx->peakctr, &ctx->res_in, &ctx->res_out, &ctx->bound,
                   &ctx->clip_res, &ctx->clip_run, &ctx->q_alloc, &ctx->q_sf, &ctx->q_mant,
                   &ctx->tap_lines, &ctx->tap_smr, &ctx->tap_npk, &ctx->pcm_dev, &ctx->out_dev, &ctx->xin_dev,
                   &ctx->sb0, &ctx->peaks, &ctx->flags, &ctx->blk_start, &ctx->blk_geom, &ctx->blk_list};

@@ -627,7 +627,8 @@ chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int 
                  int tabw, const int* __restrict__ tab, int segw, const int* __restrict__ comp,
                  const int* __restrict__ segx, int* __restrict__ rin, int fb_blocks,
                  const int32_t* __restrict__ reservoir_in, int32_t* __restrict__ reservoir_out,
-                 unsigned long long* __restrict__ iter_counter) {
+                 unsigned long long* __restrict__ iter_counter, int* __restrict__ bound_rec,
+                 const int* __restrict__ bound_ref) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[CS_STAGES + 1];
     const int lane = threadIdx.x;
@@ -660,9 +661,18 @@ chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int 
     int R = (b_lo == 0) ? (reservoir_in ? reservoir_in[clip] : 0) : io.clip_res[clip];
     unsigned n_slow = 0, n_blk = 0, n_pair = 0, n_closed = 0, n_esc = 0, n_nopair = 0, n_impure = 0, fb_parity = 0, dummy = 0;
     int lb = lb_lo;
+    const int nseg_all = (nblk_wave + S - 1) / S;
+    bool merged = false;
     while (lb < lb_hi) {
         int end;
         const int seg = lb / S;
+        // A shard that walks ahead of its reservoir (bound_rec: from a guessed value) leaves the reservoir at every segment
+        // boundary; the walk from the true value (bound_ref) stops where it meets that trajectory: from a common value on
+        // the two walks are the same, and everything the guessed one wrote beyond that point stands.
+        if (lb % S == 0) {
+            if (bound_ref && bound_ref[seg] == R) { merged = true; break; }
+            if (bound_rec && lane == 0) bound_rec[seg] = R;
+        }
         if (lb % S == 0 && seg >= seg_first && seg < seg_lim) {
             const int k = seg - seg_first, st = k % CS_STAGES;
             mbar_wait(&s_bar[st], (unsigned)((k / CS_STAGES) & 1));
@@ -692,6 +702,7 @@ chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int 
             if (!pure) ++n_impure;
             else if ((unsigned)idx < (unsigned)ntab) ++n_esc;
             else ++n_nopair;
+            if (lane == 0) rin[seg] = RIN_NONE;      // (a walk from a guessed reservoir may have stepped over it)
             end = seg_end;
         } else {
             end = min((seg + 1) * S, lb_hi);         // a piece of a segment shared with another clip or wave edge
@@ -741,6 +752,14 @@ chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int 
         }
         lb = end;
     }
+    if (merged) {
+        // rows still on their way into this CTA's shared memory must land before it is given up
+        const int sg0 = max(lb / S, seg_first), sg1 = min(seg_lim, lb / S + CS_STAGES);
+        for (int sg = sg0; sg < sg1; ++sg) {
+            const int k = sg - seg_first;
+            mbar_wait(&s_bar[k % CS_STAGES], (unsigned)((k / CS_STAGES) & 1));
+        }
+    }
     if (lane == 0) {
         if (iter_counter) {
             atomicAdd(iter_counter, (unsigned long long)n_slow);           // complete walks taken by the serial pass
@@ -751,8 +770,11 @@ chain_seg_kernel(CodecParams cp, ClipMap cm, int c0, int g0, int nblk_wave, int 
             atomicAdd(iter_counter + 5, (unsigned long long)n_nopair);     // entered outside the range, value not anticipated
             atomicAdd(iter_counter + 6, (unsigned long long)n_impure);
         }
+        if (merged) R = bound_ref[nseg_all];          // where the guessed walk ended
+        if (bound_rec) bound_rec[nseg_all] = R;
         io.clip_res[clip] = R;
         if (b_hi == nblk_clip && reservoir_out) reservoir_out[clip] = R;
+        if (bound_ref && iter_counter) atomicAdd(iter_counter + 7, (unsigned long long)(merged ? lb / S + 1 : 0));
     }
 }
 
@@ -922,7 +944,7 @@ void launch_segments(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, 
 void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
                       int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp,
                       const int* segx, int* rin, const int32_t* reservoir_in, int32_t* reservoir_out,
-                      unsigned long long* iter_counter) {
+                      unsigned long long* iter_counter, int* bound_rec, const int* bound_ref) {
     if (nclips <= 0 || nblk <= 0) return;
     // shared memory: the ring of composed rows + as many per-block tables as fit (at most CS_FB, at least one)
     const size_t ring = (size_t)CS_STAGES * ((size_t)segw * 4 + SEGX_W * 4), tb = (size_t)2 * tabw * 4;
@@ -931,7 +953,7 @@ void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm,
     const size_t smem = ring + (size_t)fbn * tb;
     cudaFuncSetAttribute(chain_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     chain_seg_kernel<<<nclips, 32, smem, st>>>(cp, cm, c0, g0, nblk, S, io, r_lo, ntab, tabw, tab, segw, comp, segx, rin, fbn,
-                                               reservoir_in, reservoir_out, iter_counter);
+                                               reservoir_in, reservoir_out, iter_counter, bound_rec, bound_ref);
 }
 
 void launch_expand(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int S, ChainIO io, int r_lo,

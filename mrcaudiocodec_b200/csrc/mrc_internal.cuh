@@ -218,7 +218,9 @@ void launch_segments(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, 
 void launch_chain_seg(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int c0, int nclips, int g0, int nblk,
                       int S, ChainIO io, int r_lo, int ntab, int tabw, const int* tab, int segw, const int* comp,
                       const int* segx, int* rin, const int32_t* reservoir_in, int32_t* reservoir_out,
-                      unsigned long long* iter_counter);
+                      unsigned long long* iter_counter, int* bound_rec = nullptr, const int* bound_ref = nullptr);
+// bound_rec [nseg + 1]: the walk leaves the reservoir at every segment boundary and, last, its result (a shard walking
+// ahead from a guessed reservoir); bound_ref: the walk from the true reservoir stops where it meets that trajectory
 // the parallel replay of the stepped-over segments (after launch_chain_seg; nothing the next shard waits for)
 void launch_expand(cudaStream_t st, const CodecParams& cp, const ClipMap& cm, int g0, int nblk, int S, ChainIO io, int r_lo,
                    int ntab, int tabw, const int* tab, const int* rin);

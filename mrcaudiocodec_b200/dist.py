@@ -27,6 +27,25 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def stream_shard_range(n_blocks, rank, world, hop_blocks=360):
+    """Block range [lo, hi) of `rank` when ONE stream is sharded over `world` ranks.  The reservoir reaches rank r one
+    hand-off later than rank r - 1, so later ranks have that much longer for the work that does not depend on it: rank r
+    gets hop_blocks more blocks than rank r - 1 (one hand-off, ~0.1 ms, is worth ~360 blocks of analysis on a B200), so
+    that every rank is ready about when its reservoir arrives.  (The first rank is no exception: its serial pass takes as
+    long as the pass the others run ahead of their reservoir.  Giving it fewer blocks was measured and only moved the wait
+    to the last rank.)  Short streams (fewer than 4096 blocks per rank) are split evenly."""
+    n_blocks, world = int(n_blocks), int(world)
+    if world <= 1 or n_blocks < world * 4096 or hop_blocks <= 0:
+        return shard_range(n_blocks, rank, world)
+    base = (n_blocks - hop_blocks * world * (world - 1) // 2) // world
+    sizes = [base + hop_blocks * r for r in range(world)]
+    rest = n_blocks - sum(sizes)                   # 0 <= rest < world: the last ranks take one more
+    for r in range(world - rest, world):
+        sizes[r] += 1
+    lo = sum(sizes[:rank])
+    return lo, lo + sizes[rank]
+
+
 def shard_sizes(n_items, world):
     return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
 
@@ -83,30 +102,37 @@ def write_concatenated(path, blobs, offsets, rank, world):
 
 
 def encode_stream_sharded(codec, pcm_shard, pcm_frame0, total_frames, group=None, device=None, out=None,
-                          device_ptrs=None):
+                          device_ptrs=None, relay_group=None):
     """One stream of total_frames frames encoded by all ranks, rank r taking the block range
-    shard_range(ceil(total_frames / L), r, world).  pcm_shard: int16 [frames, 2] starting at stream frame pcm_frame0 and
+    stream_shard_range(ceil(total_frames / L), r, world).  pcm_shard: int16 [frames, 2] starting at stream frame pcm_frame0 and
     covering codec.shard_pcm_range(total_frames, first_block, n_blocks) (each rank only needs its own range: generate or
     read per rank).  Returns (this rank's bytes, shard byte offsets int64 [world + 1]): rank r's bytes belong at
-    offsets[r] of the .pac file."""
+    offsets[r] of the .pac file.  relay_group: a process group with a CPU backend (gloo) for the hand-off of the reservoir
+    -- the value is on the host on both sides anyway (the library's callbacks), so a CPU message saves the device round
+    trip of an NCCL send/recv pair; default: point-to-point messages on `group`."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     nblk = (int(total_frames) + codec.L - 1) // codec.L
-    lo, hi = shard_range(nblk, rank, world)
-    box = torch.zeros(1, dtype=torch.int32, device=device)
+    lo, hi = stream_shard_range(nblk, rank, world)
+    if relay_group is not None:
+        box = torch.zeros(1, dtype=torch.int32)
+        pg = relay_group
+    else:
+        box = torch.zeros(1, dtype=torch.int32, device=device)
+        pg = group
 
     def recv():
         if rank == 0:
             return 0
-        dist.recv(box, src=rank - 1, group=group)
+        dist.recv(box, src=rank - 1, group=pg)
         return int(box.item())
 
     def send(r):
         if rank + 1 < world:
             box.fill_(int(r))
-            dist.send(box, dst=rank + 1, group=group)
+            dist.send(box, dst=rank + 1, group=pg)
 
     blob = codec.encode_shard(pcm_shard, pcm_frame0, total_frames, lo, hi - lo, rank == 0, rank == world - 1, recv, send,
                               out=out, device_ptrs=device_ptrs)

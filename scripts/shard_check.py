@@ -26,7 +26,7 @@ def main():
     L = codec.L
     total = int(round(seconds * 48000)) - 777                      # ragged tail
     nblk = (total + L - 1) // L
-    lo, hi = mdist.shard_range(nblk, rank, world)
+    lo, hi = mdist.stream_shard_range(nblk, rank, world)
     f0, f1 = codec.shard_pcm_range(total, lo, hi - lo)
     pcm = synth.synth_range(0, f0, f1, seconds, threads=4, fast=True)[:max(0, min(f1, total) - f0)]
     blob, offsets = mdist.encode_stream_sharded(codec, pcm, f0, total, device=dev)

@@ -81,6 +81,23 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_stream_shard_range_partitions():
+    """block ranges of one sharded stream: contiguous, complete, even for short streams, and for long ones every rank
+    gets one hand-off's worth of blocks more than the rank before it"""
+    from mrcaudiocodec_b200 import dist as mdist
+    for n in (0, 3, 4095, 8192, 32767, 32768, 33000, 168751, 1 << 20):
+        for w in (1, 2, 3, 8):
+            r = [mdist.stream_shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert min(sizes) >= 0
+            if w == 1 or n < w * 4096:
+                assert max(sizes) - min(sizes) <= 1
+            else:
+                assert all(0 <= sizes[i + 1] - sizes[i] - 360 <= 1 for i in range(w - 1)), sizes
+
+
 class _FakeShardCodec(object):
     """stands in for Codec.encode_shard: the "reservoir" a shard hands on is a running checksum of the block indices it
     was given, so the test sees both the block ranges and the order of the hand-offs"""
@@ -111,7 +128,7 @@ def _shard_worker(rank, world, port, total_frames, tmp):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     codec = _FakeShardCodec()
     nblk = (total_frames + codec.L - 1) // codec.L
-    lo, hi = mdist.shard_range(nblk, rank, world)
+    lo, hi = mdist.stream_shard_range(nblk, rank, world)
     f0, f1 = codec.shard_pcm_range(total_frames, lo, hi - lo)
     pcm = np.zeros((f1 - f0, 2), np.int16)
     blob, offsets = mdist.encode_stream_sharded(codec, pcm, f0, total_frames)

@@ -50,6 +50,48 @@ def test_one_hour_stream_properties():
     c.close()
 
 
+def test_decode_scouts_change_nothing(monkeypatch):
+    """The host's walk over the <L nBytes> chain with scouts (worker threads that walk later byte ranges ahead of the
+    parser, from guessed chunk starts) and without: same PCM on a valid stream; on a stream whose length prefixes are
+    damaged inside a scouted range, the same error, or the same PCM where the damage still parses (a prefix changed so
+    that the chain lands on a later chunk start)."""
+    from mrcaudiocodec_b200 import Codec, synth, pacfile, _lib
+    pcm = synth.synth_clip(3, 240.0, threads=8, fast=True)           # ~7.7 MB of .pac: three scouted ranges
+    c = Codec()
+    blob = c.encode_clips([pcm])[0]
+    idx = pacfile.chunk_index(blob)
+
+    def run(b, scouts):
+        monkeypatch.setenv("MRC_DECODE_SCOUTS", str(scouts))
+        try:
+            return c.decode_clips([b])[0]
+        except _lib.MrcError as e:
+            return (e.code, str(e))
+
+    ref = run(blob, 0)
+    for k in (1, 3, 8):
+        got = run(blob, k)
+        assert isinstance(got, np.ndarray) and np.array_equal(got, ref)
+    # also as one clip of a batch next to small ones (exact scouts at clip starts)
+    monkeypatch.setenv("MRC_DECODE_SCOUTS", "4")
+    small = c.encode_clips([pcm[:48000], pcm[48000:2 * 48000]])
+    multi = c.decode_clips([small[0], blob, small[1], blob])
+    assert np.array_equal(multi[1], ref) and np.array_equal(multi[3], ref)
+    assert np.array_equal(multi[0], run(small[0], 0)) and np.array_equal(multi[2], run(small[1], 0))
+    for frac in (0.3, 0.55, 0.9):
+        off, n = idx[int(frac * len(idx)) | 1]                        # a pair's second chunk, deep inside the stream
+        bad = bytearray(blob)
+        bad[off - 4:off] = (n + 1 << 20).to_bytes(4, "little")        # prefix far too long
+        a, b = run(bytes(bad), 0), run(bytes(bad), 6)
+        assert isinstance(a, tuple) and a == b, (a, b)
+        bad = bytearray(blob)
+        bad[off - 4:off] = (n - 1).to_bytes(4, "little")              # one byte short: the chain falls between chunks
+        a, b = run(bytes(bad), 0), run(bytes(bad), 6)
+        assert type(a) is type(b)
+        assert a == b if isinstance(a, tuple) else np.array_equal(a, b)
+    c.close()
+
+
 def test_batch_of_clips_equals_singles():
     from mrcaudiocodec_b200 import Codec, synth
     n_clips = int(os.environ.get("MRC_FULLSIZE_CLIPS", "96"))
