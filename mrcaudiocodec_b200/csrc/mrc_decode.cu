@@ -98,23 +98,41 @@ __device__ __forceinline__ void synthesize(const DevTables<T>& tb, const CodecPa
         const int grp = tid / (NT / 2), lt = tid - grp * (NT / 2), gthr = NT / 2;
         const T* X = sm.lines + grp * L;
         cpx<T>* a = sm.buf + grp * Q;
-        // FFT twiddles staged in `v` (written only after the transform): three twiddle loads per butterfly and stage
-        // from shared memory instead of through L1
-        cpx<T>* const tws = reinterpret_cast<cpx<T>*>(sm.v);
-        for (int i = tid; i < (1 << (tb.logLtab - 1)); i += NT) tws[i] = tb.tw_fft[i];
-        for (int n = lt; n < Q; n += gthr) {
-            const T re = X[2 * n], im = X[L - 1 - 2 * n];
-            const cpx<T> w = tb.tw_pre[n];
-            const int r = fft_pos<Q>(n);
-            a[r].x = re * w.x - im * w.y;
-            a[r].y = re * w.y + im * w.x;
+        // Power-of-two L: the analysis kernel's conflict-free transform (mrc_fft.cuh: swizzled work buffer, per-stage
+        // twiddle tables, lane-mapped input placement); the stage tables of the L/2-point transform are staged in `v`
+        // (written only after the transform).  9 * 2^p lines (transition blocks): the root table, as before.
+        if constexpr (FftShape<L>::pow2) {
+            constexpr int LOGQ = FftShape<L>::logP - 1;
+            cpx<T>* const st = reinterpret_cast<cpx<T>*>(sm.v);
+            for (int i = tid; i < fft_stage_entries(LOGQ); i += NT) st[i] = tb.tw_stage[fft_stage_entries(LOGQ + 1) + i];
+            for (int i = lt; i < Q; i += gthr) {
+                const int n = fft_place_index<LOGQ>(i);
+                const T re = X[2 * n], im = X[L - 1 - 2 * n];
+                const cpx<T> w = tb.tw_pre[n];
+                cpx<T> t;
+                t.x = re * w.x - im * w.y;
+                t.y = re * w.y + im * w.x;
+                a[fft_swz<T>(fft_r4_pos(n, LOGQ))] = t;
+            }
+            __syncthreads();
+            fft_sw<T, LOGQ>(a, lt, gthr, st);
+        } else {
+            cpx<T>* const tws = reinterpret_cast<cpx<T>*>(sm.v);
+            for (int i = tid; i < (1 << (tb.logLtab - 1)); i += NT) tws[i] = tb.tw_fft[i];
+            for (int n = lt; n < Q; n += gthr) {
+                const T re = X[2 * n], im = X[L - 1 - 2 * n];
+                const cpx<T> w = tb.tw_pre[n];
+                const int r = fft_pos<Q>(n);
+                a[r].x = re * w.x - im * w.y;
+                a[r].y = re * w.y + im * w.x;
+            }
+            __syncthreads();
+            fft_any<T, Q>(a, lt, gthr, tws, tb.logLtab, tb.tw9, L, tb.w9);
         }
-        __syncthreads();
-        fft_any<T, Q>(a, lt, gthr, tws, tb.logLtab, tb.tw9, L, tb.w9);
         T* v = sm.v + grp * L;
         for (int k = lt; k < Q; k += gthr) {
             const cpx<T> w = tb.tw_post[k];
-            const cpx<T> t = a[k];
+            const cpx<T> t = a[FftShape<L>::pow2 ? fft_swz<T>(k) : k];
             v[2 * k] = t.x * w.x - t.y * w.y;
             v[L - 1 - 2 * k] = -(t.x * w.y + t.y * w.x);
         }
