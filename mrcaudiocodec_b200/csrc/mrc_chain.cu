@@ -240,7 +240,7 @@ constexpr int TAB_THREADS = 256;
 
 __global__ void __launch_bounds__(TAB_THREADS)
 table_kernel(CodecParams cp, ClipMap cm, int g0, ChainIO io, int r_lo, int ntab, int tabw, int* __restrict__ tab) {
-    __shared__ uint32_t s_tn[MRC_NSLOT];
+    __shared__ uint2 s_nc[MRC_NSLOT];            // per token: lines of its band (never granted: INT_MAX), bits it costs
     __shared__ uint32_t s_dsp[MRC_NSLOT];
     __shared__ uint4 s_dpc[MRC_NSLOT];
     __shared__ int s_mx[32];
@@ -263,7 +263,9 @@ table_kernel(CodecParams cp, ClipMap cm, int g0, ChainIO io, int r_lo, int ntab,
     }
     if (tid < 32) s_mx[tid] = mx[tid];
     for (int j = tid; j < MRC_NSLOT; j += TAB_THREADS) {
-        s_tn[j] = tn[j];
+        const uint32_t t = tn[j];
+        const unsigned n = t >> 16;
+        s_nc[j] = (t == INVALID_TOKEN) ? make_uint2(0x7fffffffu, 0u) : make_uint2(n, (t & 0xff00u) ? n : 2u * n);
         const int j1 = (j + 1 < MRC_NSLOT) ? j + 1 : j;          // the last slot is never a token
         s_dsp[j] = cpre[j1] - cpre[j];
         s_dpc[j] = sub4(pc[j1], pc[j]);
@@ -287,9 +289,8 @@ table_kernel(CodecParams cp, ClipMap cm, int g0, ChainIO io, int r_lo, int ntab,
             // first chunk the smallest budget of this warp (lane 0's) cannot fully pay: everything before it is granted
             // for all 32 budgets, and the prefix sums at its start stand for that
             const int b0min = __shfl_sync(0xffffffffu, B0, 0);
-            int klo = nck - 1;
-            for (int k = nck - 1; k >= 0; --k)
-                if (s_mx[k0 + k] > b0min) klo = k;
+            const unsigned over = __ballot_sync(0xffffffffu, (tid & 31) < nck && s_mx[k0 + (tid & 31)] > b0min);
+            const int klo = over ? __ffs(over) - 1 : nck - 1;
             const int j0 = (k0 + klo) * 32;
             const unsigned sp0 = cpre[j0];
             const uint4 pc0 = pc[j0];
@@ -298,16 +299,22 @@ table_kernel(CodecParams cp, ClipMap cm, int g0, ChainIO io, int r_lo, int ntab,
             int rem = B0 - (int)((sp0 & 0xffffu) + (sp0 >> 16));
             for (int jb = j0; jb < jend; jb += 16) {
                 if (__all_sync(0xffffffffu, rem < min_nl)) break;
-#pragma unroll 4
-                for (int j = jb; j < jb + 16; ++j) {
-                    const uint32_t t = s_tn[j];
-                    if (t == INVALID_TOKEN) continue;
-                    const int n = (int)(t >> 16);
-                    if (n <= rem) {
-                        rem -= (t & 0xff00u) ? n : 2 * n;
-                        gt.spent += s_dsp[j];
-                        gt.cost = add4(gt.cost, s_dpc[j]);
+                // which of the 16 tokens this budget grants: one load, one compare, one subtraction and one mask bit each;
+                // the sums of what was granted -- few tokens past the first refusal -- are added afterwards
+                unsigned granted = 0u;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint2 nc = s_nc[jb + i];
+                    if ((int)nc.x <= rem) {
+                        rem -= (int)nc.y;
+                        granted |= 1u << i;
                     }
+                }
+                while (granted) {
+                    const int j = jb + __ffs(granted) - 1;
+                    granted &= granted - 1;
+                    gt.spent += s_dsp[j];
+                    gt.cost = add4(gt.cost, s_dpc[j]);
                 }
             }
             if (idx < ntab) {
