@@ -38,6 +38,8 @@ def stream_shard_range(n_blocks, rank, world, hop_blocks=360):
     if world <= 1 or n_blocks < world * 4096 or hop_blocks <= 0:
         return shard_range(n_blocks, rank, world)
     base = (n_blocks - hop_blocks * world * (world - 1) // 2) // world
+    if base < 8 * hop_blocks:                      # many ranks on a short stream: the skew would eat the first shards
+        return shard_range(n_blocks, rank, world)
     sizes = [base + hop_blocks * r for r in range(world)]
     rest = n_blocks - sum(sizes)                   # 0 <= rest < world: the last ranks take one more
     for r in range(world - rest, world):
