@@ -103,8 +103,8 @@ __host__ __device__ constexpr int fft_stage_entries(int logn) {
 }
 
 // Which input goes where, lane by lane.  Thread index idx (0 .. n-1 over the threads and their trips) handles input
-// element place_index(idx); it is stored at fft_swz(fft_r4_pos(.)).  For n >= 512 the map is chosen so that a warp
-// reads 32 consecutive inputs while the 8 lanes of every quarter warp write 8 different bank slots: the three input
+// element place_index(idx); it is stored at fft_swz(fft_r4_pos(.)).  For n >= 512 the map is chosen so that the 8 lanes
+// of every quarter warp read 8 consecutive inputs and write 8 different bank slots: the three input
 // bits that the digit reversal sends to the lowest three output bits are the lane's low bits XORed with three bits of
 // the warp index (a bijection of 0 .. n-1).
 template <int LOGN>

@@ -112,3 +112,75 @@ def test_pcm_division_by_reciprocal_is_exact():
         r = float(r_exact)
         assert F(r) == r_exact
         assert float(F(y0) + F(r) * F(rcp)) == q / 65535.0
+
+
+def _fft_r4_pos(n, logn):
+    """mrc_fft.cuh: fft_r4_pos -- digit reversal in radix 4 with one innermost radix-2 digit when logn is odd"""
+    m2 = logn & ~1
+    t = n & ((1 << m2) - 1)
+    b = int(format(t, "0%db" % m2)[::-1], 2) if m2 else 0
+    b = ((b & 0xaaaaaaaa) >> 1) | ((b & 0x55555555) << 1)
+    return ((n >> m2) | (b << 1)) if (logn & 1) else b
+
+
+def _fft_swz(e, elem):
+    """mrc_fft.cuh: fft_swz<double> (16-byte elements) / fft_swz<float> (8-byte elements)"""
+    if elem == 16:
+        return e ^ (((e >> 3) & 1) * 3) ^ (((e >> 4) & 1) * 6)
+    return e ^ (((e >> 4) & 1) * 5) ^ (((e >> 5) & 1) * 10)
+
+
+def _fft_place_index(idx, logn):
+    """mrc_fft.cuh: fft_place_index"""
+    if logn < 9:
+        return idx
+    lane, hi = idx & 31, idx >> 5
+    y, rest = (lane ^ hi) & 7, hi >> 3
+    if logn == 9:
+        return lane | ((rest & 1) << 5) | (y << 6)
+    if logn == 10:
+        return lane | ((rest & 1) << 5) | ((y & 1) << 6) | (((rest >> 1) & 1) << 7) | ((y >> 1) << 8)
+    return lane | ((rest & 7) << 5) | (y << 8) | ((rest >> 3) << 11)
+
+
+def test_fft_swizzle_and_placement_are_conflict_free():
+    """The index maps of the analysis kernel's transforms (mrc_fft.cuh), restated here: the swizzle is a bijection that
+    is linear over GF(2); in every access pattern of the transform the lanes that share a shared-memory wavefront -- 8 for
+    16-byte elements (fp64), 16 for 8-byte ones (fp32) -- hit that many different bank slots; the input placement is a
+    bijection whose quarter warps read 8 different slots and write 8 different slots."""
+    for elem, group in ((16, 8), (8, 16)):
+        swz = lambda e: _fft_swz(e, elem)
+        for logn in (6, 7, 8, 9, 10, 11):
+            n = 1 << logn
+            assert sorted(swz(e) for e in range(n)) == list(range(n))
+            assert all(swz(a ^ b) == swz(a) ^ swz(b) for a in range(0, n, 7) for b in (1, 2, 3, 5, 64, n >> 1))
+            slots = lambda es: len({swz(e) % group for e in es})
+            if logn & 1:        # radix-2 stage: butterfly q of a warp covers elements 2q, 2q + 1
+                for leg in (0, 1):
+                    for q0 in range(0, n // 2, group):
+                        assert slots(2 * (q0 + l) + leg for l in range(group)) == group
+            h = 2 if (logn & 1) else 1
+            while 4 * h <= n:
+                logh = h.bit_length() - 1
+                for leg in range(4):
+                    for b0 in range(0, n // 4, group):
+                        es = []
+                        for l in range(group):
+                            bi = b0 + l
+                            j = bi & (h - 1)
+                            es.append((((bi >> logh) << (logh + 2)) + j) + leg * h)
+                        assert slots(es) == group, (elem, logn, h, leg)
+                h *= 4
+    # placement (fp64: the lanes of a quarter warp read 8 consecutive inputs and write 8 different slots)
+    for logn in (9, 10, 11):
+        n = 1 << logn
+        src = [_fft_place_index(i, logn) for i in range(n)]
+        assert sorted(src) == list(range(n))
+        for q0 in range(0, n, 8):
+            reads = src[q0:q0 + 8]
+            assert len({r % 8 for r in reads}) == 8
+            writes = [_fft_swz(_fft_r4_pos(r, logn), 16) for r in reads]
+            assert len({w % 8 for w in writes}) == 8
+        for w0 in range(0, n, 32):      # a warp reads 32 consecutive inputs
+            assert sorted(src[w0:w0 + 32]) == list(range(min(src[w0:w0 + 32]), min(src[w0:w0 + 32]) + 32)) or \
+                len({s & 31 for s in src[w0:w0 + 32]}) == 32
