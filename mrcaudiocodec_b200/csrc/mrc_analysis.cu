@@ -64,9 +64,11 @@ namespace {
 
 constexpr int MRC_ZLUT = 832;         // cells of 1/32 Bark: Bark(24 kHz) = 24.6
 #ifndef MRC_NEAR_LOUD_N
-#define MRC_NEAR_LOUD_N 4
+#define MRC_NEAR_LOUD_N 2
 #endif
 constexpr int MRC_NEAR_LOUD = MRC_NEAR_LOUD_N;     // loud maskers included in the pass-1 bound of a line's threshold
+// (any number is exact: it only decides how tight the bound is.  30 min of the bench stream, audio-s/s and 10**x pairs per
+// hour: 6 -> 55.8 k / 1.78 G, 4 -> 56.4 k / 1.26 G, 3 -> 56.6 k / 1.00 G, 2 -> 56.8 k / 0.73 G; scripts/lib_variant_bench.py)
 
 // What pass 1 leaves per line for pass 2: an UPPER bound of the line's rho (rounded up to float: it only selects
 // candidates) and the line's position among the maskers (m_lo | m_hi << 16), so that the warp that completes a line's
