@@ -38,11 +38,12 @@ def write_wav(path, sr, pcm):
         w.writeframes(np.ascontiguousarray(pcm, dtype="<i2").tobytes())
 
 
-def _codec(sr, args, L=1024, tbps=None, switching=False):
+def _codec(sr, args, L=1024, tbps=None, switching=False, n_scale_bits=4, n_mant_size_bits=4):
     from .codec import Codec
     if tbps is None:
         tbps = args.kbps * 1000.0 / sr
-    return Codec(sample_rate=sr, n_mdct_lines=L, target_bits_per_sample=tbps, joint=not args.independent,
+    return Codec(sample_rate=sr, n_mdct_lines=L, n_scale_bits=n_scale_bits, n_mant_size_bits=n_mant_size_bits,
+                 target_bits_per_sample=tbps, joint=not args.independent,
                  precision=args.precision, device=args.device,
                  block_switching=switching, switch_tables=(L == 1024))
 
@@ -62,8 +63,11 @@ def cmd_decode(args):
     from . import pacfile
     blob = open(args.input, "rb").read()
     h = pacfile.parse_header(blob)
-    # the bit rate is not needed to decode; any value builds the same tables
-    c = _codec(h["sampleRate"], args, L=h["nMDCTLines"], tbps=2.0)
+    # the bit rate is not needed to decode; any value builds the same tables.  Field widths come from the header
+    # (pacfileThem.py:161-176 reads nScaleBits / nMantSizeBits there: the reference's training files use 3 / 5); the
+    # header's band table must equal the one the sample rate and block size give (the library checks it)
+    c = _codec(h["sampleRate"], args, L=h["nMDCTLines"], tbps=2.0, n_scale_bits=h["nScaleBits"],
+               n_mant_size_bits=h["nMantSizeBits"])
     pcm = c.decode_clips([blob])[0]
     c.close()
     write_wav(args.output, h["sampleRate"], pcm)
