@@ -403,7 +403,7 @@ def main():
                                         "gbs_at_this_step_rate": wv["dram_bytes_per_block"] * nblk /
                                         (1e-3 * 1000.0 * r_dev["dev"] / args.steps) / 1e9,
                                         "source": "ncu dram__bytes of every kernel of one %d-block wave (%s)" %
-                                                  (wv["blocks"], cnt.get("source", "profiles/"))}
+                                                  (wv["blocks"], wv.get("source") or cnt.get("source", "profiles/"))}
         if args.block_switching:
             line["config"]["workload"] += (", BLOCK SWITCHING on (transient detector + look-ahead, short blocks of 128: "
                                            "%d blocks written for %d blocks of 1024 frames)" %
