@@ -409,7 +409,8 @@ def main():
                                            "%d blocks written for %d blocks of 1024 frames)" %
                                            (r_dev["extra"]["blocks_written"], nblk))
             line["stage_ms_per_step"]["transient_detector"] = r_dev["extra"]["transient_ms"]
-        if args.spreading == "factorised" and not args.no_sequential_sample and not args.block_switching and not strong:
+        solo = world == 1                # the side measurements below belong to the N = 1 line (cpu_baseline: "rank 0 at N=1 only")
+        if args.spreading == "factorised" and not args.no_sequential_sample and not args.block_switching and solo:
             # the same analysis kernel summing the maskers pair by pair in the reference's order, on a bounded
             # sample of the same stream: the kernel SURVEY 8d's 40-flop-per-pair work formula describes (here the formula
             # IS roughly what runs, so the reference-formulation flop count is used)
@@ -428,7 +429,7 @@ def main():
                                            "sample": "first %.0f s of the stream, 1 launch" % sample_s,
                                            "avg_launch_ms": ts["analysis_ms"]}
             cs.close()
-        if not args.no_decode and not strong:
+        if not args.no_decode and solo:
             # the mirror path (rows a14-a17): .pac bytes in pinned host memory -> int16 PCM in host memory
             nbytes = int(last_boff[0][-1])
             pac = h_out_np[:nbytes]
@@ -449,7 +450,7 @@ def main():
                               "d2h_bytes_per_step": int(pcm_out.nbytes),
                               "note": "decode of this rank's stream through Codec.decode_batch, host buffers, 3 steps"}
             del h_dec
-        if not args.no_music and args.workload == "stream" and not args.block_switching and not strong:
+        if not args.no_music and args.workload == "stream" and not args.block_switching and solo:
             # the same encode on dense-masker material (synth_music: chords of harmonic notes, most of the spectrum above
             # 40 dB SPL): the band-maximum search prunes far less there, so this is the unfriendly end of the input range
             ms_ = min(args.music_seconds, seconds)
@@ -474,7 +475,7 @@ def main():
                              "general_pairs_per_block": tm["general_pairs"] / max(tm["blocks"], 1),
                              "note": "device-resident encode of synth_music material (dense loud maskers), same codec"}
             del d_mus
-        if not args.no_cpu_baseline and not strong:
+        if not args.no_cpu_baseline and solo:
             line["cpu_baseline"] = cpu_baseline(pcm, args.cpu_sample_seconds)
         print(json.dumps(line))
     codec.close()
