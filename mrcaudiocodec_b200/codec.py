@@ -134,6 +134,13 @@ class Codec(object):
 
     @staticmethod
     def _concat(clips):
+        # frames x 2, nothing else: a mono array reshaped to (-1, 2) would be encoded as if its even and odd samples were
+        # the two channels.  One channel goes through the per-block seam (codec_gpu, nChannels = 1)
+        for i, c in enumerate(clips):
+            sh = np.shape(c)
+            if np.size(c) and (len(sh) != 2 or sh[1] != 2):
+                raise ValueError("clip %d has shape %r: the whole-file entry points take int16 [frames, 2] (stereo)"
+                                 % (i, tuple(sh)))
         clips = [np.ascontiguousarray(c, dtype=np.int16).reshape(-1, 2) for c in clips]
         off = np.zeros(len(clips) + 1, dtype=np.int64)
         off[1:] = np.cumsum([c.shape[0] for c in clips])

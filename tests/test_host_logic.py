@@ -184,3 +184,35 @@ def test_fft_swizzle_and_placement_are_conflict_free():
         for w0 in range(0, n, 32):      # a warp reads 32 consecutive inputs
             assert sorted(src[w0:w0 + 32]) == list(range(min(src[w0:w0 + 32]), min(src[w0:w0 + 32]) + 32)) or \
                 len({s & 31 for s in src[w0:w0 + 32]}) == 32
+
+
+def test_whole_file_entry_points_reject_non_stereo_clips():
+    """A mono array must not be re-read as stereo frames (even / odd samples as L / R); empty clips of any shape pass."""
+    from mrcaudiocodec_b200.codec import Codec
+    pcm, off = Codec._concat([np.zeros((0, 2), np.int16), np.ones((5, 2), np.int16), np.zeros(0, np.int16)])
+    assert pcm.shape == (5, 2) and off.tolist() == [0, 0, 5, 5]
+    for bad in (np.ones(10, np.int16), np.ones((10, 1), np.int16), np.ones((2, 10), np.int16)):
+        with pytest.raises(ValueError):
+            Codec._concat([bad])
+
+
+def test_pac_header_and_chunk_index_on_golden_files():
+    """pacfile.parse_header / chunk_index (host bookkeeping the CLI's decode uses) on the reference's own files: fields
+    as pacfileThem.py:592-613 writes them, chunk chain ends exactly at the end of the file, two chunks per block."""
+    import glob
+    from mrcaudiocodec_b200 import pacfile
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+    assert files
+    seen = 0
+    for f in files:
+        g = np.load(f, allow_pickle=True)
+        if "pac" not in g.files:
+            continue
+        blob = g["pac"].tobytes()
+        h = pacfile.parse_header(blob)
+        assert h["nChannels"] == 2 and h["nBands"] == len(h["nLines"]) and sum(h["nLines"]) == h["nMDCTLines"]
+        idx = pacfile.chunk_index(blob)
+        assert idx and idx[-1][0] + idx[-1][1] == len(blob) and len(idx) % 2 == 0
+        assert pacfile.huff_table_ids(blob).shape == (len(idx),)
+        seen += 1
+    assert seen >= 5
