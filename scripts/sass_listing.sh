@@ -17,7 +17,7 @@ for ln in txt:
     elif cur is not None:
         cur[1].append(ln)
 def short(name):
-    for k in ("analysis_kernelIdLi1024", "analysis_kernelIfLi1024", "cost_kernelId", "chain_table_kernel", "table_kernel", "chain_kernel",
+    for k in ("analysis_kernelIdLi1024ELb0", "analysis_kernelIfLi1024ELb0", "cost_kernelId", "chain_table_kernel", "chain_seg_kernel", "segment_kernel", "extras_kernel", "expand_kernel", "table_kernel", "chain_kernel", "parse_kernel",
               "finish_kernel", "offsets_kernel", "pack_kernelId", "decode_kernelIdLi1024", "ola_kernelId", "clip_scan_kernel", "analysis_kernelIdLi576", "analysis_kernelIdLi128", "peaks_kernelILi10", "decide_kernel"):
         if k in name: return k
     return None
@@ -36,10 +36,11 @@ for name, body in funcs:
     cols = ["DFMA", "DADD", "DMUL", "DSETP", "MUFU", "LDS", "STS", "LDG", "STG", "SHFL", "BAR", "REDUX", "VOTE", "ATOMS", "UBLKCP", "SYNCS", "HMMA"]
     utc = sum(v for k, v in ops.items() if k.startswith("UTC"))
     hist_lines.append("%s,%d,%s,%d" % (s, n, ",".join(str(ops[c]) for c in cols), utc))
-    if s in ("analysis_kernelIdLi1024", "chain_table_kernel", "chain_kernel"):
+    if s in ("analysis_kernelIdLi1024ELb0", "chain_seg_kernel", "chain_kernel"):
         keep[s] = body
 open('profiles/%s_sass_mnemonics.csv' % tag, 'w').write("\n".join(hist_lines) + "\n")
-for s, body in keep.items():
+import os
+for s, body in (keep.items() if os.environ.get("SASS_FULL_LISTINGS") else ()):     # ~350 KB each: only on request
     with open('profiles/%s_sass_%s.txt' % (tag, s), 'w') as fh:
         for ln in body:
             m = re.match(r'\s+/\*([0-9a-f]{4,6})\*/\s+(.*?)\s*/\*', ln)
